@@ -1,0 +1,178 @@
+/*
+ * itb200.h — C ABI of the B200-native block-sparse contraction path (libitb200.so).
+ *
+ * This is the thin `extern "C"` layer that the storage-type plugin (itensor_b200/plugin/*.h:
+ * DenseGPU<T>, QDenseGPU<T> and their doTask overloads) calls. Plain pointers and sizes only.
+ * All Index / QN / TagSet bookkeeping stays in the caller; what crosses this boundary is
+ *   - integer block structure (sector sizes, block coordinates, element offsets), and
+ *   - flat device (or host, for the *_host entry points) data pointers.
+ *
+ * Reference interfaces replaced (paths relative to the ITensor v3 tree):
+ *   itb_contract_*      doTask(Contract&,QDense<VA>,QDense<VB>,ManageStore&)   itensor/itdata/qdense.cc:671-747
+ *                       doTask(Contract&,Dense<T1>,Dense<T2>,ManageStore&)     itensor/itdata/dense.cc:262-330
+ *                       getContractedOffsets / loopContractedBlocks            itensor/itdata/qutil.h:93-371
+ *                       computeLabels / contractIS                             itensor/tensor/contract.h:155-202,
+ *                                                                              itensor/indexset_impl.h:77-129
+ *                       contract(TenRefc,Labels,TenRefc,Labels,TenRef,Labels)  itensor/tensor/contract.cc:843-866
+ *                       gemm                                                   itensor/tensor/gemm.cc:253-288
+ *   itb_permute_*       doTask(Order const&,QDense<T>&) / permuteQDense         itensor/itdata/qdense.cc:847-893
+ *                       doTask(Order const&,Dense<T>&)  / permuteDense          itensor/itdata/dense.cc:417-439
+ *                       add(PlusEQ,QDense,QDense) (permuting accumulate)        itensor/itdata/qdense.cc:515-549
+ *                       transform()                                             itensor/tensor/ten_impl.h:107-160
+ *   itb_nrm2            doTask(NormNoScale,QDense/Dense) -> dnrm2               qdense.cc:409-417, dense.cc:150-162
+ *   itb_axpy            PlusEQ trivial-permutation fast path -> daxpy           qdense.cc:523-529, dense.cc:380-385
+ *   itb_scal            doTask(Mult<Real/Cplx>,...)                             qdense.cc:303-325, dense.cc:112-136
+ *   itb_fill            doTask(Fill<T>,...)                                     qdense.cc:356-373, dense.cc:90-109
+ *   itb_conj            doTask(Conj,...)                                        qdense.cc:376-380, dense.cc:167-171
+ *   itb_get_elt         doTask(GetElt,...) (host read-back of one element)      qdense.cc:232-245, dense.cc:37-47
+ *   itb_flux_blocks     getBlockOffsets(IndexSet,QN)                            qdense.cc:133-173
+ *
+ * Conventions
+ *   - Everything is column-major inside a block: the FIRST index is the fastest
+ *     (itensor/tensor/range.h:197-206).
+ *   - Block lists are sorted by the reference's Block ordering: reverse-lexicographic,
+ *     i.e. the LAST index is most significant (itensor/itdata/qdense.cc:60-65).
+ *   - Complex data is interleaved (re,im) doubles, exactly std::complex<double>.
+ *   - A dense tensor is the special case of one sector per index and a single block.
+ *   - Every function returns ITB_OK (0) or a negative error code; itb_last_error() gives the
+ *     message. There is NO CPU fallback: entry points that need the device fail with
+ *     ITB_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef ITB200_H
+#define ITB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITB_OK 0
+#define ITB_ERR_INVALID (-1)     /* malformed arguments / structure */
+#define ITB_ERR_CUDA (-2)        /* CUDA runtime failure (message has the CUDA string) */
+#define ITB_ERR_UNSUPPORTED (-3) /* valid input outside what the kernels support */
+#define ITB_ERR_NOMEM (-4)
+
+#define ITB_MAX_ORDER 12 /* indices per tensor (reference Block = InfArray<long,11> + heap) */
+
+enum { ITB_F64 = 0, ITB_C64 = 1 };
+
+typedef struct itb_ctx itb_ctx;                     /* one per (process, GPU): stream + memory pool */
+typedef struct itb_contract_plan itb_contract_plan; /* host-computed block-pair tables */
+typedef struct itb_permute_plan itb_permute_plan;   /* host-computed block-permute tables */
+
+/* Integer structure of a (block-sparse or dense) tensor; pointers are borrowed for the call. */
+typedef struct itb_tensor_desc {
+    int32_t order;          /* number of indices */
+    int32_t dtype;          /* ITB_F64 | ITB_C64 */
+    const int32_t* nsect;   /* [order] sectors (QN blocks) per index */
+    const int64_t* sect;    /* concatenated sector sizes, sum(nsect) entries (Index::blocksize0) */
+    int64_t nblocks;        /* stored blocks */
+    const int32_t* blocks;  /* [nblocks*order] block coordinates, reference-sorted */
+    const int64_t* offsets; /* [nblocks] element offset of each block in the flat store */
+    int64_t nelems;         /* elements in the flat store (QDense::store.size()) */
+} itb_tensor_desc;
+
+typedef struct itb_contract_info {
+    int32_t c_order;
+    int32_t c_dtype;
+    int64_t c_nblocks;
+    int64_t c_nelems;
+    int64_t npairs;       /* (A block, B block) pairs == reference blockContractions.size() */
+    double flops;         /* sum_pairs 2*M*N*K (x2 real*cplx, x4 cplx*cplx)  — SURVEY §8(d) */
+    int64_t n_gemm_tiles; /* work items of the DMMA tile kernel */
+    int64_t n_skinny;     /* work items of the streaming (min(M,N) small) kernel */
+    int64_t n_dot;        /* work items of the split-K reduction kernel */
+    int64_t table_bytes;  /* bytes of compact tables uploaded to the device */
+} itb_contract_info;
+
+/* ---- library / context ------------------------------------------------------------------ */
+const char* itb_version(void);
+const char* itb_last_error(void);
+int itb_device_count(void);
+int itb_ctx_create(int device, itb_ctx** out);
+int itb_ctx_destroy(itb_ctx* ctx);
+void* itb_ctx_stream(itb_ctx* ctx);                 /* the cudaStream_t every launch goes to */
+int itb_ctx_set_stream(itb_ctx* ctx, void* stream); /* adopt a caller-owned stream */
+int itb_synchronize(itb_ctx* ctx);
+int64_t itb_launch_count(itb_ctx* ctx);             /* kernels launched through this context */
+
+/* ---- device memory (stream-ordered caching pool) ---------------------------------------- */
+int itb_malloc(itb_ctx* ctx, size_t bytes, void** dptr);
+int itb_free(itb_ctx* ctx, void* dptr);
+int itb_memcpy_h2d(itb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int itb_memcpy_d2h(itb_ctx* ctx, void* dst, const void* src, size_t bytes); /* synchronises */
+int itb_memcpy_d2d(itb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int itb_memset0(itb_ctx* ctx, void* dst, size_t bytes);
+int itb_pool_trim(itb_ctx* ctx);
+
+/* ---- host-only integer planning (no device needed) --------------------------------------- */
+/* labels: arbitrary ints; a label present in both labA and labB marks a contracted index. */
+int itb_contract_plan_create(const itb_tensor_desc* A, const int32_t* labA,
+                             const itb_tensor_desc* B, const int32_t* labB,
+                             itb_contract_plan** out);
+int itb_contract_plan_destroy(itb_contract_plan* plan);
+int itb_contract_plan_info(const itb_contract_plan* plan, itb_contract_info* out);
+/* result structure, in the reference's order (contractIS with sortResult=false) */
+int itb_contract_plan_c_labels(const itb_contract_plan* plan, int32_t* labels /*[c_order]*/);
+int itb_contract_plan_c_nsect(const itb_contract_plan* plan, int32_t* nsect /*[c_order]*/);
+int itb_contract_plan_c_sect(const itb_contract_plan* plan, int64_t* sect /*[sum nsect]*/);
+int itb_contract_plan_c_blocks(const itb_contract_plan* plan, int32_t* blocks /*[c_nblocks*c_order]*/);
+int itb_contract_plan_c_offsets(const itb_contract_plan* plan, int64_t* offsets /*[c_nblocks]*/);
+/* (iA,iB,iC) positions into the three block lists, in the reference's enumeration order */
+int itb_contract_plan_pairs(const itb_contract_plan* plan, int64_t* triples /*[npairs*3]*/);
+/* restrict execution to C blocks [first,last) — the output-block sharding unit for multi-GPU */
+int itb_contract_plan_set_cblock_range(itb_contract_plan* plan, int64_t first, int64_t last);
+
+/* blocks allowed by a total flux: sum_j dir[j]*qn(index j, sector) == flux (component-wise,
+ * component c taken modulo |mod[c]| when |mod[c]|>1). qn: for index j, sector s, component c:
+ * qn[(sect_start[j]+s)*nqn + c]. Returns the count; writes at most cap blocks (may be NULL). */
+int64_t itb_flux_blocks(int32_t order, const int32_t* nsect, const int32_t* qn, int32_t nqn,
+                        const int32_t* mod, const int32_t* dir, const int32_t* flux,
+                        int32_t* blocks, int64_t cap);
+
+/* ---- contraction -------------------------------------------------------------------------- */
+/* C = A*B over all matching block pairs; dA,dB,dC device pointers; C is fully overwritten. */
+int itb_contract_run(itb_ctx* ctx, itb_contract_plan* plan, const void* dA, const void* dB, void* dC);
+/* same through HOST buffers: H2D(A,B) + run + D2H(C) (the end-to-end path) */
+int itb_contract_host(itb_ctx* ctx, itb_contract_plan* plan, const void* hA, const void* hB, void* hC);
+
+/* ---- permute / permuting accumulate ------------------------------------------------------- */
+/* perm[i] = position in dst of src index i (reference Permutation::dest(i)). Every src block
+ * must have its image in dst; dst blocks without a source are zero-filled when !accumulate.
+ * dst dtype may be C64 with src F64 (promotion). */
+int itb_permute_plan_create(const itb_tensor_desc* src, const itb_tensor_desc* dst,
+                            const int32_t* perm, itb_permute_plan** out);
+int itb_permute_plan_destroy(itb_permute_plan* plan);
+int64_t itb_permute_plan_bytes(const itb_permute_plan* plan); /* algorithmic bytes: read src + write dst */
+/* dst = alpha*P(src)   (accumulate==0)   or   dst += alpha*P(src)   (accumulate!=0) */
+int itb_permute_run(itb_ctx* ctx, itb_permute_plan* plan, const void* dSrc, void* dDst,
+                    double alpha_re, double alpha_im, int accumulate);
+int itb_permute_host(itb_ctx* ctx, itb_permute_plan* plan, const void* hSrc, void* hDst,
+                     double alpha_re, double alpha_im, int accumulate);
+
+/* ---- BLAS-1 style storage tasks (n counts ELEMENTS of the given dtype) -------------------- */
+int itb_nrm2(itb_ctx* ctx, int32_t dtype, int64_t n, const void* dX, double* out); /* syncs */
+int itb_scal(itb_ctx* ctx, int32_t dtype, int64_t n, void* dX, double alpha_re, double alpha_im);
+int itb_axpy(itb_ctx* ctx, int32_t dtype, int64_t n, double alpha_re, double alpha_im,
+             const void* dX, void* dY); /* Y += alpha X, same dtype */
+int itb_fill(itb_ctx* ctx, int32_t dtype, int64_t n, void* dX, double re, double im);
+int itb_conj(itb_ctx* ctx, int64_t n, void* dX);                 /* C64 in place */
+int itb_real_to_cplx(itb_ctx* ctx, int64_t n, const void* dX, void* dY);
+int itb_take_part(itb_ctx* ctx, int64_t n, const void* dX, void* dY, int imag);
+int itb_get_elt(itb_ctx* ctx, int32_t dtype, const void* dX, int64_t offset, double out[2]); /* syncs */
+int itb_dot(itb_ctx* ctx, int32_t dtype, int64_t n, const void* dX, const void* dY, int conj_x,
+            double out[2]); /* syncs */
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* bare DMMA (mma.sync f64) and DFMA issue loops, no memory traffic; returns TFLOP/s */
+int itb_peak_fp64(itb_ctx* ctx, int which /*0=dmma m8n8k4, 1=dfma, 2=dmma m16n8k8*/, int iters, double* tflops);
+/* device-side timing on the context's stream (CUDA events) */
+int itb_timer_start(itb_ctx* ctx);
+int itb_timer_stop_ms(itb_ctx* ctx, float* ms); /* syncs */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITB200_H */

@@ -1,0 +1,523 @@
+// api.cu — device-facing half of the C ABI (include/itb200.h): context, stream-ordered memory pool,
+// table upload and kernel launches. Host-only planning lives in plan.cc.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "plan.h"
+
+namespace itb {
+cudaError_t launch_gemm(int cfg, const ItbTile* tiles, int ntiles, const ItbCBlk* cblks, const ItbPair* pairs, const double* A,
+                        const double* B, double* C, int* counter, int num_sms, cudaStream_t st);
+cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbCBlk* cblks, const ItbPair* pairs, const double* A,
+                          const double* B, double* C, cudaStream_t st);
+cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
+                       const double* A, const double* B, double* partial, double* C, cudaStream_t st);
+cudaError_t launch_peak(int which, int iters, double* out, int num_sms, cudaStream_t st);
+cudaError_t launch_permute(int src_cplx, int dst_cplx, const ItbPermBlk* bc, int nbc, int64_t items_c, const ItbPermBlk* bt, int nbt,
+                           int64_t items_t, const void* src, void* dst, double ar, double ai, int accum, cudaStream_t st,
+                           int* launches);
+cudaError_t launch_scal(int cplx, int64_t n, void* x, double ar, double ai, int sms, cudaStream_t st);
+cudaError_t launch_axpy(int cplx, int64_t n, double ar, double ai, const void* x, void* y, int sms, cudaStream_t st);
+cudaError_t launch_fill(int cplx, int64_t n, void* x, double re, double im, int sms, cudaStream_t st);
+cudaError_t launch_conj(int64_t n, void* x, int sms, cudaStream_t st);
+cudaError_t launch_r2c(int64_t n, const void* x, void* y, int sms, cudaStream_t st);
+cudaError_t launch_part(int64_t n, const void* x, void* y, int imag, int sms, cudaStream_t st);
+cudaError_t launch_ssq(int64_t nreal, const void* x, double scale, double* scratch, int* grid_out, int sms, cudaStream_t st);
+cudaError_t launch_dot1(int cplx, int64_t n, const void* x, const void* y, int conj_x, double* scratch, int* grid_out, int sms,
+                        cudaStream_t st);
+
+struct DeviceTables {
+    void* base = nullptr; // one pooled allocation holding every table of the plan
+    size_t bytes = 0;
+    const ItbPair* pairs = nullptr;
+    const ItbCBlk* cblks = nullptr;
+    const ItbTile* tiles[ITB_NCFG] = {nullptr, nullptr, nullptr};
+    const ItbSkinny* skinny = nullptr;
+    const ItbDot* dots = nullptr;
+    const ItbDotOut* dot_outs = nullptr;
+    double* dot_partial = nullptr;
+    int* counters = nullptr; // ITB_NCFG work-queue heads
+    const ItbPermBlk* pcopy = nullptr;
+    const ItbPermBlk* ptiled = nullptr;
+};
+} // namespace itb
+
+using namespace itb;
+
+struct itb_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int64_t launches = 0;
+    // caching pool: freed blocks are kept by rounded size; everything runs on one stream so reuse
+    // is stream-ordered and needs no events
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    size_t pooled_bytes = 0;
+    void* staging = nullptr; // pinned host staging for small uploads (tables)
+    size_t staging_bytes = 0;
+    double* scratch = nullptr; // device scratch for reductions
+    size_t scratch_doubles = 0;
+    double* h_result = nullptr; // pinned 4 doubles
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                               \
+            return ITB_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static size_t round_size(size_t b) {
+    if (b < 512) return 512;
+    if (b < (1u << 20)) return (b + 511) & ~(size_t)511;
+    return (b + ((1u << 20) - 1)) & ~(size_t)((1u << 20) - 1);
+}
+
+static int pool_alloc(itb_ctx* c, size_t bytes, void** out) {
+    const size_t r = round_size(bytes);
+    auto it = c->free_blocks.lower_bound(r);
+    if (it != c->free_blocks.end() && it->first <= r + r / 4 + 4096) {
+        *out = it->second;
+        c->live[*out] = it->first;
+        c->pooled_bytes -= it->first;
+        c->free_blocks.erase(it);
+        return ITB_OK;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, r);
+    if (e != cudaSuccess) {
+        // trim the cache and retry once
+        for (auto& kv : c->free_blocks) cudaFree(kv.second);
+        c->free_blocks.clear();
+        c->pooled_bytes = 0;
+        (void)cudaGetLastError();
+        e = cudaMalloc(&p, r);
+        if (e != cudaSuccess) {
+            set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? ITB_ERR_NOMEM : ITB_ERR_CUDA;
+        }
+    }
+    c->live[p] = r;
+    *out = p;
+    return ITB_OK;
+}
+static int pool_free(itb_ctx* c, void* p) {
+    if (!p) return ITB_OK;
+    auto it = c->live.find(p);
+    if (it == c->live.end()) { set_error("itb_free: pointer not owned by this context"); return ITB_ERR_INVALID; }
+    c->free_blocks.emplace(it->second, p);
+    c->pooled_bytes += it->second;
+    c->live.erase(it);
+    return ITB_OK;
+}
+
+static int ensure_scratch(itb_ctx* c, size_t doubles) {
+    if (c->scratch_doubles >= doubles) return ITB_OK;
+    if (c->scratch) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->scratch); c->scratch = nullptr; }
+    CUDA_TRY(cudaMalloc(&c->scratch, doubles * sizeof(double)));
+    c->scratch_doubles = doubles;
+    return ITB_OK;
+}
+static int ensure_staging(itb_ctx* c, size_t bytes) {
+    if (c->staging_bytes >= bytes) return ITB_OK;
+    if (c->staging) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->staging); c->staging = nullptr; }
+    size_t nb = std::max<size_t>(bytes, 1u << 20);
+    CUDA_TRY(cudaMallocHost(&c->staging, nb));
+    c->staging_bytes = nb;
+    return ITB_OK;
+}
+
+// pack host vectors into one staging buffer, one H2D copy, carve device pointers
+struct Packer {
+    std::vector<std::pair<const void*, size_t>> parts;
+    std::vector<size_t> offs;
+    size_t total = 0;
+    size_t add(const void* p, size_t bytes) {
+        const size_t o = total;
+        parts.push_back({p, bytes});
+        offs.push_back(o);
+        total += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+extern "C" {
+
+const char* itb_version(void) { return "itb200 0.1 (sm_100a)"; }
+
+int itb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+int itb_ctx_create(int device, itb_ctx** out) {
+    if (!out) { set_error("ctx_create: null out"); return ITB_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        set_error("itb_ctx_create: no usable CUDA device (this library has no CPU fallback)");
+        return ITB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("ctx_create: bad device ordinal"); return ITB_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(device));
+    auto* c = new itb_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        set_error("itb_ctx_create: kernels are built for sm_100a only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+        delete c;
+        return ITB_ERR_CUDA;
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMallocHost(&c->h_result, 8 * sizeof(double)));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    *out = c;
+    return ITB_OK;
+}
+
+int itb_ctx_destroy(itb_ctx* c) {
+    if (!c) return ITB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->free_blocks) cudaFree(kv.second);
+    for (auto& kv : c->live) cudaFree(kv.first);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->staging) cudaFreeHost(c->staging);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return ITB_OK;
+}
+
+void* itb_ctx_stream(itb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int itb_ctx_set_stream(itb_ctx* c, void* s) {
+    if (!c) { set_error("set_stream: null ctx"); return ITB_ERR_INVALID; }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return ITB_OK;
+}
+int itb_synchronize(itb_ctx* c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return ITB_OK; }
+int64_t itb_launch_count(itb_ctx* c) { return c ? c->launches : 0; }
+
+int itb_malloc(itb_ctx* c, size_t bytes, void** dptr) {
+    if (!c || !dptr) { set_error("itb_malloc: null"); return ITB_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    return pool_alloc(c, bytes ? bytes : 1, dptr);
+}
+int itb_free(itb_ctx* c, void* p) { return pool_free(c, p); }
+int itb_memcpy_h2d(itb_ctx* c, void* d, const void* s, size_t b) {
+    if (b) CUDA_TRY(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, c->stream));
+    return ITB_OK;
+}
+int itb_memcpy_d2h(itb_ctx* c, void* d, const void* s, size_t b) {
+    if (b) CUDA_TRY(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ITB_OK;
+}
+int itb_memcpy_d2d(itb_ctx* c, void* d, const void* s, size_t b) {
+    if (b) CUDA_TRY(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, c->stream));
+    return ITB_OK;
+}
+int itb_memset0(itb_ctx* c, void* d, size_t b) {
+    if (b) CUDA_TRY(cudaMemsetAsync(d, 0, b, c->stream));
+    return ITB_OK;
+}
+int itb_pool_trim(itb_ctx* c) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (auto& kv : c->free_blocks) cudaFree(kv.second);
+    c->free_blocks.clear();
+    c->pooled_bytes = 0;
+    return ITB_OK;
+}
+
+// ---- plan device tables ---------------------------------------------------------------------------
+static void release_tables(DeviceTables*& dev, void*& dev_ctx) {
+    if (!dev) return;
+    auto* c = (itb_ctx*)dev_ctx;
+    if (c && dev->base) pool_free(c, dev->base);
+    delete dev;
+    dev = nullptr;
+    dev_ctx = nullptr;
+}
+void itb_contract_plan_release_device(itb_contract_plan* P) { release_tables(P->dev, P->dev_ctx); }
+void itb_permute_plan_release_device(itb_permute_plan* P) { release_tables(P->dev, P->dev_ctx); }
+
+static int upload(itb_ctx* c, Packer& pk, size_t extra_dev_bytes, DeviceTables* dev) {
+    const size_t total = pk.total + extra_dev_bytes;
+    int rc = pool_alloc(c, total ? total : 256, &dev->base);
+    if (rc != ITB_OK) return rc;
+    dev->bytes = total;
+    if (pk.total) {
+        rc = ensure_staging(c, pk.total);
+        if (rc != ITB_OK) return rc;
+        // the staging buffer may still be in flight from a previous upload
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < pk.parts.size(); ++i)
+            if (pk.parts[i].second) std::memcpy((char*)c->staging + pk.offs[i], pk.parts[i].first, pk.parts[i].second);
+        CUDA_TRY(cudaMemcpyAsync(dev->base, c->staging, pk.total, cudaMemcpyHostToDevice, c->stream));
+    }
+    return ITB_OK;
+}
+
+static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
+    if (P->dev && P->dev_ctx == c) return ITB_OK;
+    if (P->dev) release_tables(P->dev, P->dev_ctx);
+    if (!P->tables_built) { int rc = build_contract_tables(*P); if (rc != ITB_OK) return rc; }
+    auto* dev = new DeviceTables();
+    Packer pk;
+    const size_t o_pairs = pk.add(P->pairs.data(), P->pairs.size() * sizeof(ItbPair));
+    const size_t o_cblk = pk.add(P->cblks.data(), P->cblks.size() * sizeof(ItbCBlk));
+    size_t o_tiles[ITB_NCFG];
+    for (int f = 0; f < ITB_NCFG; ++f) o_tiles[f] = pk.add(P->tiles[f].data(), P->tiles[f].size() * sizeof(ItbTile));
+    const size_t o_sk = pk.add(P->skinny.data(), P->skinny.size() * sizeof(ItbSkinny));
+    const size_t o_dot = pk.add(P->dots.data(), P->dots.size() * sizeof(ItbDot));
+    const size_t o_dout = pk.add(P->dot_outs.data(), P->dot_outs.size() * sizeof(ItbDotOut));
+    const size_t partial_bytes = ((size_t)P->ndot_slots * 4 * sizeof(double) + 255) & ~(size_t)255;
+    const size_t extra = partial_bytes + 256;
+    int rc = upload(c, pk, extra, dev);
+    if (rc != ITB_OK) { delete dev; return rc; }
+    char* b = (char*)dev->base;
+    dev->pairs = (const ItbPair*)(b + o_pairs);
+    dev->cblks = (const ItbCBlk*)(b + o_cblk);
+    for (int f = 0; f < ITB_NCFG; ++f) dev->tiles[f] = (const ItbTile*)(b + o_tiles[f]);
+    dev->skinny = (const ItbSkinny*)(b + o_sk);
+    dev->dots = (const ItbDot*)(b + o_dot);
+    dev->dot_outs = (const ItbDotOut*)(b + o_dout);
+    dev->dot_partial = (double*)(b + pk.total);
+    dev->counters = (int*)(b + pk.total + partial_bytes);
+    P->dev = dev;
+    P->dev_ctx = c;
+    return ITB_OK;
+}
+
+int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC) {
+    if (!c || !P) { set_error("contract_run: null"); return ITB_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK; // no output blocks: nothing to do
+    int rc = ensure_contract_tables(c, P);
+    if (rc != ITB_OK) return rc;
+    DeviceTables* d = P->dev;
+    const double* A = (const double*)dA;
+    const double* B = (const double*)dB;
+    double* C = (double*)dC;
+    bool any_tiles = false;
+    for (int f = 0; f < ITB_NCFG; ++f) any_tiles |= !P->tiles[f].empty();
+    if (any_tiles) CUDA_TRY(cudaMemsetAsync(d->counters, 0, ITB_NCFG * sizeof(int), c->stream));
+    for (int f = 0; f < ITB_NCFG; ++f) {
+        if (P->tiles[f].empty()) continue;
+        CUDA_TRY(launch_gemm(f, d->tiles[f], (int)P->tiles[f].size(), d->cblks, d->pairs, A, B, C, d->counters + f, c->num_sms, c->stream));
+        ++c->launches;
+    }
+    if (!P->skinny.empty()) {
+        CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->cblks, d->pairs, A, B, C, c->stream));
+        ++c->launches;
+    }
+    if (!P->dots.empty()) {
+        CUDA_TRY(launch_dot(d->dots, (int)P->dots.size(), d->dot_outs, (int)P->dot_outs.size(), d->cblks, d->pairs, A, B, d->dot_partial, C, c->stream));
+        c->launches += 2;
+    }
+    return ITB_OK;
+}
+
+int itb_contract_host(itb_ctx* c, itb_contract_plan* P, const void* hA, const void* hB, void* hC) {
+    if (!c || !P) { set_error("contract_host: null"); return ITB_ERR_INVALID; }
+    const size_t ba = (size_t)P->A.nelems * (P->A.dtype == ITB_C64 ? 16 : 8);
+    const size_t bb = (size_t)P->B.nelems * (P->B.dtype == ITB_C64 ? 16 : 8);
+    const size_t bc = (size_t)P->C.nelems * (P->C.dtype == ITB_C64 ? 16 : 8);
+    void *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    int rc = itb_malloc(c, ba, &dA);
+    if (rc == ITB_OK) rc = itb_malloc(c, bb, &dB);
+    if (rc == ITB_OK) rc = itb_malloc(c, bc, &dC);
+    if (rc == ITB_OK) rc = itb_memcpy_h2d(c, dA, hA, ba);
+    if (rc == ITB_OK) rc = itb_memcpy_h2d(c, dB, hB, bb);
+    if (rc == ITB_OK) rc = itb_contract_run(c, P, dA, dB, dC);
+    if (rc == ITB_OK) rc = itb_memcpy_d2h(c, hC, dC, bc);
+    if (dA) pool_free(c, dA);
+    if (dB) pool_free(c, dB);
+    if (dC) pool_free(c, dC);
+    return rc;
+}
+
+static int ensure_permute_tables(itb_ctx* c, itb_permute_plan* P) {
+    if (P->dev && P->dev_ctx == c) return ITB_OK;
+    if (P->dev) release_tables(P->dev, P->dev_ctx);
+    auto* dev = new DeviceTables();
+    Packer pk;
+    const size_t o_c = pk.add(P->blks_copy.data(), P->blks_copy.size() * sizeof(ItbPermBlk));
+    const size_t o_t = pk.add(P->blks_tiled.data(), P->blks_tiled.size() * sizeof(ItbPermBlk));
+    int rc = upload(c, pk, 0, dev);
+    if (rc != ITB_OK) { delete dev; return rc; }
+    dev->pcopy = (const ItbPermBlk*)((char*)dev->base + o_c);
+    dev->ptiled = (const ItbPermBlk*)((char*)dev->base + o_t);
+    P->dev = dev;
+    P->dev_ctx = c;
+    return ITB_OK;
+}
+
+int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* dSrc, void* dDst, double ar, double ai, int accumulate) {
+    if (!c || !P) { set_error("permute_run: null"); return ITB_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (P->S.dtype == ITB_F64 && P->D.dtype == ITB_F64 && ai != 0.0) { set_error("permute_run: complex alpha on a real destination"); return ITB_ERR_INVALID; }
+    if (!accumulate && P->need_zero && P->D.nelems > 0)
+        CUDA_TRY(cudaMemsetAsync(dDst, 0, (size_t)P->D.nelems * (P->D.dtype == ITB_C64 ? 16 : 8), c->stream));
+    if (P->S.nblocks == 0) return ITB_OK;
+    int rc = ensure_permute_tables(c, P);
+    if (rc != ITB_OK) return rc;
+    int launches = 0;
+    CUDA_TRY(launch_permute(P->S.dtype == ITB_C64, P->D.dtype == ITB_C64, P->dev->pcopy, (int)P->blks_copy.size(), P->items_copy,
+                            P->dev->ptiled, (int)P->blks_tiled.size(), P->items_tiled, dSrc, dDst, ar, ai, accumulate, c->stream, &launches));
+    c->launches += launches;
+    return ITB_OK;
+}
+
+int itb_permute_host(itb_ctx* c, itb_permute_plan* P, const void* hSrc, void* hDst, double ar, double ai, int accumulate) {
+    if (!c || !P) { set_error("permute_host: null"); return ITB_ERR_INVALID; }
+    const size_t bs = (size_t)P->S.nelems * (P->S.dtype == ITB_C64 ? 16 : 8);
+    const size_t bd = (size_t)P->D.nelems * (P->D.dtype == ITB_C64 ? 16 : 8);
+    void *dS = nullptr, *dD = nullptr;
+    int rc = itb_malloc(c, bs, &dS);
+    if (rc == ITB_OK) rc = itb_malloc(c, bd, &dD);
+    if (rc == ITB_OK) rc = itb_memcpy_h2d(c, dS, hSrc, bs);
+    if (rc == ITB_OK && accumulate) rc = itb_memcpy_h2d(c, dD, hDst, bd);
+    if (rc == ITB_OK) rc = itb_permute_run(c, P, dS, dD, ar, ai, accumulate);
+    if (rc == ITB_OK) rc = itb_memcpy_d2h(c, hDst, dD, bd);
+    if (dS) pool_free(c, dS);
+    if (dD) pool_free(c, dD);
+    return rc;
+}
+
+// ---- BLAS-1 ---------------------------------------------------------------------------------------------
+int itb_scal(itb_ctx* c, int32_t dtype, int64_t n, void* x, double ar, double ai) {
+    if (dtype == ITB_F64 && ai != 0.0) { set_error("itb_scal: complex factor on real data"); return ITB_ERR_INVALID; }
+    CUDA_TRY(launch_scal(dtype == ITB_C64, n, x, ar, ai, c->num_sms, c->stream));
+    if (n > 0) ++c->launches;
+    return ITB_OK;
+}
+int itb_axpy(itb_ctx* c, int32_t dtype, int64_t n, double ar, double ai, const void* x, void* y) {
+    if (dtype == ITB_F64 && ai != 0.0) { set_error("itb_axpy: complex factor on real data"); return ITB_ERR_INVALID; }
+    CUDA_TRY(launch_axpy(dtype == ITB_C64, n, ar, ai, x, y, c->num_sms, c->stream));
+    if (n > 0) ++c->launches;
+    return ITB_OK;
+}
+int itb_fill(itb_ctx* c, int32_t dtype, int64_t n, void* x, double re, double im) {
+    CUDA_TRY(launch_fill(dtype == ITB_C64, n, x, re, im, c->num_sms, c->stream));
+    if (n > 0) ++c->launches;
+    return ITB_OK;
+}
+int itb_conj(itb_ctx* c, int64_t n, void* x) {
+    CUDA_TRY(launch_conj(n, x, c->num_sms, c->stream));
+    if (n > 0) ++c->launches;
+    return ITB_OK;
+}
+int itb_real_to_cplx(itb_ctx* c, int64_t n, const void* x, void* y) {
+    CUDA_TRY(launch_r2c(n, x, y, c->num_sms, c->stream));
+    if (n > 0) ++c->launches;
+    return ITB_OK;
+}
+int itb_take_part(itb_ctx* c, int64_t n, const void* x, void* y, int imag) {
+    CUDA_TRY(launch_part(n, x, y, imag, c->num_sms, c->stream));
+    if (n > 0) ++c->launches;
+    return ITB_OK;
+}
+
+int itb_nrm2(itb_ctx* c, int32_t dtype, int64_t n, const void* x, double* out) {
+    if (!out) { set_error("itb_nrm2: null out"); return ITB_ERR_INVALID; }
+    *out = 0.0;
+    if (n <= 0) return ITB_OK;
+    const int64_t nr = dtype == ITB_C64 ? 2 * n : n;
+    int rc = ensure_scratch(c, (size_t)c->num_sms * 8 * 2 + 8);
+    if (rc != ITB_OK) return rc;
+    int g = 0;
+    CUDA_TRY(launch_ssq(nr, x, 1.0, c->scratch, &g, c->num_sms, c->stream));
+    c->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(c->h_result, c->scratch + 2 * g, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double ssq = c->h_result[0];
+    const double mx = c->h_result[1];
+    // dnrm2 is overflow/underflow safe (scaled sum of squares); redo scaled only when the plain sum left the
+    // comfortable range
+    if (mx > 0.0 && (!(ssq < 1e300) || ssq < 1e-280)) {
+        CUDA_TRY(launch_ssq(nr, x, 1.0 / mx, c->scratch, &g, c->num_sms, c->stream));
+        c->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(c->h_result, c->scratch + 2 * g, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        *out = mx * std::sqrt(c->h_result[0]);
+        return ITB_OK;
+    }
+    *out = std::sqrt(ssq);
+    return ITB_OK;
+}
+
+int itb_dot(itb_ctx* c, int32_t dtype, int64_t n, const void* x, const void* y, int conj_x, double out[2]) {
+    out[0] = out[1] = 0.0;
+    if (n <= 0) return ITB_OK;
+    int rc = ensure_scratch(c, (size_t)c->num_sms * 8 * 2 + 8);
+    if (rc != ITB_OK) return rc;
+    int g = 0;
+    CUDA_TRY(launch_dot1(dtype == ITB_C64, n, x, y, conj_x, c->scratch, &g, c->num_sms, c->stream));
+    c->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(c->h_result, c->scratch + 2 * g, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out[0] = c->h_result[0];
+    out[1] = c->h_result[1];
+    return ITB_OK;
+}
+
+int itb_get_elt(itb_ctx* c, int32_t dtype, const void* x, int64_t offset, double out[2]) {
+    const size_t es = dtype == ITB_C64 ? 16 : 8;
+    out[1] = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(c->h_result, (const char*)x + offset * es, es, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out[0] = c->h_result[0];
+    if (dtype == ITB_C64) out[1] = c->h_result[1];
+    return ITB_OK;
+}
+
+int itb_peak_fp64(itb_ctx* c, int which, int iters, double* tflops) {
+    int rc = ensure_scratch(c, 64);
+    if (rc != ITB_OK) return rc;
+    CUDA_TRY(launch_peak(which, 16, c->scratch, c->num_sms, c->stream)); // warm-up
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    CUDA_TRY(launch_peak(which, iters, c->scratch, c->num_sms, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double warps = (double)c->num_sms * 8 * 8;
+    const double flops = which == 1 ? warps * 32.0 * 16.0 * 2.0 * iters : warps * 8.0 * 512.0 * iters;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    c->launches += 2;
+    return ITB_OK;
+}
+
+int itb_timer_start(itb_ctx* c) { CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); return ITB_OK; }
+int itb_timer_stop_ms(itb_ctx* c, float* ms) {
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return ITB_OK;
+}
+
+} // extern "C"

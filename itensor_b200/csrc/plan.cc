@@ -1,0 +1,605 @@
+// plan.cc — host-side integer planning for the block-sparse contraction and permute paths.
+//
+// What the reference does per call on the CPU, restated for a table-driven GPU launch:
+//   * label matching + result index order : computeLabels (itensor/tensor/contract.h:155-202),
+//                                           contractIS   (itensor/indexset_impl.h:77-129)
+//   * block-pair enumeration + C offsets  : getContractedOffsets (itensor/itdata/qutil.h:93-242)
+//   * per-pair GEMM shape analysis        : CProps::compute (itensor/tensor/contract.cc:240-548)
+//
+// Differences by design (B200-first, not a port):
+//   * pairs are found through a hash on the contracted block coordinates (O(nA+nB+npairs))
+//     instead of the O(nA*nB) scan, but are emitted in the SAME order (A outer, B inner);
+//   * no operand is ever permuted/materialised: each pair carries separable offset tables
+//     (extent/stride lists for its M, K, N index groups) and the kernel gathers tiles directly;
+//   * all pairs of one C block form one K-loop owned by one CTA tile (no beta, no atomics);
+//   * complex operands are folded into a REAL problem (see fold_complex) so one FP64 kernel
+//     serves the four real/complex pairings (reference: 4 DGEMMs, tensor/gemm.cc:165-230).
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <unordered_map>
+
+namespace itb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+int parse_desc(const itb_tensor_desc* d, TensorStruct& t, const char* what) {
+    if (!d) { set_error(std::string(what) + ": null descriptor"); return ITB_ERR_INVALID; }
+    if (d->order < 0 || d->order > ITB_MAX_ORDER) {
+        set_error(std::string(what) + ": order out of range");
+        return ITB_ERR_INVALID;
+    }
+    if (d->dtype != ITB_F64 && d->dtype != ITB_C64) {
+        set_error(std::string(what) + ": bad dtype");
+        return ITB_ERR_INVALID;
+    }
+    t.order = d->order;
+    t.dtype = d->dtype;
+    t.nsect.assign(d->nsect, d->nsect + d->order);
+    t.sect_start.assign(d->order + 1, 0);
+    for (int j = 0; j < d->order; ++j) {
+        if (t.nsect[j] <= 0) { set_error(std::string(what) + ": index with no sectors"); return ITB_ERR_INVALID; }
+        t.sect_start[j + 1] = t.sect_start[j] + t.nsect[j];
+    }
+    t.sect.assign(d->sect, d->sect + t.sect_start[d->order]);
+    for (auto s : t.sect)
+        if (s <= 0) { set_error(std::string(what) + ": non-positive sector size"); return ITB_ERR_INVALID; }
+    t.nblocks = d->nblocks;
+    if (t.nblocks < 0) { set_error(std::string(what) + ": negative block count"); return ITB_ERR_INVALID; }
+    t.blocks.assign(d->blocks, d->blocks + t.nblocks * d->order);
+    t.offsets.assign(d->offsets, d->offsets + t.nblocks);
+    t.nelems = d->nelems;
+    for (int64_t b = 0; b < t.nblocks; ++b) {
+        int64_t sz = 1;
+        for (int j = 0; j < t.order; ++j) {
+            int32_t c = t.block(b)[j];
+            if (c < 0 || c >= t.nsect[j]) { set_error(std::string(what) + ": block coordinate out of range"); return ITB_ERR_INVALID; }
+            sz *= t.ext(j, c);
+        }
+        if (t.offsets[b] < 0 || t.offsets[b] + sz > t.nelems) {
+            set_error(std::string(what) + ": block exceeds storage");
+            return ITB_ERR_INVALID;
+        }
+    }
+    return ITB_OK;
+}
+
+// reference Block ordering (itensor/itdata/qdense.cc:60-65): lexicographic on the REVERSED coordinates
+static bool block_less(const int32_t* a, const int32_t* b, int r) {
+    for (int j = r - 1; j >= 0; --j) {
+        if (a[j] != b[j]) return a[j] < b[j];
+    }
+    return false;
+}
+
+struct VecHash {
+    size_t operator()(const std::vector<int32_t>& v) const {
+        uint64_t h = 1469598103934665603ull;
+        for (auto x : v) { h ^= (uint32_t)x + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); }
+        return (size_t)h;
+    }
+};
+
+int build_contract_plan(itb_contract_plan& P) {
+    const TensorStruct &A = P.A, &B = P.B;
+    TensorStruct& C = P.C;
+    const int rA = A.order, rB = B.order;
+    // ---- label matching (computeLabels: first match wins) -------------------------------------
+    std::vector<int> AtoB(rA, -1), BtoA(rB, -1);
+    for (int i = 0; i < rA; ++i)
+        for (int j = 0; j < rB; ++j)
+            if (P.labA[i] == P.labB[j] && BtoA[j] < 0) { AtoB[i] = j; BtoA[j] = i; break; }
+    for (int i = 0; i < rA; ++i) {
+        if (AtoB[i] < 0) continue;
+        int j = AtoB[i];
+        if (A.nsect[i] != B.nsect[j]) { set_error("contract: contracted indices have different sector counts"); return ITB_ERR_INVALID; }
+        for (int s = 0; s < A.nsect[i]; ++s)
+            if (A.ext(i, s) != B.ext(j, s)) { set_error("contract: contracted indices have different sector sizes"); return ITB_ERR_INVALID; }
+    }
+    // ---- result index order (contractIS, sortResult=false) -----------------------------------
+    std::vector<int> AtoC(rA, -1), BtoC(rB, -1);
+    C = TensorStruct();
+    C.dtype = (A.dtype == ITB_C64 || B.dtype == ITB_C64) ? ITB_C64 : ITB_F64;
+    P.labC.clear();
+    C.sect_start.assign(1, 0);
+    auto push_index = [&](const TensorStruct& T, int j, int32_t lab) {
+        C.nsect.push_back(T.nsect[j]);
+        for (int s = 0; s < T.nsect[j]; ++s) C.sect.push_back(T.ext(j, s));
+        C.sect_start.push_back((int64_t)C.sect.size());
+        P.labC.push_back(lab);
+    };
+    for (int i = 0; i < rA; ++i)
+        if (AtoB[i] < 0) { AtoC[i] = (int)C.nsect.size(); push_index(A, i, P.labA[i]); }
+    for (int j = 0; j < rB; ++j)
+        if (BtoA[j] < 0) { BtoC[j] = (int)C.nsect.size(); push_index(B, j, P.labB[j]); }
+    const int rC = (int)C.nsect.size();
+    if (rC > ITB_MAX_ORDER) { set_error("contract: result order too large"); return ITB_ERR_UNSUPPORTED; }
+    C.order = rC;
+
+    // ---- pair enumeration: bucket B blocks by contracted coordinates --------------------------
+    std::vector<int> contA, contB;
+    for (int i = 0; i < rA; ++i)
+        if (AtoB[i] >= 0) { contA.push_back(i); contB.push_back(AtoB[i]); }
+    std::unordered_map<std::vector<int32_t>, std::vector<int64_t>, VecHash> bucket;
+    std::vector<int32_t> key(contA.size());
+    for (int64_t b = 0; b < B.nblocks; ++b) {
+        for (size_t c = 0; c < contB.size(); ++c) key[c] = B.block(b)[contB[c]];
+        bucket[key].push_back(b);
+    }
+    struct PairRec { int64_t a, b; std::vector<int32_t> cb; };
+    std::vector<PairRec> recs;
+    std::vector<int32_t> cb(rC);
+    for (int64_t a = 0; a < A.nblocks; ++a) {
+        for (size_t c = 0; c < contA.size(); ++c) key[c] = A.block(a)[contA[c]];
+        auto it = bucket.find(key);
+        if (it == bucket.end()) continue;
+        for (int i = 0; i < rA; ++i)
+            if (AtoC[i] >= 0) cb[AtoC[i]] = A.block(a)[i];
+        for (int64_t b : it->second) {
+            for (int j = 0; j < rB; ++j)
+                if (BtoC[j] >= 0) cb[BtoC[j]] = B.block(b)[j];
+            recs.push_back({a, b, cb});
+        }
+    }
+    // ---- C block list: sort + unique by the reference ordering, prefix-sum offsets ------------
+    std::vector<std::vector<int32_t>> cblocks;
+    cblocks.reserve(recs.size());
+    for (auto& r : recs) cblocks.push_back(r.cb);
+    std::sort(cblocks.begin(), cblocks.end(),
+              [rC](const std::vector<int32_t>& x, const std::vector<int32_t>& y) { return block_less(x.data(), y.data(), rC); });
+    cblocks.erase(std::unique(cblocks.begin(), cblocks.end()), cblocks.end());
+    C.nblocks = (int64_t)cblocks.size();
+    C.blocks.resize(C.nblocks * rC);
+    C.offsets.resize(C.nblocks);
+    std::unordered_map<std::vector<int32_t>, int64_t, VecHash> cpos;
+    int64_t off = 0;
+    for (int64_t c = 0; c < C.nblocks; ++c) {
+        int64_t sz = 1;
+        for (int j = 0; j < rC; ++j) {
+            C.blocks[c * rC + j] = cblocks[c][j];
+            sz *= C.ext(j, cblocks[c][j]);
+        }
+        C.offsets[c] = off;
+        off += sz;
+        cpos[cblocks[c]] = c;
+    }
+    C.nelems = off;
+    // ---- triples + flops -----------------------------------------------------------------------
+    P.triples.resize(recs.size() * 3);
+    P.flops = 0;
+    const double cmul = (A.dtype == ITB_C64 ? 2.0 : 1.0) * (B.dtype == ITB_C64 ? 2.0 : 1.0);
+    for (size_t p = 0; p < recs.size(); ++p) {
+        P.triples[3 * p + 0] = recs[p].a;
+        P.triples[3 * p + 1] = recs[p].b;
+        P.triples[3 * p + 2] = cpos[recs[p].cb];
+        double m = 1, n = 1, k = 1;
+        for (int i = 0; i < rA; ++i) {
+            double e = (double)A.ext(i, A.block(recs[p].a)[i]);
+            if (AtoB[i] >= 0) k *= e; else m *= e;
+        }
+        for (int j = 0; j < rB; ++j)
+            if (BtoA[j] < 0) n *= (double)B.ext(j, B.block(recs[p].b)[j]);
+        P.flops += 2.0 * m * n * k * cmul;
+    }
+    P.tables_built = false;
+    return ITB_OK;
+}
+
+// ---- per-pair index-group analysis ---------------------------------------------------------------
+struct Dim {
+    int64_t ext;
+    int64_t sa, sb; // strides (REAL units) in the tensors that carry this dim (sb unused for M/N)
+};
+
+// drop unit dims, then fuse neighbours that are contiguous in every tensor carrying the group
+static void canon(std::vector<Dim>& g, bool two) {
+    std::vector<Dim> out;
+    for (auto& d : g) {
+        if (d.ext == 1) continue;
+        if (!out.empty()) {
+            Dim& l = out.back();
+            bool ok = (d.sa == l.sa * l.ext) && (!two || d.sb == l.sb * l.ext);
+            if (ok) { l.ext *= d.ext; continue; }
+        }
+        out.push_back(d);
+    }
+    g.swap(out);
+}
+
+int build_contract_tables(itb_contract_plan& P) {
+    const TensorStruct &A = P.A, &B = P.B, &C = P.C;
+    const int rA = A.order, rB = B.order;
+    std::vector<int> AtoB(rA, -1), BtoA(rB, -1);
+    for (int i = 0; i < rA; ++i)
+        for (int j = 0; j < rB; ++j)
+            if (P.labA[i] == P.labB[j] && BtoA[j] < 0) { AtoB[i] = j; BtoA[j] = i; break; }
+    const bool cA = A.dtype == ITB_C64, cB = B.dtype == ITB_C64;
+    const int64_t csA = cA ? 2 : 1, csB = cB ? 2 : 1, csC = (cA || cB) ? 2 : 1;
+
+    P.pairs.clear(); P.cblks.clear(); P.skinny.clear(); P.dots.clear(); P.dot_outs.clear();
+    for (auto& t : P.tiles) t.clear();
+    P.ndot_slots = 0;
+
+    const int64_t npairs = (int64_t)P.triples.size() / 3;
+    // group pairs by C block, keeping the reference enumeration order inside a block
+    std::vector<int64_t> order(npairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int64_t x, int64_t y) { return P.triples[3 * x + 2] < P.triples[3 * y + 2]; });
+    const int64_t cb_first = P.cb_first, cb_last = (P.cb_last < 0 ? C.nblocks : P.cb_last);
+
+    std::vector<int64_t> strA(rA), strB(rB);
+    int64_t pos = 0;
+    while (pos < npairs) {
+        const int64_t ic = P.triples[3 * order[pos] + 2];
+        int64_t end = pos;
+        while (end < npairs && P.triples[3 * order[end] + 2] == ic) ++end;
+        if (ic < cb_first || ic >= cb_last) { pos = end; continue; }
+
+        ItbCBlk cbk;
+        std::memset(&cbk, 0, sizeof(cbk));
+        cbk.pair_begin = (int32_t)P.pairs.size();
+        int64_t M = 1, N = 1; // complex-element dims of this C block
+        for (int64_t q = pos; q < end; ++q) {
+            const int64_t p = order[q];
+            const int64_t ia = P.triples[3 * p], ib = P.triples[3 * p + 1];
+            const int32_t* ab = A.block(ia);
+            const int32_t* bb = B.block(ib);
+            int64_t s = csA;
+            for (int i = 0; i < rA; ++i) { strA[i] = s; s *= A.ext(i, ab[i]); }
+            s = csB;
+            for (int j = 0; j < rB; ++j) { strB[j] = s; s *= B.ext(j, bb[j]); }
+            std::vector<Dim> gm, gk, gn;
+            // which operand-fastest (non-unit) index is contracted?
+            int fa = -1, fb = -1;
+            for (int i = 0; i < rA && fa < 0; ++i) if (A.ext(i, ab[i]) > 1) fa = i;
+            for (int j = 0; j < rB && fb < 0; ++j) if (B.ext(j, bb[j]) > 1) fb = j;
+            const bool a_kfast = fa >= 0 && AtoB[fa] >= 0;
+            const bool b_kfast = fb >= 0 && BtoA[fb] >= 0;
+            for (int i = 0; i < rA; ++i)
+                if (AtoB[i] < 0) gm.push_back({A.ext(i, ab[i]), strA[i], 0});
+            for (int j = 0; j < rB; ++j)
+                if (BtoA[j] < 0) gn.push_back({B.ext(j, bb[j]), strB[j], 0});
+            // K order: follow A unless only B is k-fast (keeps the k-fast operand contiguous in k)
+            if (a_kfast || !b_kfast) {
+                for (int i = 0; i < rA; ++i)
+                    if (AtoB[i] >= 0) gk.push_back({A.ext(i, ab[i]), strA[i], strB[AtoB[i]]});
+            } else {
+                for (int j = 0; j < rB; ++j)
+                    if (BtoA[j] >= 0) gk.push_back({B.ext(j, bb[j]), strA[BtoA[j]], strB[j]});
+            }
+            int64_t m = 1, n = 1, k = 1;
+            for (auto& d : gm) m *= d.ext;
+            for (auto& d : gn) n *= d.ext;
+            for (auto& d : gk) k *= d.ext;
+            M = m; N = n;
+            // ---- complex folding: prepend a pseudo-dim of extent 2 (re,im) -------------------------
+            int flags = 0;
+            if (cA && cB) { // [Cr;Ci] = [[Ar,-Ai],[Ai,Ar]] [Br;Bi]
+                gm.insert(gm.begin(), {2, 1, 0});
+                gk.insert(gk.begin(), {2, 1, 1});
+                flags |= ITB_PF_CCA;
+            } else if (cA) { // rows of A doubled: C'(2m+p,n) = sum_k A(m,k).comp(p) B(k,n)
+                gm.insert(gm.begin(), {2, 1, 0});
+            } else if (cB) { // columns of B doubled: C'(m,2n+q) = sum_k A(m,k) B(k,n).comp(q)
+                gn.insert(gn.begin(), {2, 1, 0});
+            }
+            canon(gm, false); canon(gk, true); canon(gn, false);
+            if (gm.size() > ITB_MAXG || gk.size() > ITB_MAXG || gn.size() > ITB_MAXG) {
+                set_error("contract: more than ITB_MAXG non-fusable indices in one group");
+                return ITB_ERR_UNSUPPORTED;
+            }
+            ItbPair pr;
+            std::memset(&pr, 0, sizeof(pr));
+            pr.a_off = A.offsets[ia] * csA;
+            pr.b_off = B.offsets[ib] * csB;
+            for (int d = 0; d < ITB_MAXG; ++d) { pr.m_ext[d] = pr.n_ext[d] = pr.k_ext[d] = 1; }
+            for (size_t d = 0; d < gm.size(); ++d) { pr.m_ext[d] = (int32_t)gm[d].ext; pr.am_str[d] = gm[d].sa; }
+            for (size_t d = 0; d < gn.size(); ++d) { pr.n_ext[d] = (int32_t)gn[d].ext; pr.bn_str[d] = gn[d].sa; }
+            for (size_t d = 0; d < gk.size(); ++d) { pr.k_ext[d] = (int32_t)gk[d].ext; pr.ak_str[d] = gk[d].sa; pr.bk_str[d] = gk[d].sb; }
+            pr.m_n = (int32_t)gm.size(); pr.n_n = (int32_t)gn.size(); pr.k_n = (int32_t)gk.size();
+            const int64_t Kr = k * ((cA && cB) ? 2 : 1);
+            if (Kr >= (1ll << 31) || m * 2 >= (1ll << 31) || n * 2 >= (1ll << 31)) {
+                set_error("contract: block dimension exceeds 2^31");
+                return ITB_ERR_UNSUPPORTED;
+            }
+            pr.K = (int32_t)Kr;
+            if (a_kfast) flags |= ITB_PF_A_KFAST;
+            if (b_kfast) flags |= ITB_PF_B_KFAST;
+            pr.flags = flags;
+            cbk.ksum += Kr;
+            P.pairs.push_back(pr);
+        }
+        cbk.pair_end = (int32_t)P.pairs.size();
+        cbk.c_off = C.offsets[ic] * csC;
+        cbk.M = (int32_t)(M * (cA ? 2 : 1));
+        cbk.N = (int32_t)(N * ((!cA && cB) ? 2 : 1));
+        if (!cA && cB) { cbk.c_ms = 2; cbk.c_nmask = 1; cbk.c_nshift = 1; cbk.c_ns = 2 * M; }
+        else { cbk.c_ms = 1; cbk.c_nmask = 0; cbk.c_nshift = 0; cbk.c_ns = cbk.M; }
+        P.cblks.push_back(cbk);
+        pos = end;
+    }
+
+    // ---- classify C blocks into kernel work lists --------------------------------------------------
+    for (int32_t c = 0; c < (int32_t)P.cblks.size(); ++c) {
+        const ItbCBlk& cb = P.cblks[c];
+        const int64_t M = cb.M, N = cb.N;
+        if (M * N <= kDotMaxMN) {
+            ItbDotOut o{c, (int32_t)P.ndot_slots, 0, 0};
+            for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
+                const int32_t K = P.pairs[p].K;
+                for (int32_t k0 = 0; k0 < K; k0 += kDotChunk) {
+                    ItbDot d{c, p, k0, std::min<int32_t>(kDotChunk, K - k0), (int32_t)P.ndot_slots, {0, 0, 0}};
+                    P.dots.push_back(d);
+                    ++P.ndot_slots; ++o.nslots;
+                }
+            }
+            P.dot_outs.push_back(o);
+        } else if (std::min(M, N) <= kSkinnyMax) {
+            const int long_is_n = (N > M) ? 1 : 0;
+            const int64_t L = long_is_n ? N : M;
+            for (int64_t r0 = 0; r0 < L; r0 += kSkinnyRows)
+                P.skinny.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyRows, L - r0), long_is_n});
+        } else {
+            // pick the tile config with the least padded work (bigger tiles run more efficiently)
+            int best = 0; double bestc = 1e300;
+            static const double eff[ITB_NCFG] = {1.0, 0.85, 0.6};
+            for (int f = 0; f < ITB_NCFG; ++f) {
+                const double tm = (double)((M + kTileM[f] - 1) / kTileM[f]), tn = (double)((N + kTileN[f] - 1) / kTileN[f]);
+                const double cost = tm * tn * kTileM[f] * kTileN[f] / eff[f];
+                if (cost < bestc) { bestc = cost; best = f; }
+            }
+            const int TM = kTileM[best], TN = kTileN[best];
+            for (int32_t tn = 0; tn < (N + TN - 1) / TN; ++tn)
+                for (int32_t tm = 0; tm < (M + TM - 1) / TM; ++tm)
+                    P.tiles[best].push_back({c, tm, tn, 0});
+        }
+    }
+    // longest-processing-time-first: heavy items to the front of each persistent queue
+    for (auto& t : P.tiles)
+        std::stable_sort(t.begin(), t.end(), [&](const ItbTile& x, const ItbTile& y) { return P.cblks[x.cblk].ksum > P.cblks[y.cblk].ksum; });
+    std::stable_sort(P.skinny.begin(), P.skinny.end(), [&](const ItbSkinny& x, const ItbSkinny& y) {
+        return P.cblks[x.cblk].ksum * (P.cblks[x.cblk].M + P.cblks[x.cblk].N) > P.cblks[y.cblk].ksum * (P.cblks[y.cblk].M + P.cblks[y.cblk].N);
+    });
+    P.table_bytes = (int64_t)(P.pairs.size() * sizeof(ItbPair) + P.cblks.size() * sizeof(ItbCBlk) +
+                              P.skinny.size() * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
+                              P.dot_outs.size() * sizeof(ItbDotOut));
+    for (auto& t : P.tiles) P.table_bytes += (int64_t)(t.size() * sizeof(ItbTile));
+    P.tables_built = true;
+    return ITB_OK;
+}
+
+// ---- permute -------------------------------------------------------------------------------------
+int build_permute_plan(itb_permute_plan& P) {
+    const TensorStruct &S = P.S, &D = P.D;
+    const int r = S.order;
+    if (D.order != r) { set_error("permute: order mismatch"); return ITB_ERR_INVALID; }
+    std::vector<int> inv(r, -1);
+    for (int i = 0; i < r; ++i) {
+        int d = P.perm[i];
+        if (d < 0 || d >= r || inv[d] >= 0) { set_error("permute: perm is not a permutation"); return ITB_ERR_INVALID; }
+        inv[d] = i;
+    }
+    for (int i = 0; i < r; ++i) {
+        int d = P.perm[i];
+        if (S.nsect[i] != D.nsect[d]) { set_error("permute: sector count mismatch"); return ITB_ERR_INVALID; }
+        for (int s = 0; s < S.nsect[i]; ++s)
+            if (S.ext(i, s) != D.ext(d, s)) { set_error("permute: sector size mismatch"); return ITB_ERR_INVALID; }
+    }
+    if (S.dtype == ITB_C64 && D.dtype == ITB_F64) { set_error("permute: cannot demote complex to real"); return ITB_ERR_INVALID; }
+    const int promote = (S.dtype == ITB_F64 && D.dtype == ITB_C64) ? 1 : 0;
+    const int cs = (S.dtype == ITB_C64) ? 2 : 1; // complex pairs move as 16-byte units
+
+    std::unordered_map<std::vector<int32_t>, int64_t, VecHash> dpos;
+    std::vector<int32_t> key(r);
+    for (int64_t b = 0; b < D.nblocks; ++b) {
+        for (int j = 0; j < r; ++j) key[j] = D.block(b)[j];
+        dpos[key] = b;
+    }
+    P.blks_copy.clear(); P.blks_tiled.clear();
+    P.items_copy = P.items_tiled = 0;
+    P.bytes = 0;
+    std::vector<char> hit(D.nblocks, 0);
+    std::vector<int64_t> ss(r), ds(r);
+    for (int64_t b = 0; b < S.nblocks; ++b) {
+        const int32_t* sb = S.block(b);
+        for (int i = 0; i < r; ++i) key[P.perm[i]] = sb[i];
+        auto it = dpos.find(key);
+        if (it == dpos.end()) { set_error("permute: destination lacks the image of a source block"); return ITB_ERR_INVALID; }
+        const int64_t db = it->second;
+        if (hit[db]) { set_error("permute: two source blocks map to one destination block"); return ITB_ERR_INVALID; }
+        hit[db] = 1;
+        int64_t s = 1;
+        for (int i = 0; i < r; ++i) { ss[i] = s; s *= S.ext(i, sb[i]); }
+        const int64_t nelem = s;
+        s = 1;
+        for (int j = 0; j < r; ++j) { ds[j] = s; s *= D.ext(j, key[j]); }
+        // dims in dst order, unit dims dropped, neighbours fused when contiguous in src too
+        struct PD { int64_t ext, sstr, dstr; };
+        std::vector<PD> dims;
+        for (int j = 0; j < r; ++j) {
+            const int64_t e = D.ext(j, key[j]);
+            if (e == 1) continue;
+            const int64_t sst = ss[inv[j]];
+            if (!dims.empty() && sst == dims.back().sstr * dims.back().ext) { dims.back().ext *= e; continue; }
+            dims.push_back({e, sst, ds[j]});
+        }
+        if (dims.empty()) dims.push_back({1, 1, 1});
+        if ((int)dims.size() > ITB_MAXG) { set_error("permute: more than ITB_MAXG non-fusable indices"); return ITB_ERR_UNSUPPORTED; }
+        ItbPermBlk pb;
+        std::memset(&pb, 0, sizeof(pb));
+        pb.s_off = S.offsets[b];
+        pb.d_off = D.offsets[db];
+        pb.n = (int32_t)dims.size();
+        pb.nelem = nelem;
+        pb.cs = cs;
+        pb.promote = promote;
+        for (int d = 0; d < ITB_MAXG; ++d) pb.ext[d] = 1;
+        int tdim = 0;
+        for (size_t d = 0; d < dims.size(); ++d) {
+            if (dims[d].ext >= (1ll << 31)) { set_error("permute: fused extent exceeds 2^31"); return ITB_ERR_UNSUPPORTED; }
+            pb.ext[d] = (int32_t)dims[d].ext;
+            pb.sstr[d] = dims[d].sstr;
+            pb.dstr[d] = dims[d].dstr;
+            if (dims[d].sstr == 1) tdim = (int)d;
+        }
+        pb.tdim = tdim;
+        if (tdim == 0) {
+            pb.item_begin = P.items_copy;
+            P.items_copy += (nelem + kPermCopyChunk - 1) / kPermCopyChunk;
+            P.blks_copy.push_back(pb);
+        } else {
+            pb.tiles0 = (pb.ext[0] + kPermTile - 1) / kPermTile;
+            pb.tilesT = (pb.ext[tdim] + kPermTile - 1) / kPermTile;
+            int64_t rest = 1;
+            for (int d = 1; d < pb.n; ++d) if (d != tdim) rest *= pb.ext[d];
+            pb.item_begin = P.items_tiled;
+            P.items_tiled += (int64_t)pb.tiles0 * pb.tilesT * rest;
+            P.blks_tiled.push_back(pb);
+        }
+        P.bytes += nelem * 8 * ((S.dtype == ITB_C64 ? 2 : 1) + (D.dtype == ITB_C64 ? 2 : 1));
+    }
+    P.need_zero = false;
+    for (auto h : hit) if (!h) P.need_zero = true;
+    return ITB_OK;
+}
+
+} // namespace itb
+
+// ---- C ABI: host-only entry points -----------------------------------------------------------------
+using namespace itb;
+
+extern "C" {
+
+const char* itb_last_error(void) { return itb::last_error_cstr(); }
+
+int itb_contract_plan_create(const itb_tensor_desc* A, const int32_t* labA, const itb_tensor_desc* B,
+                             const int32_t* labB, itb_contract_plan** out) {
+    if (!out) { set_error("plan_create: null out"); return ITB_ERR_INVALID; }
+    *out = nullptr;
+    auto* P = new itb_contract_plan();
+    int rc = parse_desc(A, P->A, "contract A");
+    if (rc == ITB_OK) rc = parse_desc(B, P->B, "contract B");
+    if (rc == ITB_OK) {
+        P->labA.assign(labA, labA + A->order);
+        P->labB.assign(labB, labB + B->order);
+        rc = build_contract_plan(*P);
+    }
+    if (rc == ITB_OK) rc = build_contract_tables(*P);
+    if (rc != ITB_OK) { delete P; return rc; }
+    *out = P;
+    return ITB_OK;
+}
+
+void itb_contract_plan_release_device(itb_contract_plan* plan); // api.cu
+void itb_permute_plan_release_device(itb_permute_plan* plan);   // api.cu
+
+int itb_contract_plan_destroy(itb_contract_plan* plan) {
+    if (!plan) return ITB_OK;
+    itb_contract_plan_release_device(plan);
+    delete plan;
+    return ITB_OK;
+}
+
+int itb_contract_plan_info(const itb_contract_plan* P, itb_contract_info* o) {
+    if (!P || !o) { set_error("plan_info: null"); return ITB_ERR_INVALID; }
+    o->c_order = P->C.order;
+    o->c_dtype = P->C.dtype;
+    o->c_nblocks = P->C.nblocks;
+    o->c_nelems = P->C.nelems;
+    o->npairs = (int64_t)P->triples.size() / 3;
+    o->flops = P->flops;
+    o->n_gemm_tiles = 0;
+    for (auto& t : P->tiles) o->n_gemm_tiles += (int64_t)t.size();
+    o->n_skinny = (int64_t)P->skinny.size();
+    o->n_dot = (int64_t)P->dots.size();
+    o->table_bytes = P->table_bytes;
+    return ITB_OK;
+}
+int itb_contract_plan_c_labels(const itb_contract_plan* P, int32_t* v) { std::copy(P->labC.begin(), P->labC.end(), v); return ITB_OK; }
+int itb_contract_plan_c_nsect(const itb_contract_plan* P, int32_t* v) { std::copy(P->C.nsect.begin(), P->C.nsect.end(), v); return ITB_OK; }
+int itb_contract_plan_c_sect(const itb_contract_plan* P, int64_t* v) { std::copy(P->C.sect.begin(), P->C.sect.end(), v); return ITB_OK; }
+int itb_contract_plan_c_blocks(const itb_contract_plan* P, int32_t* v) { std::copy(P->C.blocks.begin(), P->C.blocks.end(), v); return ITB_OK; }
+int itb_contract_plan_c_offsets(const itb_contract_plan* P, int64_t* v) { std::copy(P->C.offsets.begin(), P->C.offsets.end(), v); return ITB_OK; }
+int itb_contract_plan_pairs(const itb_contract_plan* P, int64_t* v) { std::copy(P->triples.begin(), P->triples.end(), v); return ITB_OK; }
+
+int itb_contract_plan_set_cblock_range(itb_contract_plan* P, int64_t first, int64_t last) {
+    if (!P) { set_error("set_cblock_range: null"); return ITB_ERR_INVALID; }
+    if (first < 0 || (last >= 0 && last < first) || last > P->C.nblocks) { set_error("set_cblock_range: bad range"); return ITB_ERR_INVALID; }
+    P->cb_first = first;
+    P->cb_last = last;
+    itb_contract_plan_release_device(P);
+    return build_contract_tables(*P);
+}
+
+int itb_permute_plan_create(const itb_tensor_desc* src, const itb_tensor_desc* dst, const int32_t* perm,
+                            itb_permute_plan** out) {
+    if (!out) { set_error("permute_plan_create: null out"); return ITB_ERR_INVALID; }
+    *out = nullptr;
+    auto* P = new itb_permute_plan();
+    int rc = parse_desc(src, P->S, "permute src");
+    if (rc == ITB_OK) rc = parse_desc(dst, P->D, "permute dst");
+    if (rc == ITB_OK) {
+        P->perm.assign(perm, perm + src->order);
+        rc = build_permute_plan(*P);
+    }
+    if (rc != ITB_OK) { delete P; return rc; }
+    *out = P;
+    return ITB_OK;
+}
+int itb_permute_plan_destroy(itb_permute_plan* plan) {
+    if (!plan) return ITB_OK;
+    itb_permute_plan_release_device(plan);
+    delete plan;
+    return ITB_OK;
+}
+int64_t itb_permute_plan_bytes(const itb_permute_plan* P) { return P ? P->bytes : 0; }
+
+// getBlockOffsets(IndexSet,QN) (itensor/itdata/qdense.cc:133-173): iterate every block with the
+// FIRST index fastest (== reference-sorted order) and keep those whose flux matches. QN values
+// follow QNum::set (itensor/qn.cc:10-29): modulo |mod| with non-negative representatives.
+static inline int32_t qn_norm(int64_t v, int32_t mod) {
+    int64_t m = mod < 0 ? -(int64_t)mod : mod;
+    if (m > 1) { int64_t a = v < 0 ? -v : v; return (int32_t)((m * a + v) % m); }
+    return (int32_t)v;
+}
+int64_t itb_flux_blocks(int32_t order, const int32_t* nsect, const int32_t* qn, int32_t nqn, const int32_t* mod,
+                        const int32_t* dir, const int32_t* flux, int32_t* blocks, int64_t cap) {
+    if (order < 0 || order > ITB_MAX_ORDER || nqn < 0 || nqn > 4) { set_error("flux_blocks: bad arguments"); return ITB_ERR_INVALID; }
+    if (order == 0) return 1; // rank-0: single block with empty coordinates
+    std::vector<int64_t> start(order + 1, 0);
+    for (int j = 0; j < order; ++j) start[j + 1] = start[j] + nsect[j];
+    std::vector<int32_t> I(order, 0);
+    int64_t count = 0;
+    while (true) {
+        bool ok = true;
+        for (int c = 0; c < nqn && ok; ++c) {
+            // blockqn += J.qn(1+I[j])*J.dir()  — each term and each partial sum is normalised
+            int32_t acc = qn_norm(0, mod[c]);
+            for (int j = 0; j < order; ++j) {
+                int32_t term = qn_norm((int64_t)qn_norm(qn[(start[j] + I[j]) * nqn + c], mod[c]) * dir[j], mod[c]);
+                acc = qn_norm((int64_t)acc + term, mod[c]);
+            }
+            if (acc != qn_norm(flux[c], mod[c])) ok = false;
+        }
+        if (ok) {
+            if (blocks && count < cap) std::copy(I.begin(), I.end(), blocks + count * order);
+            ++count;
+        }
+        int j = 0;
+        while (j < order) {
+            if (++I[j] < nsect[j]) break;
+            I[j] = 0;
+            ++j;
+        }
+        if (j == order) break;
+    }
+    return count;
+}
+
+} // extern "C"

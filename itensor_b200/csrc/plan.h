@@ -1,0 +1,83 @@
+// plan.h — host-side planner objects (integer bookkeeping only; no CUDA types).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/itb200.h"
+#include "tables.h"
+
+namespace itb {
+
+struct TensorStruct { // owning copy of an itb_tensor_desc
+    int order = 0;
+    int dtype = ITB_F64;
+    std::vector<int32_t> nsect;
+    std::vector<int64_t> sect;       // concatenated
+    std::vector<int64_t> sect_start; // prefix into sect, order+1 entries
+    int64_t nblocks = 0;
+    std::vector<int32_t> blocks;
+    std::vector<int64_t> offsets;
+    int64_t nelems = 0;
+    int64_t ext(int j, int s) const { return sect[sect_start[j] + s]; }
+    const int32_t* block(int64_t b) const { return blocks.data() + b * order; }
+};
+
+// Tile configurations of the DMMA kernel (kernels_gemm.cu instantiates the same list).
+enum { ITB_CFG_BIG = 0, ITB_CFG_MED = 1, ITB_CFG_SMALL = 2, ITB_NCFG = 3 };
+static const int kTileM[ITB_NCFG] = {128, 64, 32};
+static const int kTileN[ITB_NCFG] = {128, 64, 32};
+
+struct DeviceTables; // defined in api.cu (device copies of the vectors below)
+
+} // namespace itb
+
+struct itb_contract_plan {
+    itb::TensorStruct A, B, C;
+    std::vector<int32_t> labA, labB, labC;
+    std::vector<int64_t> triples; // (iA,iB,iC) per pair, reference enumeration order
+    double flops = 0;
+    int64_t cb_first = 0, cb_last = -1; // execution range of C blocks (sharding); -1 => all
+
+    // device-format tables (built by build_tables(), rebuilt when the range changes)
+    bool tables_built = false;
+    std::vector<ItbPair> pairs;
+    std::vector<ItbCBlk> cblks;
+    std::vector<ItbTile> tiles[itb::ITB_NCFG];
+    std::vector<ItbSkinny> skinny;
+    std::vector<ItbDot> dots;
+    std::vector<ItbDotOut> dot_outs;
+    int64_t ndot_slots = 0;
+    std::vector<int64_t> zero_ranges; // (offset,len) REAL ranges of C blocks to zero: none today (every
+                                      // C block has >=1 pair) but kept for range-restricted runs
+    int64_t table_bytes = 0;
+    itb::DeviceTables* dev = nullptr; // owned by api.cu
+    void* dev_ctx = nullptr;
+};
+
+struct itb_permute_plan {
+    itb::TensorStruct S, D;
+    std::vector<int32_t> perm;
+    std::vector<ItbPermBlk> blks_copy;  // blocks whose src/dst fastest dims coincide
+    std::vector<ItbPermBlk> blks_tiled; // blocks needing a shared-memory transpose
+    int64_t items_copy = 0, items_tiled = 0;
+    bool need_zero = false; // dst has blocks no src block maps to
+    int64_t bytes = 0;
+    itb::DeviceTables* dev = nullptr;
+    void* dev_ctx = nullptr;
+};
+
+namespace itb {
+void set_error(const std::string& msg);
+int parse_desc(const itb_tensor_desc* d, TensorStruct& out, const char* what);
+int build_contract_plan(itb_contract_plan& P);
+int build_contract_tables(itb_contract_plan& P);
+int build_permute_plan(itb_permute_plan& P);
+
+constexpr int kPermCopyChunk = 4096; // elements per work item, copy-like path
+constexpr int kPermTile = 32;        // tile edge, transposing path
+constexpr int kDotChunk = 8192;      // k-range per split-K item
+constexpr int kSkinnyRows = 256;     // long-side rows per streaming item
+constexpr int kSkinnyMax = 8;        // short side <= this -> streaming kernel
+constexpr int kDotMaxMN = 4;        // M*N <= this -> reduction kernel (scalar results, re/im pairs)
+} // namespace itb

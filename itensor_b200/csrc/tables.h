@@ -1,0 +1,78 @@
+// tables.h — compact POD tables shared by the host planner (plan.cc) and the sm_100a kernels.
+//
+// The host turns IndexSet/QN block bookkeeping into these tables (the role of
+// getContractedOffsets + CProps::compute in the reference, itensor/itdata/qutil.h:93-242 and
+// itensor/tensor/contract.cc:240-548); the device only ever sees flat data pointers plus
+// {offsets, extents, strides}. All offsets/strides are in units of REAL doubles: complex
+// tensors are addressed through their interleaved (re,im) storage.
+#pragma once
+#include <stdint.h>
+
+#define ITB_MAXG 6 // fused dims per index group (M / K / N); more -> ITB_ERR_UNSUPPORTED
+
+// ---- contraction -------------------------------------------------------------------------------
+// A block pair contributes  C(m,n) += sum_k A[a_off + offM(m) + offK_a(k)] * B[b_off + offK_b(k) + offN(n)]
+// where offX(i) decomposes i over the group's extents (fastest first) and dots with strides.
+// Complex operands are folded into this REAL problem by the planner (pseudo-dim of extent 2,
+// see plan.cc "complex folding"); ITB_PF_CCA marks the A operand of a complex*complex pair:
+// element (m',k') with p=m'&1, q=k'&1 is  (q&!p ? -1 : 1) * A[off - 2*(p&q)].
+enum { ITB_PF_CCA = 1, ITB_PF_A_KFAST = 2, ITB_PF_B_KFAST = 4 };
+
+struct ItbPair {
+    int64_t a_off, b_off;
+    int64_t am_str[ITB_MAXG];
+    int64_t bn_str[ITB_MAXG];
+    int64_t ak_str[ITB_MAXG];
+    int64_t bk_str[ITB_MAXG];
+    int32_t m_ext[ITB_MAXG]; // fusion pattern can differ between pairs of one C block
+    int32_t n_ext[ITB_MAXG];
+    int32_t k_ext[ITB_MAXG];
+    int32_t m_n, n_n, k_n;
+    int32_t K;     // prod(k_ext) (real-expanded)
+    int32_t flags; // ITB_PF_*
+    int32_t pad_;
+};
+
+struct ItbCBlk {
+    int64_t c_off;
+    int64_t c_ms;     // C address = c_off + m*c_ms + (n & c_nmask) + (n >> c_nshift)*c_ns
+    int64_t c_ns;
+    int32_t c_nmask;  // 1 for real(A)*cplx(B) (interleaved re/im along n'), else 0
+    int32_t c_nshift; // 1 for real*cplx, else 0
+    int32_t M, N;     // real-expanded block dims
+    int32_t pair_begin, pair_end; // pairs of this C block, in reference enumeration order
+    int64_t ksum;     // sum of K over the pairs (work estimate)
+};
+
+struct ItbTile { // work item of the DMMA tile kernel
+    int32_t cblk, tm, tn, pad_;
+};
+struct ItbSkinny { // work item of the streaming kernel: rows [row0,row0+rows) of the long side
+    int32_t cblk, row0, rows, long_is_n; // long_is_n: 1 -> threads run over n, short side is m
+};
+struct ItbDot { // work item of the split-K reduction kernel
+    int32_t cblk, pair, k0, klen;
+    int32_t slot; // partial-sum slot (row in the partial buffer, 16 doubles each)
+    int32_t pad_[3];
+};
+struct ItbDotOut { // per tiny C block: partial slots [slot0, slot0+nslots) summed in order
+    int32_t cblk, slot0, nslots, pad_;
+};
+
+// ---- permute -----------------------------------------------------------------------------------
+// dst[d_off + sum_j i_j*dstr_j] (op)= alpha * src[s_off + sum_j i_j*sstr_j], dims fused/canonical,
+// listed in DST order (dim 0 = fastest in dst, dstr[0] == cs). tiled: the smem-transpose path is
+// used over (dim 0 = dst-fastest, dim tdim = src-fastest); otherwise src and dst share dim 0.
+struct ItbPermBlk {
+    int64_t s_off, d_off;
+    int64_t sstr[ITB_MAXG];
+    int64_t dstr[ITB_MAXG];
+    int32_t ext[ITB_MAXG];
+    int32_t n;
+    int32_t tdim;       // index (in this list) of the src-fastest dim; 0 => copy-like
+    int64_t item_begin; // first work item (tile / chunk) of this block in the launch
+    int64_t nelem;
+    int32_t tiles0, tilesT; // tile counts along dim 0 and dim tdim (tiled path)
+    int32_t cs;             // 2 if elements are complex pairs moved as units, else 1
+    int32_t promote;        // 1: src real -> dst complex
+};
