@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — block-sparse contraction FP64 throughput on the DMRG effective-Hamiltonian product.
+
+A "step" is one H_eff*phi = LocalOp::product (itensor/mps/localop.h:324-365): the four chained
+block-sparse contractions phi*L, *W1, *W2, *R, on a synthetic S=1/2 Heisenberg centre-bond structure
+(Sz-conserving QDense blocks) at maxdim m (BASELINE.json configs[1], default m=2000).
+
+  value        whole-job FP64 TFLOP/s with all operands resident in HBM (algorithmic flops =
+               sum over block pairs of 2*M*N*K), CUDA-event timed, L2 flushed between steps
+  e2e          same metric through the C ABI with HOST buffers: per step H2D(phi,L,W1,W2,R) from
+               pinned memory + table upload + 4 contractions + D2H(H phi)
+  roofline     dominant kernel (bsc_gemm_kernel 128x128 DMMA tiles) against the FP64 tensor ceiling
+               measured in this run (cuBLAS DGEMM 8192^3 via torch.matmul; MEASURED_PEAKS.json has no
+               FP64 entry), per-launch times from CUDA events on the launching stream
+  cpu_baseline the UNMODIFIED reference (oracle/_ref/libitref.so, OpenBLAS) on this box's host cores
+               on a bounded sample (one H_eff*phi at a smaller m)
+  --impl reference   times the reference CPU build on the same metric (bounded sample per step)
+
+Multi-GPU (--gpus N under torchrun): the output blocks of the chain are sharded by the sector of the
+persistent primed link l' (SURVEY §8(e)); each rank runs its shard with no communication until one
+NCCL all-gather of the H phi shards per step. Total work is fixed -> "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "block-sparse contraction FP64 TFLOP/s (H_eff*phi, S=1/2 Heisenberg Sz blocks)"
+
+
+def workload(m: int, nsect: int, dtype: int):
+    from itensor_b200 import synth
+
+    sizes = synth.gaussian_sectors(m, nsect)
+    structs = synth.heff_chain(sizes, dtype=dtype)
+    return sizes, structs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_dgemm_peak(torch, dev, n=8192, reps=6):
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n**3 / (best * 1e-3) / 1e12
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the same step, bounded sample."""
+    if rank != 0:
+        return
+    from itensor_b200 import ITB_F64, synth
+    import itensor_b200 as itb
+    from oracle import orc
+
+    if not orc.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libitref.so not built (needs /root/reference at build time)"}))
+        return
+    m = args.ref_m
+    sizes, structs = workload(m, args.nsect, ITB_F64)
+    hosts = [synth.random_values(s, 10 + i) for i, s in enumerate(structs)]
+    flops, s = 0.0, structs[0]
+    for t in structs[1:]:
+        p = itb.ContractPlan(s, t)
+        flops += p.flops
+        s = p.C
+    for _ in range(max(args.warmup, 0) and 1):
+        orc.ref_time_heff(structs, hosts, 1)
+    t0 = time.perf_counter()
+    secs = [orc.ref_time_heff(structs, hosts, 1)[0] for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    per = float(np.mean(secs))
+    val = flops / per / 1e12
+    cores = os.cpu_count()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"H_eff*phi (LocalOp::product, 4 contractions) S=1/2 Heisenberg Sz sectors, maxdim {args.m}",
+                   "sample_maxdim": m, "sectors": sizes, "flops_per_step": flops},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
+                         "sample": f"unmodified ITensor (OpenBLAS threads={os.environ.get('OPENBLAS_NUM_THREADS', 'all')}) "
+                                   f"phi*L*W1*W2*R at maxdim {m} (bounded sample of the maxdim-{args.m} workload), wall {wall:.1f}s"},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=2000, help="maxdim (MPS bond dimension)")
+    ap.add_argument("--nsect", type=int, default=9, help="Sz sectors on the MPS links")
+    ap.add_argument("--complex", action="store_true")
+    ap.add_argument("--ref-m", type=int, default=800, help="maxdim of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import itensor_b200 as itb
+    from itensor_b200 import ITB_C64, ITB_F64, synth
+    from itensor_b200._lib import check, lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = itb.Context(local)
+    dtype = ITB_C64 if args.complex else ITB_F64
+    sizes, structs = workload(args.m, args.nsect, dtype)
+    hosts = [synth.random_values(s, 10 + i) for i, s in enumerate(structs)]
+
+    # ---- plans (host integer work, done once: structure is fixed across Davidson iterations) -----
+    plans, s = [], structs[0]
+    for t in structs[1:]:
+        p = itb.ContractPlan(s, t)
+        plans.append(p)
+        s = p.C
+    total_flops = sum(p.flops for p in plans)
+    # multi-GPU: shard the C blocks of every step by the sector of l' (last index of step 1's C, and it
+    # stays an uncontracted index of every later intermediate) -> contiguous C-block ranges per rank
+    shard = None
+    if world > 1:
+        from itensor_b200.shard import shard_chain
+
+        shard = shard_chain(plans, world, rank)
+    my_flops = sum(p.info.class_flops[i] for p in plans for i in range(5))
+
+    pinned = [torch.from_numpy(np.ascontiguousarray(h).view(np.float64).reshape(-1)).pin_memory() for h in hosts]
+    dts = [itb.QTensor(ctx, st, ctx.empty(st.nreal)) for st in structs]
+    for d, p in zip(dts, pinned):
+        d.data.copy_(p, non_blocking=True)
+    outs = [itb.QTensor(ctx, p.C, ctx.empty(p.C.nreal)) for p in plans]
+    h_out = torch.empty(plans[-1].C.nreal, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        cur = dts[0]
+        for k, p in enumerate(plans):
+            check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
+            cur = outs[k]
+        if shard is not None:
+            shard.allgather(outs[-1].data)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()  # flush L2 between timed iterations
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    launches = ctx.launches() - l0
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) / args.steps
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = total_flops / (ms * 1e-3) / 1e12
+
+    # ---- e2e: host buffers in, host buffer out, every step ---------------------------------------
+    def e2e_step():
+        # what a caller of the reference-facing API pays per product: upload the operands, plan every
+        # contraction afresh (host integer work + table upload, as operator* does on every call), run,
+        # read H phi back
+        for d, p in zip(dts, pinned):
+            d.data.copy_(p, non_blocking=True)
+        if world == 1:
+            cur = dts[0]
+            for k in range(4):
+                p = itb.ContractPlan(cur.struct, structs[k + 1])
+                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
+                cur = itb.QTensor(ctx, p.C, outs[k].data)
+                keep.append(p)
+        else:
+            step()
+        h_out.copy_(outs[-1].data, non_blocking=True)
+        torch.cuda.synchronize()
+        keep.clear()
+
+    keep = []
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = int(sum(p.numel() * 8 for p in pinned))
+    d2h = int(h_out.numel() * 8)
+
+    # ---- roofline of the dominant kernel (128x128 DMMA tile kernel of step 1), live CUDA events ----
+    roof = None
+    if rank == 0:
+        peak = measure_dgemm_peak(torch, dev)
+        lib().itb_ctx_set_profile(ctx.handle, 1)
+        cls_ms = np.zeros(5)
+        cls_fl = np.zeros(5)
+        reps = 5
+        for _ in range(reps):
+            flush.zero_()
+            cur = dts[0]
+            for k, p in enumerate(plans):
+                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
+                msv = (C.c_float * 5)()
+                lib().itb_contract_last_ms(ctx.handle, msv)
+                cls_ms += np.array(list(msv))
+                cls_fl += np.array(list(p.info.class_flops))
+                cur = outs[k]
+        lib().itb_ctx_set_profile(ctx.handle, 0)
+        cls_ms /= reps
+        cls_fl /= reps
+        dom = int(np.argmax(cls_ms[:3]))
+        n_launch = sum(1 for p in plans if p.info.class_flops[dom] > 0)
+        ach = cls_fl[dom] / (cls_ms[dom] * 1e-3) / 1e12 if cls_ms[dom] > 0 else 0.0
+        dmma = C.c_double()
+        lib().itb_peak_fp64(ctx.handle, 0, 4096, C.byref(dmma))
+        dfma = C.c_double()
+        lib().itb_peak_fp64(ctx.handle, 1, 4096, C.byref(dfma))
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                "traffic": None, "kernel": ["bsc_gemm_kernel<128x128>", "bsc_gemm_kernel<64x64>", "bsc_gemm_kernel<32x32>"][dom],
+                "peak_source": "measured in this run: torch.matmul fp64 8192^3 best of 6 (MEASURED_PEAKS.json has no FP64 entry)",
+                "launches_per_step": n_launch, "ms_per_step_by_class": [float(x) for x in cls_ms],
+                "flops_per_step_by_class": [float(x) for x in cls_fl], "bare_dmma_tflops": dmma.value, "bare_dfma_tflops": dfma.value,
+                "hbm_peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None,
+                "streaming_class_gbs": None}
+        # the streaming (MPO) steps are HBM-bound: report their achieved bytes/s too
+        sk_bytes = 0.0
+        for k, p in enumerate(plans):
+            if p.info.class_flops[3] > 0.5 * p.flops:
+                sk_bytes += 8.0 * ((structs[0].nreal if k == 0 else plans[k - 1].C.nreal) + p.C.nreal)
+        if cls_ms[3] > 0:
+            roof["streaming_class_gbs"] = sk_bytes / (cls_ms[3] * 1e-3) / 1e9
+
+    # ---- CPU baseline: the reference itself on this box's host cores, bounded sample ----------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import orc
+
+        if orc.have_ref():
+            _, cs = workload(args.ref_m, args.nsect, dtype)
+            ch = [synth.random_values(s_, 10 + i) for i, s_ in enumerate(cs)]
+            fl, s_ = 0.0, cs[0]
+            for t_ in cs[1:]:
+                p_ = itb.ContractPlan(s_, t_)
+                fl += p_.flops
+                s_ = p_.C
+            t0 = time.perf_counter()
+            secs, _ = orc.ref_time_heff(cs, ch, 2)
+            wall = time.perf_counter() - t0
+            cpu = {"value": fl / secs / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference",
+                   "sample": f"unmodified ITensor CPU build (OpenBLAS, threads={os.environ.get('OPENBLAS_NUM_THREADS', 'all')}), one "
+                             f"H_eff*phi at maxdim {args.ref_m} best of 2 ({fl:.3g} flop, {wall:.1f}s wall)"}
+        else:
+            cpu = {"value": None, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref not built"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128" if args.complex else "f64",
+            "data": "synthetic",
+            "config": {"workload": f"H_eff*phi (LocalOp::product: phi*L*W1*W2*R) S=1/2 Heisenberg N=100 centre bond, Sz QDense blocks, maxdim {args.m}",
+                       "maxdim": args.m, "sectors": sizes, "d": 2, "mpo_link_sectors": [3, 1, 1],
+                       "pairs_per_step": [int(p.npairs) for p in plans], "flops_per_step": total_flops,
+                       "l2": "flushed between timed iterations (256 MiB memset)", "sharding": "C blocks by l' sector" if world > 1 else "none"},
+            "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,7 @@ typedef struct itb_contract_info {
     int64_t n_skinny;     /* work items of the streaming (min(M,N) small) kernel */
     int64_t n_dot;        /* work items of the split-K reduction kernel */
     int64_t table_bytes;  /* bytes of compact tables uploaded to the device */
+    double class_flops[5]; /* flops by kernel class: tile 128x128, tile 64x64, tile 32x32, streaming, split-K */
 } itb_contract_info;
 
 /* ---- library / context ------------------------------------------------------------------ */
@@ -166,6 +167,11 @@ int itb_dot(itb_ctx* ctx, int32_t dtype, int64_t n, const void* dX, const void* 
             double out[2]); /* syncs */
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
+/* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement
+ * only). itb_contract_last_ms then returns the device time of the last run by kernel class
+ * (same order as itb_contract_info.class_flops; 0 for classes that did not launch). */
+int itb_ctx_set_profile(itb_ctx* ctx, int profile);
+int itb_contract_last_ms(itb_ctx* ctx, float ms[5]);
 /* bare DMMA (mma.sync f64) and DFMA issue loops, no memory traffic; returns TFLOP/s */
 int itb_peak_fp64(itb_ctx* ctx, int which /*0=dmma m8n8k4, 1=dfma, 2=dmma m16n8k8*/, int iters, double* tflops);
 /* device-side timing on the context's stream (CUDA events) */

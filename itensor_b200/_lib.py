@@ -43,6 +43,7 @@ class ContractInfo(C.Structure):
         ("n_skinny", C.c_int64),
         ("n_dot", C.c_int64),
         ("table_bytes", C.c_int64),
+        ("class_flops", C.c_double * 5),
     ]
 
 
@@ -101,6 +102,8 @@ SYMBOLS = {
     "itb_get_elt": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _DP]),
     "itb_dot": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, C.c_int, _DP]),
     "itb_peak_fp64": (C.c_int, [_P, C.c_int, C.c_int, _DP]),
+    "itb_ctx_set_profile": (C.c_int, [_P, C.c_int]),
+    "itb_contract_last_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "itb_timer_start": (C.c_int, [_P]),
     "itb_timer_stop_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
 }

@@ -68,6 +68,9 @@ struct itb_ctx {
     size_t scratch_doubles = 0;
     double* h_result = nullptr; // pinned 4 doubles
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool profile = false;
+    float last_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t pev[10] = {};
 };
 
 #define CUDA_TRY(expr)                                                                                    \
@@ -325,18 +328,38 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     bool any_tiles = false;
     for (int f = 0; f < ITB_NCFG; ++f) any_tiles |= !P->tiles[f].empty();
     if (any_tiles) CUDA_TRY(cudaMemsetAsync(d->counters, 0, ITB_NCFG * sizeof(int), c->stream));
+    bool ran[5] = {false, false, false, false, false};
+    if (c->profile && !c->pev[0])
+        for (auto& e : c->pev) CUDA_TRY(cudaEventCreate(&e));
+#define PROF_BEGIN(i) do { if (c->profile) CUDA_TRY(cudaEventRecord(c->pev[2 * (i)], c->stream)); } while (0)
+#define PROF_END(i) do { if (c->profile) { CUDA_TRY(cudaEventRecord(c->pev[2 * (i) + 1], c->stream)); ran[i] = true; } } while (0)
     for (int f = 0; f < ITB_NCFG; ++f) {
         if (P->tiles[f].empty()) continue;
+        PROF_BEGIN(f);
         CUDA_TRY(launch_gemm(f, d->tiles[f], (int)P->tiles[f].size(), d->cblks, d->pairs, A, B, C, d->counters + f, c->num_sms, c->stream));
+        PROF_END(f);
         ++c->launches;
     }
     if (!P->skinny.empty()) {
+        PROF_BEGIN(3);
         CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->cblks, d->pairs, A, B, C, c->stream));
+        PROF_END(3);
         ++c->launches;
     }
     if (!P->dots.empty()) {
+        PROF_BEGIN(4);
         CUDA_TRY(launch_dot(d->dots, (int)P->dots.size(), d->dot_outs, (int)P->dot_outs.size(), d->cblks, d->pairs, A, B, d->dot_partial, C, c->stream));
+        PROF_END(4);
         c->launches += 2;
+    }
+#undef PROF_BEGIN
+#undef PROF_END
+    if (c->profile) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 5; ++i) {
+            c->last_ms[i] = 0.f;
+            if (ran[i]) CUDA_TRY(cudaEventElapsedTime(&c->last_ms[i], c->pev[2 * i], c->pev[2 * i + 1]));
+        }
     }
     return ITB_OK;
 }
@@ -509,6 +532,12 @@ int itb_peak_fp64(itb_ctx* c, int which, int iters, double* tflops) {
     const double flops = which == 1 ? warps * 32.0 * 16.0 * 2.0 * iters : warps * 8.0 * 512.0 * iters;
     *tflops = flops / (ms * 1e-3) / 1e12;
     c->launches += 2;
+    return ITB_OK;
+}
+
+int itb_ctx_set_profile(itb_ctx* c, int profile) { c->profile = profile != 0; return ITB_OK; }
+int itb_contract_last_ms(itb_ctx* c, float ms[5]) {
+    for (int i = 0; i < 5; ++i) ms[i] = c->last_ms[i];
     return ITB_OK;
 }
 

@@ -326,10 +326,13 @@ int build_contract_tables(itb_contract_plan& P) {
     }
 
     // ---- classify C blocks into kernel work lists --------------------------------------------------
+    for (double& f : P.class_flops) f = 0;
     for (int32_t c = 0; c < (int32_t)P.cblks.size(); ++c) {
         const ItbCBlk& cb = P.cblks[c];
         const int64_t M = cb.M, N = cb.N;
+        const double cflops = 2.0 * (double)M * (double)N * (double)cb.ksum; // real-expanded == x2/x4 complex count
         if (M * N <= kDotMaxMN) {
+            P.class_flops[4] += cflops;
             ItbDotOut o{c, (int32_t)P.ndot_slots, 0, 0};
             for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
                 const int32_t K = P.pairs[p].K;
@@ -341,6 +344,7 @@ int build_contract_tables(itb_contract_plan& P) {
             }
             P.dot_outs.push_back(o);
         } else if (std::min(M, N) <= kSkinnyMax) {
+            P.class_flops[3] += cflops;
             const int long_is_n = (N > M) ? 1 : 0;
             const int64_t L = long_is_n ? N : M;
             for (int64_t r0 = 0; r0 < L; r0 += kSkinnyRows)
@@ -354,6 +358,7 @@ int build_contract_tables(itb_contract_plan& P) {
                 const double cost = tm * tn * kTileM[f] * kTileN[f] / eff[f];
                 if (cost < bestc) { bestc = cost; best = f; }
             }
+            P.class_flops[best] += cflops;
             const int TM = kTileM[best], TN = kTileN[best];
             for (int32_t tn = 0; tn < (N + TN - 1) / TN; ++tn)
                 for (int32_t tm = 0; tm < (M + TM - 1) / TM; ++tm)
@@ -519,6 +524,7 @@ int itb_contract_plan_info(const itb_contract_plan* P, itb_contract_info* o) {
     o->n_skinny = (int64_t)P->skinny.size();
     o->n_dot = (int64_t)P->dots.size();
     o->table_bytes = P->table_bytes;
+    for (int i = 0; i < 5; ++i) o->class_flops[i] = P->class_flops[i];
     return ITB_OK;
 }
 int itb_contract_plan_c_labels(const itb_contract_plan* P, int32_t* v) { std::copy(P->labC.begin(), P->labC.end(), v); return ITB_OK; }

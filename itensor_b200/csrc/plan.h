@@ -37,6 +37,7 @@ struct itb_contract_plan {
     std::vector<int32_t> labA, labB, labC;
     std::vector<int64_t> triples; // (iA,iB,iC) per pair, reference enumeration order
     double flops = 0;
+    double class_flops[5] = {0, 0, 0, 0, 0};
     int64_t cb_first = 0, cb_last = -1; // execution range of C blocks (sharding); -1 => all
 
     // device-format tables (built by build_tables(), rebuilt when the range changes)

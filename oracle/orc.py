@@ -304,3 +304,14 @@ def ref_dmrg_heisenberg(N, spin2, conserve_qns, maxdim, cutoff, niter, noise):
     ref().ref_dmrg_heisenberg(C.c_int(N), C.c_int(spin2), C.c_int(1 if conserve_qns else 0), C.c_int(n), _p(md, C.c_int32),
                               _p(co, C.c_double), _p(ni, C.c_int32), _p(no, C.c_double), C.byref(e), C.byref(s), C.byref(ml))
     return e.value, s.value, ml.value
+
+
+def ref_time_heff(structs, hosts, reps=1, want_result=False):
+    """seconds for one LocalOp::product chain phi*L*W1*W2*R through the reference (best of reps)"""
+    L = ref()
+    L.ref_time_heff.restype = C.c_double
+    keeps = [_Keep(s, h) for s, h in zip(structs, hosts)]
+    out = C.c_void_p()
+    secs = L.ref_time_heff(*[C.byref(k.t) for k in keeps], C.c_int(reps), C.byref(out) if want_result else None)
+    res = RefResult(out.value) if want_result else None
+    return float(secs), res

@@ -221,6 +221,36 @@ ref_time_contract(ref_tensor const* A, ref_tensor const* B, int reps)
     return best;
     }
 
+// One effective-Hamiltonian product the way LocalOp::product does it (mps/localop.h:346-362):
+// phip = phi*L; phip *= W1; phip *= W2; phip *= R.  Returns best-of-reps seconds for the chain and
+// (optionally) the result of the last repetition.
+double
+ref_time_heff(ref_tensor const* phi, ref_tensor const* L, ref_tensor const* W1, ref_tensor const* W2,
+              ref_tensor const* R, int reps, ref_result** out)
+    {
+    Registry reg;
+    auto p = makeTensor(*phi,reg);
+    auto l = makeTensor(*L,reg);
+    auto w1 = makeTensor(*W1,reg);
+    auto w2 = makeTensor(*W2,reg);
+    auto r = makeTensor(*R,reg);
+    double best = 1e300;
+    ITensor res;
+    for(int i = 0; i < reps; ++i)
+        {
+        auto t0 = std::chrono::steady_clock::now();
+        auto phip = p*l;
+        phip *= w1;
+        phip *= w2;
+        phip *= r;
+        auto t1 = std::chrono::steady_clock::now();
+        best = std::min(best,std::chrono::duration<double>(t1-t0).count());
+        res = phip;
+        }
+    if(out) *out = extract(res,reg);
+    return best;
+    }
+
 // permute T so that its indices appear in the order new_labels (reference ITensor::permute)
 ref_result*
 ref_permute(ref_tensor const* T, int64_t const* new_labels)
