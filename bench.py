@@ -307,18 +307,21 @@ def main():
         lib().itb_ctx_set_profile(ctx.handle, 0)
         cls_ms /= reps
         cls_fl /= reps
-        dom = int(np.argmax(cls_ms[:3]))
-        n_launch = sum(1 for p in plans if p.info.class_flops[dom] > 0)
-        ach = cls_fl[dom] / (cls_ms[dom] * 1e-3) / 1e12 if cls_ms[dom] > 0 else 0.0
+        # timing slots: [0] persistent DMMA tile kernel (+ split-K reduce), [3] streaming kernel, [4] split-K dots
+        tile_fl = float(cls_fl[0] + cls_fl[1] + cls_fl[2])
+        n_launch = sum(1 for p in plans if p.info.n_gemm_tiles > 0)
+        ach = tile_fl / (cls_ms[0] * 1e-3) / 1e12 if cls_ms[0] > 0 else 0.0
         dmma = C.c_double()
         lib().itb_peak_fp64(ctx.handle, 0, 4096, C.byref(dmma))
         dfma = C.c_double()
         lib().itb_peak_fp64(ctx.handle, 1, 4096, C.byref(dfma))
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                "traffic": None, "kernel": ["bsc_gemm_kernel<128x128>", "bsc_gemm_kernel<64x64>", "bsc_gemm_kernel<32x32>"][dom],
+                "traffic": None, "kernel": "bsc_gemm_kernel (persistent DMMA tiles 128/64/32, split-K)",
                 "peak_source": "measured in this run: torch.matmul fp64 8192^3 best of 6 (MEASURED_PEAKS.json has no FP64 entry)",
-                "launches_per_step": n_launch, "ms_per_step_by_class": [float(x) for x in cls_ms],
-                "flops_per_step_by_class": [float(x) for x in cls_fl], "bare_dmma_tflops": dmma.value, "bare_dfma_tflops": dfma.value,
+                "launches_per_step": n_launch, "ms_per_step": {"tile_kernel": float(cls_ms[0]), "streaming_kernel": float(cls_ms[3]), "dot_kernel": float(cls_ms[4])},
+                "flops_per_step_by_class": {"tile128": float(cls_fl[0]), "tile64": float(cls_fl[1]), "tile32": float(cls_fl[2]),
+                                            "streaming": float(cls_fl[3]), "dot": float(cls_fl[4])},
+                "bare_dmma_tflops": dmma.value, "bare_dfma_tflops": dfma.value,
                 "hbm_peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else None,
                 "streaming_class_gbs": None}
         # the streaming (MPO) steps are HBM-bound: report their achieved bytes/s too

@@ -13,10 +13,11 @@
 #include "plan.h"
 
 namespace itb {
-cudaError_t launch_gemm(int cfg, const ItbTile* tiles, int ntiles, const ItbCBlk* cblks, const ItbPair* pairs, const double* A,
-                        const double* B, double* C, int* counter, int num_sms, cudaStream_t st);
-cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbCBlk* cblks, const ItbPair* pairs, const double* A,
-                          const double* B, double* C, cudaStream_t st);
+cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks,
+                        const ItbPair* pairs, const double* A, const double* B, double* C, double* ws, int* counter, int num_sms,
+                        cudaStream_t st);
+cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
+                          const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st);
 cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
                        const double* A, const double* B, double* partial, double* C, cudaStream_t st);
 cudaError_t launch_peak(int which, int iters, double* out, int num_sms, cudaStream_t st);
@@ -38,12 +39,15 @@ struct DeviceTables {
     size_t bytes = 0;
     const ItbPair* pairs = nullptr;
     const ItbCBlk* cblks = nullptr;
-    const ItbTile* tiles[ITB_NCFG] = {nullptr, nullptr, nullptr};
+    const ItbTile* tiles = nullptr;
+    const ItbSplitOut* splits = nullptr;
     const ItbSkinny* skinny = nullptr;
+    const ItbSkinny* skinny_q4 = nullptr;
+    const ItbSkinny* skinny_q8 = nullptr;
     const ItbDot* dots = nullptr;
     const ItbDotOut* dot_outs = nullptr;
     double* dot_partial = nullptr;
-    int* counters = nullptr; // ITB_NCFG work-queue heads
+    int* counters = nullptr; // work-queue head
     const ItbPermBlk* pcopy = nullptr;
     const ItbPermBlk* ptiled = nullptr;
 };
@@ -65,6 +69,8 @@ struct itb_ctx {
     void* staging = nullptr; // pinned host staging for small uploads (tables)
     size_t staging_bytes = 0;
     double* scratch = nullptr; // device scratch for reductions
+    double* ws = nullptr;      // split-K workspace (grow-only, stream-ordered reuse)
+    size_t ws_doubles = 0;
     size_t scratch_doubles = 0;
     double* h_result = nullptr; // pinned 4 doubles
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -131,6 +137,13 @@ static int ensure_scratch(itb_ctx* c, size_t doubles) {
     if (c->scratch) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->scratch); c->scratch = nullptr; }
     CUDA_TRY(cudaMalloc(&c->scratch, doubles * sizeof(double)));
     c->scratch_doubles = doubles;
+    return ITB_OK;
+}
+static int ensure_ws(itb_ctx* c, size_t doubles) {
+    if (c->ws_doubles >= doubles) return ITB_OK;
+    if (c->ws) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->ws); c->ws = nullptr; }
+    CUDA_TRY(cudaMalloc(&c->ws, doubles * sizeof(double)));
+    c->ws_doubles = doubles;
     return ITB_OK;
 }
 static int ensure_staging(itb_ctx* c, size_t bytes) {
@@ -203,6 +216,7 @@ int itb_ctx_destroy(itb_ctx* c) {
     for (auto& kv : c->free_blocks) cudaFree(kv.second);
     for (auto& kv : c->live) cudaFree(kv.first);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->ws) cudaFree(c->ws);
     if (c->staging) cudaFreeHost(c->staging);
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -292,9 +306,11 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     Packer pk;
     const size_t o_pairs = pk.add(P->pairs.data(), P->pairs.size() * sizeof(ItbPair));
     const size_t o_cblk = pk.add(P->cblks.data(), P->cblks.size() * sizeof(ItbCBlk));
-    size_t o_tiles[ITB_NCFG];
-    for (int f = 0; f < ITB_NCFG; ++f) o_tiles[f] = pk.add(P->tiles[f].data(), P->tiles[f].size() * sizeof(ItbTile));
+    const size_t o_tiles = pk.add(P->tiles.data(), P->tiles.size() * sizeof(ItbTile));
+    const size_t o_splits = pk.add(P->splits.data(), P->splits.size() * sizeof(ItbSplitOut));
     const size_t o_sk = pk.add(P->skinny.data(), P->skinny.size() * sizeof(ItbSkinny));
+    const size_t o_sq4 = pk.add(P->skinny_q4.data(), P->skinny_q4.size() * sizeof(ItbSkinny));
+    const size_t o_sq8 = pk.add(P->skinny_q8.data(), P->skinny_q8.size() * sizeof(ItbSkinny));
     const size_t o_dot = pk.add(P->dots.data(), P->dots.size() * sizeof(ItbDot));
     const size_t o_dout = pk.add(P->dot_outs.data(), P->dot_outs.size() * sizeof(ItbDotOut));
     const size_t partial_bytes = ((size_t)P->ndot_slots * 4 * sizeof(double) + 255) & ~(size_t)255;
@@ -304,8 +320,11 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     char* b = (char*)dev->base;
     dev->pairs = (const ItbPair*)(b + o_pairs);
     dev->cblks = (const ItbCBlk*)(b + o_cblk);
-    for (int f = 0; f < ITB_NCFG; ++f) dev->tiles[f] = (const ItbTile*)(b + o_tiles[f]);
+    dev->tiles = (const ItbTile*)(b + o_tiles);
+    dev->splits = (const ItbSplitOut*)(b + o_splits);
     dev->skinny = (const ItbSkinny*)(b + o_sk);
+    dev->skinny_q4 = (const ItbSkinny*)(b + o_sq4);
+    dev->skinny_q8 = (const ItbSkinny*)(b + o_sq8);
     dev->dots = (const ItbDot*)(b + o_dot);
     dev->dot_outs = (const ItbDotOut*)(b + o_dout);
     dev->dot_partial = (double*)(b + pk.total);
@@ -325,26 +344,26 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     const double* A = (const double*)dA;
     const double* B = (const double*)dB;
     double* C = (double*)dC;
-    bool any_tiles = false;
-    for (int f = 0; f < ITB_NCFG; ++f) any_tiles |= !P->tiles[f].empty();
-    if (any_tiles) CUDA_TRY(cudaMemsetAsync(d->counters, 0, ITB_NCFG * sizeof(int), c->stream));
     bool ran[5] = {false, false, false, false, false};
     if (c->profile && !c->pev[0])
         for (auto& e : c->pev) CUDA_TRY(cudaEventCreate(&e));
 #define PROF_BEGIN(i) do { if (c->profile) CUDA_TRY(cudaEventRecord(c->pev[2 * (i)], c->stream)); } while (0)
 #define PROF_END(i) do { if (c->profile) { CUDA_TRY(cudaEventRecord(c->pev[2 * (i) + 1], c->stream)); ran[i] = true; } } while (0)
-    for (int f = 0; f < ITB_NCFG; ++f) {
-        if (P->tiles[f].empty()) continue;
-        PROF_BEGIN(f);
-        CUDA_TRY(launch_gemm(f, d->tiles[f], (int)P->tiles[f].size(), d->cblks, d->pairs, A, B, C, d->counters + f, c->num_sms, c->stream));
-        PROF_END(f);
-        ++c->launches;
+    if (!P->tiles.empty()) {
+        if (P->ws_slots > 0) { rc = ensure_ws(c, (size_t)P->ws_slots * ITB_WS_TILE); if (rc != ITB_OK) return rc; }
+        CUDA_TRY(cudaMemsetAsync(d->counters, 0, sizeof(int), c->stream));
+        PROF_BEGIN(0);
+        CUDA_TRY(launch_gemm(d->tiles, (int)P->tiles.size(), d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
+                             d->counters, c->num_sms, c->stream));
+        PROF_END(0);
+        c->launches += P->splits.empty() ? 1 : 2;
     }
-    if (!P->skinny.empty()) {
+    if (!P->skinny.empty() || !P->skinny_q4.empty() || !P->skinny_q8.empty()) {
         PROF_BEGIN(3);
-        CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->cblks, d->pairs, A, B, C, c->stream));
+        CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->skinny_q4, (int)P->skinny_q4.size(), d->skinny_q8,
+                               (int)P->skinny_q8.size(), d->cblks, d->pairs, A, B, C, c->stream));
         PROF_END(3);
-        ++c->launches;
+        c->launches += (P->skinny.empty() ? 0 : 1) + (P->skinny_q4.empty() ? 0 : 1) + (P->skinny_q8.empty() ? 0 : 1);
     }
     if (!P->dots.empty()) {
         PROF_BEGIN(4);

@@ -48,167 +48,171 @@ __device__ __forceinline__ int64_t grp_off(int idx, const int32_t* __restrict__ 
     return o;
 }
 
-template <int BM_, int BN_, int WM_, int WN_>
-struct GemmCfg {
-    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = 16;
-    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
-    static constexpr int NT = WARPS_M * WARPS_N * 32;
-    static constexpr int LD_XF = 4;                                   // padding: ld == 4 (mod 16) -> conflict-free frags
-    static constexpr int A_ELEMS = (BM * (BK + LD_XF) > BK * (BM + LD_XF)) ? BM * (BK + LD_XF) : BK * (BM + LD_XF);
-    static constexpr int B_ELEMS = (BN * (BK + LD_XF) > BK * (BN + LD_XF)) ? BN * (BK + LD_XF) : BK * (BN + LD_XF);
-    static constexpr int EA = BM * BK / NT, EB = BN * BK / NT;        // elements staged per thread per k-chunk
-    static constexpr int KSLOTS = 4;                                  // ring of per-chunk k-offset tables
-    static constexpr size_t SMEM = (size_t)(2 * (A_ELEMS + B_ELEMS)) * 8 + (size_t)(BM + BN + 2 * KSLOTS * BK) * 8 + 16;
-    static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile/threads mismatch");
-};
+// ---- persistent DMMA tile kernel -------------------------------------------------------------------------
+// One launch serves every tile class: items carry their configuration (128x128 / 64x64 / 32x32) and a
+// range of K-chunks (split-K for C blocks with few tiles but long K loops). 256 threads = 8 warps laid
+// out 2 (m) x 4 (n); 4-stage cp.async ring of BK=16 chunks; fragments read conflict-free from padded smem.
+constexpr int G_NT = 256, G_STAGES = 4, G_BK = ITB_BK, G_KS = 8, G_PAD = 4;
+constexpr int G_MAXT = 128;
+constexpr int G_STAGE_ELEMS = G_MAXT * (G_BK + G_PAD); // per operand per stage (covers both layouts)
+constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT + 2 * G_KS * G_BK) * 8 + 16;
 
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NT) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, int ntiles,
-                                                           const ItbCBlk* __restrict__ cblks,
-                                                           const ItbPair* __restrict__ pairs,
-                                                           const double* __restrict__ A, const double* __restrict__ B,
-                                                           double* __restrict__ C, int* __restrict__ counter) {
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, WM = Cfg::WM, WN = Cfg::WN, NT = Cfg::NT;
-    constexpr int FM = WM / 8, FN = WN / 8, EA = Cfg::EA, EB = Cfg::EB, KS = Cfg::KSLOTS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* As = reinterpret_cast<double*>(smem_raw);            // [2][A_ELEMS]
-    double* Bs = As + 2 * Cfg::A_ELEMS;                          // [2][B_ELEMS]
-    int64_t* offM_s = reinterpret_cast<int64_t*>(Bs + 2 * Cfg::B_ELEMS); // [BM]
-    int64_t* offN_s = offM_s + BM;                               // [BN]
-    int64_t* offKa_s = offN_s + BN;                              // [KS][BK]
-    int64_t* offKb_s = offKa_s + KS * BK;                        // [KS][BK]
-    int* item_s = reinterpret_cast<int*>(offKb_s + KS * BK);
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int BM, int BN>
+__device__ __forceinline__ void run_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
+                                         const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                                         double* __restrict__ ws, double* As, double* Bs, int64_t* offM_s, int64_t* offN_s,
+                                         int64_t* offKa_s, int64_t* offKb_s) {
+    constexpr int BK = G_BK, NT = G_NT, ST = G_STAGES, KS = G_KS;
+    constexpr int WM = BM / 2, WN = BN / 4, FM = WM / 8, FN = WN / 8;
+    constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
+    static_assert(FM >= 1 && FN >= 1 && EA >= 1 && EB >= 1, "tile too small for 8 warps");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int wm0 = (warp % Cfg::WARPS_M) * WM, wn0 = (warp / Cfg::WARPS_M) * WN;
+    const int wm0 = (warp & 1) * WM, wn0 = (warp >> 1) * WN;
+    const int M = cb->M, N = cb->N;
+    const int m0 = tile.tm * BM, n0 = tile.tn * BN;
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) *item_s = atomicAdd(counter, 1);
-        __syncthreads();
-        const int item = *item_s;
-        if (item >= ntiles) break;
-        const ItbTile tile = tiles[item];
-        const ItbCBlk* cb = cblks + tile.cblk;
-        const int M = cb->M, N = cb->N;
-        const int m0 = tile.tm * BM, n0 = tile.tn * BN;
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        double acc[FM][FN][2];
-#pragma unroll
-        for (int i = 0; i < FM; ++i)
-#pragma unroll
-            for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    int gchunk = 0; // global chunk index of the current pair's first chunk
+    for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
+        const ItbPair* pr = pairs + p;
+        const int K = pr->K;
+        const int nk = (K + BK - 1) / BK;
+        const int c0 = max(tile.chunk_begin - gchunk, 0), c1 = min(tile.chunk_end - gchunk, nk);
+        gchunk += nk;
+        if (c0 >= c1) continue;
+        const int flags = pr->flags;
+        const bool cca = flags & ITB_PF_CCA, akf = flags & ITB_PF_A_KFAST, bkf = flags & ITB_PF_B_KFAST;
+        const double* __restrict__ Ap = A + pr->a_off;
+        const double* __restrict__ Bp = B + pr->b_off;
+        const int sAm = akf ? (BK + G_PAD) : 1, sAk = akf ? 1 : (BM + G_PAD);
+        const int sBn = bkf ? (BK + G_PAD) : 1, sBk = bkf ? 1 : (BN + G_PAD);
+        // sign of the A' = [[Ar,-Ai],[Ai,Ar]] expansion, applied when the fragment is read (row even, col odd)
+        const int sgn = (cca && !(g & 1) && (t4 & 1)) ? (int)0x80000000 : 0;
 
-        for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
-            const ItbPair* pr = pairs + p;
-            const int K = pr->K, flags = pr->flags;
-            const bool cca = flags & ITB_PF_CCA, akf = flags & ITB_PF_A_KFAST, bkf = flags & ITB_PF_B_KFAST;
-            const double* __restrict__ Ap = A + pr->a_off;
-            const double* __restrict__ Bp = B + pr->b_off;
-            const int nk = (K + BK - 1) / BK;
-            // smem strides of the two possible tile layouts
-            const int sAm = akf ? (BK + 4) : 1, sAk = akf ? 1 : (BM + 4);
-            const int sBn = bkf ? (BK + 4) : 1, sBk = bkf ? 1 : (BN + 4);
-
-            __syncthreads(); // previous pair's tables / buffers are dead
-            for (int i = tid; i < BM + BN; i += NT) {
-                if (i < BM) {
-                    const int m = m0 + i;
-                    offM_s[i] = (m < M) ? grp_off(m, pr->m_ext, pr->am_str, pr->m_n) : -1;
-                } else {
-                    const int n = n0 + i - BM;
-                    offN_s[i - BM] = (n < N) ? grp_off(n, pr->n_ext, pr->bn_str, pr->n_n) : -1;
-                }
-            }
-            // k-offset tables for chunks 0 and 1
-            for (int i = tid; i < 4 * BK; i += NT) {
-                const int c = i / (2 * BK), r = i % (2 * BK), kk = r % BK;
-                const int k = c * BK + kk;
-                if (r < BK) offKa_s[c * BK + kk] = (k < K) ? grp_off(k, pr->k_ext, pr->ak_str, pr->k_n) : -1;
-                else offKb_s[c * BK + kk] = (k < K) ? grp_off(k, pr->k_ext, pr->bk_str, pr->k_n) : -1;
-            }
-            __syncthreads();
-
-            double ra[EA], rb[EB];
-            auto ldg_chunk = [&](int kc) {
-                const int64_t* oka = offKa_s + (kc % KS) * BK;
-                const int64_t* okb = offKb_s + (kc % KS) * BK;
-#pragma unroll
-                for (int e = 0; e < EA; ++e) {
-                    const int idx = tid + e * NT;
-                    const int mm = akf ? idx / BK : idx % BM, kk = akf ? idx % BK : idx / BM;
-                    const int64_t om = offM_s[mm], ok = oka[kk];
-                    double v = 0.0;
-                    if ((om | ok) >= 0) {
-                        int64_t off = om + ok;
-                        if (cca) {
-                            const int pq = (mm & 1) | ((kk & 1) << 1); // m0, k0 are even
-                            if (pq == 3) off -= 2;
-                            v = Ap[off];
-                            if (pq == 2) v = -v;
-                        } else {
-                            v = Ap[off];
-                        }
-                    }
-                    ra[e] = v;
-                }
-#pragma unroll
-                for (int e = 0; e < EB; ++e) {
-                    const int idx = tid + e * NT;
-                    const int nn = bkf ? idx / BK : idx % BN, kk = bkf ? idx % BK : idx / BN;
-                    const int64_t on = offN_s[nn], ok = okb[kk];
-                    rb[e] = ((on | ok) >= 0) ? Bp[on + ok] : 0.0;
-                }
-            };
-            auto sts_chunk = [&](int buf) {
-                double* as = As + buf * Cfg::A_ELEMS;
-                double* bs = Bs + buf * Cfg::B_ELEMS;
-#pragma unroll
-                for (int e = 0; e < EA; ++e) {
-                    const int idx = tid + e * NT;
-                    const int mm = akf ? idx / BK : idx % BM, kk = akf ? idx % BK : idx / BM;
-                    as[mm * sAm + kk * sAk] = ra[e];
-                }
-#pragma unroll
-                for (int e = 0; e < EB; ++e) {
-                    const int idx = tid + e * NT;
-                    const int nn = bkf ? idx / BK : idx % BN, kk = bkf ? idx % BK : idx / BN;
-                    bs[nn * sBn + kk * sBk] = rb[e];
-                }
-            };
-
-            ldg_chunk(0);
-            sts_chunk(0);
-            __syncthreads();
-            for (int kc = 0; kc < nk; ++kc) {
-                const int buf = kc & 1;
-                if (kc + 1 < nk) ldg_chunk(kc + 1);
-                // k-offsets for chunk kc+2 (read after the sync that ends iteration kc)
-                if (kc + 2 < nk && tid < 2 * BK) {
-                    const int kk = tid % BK, k = (kc + 2) * BK + kk;
-                    if (tid < BK) offKa_s[((kc + 2) % KS) * BK + kk] = (k < K) ? grp_off(k, pr->k_ext, pr->ak_str, pr->k_n) : -1;
-                    else offKb_s[((kc + 2) % KS) * BK + kk] = (k < K) ? grp_off(k, pr->k_ext, pr->bk_str, pr->k_n) : -1;
-                }
-                const double* as = As + buf * Cfg::A_ELEMS;
-                const double* bs = Bs + buf * Cfg::B_ELEMS;
-#pragma unroll
-                for (int ks = 0; ks < BK / 4; ++ks) {
-                    double fa[FM], fb[FN];
-#pragma unroll
-                    for (int i = 0; i < FM; ++i) fa[i] = as[(wm0 + i * 8 + g) * sAm + (ks * 4 + t4) * sAk];
-#pragma unroll
-                    for (int j = 0; j < FN; ++j) fb[j] = bs[(wn0 + j * 8 + g) * sBn + (ks * 4 + t4) * sBk];
-#pragma unroll
-                    for (int i = 0; i < FM; ++i)
-#pragma unroll
-                        for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-                }
-                if (kc + 1 < nk) sts_chunk(buf ^ 1);
-                __syncthreads();
+        __syncthreads(); // previous pair / tile is done with tables and stages
+        for (int i = tid; i < BM + BN; i += NT) {
+            if (i < BM) {
+                const int m = m0 + i;
+                offM_s[i] = (m < M) ? grp_off(m, pr->m_ext, pr->am_str, pr->m_n) : -1;
+            } else {
+                const int n = n0 + i - BM;
+                offN_s[i - BM] = (n < N) ? grp_off(n, pr->n_ext, pr->bn_str, pr->n_n) : -1;
             }
         }
-        // ---- epilogue: C is written exactly once (all pairs of the block were accumulated above) ----
+        for (int i = tid; i < ST * 2 * BK; i += NT) { // k-offset tables of chunks c0 .. c0+ST-1
+            const int c = c0 + i / (2 * BK), r = i % (2 * BK), kk = r % BK;
+            const int k = c * BK + kk;
+            int64_t* dst = (r < BK ? offKa_s : offKb_s) + (c % KS) * BK + kk;
+            *dst = (k < K) ? grp_off(k, pr->k_ext, r < BK ? pr->ak_str : pr->bk_str, pr->k_n) : -1;
+        }
+        __syncthreads();
+
+        // ---- per-thread loader state, hoisted out of the K loop -------------------------------------------
+        // m-fast mapping: thread owns row mm = tid % BM and k-columns kk = tid/BM + e*(NT/BM)
+        // k-fast mapping: thread owns k-column kk = tid % BK and rows mm = tid/BK + e*(NT/BK)
+        // (NT/BM, NT/BK are even, so the (p,q) parity of the complex fold is a per-thread constant)
+        const int a_fix = akf ? tid % BK : tid % BM, a_run0 = akf ? tid / BK : tid / BM;
+        const int b_fix = bkf ? tid % BK : tid % BN, b_run0 = bkf ? tid / BK : tid / BN;
+        const bool a_odd_odd = akf ? ((a_fix & 1) && (a_run0 & 1)) : ((a_fix & 1) && (a_run0 & 1));
+        const double* __restrict__ Apt = Ap - ((cca && a_odd_odd) ? 2 : 0); // (p,q)=(1,1) reads the real part again
+        const int64_t a_om = akf ? 0 : offM_s[a_fix];
+        const int64_t b_on = bkf ? 0 : offN_s[b_fix];
+        const int a_sdst0 = akf ? a_run0 * (BK + G_PAD) + a_fix : a_fix + a_run0 * (BM + G_PAD);
+        const int b_sdst0 = bkf ? b_run0 * (BK + G_PAD) + b_fix : b_fix + b_run0 * (BN + G_PAD);
+
+        auto issue_chunk = [&](int c) { // gather chunk c of both operands into stage c % ST
+            double* as = As + (c % ST) * G_STAGE_ELEMS + a_sdst0;
+            double* bs = Bs + (c % ST) * G_STAGE_ELEMS + b_sdst0;
+            const int64_t* oka = offKa_s + (c % KS) * BK;
+            const int64_t* okb = offKb_s + (c % KS) * BK;
+            if (akf) {
+                const int64_t ok = oka[a_fix];
+#pragma unroll
+                for (int e = 0; e < EA; ++e) {
+                    const int64_t om = offM_s[a_run0 + e * (NT / BK)];
+                    const bool v = (om | ok) >= 0;
+                    cp_async8(as + e * (NT / BK) * (BK + G_PAD), v ? Apt + om + ok : Ap, v);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EA; ++e) {
+                    const int64_t ok = oka[a_run0 + e * (NT / BM)];
+                    const bool v = (a_om | ok) >= 0;
+                    cp_async8(as + e * (NT / BM) * (BM + G_PAD), v ? Apt + a_om + ok : Ap, v);
+                }
+            }
+            if (bkf) {
+                const int64_t ok = okb[b_fix];
+#pragma unroll
+                for (int e = 0; e < EB; ++e) {
+                    const int64_t on = offN_s[b_run0 + e * (NT / BK)];
+                    const bool v = (on | ok) >= 0;
+                    cp_async8(bs + e * (NT / BK) * (BK + G_PAD), v ? Bp + on + ok : Bp, v);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < EB; ++e) {
+                    const int64_t ok = okb[b_run0 + e * (NT / BN)];
+                    const bool v = (b_on | ok) >= 0;
+                    cp_async8(bs + e * (NT / BN) * (BN + G_PAD), v ? Bp + b_on + ok : Bp, v);
+                }
+            }
+        };
+
+#pragma unroll
+        for (int s = 0; s < ST - 1; ++s) {
+            if (c0 + s < c1) issue_chunk(c0 + s);
+            cp_async_commit();
+        }
+        for (int kc = c0; kc < c1; ++kc) {
+            cp_async_wait<ST - 2>();
+            __syncthreads();
+            const int L = kc + ST - 1;
+            if (L < c1) issue_chunk(L);
+            cp_async_commit();
+            if (L + 1 < c1 && tid < 2 * BK) { // k-offsets of chunk L+1, visible after the next barrier
+                const int kk = tid % BK, k = (L + 1) * BK + kk;
+                int64_t* dst = (tid < BK ? offKa_s : offKb_s) + ((L + 1) % KS) * BK + kk;
+                *dst = (k < K) ? grp_off(k, pr->k_ext, tid < BK ? pr->ak_str : pr->bk_str, pr->k_n) : -1;
+            }
+            const double* as = As + (kc % ST) * G_STAGE_ELEMS;
+            const double* bs = Bs + (kc % ST) * G_STAGE_ELEMS;
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                double fa[FM], fb[FN];
+#pragma unroll
+                for (int i = 0; i < FM; ++i) fa[i] = as[(wm0 + i * 8 + g) * sAm + (ks * 4 + t4) * sAk];
+                if (cca) {
+#pragma unroll
+                    for (int i = 0; i < FM; ++i) fa[i] = __hiloint2double(__double2hiint(fa[i]) ^ sgn, __double2loint(fa[i]));
+                }
+#pragma unroll
+                for (int j = 0; j < FN; ++j) fb[j] = bs[(wn0 + j * 8 + g) * sBn + (ks * 4 + t4) * sBk];
+#pragma unroll
+                for (int i = 0; i < FM; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            }
+        }
+        cp_async_wait<0>();
+    }
+    // ---- epilogue: each C element is written exactly once (or one partial per split) ----------------------
+    if (tile.ws_slot < 0) {
         double* __restrict__ Cp = C + cb->c_off;
         const int64_t cms = cb->c_ms, cns = cb->c_ns;
         const int nmask = cb->c_nmask, nshift = cb->c_nshift;
@@ -224,27 +228,83 @@ __global__ void __launch_bounds__(Cfg::NT) bsc_gemm_kernel(const ItbTile* __rest
                 }
             }
         }
+    } else {
+        double* __restrict__ W = ws + (int64_t)tile.ws_slot * ITB_WS_TILE;
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) W[(wm0 + i * 8 + g) + BM * (wn0 + j * 8 + 2 * t4 + h)] = acc[i][j][h];
+    }
+}
+
+__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, int ntiles,
+                                                            const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
+                                                            const double* __restrict__ A, const double* __restrict__ B,
+                                                            double* __restrict__ C, double* __restrict__ ws,
+                                                            int* __restrict__ counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + G_STAGES * G_STAGE_ELEMS;
+    int64_t* offM_s = reinterpret_cast<int64_t*>(Bs + G_STAGES * G_STAGE_ELEMS);
+    int64_t* offN_s = offM_s + G_MAXT;
+    int64_t* offKa_s = offN_s + G_MAXT;
+    int64_t* offKb_s = offKa_s + G_KS * G_BK;
+    int* item_s = reinterpret_cast<int*>(offKb_s + G_KS * G_BK);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *item_s = atomicAdd(counter, 1);
+        __syncthreads();
+        const int item = *item_s;
+        if (item >= ntiles) break;
+        const ItbTile tile = tiles[item];
+        const ItbCBlk* cb = cblks + tile.cblk;
+        if (tile.cfg == 0) run_tile<128, 128>(tile, cb, pairs, A, B, C, ws, As, Bs, offM_s, offN_s, offKa_s, offKb_s);
+        else if (tile.cfg == 1) run_tile<64, 64>(tile, cb, pairs, A, B, C, ws, As, Bs, offM_s, offN_s, offKa_s, offKb_s);
+        else run_tile<32, 32>(tile, cb, pairs, A, B, C, ws, As, Bs, offM_s, offN_s, offKa_s, offKb_s);
+    }
+}
+
+// C tile = sum of its split-K partials, in split order (deterministic)
+__global__ void __launch_bounds__(256) bsc_splitk_reduce_kernel(const ItbSplitOut* __restrict__ outs, const ItbCBlk* __restrict__ cblks,
+                                                                 const double* __restrict__ ws, double* __restrict__ C) {
+    const ItbSplitOut o = outs[blockIdx.x];
+    const ItbCBlk* cb = cblks + o.cblk;
+    const int T = o.cfg == 0 ? 128 : (o.cfg == 1 ? 64 : 32);
+    const int M = cb->M, N = cb->N, m0 = o.tm * T, n0 = o.tn * T;
+    double* __restrict__ Cp = C + cb->c_off;
+    for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+        const int ml = e % T, nl = e / T;
+        const int m = m0 + ml, n = n0 + nl;
+        if (m >= M || n >= N) continue;
+        double s = 0.0;
+        for (int q = 0; q < o.nsplit; ++q) s += ws[(int64_t)(o.ws_slot0 + q) * ITB_WS_TILE + ml + T * nl];
+        Cp[(int64_t)m * cb->c_ms + (n & cb->c_nmask) + (int64_t)(n >> cb->c_nshift) * cb->c_ns] = s;
     }
 }
 
 // ---- streaming kernel: short side S <= 8 -------------------------------------------------------------
-constexpr int SK_NT = 256, SK_KC = 64, SK_S = 8;
+// HBM-bound class (the MPO steps of H_eff*phi: K,N <= 4 against a multi-million-element operand).
+// One thread owns SK_RPT rows of the long side (coalesced across the warp), the short operand chunk
+// sits in shared memory and is read as two broadcast 256-bit rows per k.
+constexpr int SK_NT = 256, SK_RPT = 4, SK_KC = 32, SK_S = 8;
 
 __global__ void __launch_bounds__(SK_NT) bsc_skinny_kernel(const ItbSkinny* __restrict__ items, const ItbCBlk* __restrict__ cblks,
                                                            const ItbPair* __restrict__ pairs, const double* __restrict__ A,
                                                            const double* __restrict__ B, double* __restrict__ C) {
-    __shared__ double Ss[SK_KC][SK_S];
+    __shared__ __align__(32) double Ss[SK_KC][SK_S];
     __shared__ int64_t offKl_s[SK_KC];
     const ItbSkinny it = items[blockIdx.x];
     const ItbCBlk* cb = cblks + it.cblk;
     const int tid = threadIdx.x;
     const bool lin = it.long_is_n; // long side is n (B is the long operand); else A is
     const int S = lin ? cb->M : cb->N;
-    const int l = it.row0 + tid;
-    const bool active = tid < it.rows;
-    double acc[SK_S];
+    double acc[SK_RPT][SK_S];
 #pragma unroll
-    for (int s = 0; s < SK_S; ++s) acc[s] = 0.0;
+    for (int j = 0; j < SK_RPT; ++j)
+#pragma unroll
+        for (int s = 0; s < SK_S; ++s) acc[j][s] = 0.0;
 
     for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
         const ItbPair* pr = pairs + p;
@@ -252,15 +312,21 @@ __global__ void __launch_bounds__(SK_NT) bsc_skinny_kernel(const ItbSkinny* __re
         const bool cca = pr->flags & ITB_PF_CCA;
         const double* __restrict__ Lp = lin ? B + pr->b_off : A + pr->a_off;
         const double* __restrict__ Sp = lin ? A + pr->a_off : B + pr->b_off;
-        int64_t offL = 0;
-        if (active) offL = lin ? grp_off(l, pr->n_ext, pr->bn_str, pr->n_n) : grp_off(l, pr->m_ext, pr->am_str, pr->m_n);
+        int64_t offL[SK_RPT];
+#pragma unroll
+        for (int j = 0; j < SK_RPT; ++j) {
+            const int l = it.row0 + tid + j * SK_NT;
+            offL[j] = -1;
+            if (tid + j * SK_NT < it.rows) offL[j] = lin ? grp_off(l, pr->n_ext, pr->bn_str, pr->n_n) : grp_off(l, pr->m_ext, pr->am_str, pr->m_n);
+        }
+        const bool fix = cca && !lin; // long operand is the complex*complex A: (p,q) fix-up per element
         for (int k0 = 0; k0 < K; k0 += SK_KC) {
             const int kn = min(SK_KC, K - k0);
             __syncthreads();
-            for (int i = tid; i < SK_KC * SK_S; i += SK_NT) {
+            for (int i = tid; i < kn * SK_S; i += SK_NT) {
                 const int kk = i / SK_S, s = i % SK_S;
                 double v = 0.0;
-                if (kk < kn && s < S) {
+                if (s < S) {
                     const int k = k0 + kk;
                     if (lin) { // short operand is A: element (m=s, k)
                         int64_t off = grp_off(s, pr->m_ext, pr->am_str, pr->m_n) + grp_off(k, pr->k_ext, pr->ak_str, pr->k_n);
@@ -278,33 +344,160 @@ __global__ void __launch_bounds__(SK_NT) bsc_skinny_kernel(const ItbSkinny* __re
             }
             if (tid < kn) offKl_s[tid] = grp_off(k0 + tid, pr->k_ext, lin ? pr->bk_str : pr->ak_str, pr->k_n);
             __syncthreads();
-            if (active) {
-                const bool fix = cca && !lin; // long operand is the complex*complex A
-#pragma unroll 4
-                for (int kk = 0; kk < kn; ++kk) {
-                    int64_t off = offL + offKl_s[kk];
-                    double x;
-                    if (fix) {
-                        const int pq = (l & 1) | (((k0 + kk) & 1) << 1);
-                        if (pq == 3) off -= 2;
-                        x = Lp[off];
-                        if (pq == 2) x = -x;
-                    } else x = Lp[off];
-                    const double4 s0 = *reinterpret_cast<const double4*>(&Ss[kk][0]);
-                    const double4 s1 = *reinterpret_cast<const double4*>(&Ss[kk][4]);
-                    acc[0] += x * s0.x; acc[1] += x * s0.y; acc[2] += x * s0.z; acc[3] += x * s0.w;
-                    acc[4] += x * s1.x; acc[5] += x * s1.y; acc[6] += x * s1.z; acc[7] += x * s1.w;
+            for (int kk = 0; kk < kn; ++kk) {
+                const int64_t ok = offKl_s[kk];
+                double x[SK_RPT];
+#pragma unroll
+                for (int j = 0; j < SK_RPT; ++j) {
+                    x[j] = 0.0;
+                    if (offL[j] >= 0) {
+                        int64_t off = offL[j] + ok;
+                        if (fix) {
+                            const int pq = ((it.row0 + tid) & 1) | (((k0 + kk) & 1) << 1); // j*SK_NT is even
+                            if (pq == 3) off -= 2;
+                            x[j] = Lp[off];
+                            if (pq == 2) x[j] = -x[j];
+                        } else x[j] = Lp[off];
+                    }
+                }
+                const double4 s0 = *reinterpret_cast<const double4*>(&Ss[kk][0]);
+                const double4 s1 = *reinterpret_cast<const double4*>(&Ss[kk][4]);
+#pragma unroll
+                for (int j = 0; j < SK_RPT; ++j) {
+                    acc[j][0] += x[j] * s0.x; acc[j][1] += x[j] * s0.y; acc[j][2] += x[j] * s0.z; acc[j][3] += x[j] * s0.w;
+                    acc[j][4] += x[j] * s1.x; acc[j][5] += x[j] * s1.y; acc[j][6] += x[j] * s1.z; acc[j][7] += x[j] * s1.w;
                 }
             }
         }
     }
-    if (active) {
-        double* __restrict__ Cp = C + cb->c_off;
+    double* __restrict__ Cp = C + cb->c_off;
+#pragma unroll
+    for (int j = 0; j < SK_RPT; ++j) {
+        if (tid + j * SK_NT >= it.rows) continue;
+        const int l = it.row0 + tid + j * SK_NT;
 #pragma unroll
         for (int s = 0; s < SK_S; ++s) {
             if (s < S) {
                 const int m = lin ? s : l, n = lin ? l : s;
-                Cp[(int64_t)m * cb->c_ms + (n & cb->c_nmask) + (int64_t)(n >> cb->c_nshift) * cb->c_ns] = acc[s];
+                Cp[(int64_t)m * cb->c_ms + (n & cb->c_nmask) + (int64_t)(n >> cb->c_nshift) * cb->c_ns] = acc[j][s];
+            }
+        }
+    }
+}
+
+// ---- streaming kernel, small-K fast path -----------------------------------------------------------------
+// The MPO steps of H_eff*phi: every pair of a C block has K <= a few, so ALL short operands of the block fit
+// in shared memory once per CTA; after that setup the CTA streams thousands of long-side rows with
+// SQ_RPT independent rows per thread in flight and no further synchronisation.
+constexpr int SQ_NT = 256, SQ_RPT = 4, SQ_MAXK = 64, SQ_MAXP = 8;
+struct SqPair {
+    const double* Lp;
+    int64_t str[ITB_MAXG];
+    int32_t ext[ITB_MAXG];
+    int32_t kbeg, K, n, fix;
+};
+
+template <int S>
+__global__ void __launch_bounds__(SQ_NT) bsc_skinny_smallk_kernel(const ItbSkinny* __restrict__ items, const ItbCBlk* __restrict__ cblks,
+                                                                  const ItbPair* __restrict__ pairs, const double* __restrict__ A,
+                                                                  const double* __restrict__ B, double* __restrict__ C) {
+    __shared__ __align__(32) double Ss[SQ_MAXK][S];
+    __shared__ int64_t okl[SQ_MAXK];
+    __shared__ SqPair sp[SQ_MAXP];
+    const ItbSkinny it = items[blockIdx.x];
+    const ItbCBlk* cb = cblks + it.cblk;
+    const int tid = threadIdx.x;
+    const bool lin = it.long_is_n;
+    const int Sact = lin ? cb->M : cb->N;
+    const int np = cb->pair_end - cb->pair_begin;
+    if (tid < np) {
+        const ItbPair* pr = pairs + cb->pair_begin + tid;
+        SqPair q;
+        q.Lp = lin ? B + pr->b_off : A + pr->a_off;
+        q.n = lin ? pr->n_n : pr->m_n;
+        for (int d = 0; d < ITB_MAXG; ++d) {
+            q.ext[d] = lin ? pr->n_ext[d] : pr->m_ext[d];
+            q.str[d] = lin ? pr->bn_str[d] : pr->am_str[d];
+        }
+        q.K = pr->K;
+        q.fix = ((pr->flags & ITB_PF_CCA) && !lin) ? 1 : 0;
+        int kb = 0;
+        for (int t = 0; t < tid; ++t) kb += pairs[cb->pair_begin + t].K;
+        q.kbeg = kb;
+        sp[tid] = q;
+    }
+    __syncthreads();
+    const int Ktot = sp[np - 1].kbeg + sp[np - 1].K;
+    for (int i = tid; i < Ktot * S; i += SQ_NT) {
+        const int kg = i / S, s = i % S;
+        int q = 0;
+        while (q + 1 < np && kg >= sp[q + 1].kbeg) ++q;
+        const ItbPair* pr = pairs + cb->pair_begin + q;
+        const int k = kg - sp[q].kbeg;
+        double v = 0.0;
+        if (s < Sact) {
+            if (lin) { // short operand is A: element (m=s, k)
+                int64_t off = grp_off(s, pr->m_ext, pr->am_str, pr->m_n) + grp_off(k, pr->k_ext, pr->ak_str, pr->k_n);
+                if (pr->flags & ITB_PF_CCA) {
+                    const int pq = (s & 1) | ((k & 1) << 1);
+                    if (pq == 3) off -= 2;
+                    v = (A + pr->a_off)[off];
+                    if (pq == 2) v = -v;
+                } else v = (A + pr->a_off)[off];
+            } else {
+                v = (B + pr->b_off)[grp_off(k, pr->k_ext, pr->bk_str, pr->k_n) + grp_off(s, pr->n_ext, pr->bn_str, pr->n_n)];
+            }
+        }
+        Ss[kg][s] = v;
+        if (s == 0) okl[kg] = grp_off(k, pr->k_ext, lin ? pr->bk_str : pr->ak_str, pr->k_n);
+    }
+    __syncthreads();
+
+    double* __restrict__ Cp = C + cb->c_off;
+    for (int r0 = 0; r0 < it.rows; r0 += SQ_NT * SQ_RPT) {
+        double acc[SQ_RPT][S];
+#pragma unroll
+        for (int j = 0; j < SQ_RPT; ++j)
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[j][s] = 0.0;
+        bool valid[SQ_RPT];
+#pragma unroll
+        for (int j = 0; j < SQ_RPT; ++j) valid[j] = r0 + tid + j * SQ_NT < it.rows;
+        for (int q = 0; q < np; ++q) {
+            const SqPair& P = sp[q];
+            const double* __restrict__ Lp = P.Lp;
+            int64_t offL[SQ_RPT];
+#pragma unroll
+            for (int j = 0; j < SQ_RPT; ++j) offL[j] = valid[j] ? grp_off(it.row0 + r0 + tid + j * SQ_NT, P.ext, P.str, P.n) : 0;
+            for (int kk = 0; kk < P.K; ++kk) {
+                const int64_t ok = okl[P.kbeg + kk];
+                double x[SQ_RPT];
+#pragma unroll
+                for (int j = 0; j < SQ_RPT; ++j) {
+                    int64_t off = offL[j] + ok;
+                    if (P.fix) { // row parity == tid parity (row0, r0, j*SQ_NT are even)
+                        const int pq = (tid & 1) | ((kk & 1) << 1);
+                        if (pq == 3) off -= 2;
+                        x[j] = valid[j] ? Lp[off] : 0.0;
+                        if (pq == 2) x[j] = -x[j];
+                    } else x[j] = valid[j] ? Lp[off] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < SQ_RPT; ++j)
+#pragma unroll
+                    for (int s = 0; s < S; ++s) acc[j][s] = fma(x[j], Ss[P.kbeg + kk][s], acc[j][s]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SQ_RPT; ++j) {
+            if (!valid[j]) continue;
+            const int l = it.row0 + r0 + tid + j * SQ_NT;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                if (s < Sact) {
+                    const int m = lin ? s : l, n = lin ? l : s;
+                    Cp[(int64_t)m * cb->c_ms + (n & cb->c_nmask) + (int64_t)(n >> cb->c_nshift) * cb->c_ns] = acc[j][s];
+                }
             }
         }
     }
@@ -419,42 +612,32 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) 
 }
 
 // ---- launchers (called from api.cu) ---------------------------------------------------------------------
-using CfgBig = GemmCfg<128, 128, 32, 32>;
-using CfgMed = GemmCfg<64, 64, 32, 32>;
-using CfgSmall = GemmCfg<32, 32, 16, 16>;
-
-template <class Cfg>
-static cudaError_t launch_gemm_cfg(const ItbTile* tiles, int ntiles, const ItbCBlk* cblks, const ItbPair* pairs,
-                                   const double* A, const double* B, double* C, int* counter, int num_sms,
-                                   cudaStream_t st) {
+cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks,
+                        const ItbPair* pairs, const double* A, const double* B, double* C, double* ws, int* counter, int num_sms,
+                        cudaStream_t st) {
     static bool configured = false;
-    static int occ = 1;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bsc_gemm_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(bsc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bsc_gemm_kernel<Cfg>, Cfg::NT, Cfg::SMEM);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) occ = 1;
         configured = true;
     }
-    int grid = num_sms * occ;
+    int grid = num_sms;
     if (grid > ntiles) grid = ntiles;
-    bsc_gemm_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(tiles, ntiles, cblks, pairs, A, B, C, counter);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_gemm(int cfg, const ItbTile* tiles, int ntiles, const ItbCBlk* cblks, const ItbPair* pairs,
-                        const double* A, const double* B, double* C, int* counter, int num_sms, cudaStream_t st) {
-    switch (cfg) {
-        case 0: return launch_gemm_cfg<CfgBig>(tiles, ntiles, cblks, pairs, A, B, C, counter, num_sms, st);
-        case 1: return launch_gemm_cfg<CfgMed>(tiles, ntiles, cblks, pairs, A, B, C, counter, num_sms, st);
-        default: return launch_gemm_cfg<CfgSmall>(tiles, ntiles, cblks, pairs, A, B, C, counter, num_sms, st);
+    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, ntiles, cblks, pairs, A, B, C, ws, counter);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (nsouts > 0) {
+        bsc_splitk_reduce_kernel<<<nsouts, 256, 0, st>>>(souts, cblks, ws, C);
+        e = cudaGetLastError();
     }
+    return e;
 }
 
-cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbCBlk* cblks, const ItbPair* pairs, const double* A,
-                          const double* B, double* C, cudaStream_t st) {
-    bsc_skinny_kernel<<<n, SK_NT, 0, st>>>(items, cblks, pairs, A, B, C);
+cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
+                          const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st) {
+    if (nq4 > 0) bsc_skinny_smallk_kernel<4><<<nq4, SQ_NT, 0, st>>>(q4, cblks, pairs, A, B, C);
+    if (nq8 > 0) bsc_skinny_smallk_kernel<8><<<nq8, SQ_NT, 0, st>>>(q8, cblks, pairs, A, B, C);
+    if (n > 0) bsc_skinny_kernel<<<n, SK_NT, 0, st>>>(items, cblks, pairs, A, B, C);
     return cudaGetLastError();
 }
 

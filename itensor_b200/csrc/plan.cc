@@ -17,6 +17,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -221,8 +222,8 @@ int build_contract_tables(itb_contract_plan& P) {
     const bool cA = A.dtype == ITB_C64, cB = B.dtype == ITB_C64;
     const int64_t csA = cA ? 2 : 1, csB = cB ? 2 : 1, csC = (cA || cB) ? 2 : 1;
 
-    P.pairs.clear(); P.cblks.clear(); P.skinny.clear(); P.dots.clear(); P.dot_outs.clear();
-    for (auto& t : P.tiles) t.clear();
+    P.pairs.clear(); P.cblks.clear(); P.skinny.clear(); P.skinny_q4.clear(); P.skinny_q8.clear(); P.dots.clear(); P.dot_outs.clear();
+    P.tiles.clear(); P.splits.clear(); P.ws_slots = 0;
     P.ndot_slots = 0;
 
     const int64_t npairs = (int64_t)P.triples.size() / 3;
@@ -327,6 +328,7 @@ int build_contract_tables(itb_contract_plan& P) {
 
     // ---- classify C blocks into kernel work lists --------------------------------------------------
     for (double& f : P.class_flops) f = 0;
+    std::vector<std::pair<int32_t, int>> tile_cblks; // (C block, tile config)
     for (int32_t c = 0; c < (int32_t)P.cblks.size(); ++c) {
         const ItbCBlk& cb = P.cblks[c];
         const int64_t M = cb.M, N = cb.N;
@@ -346,35 +348,78 @@ int build_contract_tables(itb_contract_plan& P) {
         } else if (std::min(M, N) <= kSkinnyMax) {
             P.class_flops[3] += cflops;
             const int long_is_n = (N > M) ? 1 : 0;
-            const int64_t L = long_is_n ? N : M;
-            for (int64_t r0 = 0; r0 < L; r0 += kSkinnyRows)
-                P.skinny.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyRows, L - r0), long_is_n});
+            const int64_t L = long_is_n ? N : M, Sh = long_is_n ? M : N;
+            if (cb.ksum <= kSkinnyQMaxK && cb.pair_end - cb.pair_begin <= kSkinnyQMaxPairs) {
+                auto& list = Sh <= 4 ? P.skinny_q4 : P.skinny_q8;
+                for (int64_t r0 = 0; r0 < L; r0 += kSkinnyQRows)
+                    list.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyQRows, L - r0), long_is_n});
+            } else {
+                for (int64_t r0 = 0; r0 < L; r0 += kSkinnyRows)
+                    P.skinny.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyRows, L - r0), long_is_n});
+            }
         } else {
             // pick the tile config with the least padded work (bigger tiles run more efficiently)
             int best = 0; double bestc = 1e300;
-            static const double eff[ITB_NCFG] = {1.0, 0.85, 0.6};
+            static const double eff[ITB_NCFG] = {1.0, 0.8, 0.5};
             for (int f = 0; f < ITB_NCFG; ++f) {
                 const double tm = (double)((M + kTileM[f] - 1) / kTileM[f]), tn = (double)((N + kTileN[f] - 1) / kTileN[f]);
                 const double cost = tm * tn * kTileM[f] * kTileN[f] / eff[f];
                 if (cost < bestc) { bestc = cost; best = f; }
             }
             P.class_flops[best] += cflops;
-            const int TM = kTileM[best], TN = kTileN[best];
-            for (int32_t tn = 0; tn < (N + TN - 1) / TN; ++tn)
-                for (int32_t tm = 0; tm < (M + TM - 1) / TM; ++tm)
-                    P.tiles[best].push_back({c, tm, tn, 0});
+            tile_cblks.push_back({c, best});
         }
     }
-    // longest-processing-time-first: heavy items to the front of each persistent queue
-    for (auto& t : P.tiles)
-        std::stable_sort(t.begin(), t.end(), [&](const ItbTile& x, const ItbTile& y) { return P.cblks[x.cblk].ksum > P.cblks[y.cblk].ksum; });
+    // ---- tile items with split-K: cap the K-chunks per item so that the persistent grid balances ---------
+    {
+        auto chunks_of = [&](const ItbCBlk& cb) {
+            int64_t n = 0;
+            for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) n += (P.pairs[p].K + ITB_BK - 1) / ITB_BK;
+            return n;
+        };
+        double total_work = 0; // in units of 128x128x16 chunk-tiles
+        for (auto& tc : tile_cblks) {
+            const ItbCBlk& cb = P.cblks[tc.first];
+            const int T = kTileM[tc.second];
+            const double nt = (double)((cb.M + T - 1) / T) * (double)((cb.N + T - 1) / T);
+            total_work += nt * (double)chunks_of(cb) * (double)(T * T) / (128.0 * 128.0);
+        }
+        const double cap_work = std::max(24.0, total_work / (kNumSMs * 4.0)); // <= 1/4 of a CTA's fair share
+        for (auto& tc : tile_cblks) {
+            const int32_t c = tc.first; const int f = tc.second;
+            const ItbCBlk& cb = P.cblks[c];
+            const int T = kTileM[f];
+            const int64_t nch = chunks_of(cb);
+            const double per_chunk = (double)(T * T) / (128.0 * 128.0);
+            int64_t nsplit = (int64_t)std::ceil((double)nch * per_chunk / cap_work);
+            nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, nch / 8 > 0 ? nch / 8 : 1)); // >= 8 chunks per split
+            const int64_t per = (nch + nsplit - 1) / nsplit;
+            nsplit = (nch + per - 1) / per;
+            for (int32_t tn = 0; tn < (cb.N + T - 1) / T; ++tn)
+                for (int32_t tm = 0; tm < (cb.M + T - 1) / T; ++tm) {
+                    if (nsplit == 1) {
+                        P.tiles.push_back({c, tm, tn, f, 0, (int32_t)nch, -1, 0});
+                    } else {
+                        P.splits.push_back({c, tm, tn, f, (int32_t)P.ws_slots, (int32_t)nsplit, {0, 0}});
+                        for (int64_t q = 0; q < nsplit; ++q)
+                            P.tiles.push_back({c, tm, tn, f, (int32_t)(q * per), (int32_t)std::min<int64_t>(nch, (q + 1) * per), (int32_t)P.ws_slots++, 0});
+                    }
+                }
+        }
+    }
+    // longest-processing-time-first: heavy items to the front of the persistent queue
+    std::stable_sort(P.tiles.begin(), P.tiles.end(), [&](const ItbTile& x, const ItbTile& y) {
+        const double wx = (double)(x.chunk_end - x.chunk_begin) * kTileM[x.cfg] * kTileN[x.cfg];
+        const double wy = (double)(y.chunk_end - y.chunk_begin) * kTileM[y.cfg] * kTileN[y.cfg];
+        return wx > wy;
+    });
     std::stable_sort(P.skinny.begin(), P.skinny.end(), [&](const ItbSkinny& x, const ItbSkinny& y) {
         return P.cblks[x.cblk].ksum * (P.cblks[x.cblk].M + P.cblks[x.cblk].N) > P.cblks[y.cblk].ksum * (P.cblks[y.cblk].M + P.cblks[y.cblk].N);
     });
     P.table_bytes = (int64_t)(P.pairs.size() * sizeof(ItbPair) + P.cblks.size() * sizeof(ItbCBlk) +
-                              P.skinny.size() * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
-                              P.dot_outs.size() * sizeof(ItbDotOut));
-    for (auto& t : P.tiles) P.table_bytes += (int64_t)(t.size() * sizeof(ItbTile));
+                              (P.skinny.size() + P.skinny_q4.size() + P.skinny_q8.size()) * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
+                              P.dot_outs.size() * sizeof(ItbDotOut) + P.tiles.size() * sizeof(ItbTile) +
+                              P.splits.size() * sizeof(ItbSplitOut));
     P.tables_built = true;
     return ITB_OK;
 }
@@ -519,9 +564,8 @@ int itb_contract_plan_info(const itb_contract_plan* P, itb_contract_info* o) {
     o->c_nelems = P->C.nelems;
     o->npairs = (int64_t)P->triples.size() / 3;
     o->flops = P->flops;
-    o->n_gemm_tiles = 0;
-    for (auto& t : P->tiles) o->n_gemm_tiles += (int64_t)t.size();
-    o->n_skinny = (int64_t)P->skinny.size();
+    o->n_gemm_tiles = (int64_t)P->tiles.size();
+    o->n_skinny = (int64_t)(P->skinny.size() + P->skinny_q4.size() + P->skinny_q8.size());
     o->n_dot = (int64_t)P->dots.size();
     o->table_bytes = P->table_bytes;
     for (int i = 0; i < 5; ++i) o->class_flops[i] = P->class_flops[i];

@@ -44,8 +44,12 @@ struct itb_contract_plan {
     bool tables_built = false;
     std::vector<ItbPair> pairs;
     std::vector<ItbCBlk> cblks;
-    std::vector<ItbTile> tiles[itb::ITB_NCFG];
-    std::vector<ItbSkinny> skinny;
+    std::vector<ItbTile> tiles;       // every tile class in one persistent queue (LPT order)
+    std::vector<ItbSplitOut> splits;  // split-K tiles to be reduced from the workspace
+    int64_t ws_slots = 0;
+    std::vector<ItbSkinny> skinny;    // generic streaming items
+    std::vector<ItbSkinny> skinny_q4; // small-K fast path, short side <= 4
+    std::vector<ItbSkinny> skinny_q8; // small-K fast path, short side <= 8
     std::vector<ItbDot> dots;
     std::vector<ItbDotOut> dot_outs;
     int64_t ndot_slots = 0;
@@ -78,7 +82,11 @@ int build_permute_plan(itb_permute_plan& P);
 constexpr int kPermCopyChunk = 4096; // elements per work item, copy-like path
 constexpr int kPermTile = 32;        // tile edge, transposing path
 constexpr int kDotChunk = 8192;      // k-range per split-K item
-constexpr int kSkinnyRows = 256;     // long-side rows per streaming item
+constexpr int kSkinnyRows = 1024;    // long-side rows per streaming item (4 per thread)
+constexpr int kSkinnyQRows = 2048;   // rows per item of the small-K fast path (2 batches of 4 rows/thread)
+constexpr int kSkinnyQMaxK = 64;     // sum of K over the pairs of a C block / max pairs for the fast path
+constexpr int kSkinnyQMaxPairs = 8;
+constexpr int kNumSMs = 148;         // B200: persistent grid size the split-K heuristic balances for
 constexpr int kSkinnyMax = 8;        // short side <= this -> streaming kernel
 constexpr int kDotMaxMN = 4;        // M*N <= this -> reduction kernel (scalar results, re/im pairs)
 } // namespace itb

@@ -44,9 +44,19 @@ struct ItbCBlk {
     int64_t ksum;     // sum of K over the pairs (work estimate)
 };
 
-struct ItbTile { // work item of the DMMA tile kernel
-    int32_t cblk, tm, tn, pad_;
+struct ItbTile { // work item of the persistent DMMA tile kernel
+    int32_t cblk, tm, tn;
+    int32_t cfg;         // tile configuration (ITB_CFG_*: 128x128 / 64x64 / 32x32)
+    int32_t chunk_begin; // range of BK-chunks of the C block's concatenated K loop (split-K)
+    int32_t chunk_end;
+    int32_t ws_slot;     // -1: write C directly; else partial tile goes to workspace slot ws_slot
+    int32_t pad_;
 };
+struct ItbSplitOut { // split-K tile: C tile = sum of workspace slots [ws_slot0, ws_slot0+nsplit) in order
+    int32_t cblk, tm, tn, cfg, ws_slot0, nsplit, pad_[2];
+};
+#define ITB_BK 16              // K-chunk of the tile kernel
+#define ITB_WS_TILE (128 * 128) // doubles per workspace slot
 struct ItbSkinny { // work item of the streaming kernel: rows [row0,row0+rows) of the long side
     int32_t cblk, row0, rows, long_is_n; // long_is_n: 1 -> threads run over n, short side is m
 };

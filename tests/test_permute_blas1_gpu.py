@@ -62,6 +62,8 @@ def test_add_with_permutation_and_block_merge(ctx, da, db):
     for trial in range(30):
         r = int(rng.integers(1, 5))
         full = _rand_qn_tensor(rng, r, F, drop=0.0)
+        if full.nblocks == 0:
+            continue
         def sub(dtype):
             keep = rng.uniform(size=full.nblocks) < 0.7
             if not keep.any():

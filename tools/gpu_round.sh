@@ -13,7 +13,7 @@ echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "== ncu full (gemm kernel)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:bsc_gemm_kernel -s 4 -c 2 -o $OUT/${TAG}_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bsc_gemm_kernel -s 8 -c 2 -o $OUT/${TAG}_gemm \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 fi
 echo "== done"
