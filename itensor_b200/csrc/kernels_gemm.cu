@@ -48,36 +48,101 @@ __device__ __forceinline__ int64_t grp_off(int idx, const int32_t* __restrict__ 
     return o;
 }
 
-// ---- persistent DMMA tile kernel -------------------------------------------------------------------------
+// ---- persistent warp-specialised DMMA tile kernel ---------------------------------------------------------
 // One launch serves every tile class: items carry their configuration (128x128 / 64x64 / 32x32) and a
-// range of K-chunks (split-K for C blocks with few tiles but long K loops). 256 threads = 8 warps laid
-// out 2 (m) x 4 (n); 4-stage cp.async ring of BK=16 chunks; fragments read conflict-free from padded smem.
-constexpr int G_NT = 256, G_STAGES = 4, G_BK = ITB_BK, G_KS = 8, G_PAD = 4;
-constexpr int G_MAXT = 128;
+// range of K-chunks (split-K for C blocks with few tiles but long K loops).
+//   warps 0-15 CONSUMERS  4 (m) x 4 (n) warp grid; per K-chunk: wait full[stage] -> 4 x (LDS fragments,
+//                         DMMA.8x8x4) -> arrive empty[stage]. They never touch global operands or tables.
+//   warps 16-19 PRODUCERS  gather the A/B chunk straight from the strided N-index blocks with 8-byte
+//                         cp.async (zero-fill past the edges) into a 4-stage ring; completion is tracked
+//                         by cp.async.mbarrier.arrive on full[stage].
+// Producers and consumers walk the same deterministic (tile, pair, chunk) sequence, so there is no
+// CTA-wide barrier anywhere in the main loop: DMMA stretches of the two consumer warps of an SMSP
+// interleave freely and the epilogue of one tile overlaps the loads of the next.
+constexpr int G_NCONS = 512, G_NPROD = 128, G_NT = G_NCONS + G_NPROD;
+constexpr int G_STAGES = 4, G_BK = ITB_BK, G_PAD = 4, G_MAXT = 128;
 constexpr int G_STAGE_ELEMS = G_MAXT * (G_BK + G_PAD); // per operand per stage (covers both layouts)
-constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT + 2 * G_KS * G_BK) * 8 + 16;
+constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT + 2 * 2 * G_BK) * 8 + 2 * G_STAGES * 8 + 16;
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t* bar) { // arrives once this thread's prior cp.asyncs landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(G_NPROD) : "memory"); }
+
+struct PipeState { // position in the stage ring; identical sequence on both sides
+    int stage = 0, phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+    }
+};
+
+// inner K loop of one block pair with the shared-memory layout of both operands fixed at compile time
+// (all fragment addresses become immediates off one base register per operand)
+template <int BM, int BN, bool AKF, bool BKF>
+__device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2], int nchunks, int sgn, int wm0, int wn0, int g, int t4,
+                                             int lane, const double* As, const double* Bs, uint64_t* full, uint64_t* empty,
+                                             PipeState& ps) {
+    constexpr int BK = G_BK, FM = BM / 32, FN = BN / 32;
+    constexpr int sAm = AKF ? (BK + G_PAD) : 1, sAk = AKF ? 1 : (BM + G_PAD);
+    constexpr int sBn = BKF ? (BK + G_PAD) : 1, sBk = BKF ? 1 : (BN + G_PAD);
+    const int a_base = (wm0 + g) * sAm + t4 * sAk, b_base = (wn0 + g) * sBn + t4 * sBk;
+    for (int kc = 0; kc < nchunks; ++kc) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        const double* as = As + ps.stage * G_STAGE_ELEMS + a_base;
+        const double* bs = Bs + ps.stage * G_STAGE_ELEMS + b_base;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double fa[FM], fb[FN];
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const double v = as[i * 8 * sAm + ks * 4 * sAk];
+                fa[i] = __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v));
+            }
+#pragma unroll
+            for (int j = 0; j < FN; ++j) fb[j] = bs[j * 8 * sBn + ks * 4 * sBk];
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[ps.stage]);
+        ps.advance();
+    }
+}
 
 template <int BM, int BN>
-__device__ __forceinline__ void run_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
-                                         const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
-                                         double* __restrict__ ws, double* As, double* Bs, int64_t* offM_s, int64_t* offN_s,
-                                         int64_t* offKa_s, int64_t* offKb_s) {
-    constexpr int BK = G_BK, NT = G_NT, ST = G_STAGES, KS = G_KS;
-    constexpr int WM = BM / 2, WN = BN / 4, FM = WM / 8, FN = WN / 8;
-    constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
-    static_assert(FM >= 1 && FN >= 1 && EA >= 1 && EB >= 1, "tile too small for 8 warps");
+__device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
+                                             double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
+                                             uint64_t* full, uint64_t* empty, PipeState& ps) {
+    constexpr int BK = G_BK;
+    constexpr int WM = BM / 4, WN = BN / 4, FM = WM / 8, FN = WN / 8;
+    static_assert(FM >= 1 && FN >= 1, "tile too small for a 4x4 warp grid");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int wm0 = (warp & 1) * WM, wn0 = (warp >> 1) * WN;
+    const int wm0 = (warp & 3) * WM, wn0 = (warp >> 2) * WN;
     const int M = cb->M, N = cb->N;
     const int m0 = tile.tm * BM, n0 = tile.tn * BN;
 
@@ -87,129 +152,22 @@ __device__ __forceinline__ void run_tile(const ItbTile& tile, const ItbCBlk* __r
 #pragma unroll
         for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    int gchunk = 0; // global chunk index of the current pair's first chunk
+    int gchunk = 0;
     for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
         const ItbPair* pr = pairs + p;
-        const int K = pr->K;
-        const int nk = (K + BK - 1) / BK;
+        const int nk = (pr->K + BK - 1) / BK;
         const int c0 = max(tile.chunk_begin - gchunk, 0), c1 = min(tile.chunk_end - gchunk, nk);
         gchunk += nk;
         if (c0 >= c1) continue;
         const int flags = pr->flags;
-        const bool cca = flags & ITB_PF_CCA, akf = flags & ITB_PF_A_KFAST, bkf = flags & ITB_PF_B_KFAST;
-        const double* __restrict__ Ap = A + pr->a_off;
-        const double* __restrict__ Bp = B + pr->b_off;
-        const int sAm = akf ? (BK + G_PAD) : 1, sAk = akf ? 1 : (BM + G_PAD);
-        const int sBn = bkf ? (BK + G_PAD) : 1, sBk = bkf ? 1 : (BN + G_PAD);
         // sign of the A' = [[Ar,-Ai],[Ai,Ar]] expansion, applied when the fragment is read (row even, col odd)
-        const int sgn = (cca && !(g & 1) && (t4 & 1)) ? (int)0x80000000 : 0;
-
-        __syncthreads(); // previous pair / tile is done with tables and stages
-        for (int i = tid; i < BM + BN; i += NT) {
-            if (i < BM) {
-                const int m = m0 + i;
-                offM_s[i] = (m < M) ? grp_off(m, pr->m_ext, pr->am_str, pr->m_n) : -1;
-            } else {
-                const int n = n0 + i - BM;
-                offN_s[i - BM] = (n < N) ? grp_off(n, pr->n_ext, pr->bn_str, pr->n_n) : -1;
-            }
+        const int sgn = ((flags & ITB_PF_CCA) && !(g & 1) && (t4 & 1)) ? (int)0x80000000 : 0;
+        switch (flags & (ITB_PF_A_KFAST | ITB_PF_B_KFAST)) {
+            case 0: consume_pair<BM, BN, false, false>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
+            case ITB_PF_A_KFAST: consume_pair<BM, BN, true, false>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
+            case ITB_PF_B_KFAST: consume_pair<BM, BN, false, true>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
+            default: consume_pair<BM, BN, true, true>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
         }
-        for (int i = tid; i < ST * 2 * BK; i += NT) { // k-offset tables of chunks c0 .. c0+ST-1
-            const int c = c0 + i / (2 * BK), r = i % (2 * BK), kk = r % BK;
-            const int k = c * BK + kk;
-            int64_t* dst = (r < BK ? offKa_s : offKb_s) + (c % KS) * BK + kk;
-            *dst = (k < K) ? grp_off(k, pr->k_ext, r < BK ? pr->ak_str : pr->bk_str, pr->k_n) : -1;
-        }
-        __syncthreads();
-
-        // ---- per-thread loader state, hoisted out of the K loop -------------------------------------------
-        // m-fast mapping: thread owns row mm = tid % BM and k-columns kk = tid/BM + e*(NT/BM)
-        // k-fast mapping: thread owns k-column kk = tid % BK and rows mm = tid/BK + e*(NT/BK)
-        // (NT/BM, NT/BK are even, so the (p,q) parity of the complex fold is a per-thread constant)
-        const int a_fix = akf ? tid % BK : tid % BM, a_run0 = akf ? tid / BK : tid / BM;
-        const int b_fix = bkf ? tid % BK : tid % BN, b_run0 = bkf ? tid / BK : tid / BN;
-        const bool a_odd_odd = akf ? ((a_fix & 1) && (a_run0 & 1)) : ((a_fix & 1) && (a_run0 & 1));
-        const double* __restrict__ Apt = Ap - ((cca && a_odd_odd) ? 2 : 0); // (p,q)=(1,1) reads the real part again
-        const int64_t a_om = akf ? 0 : offM_s[a_fix];
-        const int64_t b_on = bkf ? 0 : offN_s[b_fix];
-        const int a_sdst0 = akf ? a_run0 * (BK + G_PAD) + a_fix : a_fix + a_run0 * (BM + G_PAD);
-        const int b_sdst0 = bkf ? b_run0 * (BK + G_PAD) + b_fix : b_fix + b_run0 * (BN + G_PAD);
-
-        auto issue_chunk = [&](int c) { // gather chunk c of both operands into stage c % ST
-            double* as = As + (c % ST) * G_STAGE_ELEMS + a_sdst0;
-            double* bs = Bs + (c % ST) * G_STAGE_ELEMS + b_sdst0;
-            const int64_t* oka = offKa_s + (c % KS) * BK;
-            const int64_t* okb = offKb_s + (c % KS) * BK;
-            if (akf) {
-                const int64_t ok = oka[a_fix];
-#pragma unroll
-                for (int e = 0; e < EA; ++e) {
-                    const int64_t om = offM_s[a_run0 + e * (NT / BK)];
-                    const bool v = (om | ok) >= 0;
-                    cp_async8(as + e * (NT / BK) * (BK + G_PAD), v ? Apt + om + ok : Ap, v);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < EA; ++e) {
-                    const int64_t ok = oka[a_run0 + e * (NT / BM)];
-                    const bool v = (a_om | ok) >= 0;
-                    cp_async8(as + e * (NT / BM) * (BM + G_PAD), v ? Apt + a_om + ok : Ap, v);
-                }
-            }
-            if (bkf) {
-                const int64_t ok = okb[b_fix];
-#pragma unroll
-                for (int e = 0; e < EB; ++e) {
-                    const int64_t on = offN_s[b_run0 + e * (NT / BK)];
-                    const bool v = (on | ok) >= 0;
-                    cp_async8(bs + e * (NT / BK) * (BK + G_PAD), v ? Bp + on + ok : Bp, v);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < EB; ++e) {
-                    const int64_t ok = okb[b_run0 + e * (NT / BN)];
-                    const bool v = (b_on | ok) >= 0;
-                    cp_async8(bs + e * (NT / BN) * (BN + G_PAD), v ? Bp + b_on + ok : Bp, v);
-                }
-            }
-        };
-
-#pragma unroll
-        for (int s = 0; s < ST - 1; ++s) {
-            if (c0 + s < c1) issue_chunk(c0 + s);
-            cp_async_commit();
-        }
-        for (int kc = c0; kc < c1; ++kc) {
-            cp_async_wait<ST - 2>();
-            __syncthreads();
-            const int L = kc + ST - 1;
-            if (L < c1) issue_chunk(L);
-            cp_async_commit();
-            if (L + 1 < c1 && tid < 2 * BK) { // k-offsets of chunk L+1, visible after the next barrier
-                const int kk = tid % BK, k = (L + 1) * BK + kk;
-                int64_t* dst = (tid < BK ? offKa_s : offKb_s) + ((L + 1) % KS) * BK + kk;
-                *dst = (k < K) ? grp_off(k, pr->k_ext, tid < BK ? pr->ak_str : pr->bk_str, pr->k_n) : -1;
-            }
-            const double* as = As + (kc % ST) * G_STAGE_ELEMS;
-            const double* bs = Bs + (kc % ST) * G_STAGE_ELEMS;
-#pragma unroll
-            for (int ks = 0; ks < BK / 4; ++ks) {
-                double fa[FM], fb[FN];
-#pragma unroll
-                for (int i = 0; i < FM; ++i) fa[i] = as[(wm0 + i * 8 + g) * sAm + (ks * 4 + t4) * sAk];
-                if (cca) {
-#pragma unroll
-                    for (int i = 0; i < FM; ++i) fa[i] = __hiloint2double(__double2hiint(fa[i]) ^ sgn, __double2loint(fa[i]));
-                }
-#pragma unroll
-                for (int j = 0; j < FN; ++j) fb[j] = bs[(wn0 + j * 8 + g) * sBn + (ks * 4 + t4) * sBk];
-#pragma unroll
-                for (int i = 0; i < FM; ++i)
-#pragma unroll
-                    for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            }
-        }
-        cp_async_wait<0>();
     }
     // ---- epilogue: each C element is written exactly once (or one partial per split) ----------------------
     if (tile.ws_slot < 0) {
@@ -239,30 +197,155 @@ __device__ __forceinline__ void run_tile(const ItbTile& tile, const ItbCBlk* __r
     }
 }
 
+template <int BM, int BN>
+__device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
+                                             const double* __restrict__ A, const double* __restrict__ B, double* As, double* Bs,
+                                             int64_t* offM_s, int64_t* offN_s, int64_t* offKa_s, int64_t* offKb_s, uint64_t* full,
+                                             uint64_t* empty, PipeState& ps) {
+    constexpr int BK = G_BK, NP = G_NPROD;
+    constexpr int EA = BM * BK / NP, EB = BN * BK / NP;
+    const int pt = threadIdx.x - G_NCONS; // 0..G_NPROD-1
+    const int M = cb->M, N = cb->N;
+    const int m0 = tile.tm * BM, n0 = tile.tn * BN;
+    int gchunk = 0;
+    int ktab = 0; // double-buffered k-offset table
+    for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
+        const ItbPair* pr = pairs + p;
+        const int K = pr->K;
+        const int nk = (K + BK - 1) / BK;
+        const int c0 = max(tile.chunk_begin - gchunk, 0), c1 = min(tile.chunk_end - gchunk, nk);
+        gchunk += nk;
+        if (c0 >= c1) continue;
+        const int flags = pr->flags;
+        const bool cca = flags & ITB_PF_CCA, akf = flags & ITB_PF_A_KFAST, bkf = flags & ITB_PF_B_KFAST;
+        const double* __restrict__ Ap = A + pr->a_off;
+        const double* __restrict__ Bp = B + pr->b_off;
+
+        producer_sync(); // every producer is done reading the previous pair's tables
+        for (int i = pt; i < BM + BN; i += NP) {
+            if (i < BM) {
+                const int m = m0 + i;
+                offM_s[i] = (m < M) ? grp_off(m, pr->m_ext, pr->am_str, pr->m_n) : -1;
+            } else {
+                const int n = n0 + i - BM;
+                offN_s[i - BM] = (n < N) ? grp_off(n, pr->n_ext, pr->bn_str, pr->n_n) : -1;
+            }
+        }
+        auto fill_ktab = [&](int c, int slot) {
+            if (pt < 2 * BK) {
+                const int kk = pt % BK, k = c * BK + kk;
+                int64_t* dst = (pt < BK ? offKa_s : offKb_s) + slot * BK + kk;
+                *dst = (k < K) ? grp_off(k, pr->k_ext, pt < BK ? pr->ak_str : pr->bk_str, pr->k_n) : -1;
+            }
+        };
+        fill_ktab(c0, ktab);
+        producer_sync();
+
+        // m-fast mapping: idx = pt + e*NP, row mm = idx % BM, column kk = idx / BM
+        // k-fast mapping: column kk = pt % BK, row mm = pt / BK + e*(NP/BK)
+        // (p,q) parity of the complex fold: m-fast: p = pt&1 (BM, NP even), q = kk&1 varies with e -> handled per e;
+        //                                   k-fast: q = pt&1, p = (pt/BK + 4e)&1 = (pt/BK)&1
+        for (int kc = c0; kc < c1; ++kc) {
+            if (kc + 1 < c1) fill_ktab(kc + 1, ktab ^ 1); // visible after this iteration's producer_sync
+            mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+            double* as = As + ps.stage * G_STAGE_ELEMS;
+            double* bs = Bs + ps.stage * G_STAGE_ELEMS;
+            const int64_t* oka = offKa_s + ktab * BK;
+            const int64_t* okb = offKb_s + ktab * BK;
+            if (akf) {
+                const int kk = pt % BK;
+                const int64_t ok = oka[kk];
+                const int adj = (cca && (kk & 1) && ((pt / BK) & 1)) ? 2 : 0;
+#pragma unroll 2
+                for (int e = 0; e < EA; ++e) {
+                    const int mm = pt / BK + e * (NP / BK);
+                    const int64_t om = offM_s[mm];
+                    const bool v = (om | ok) >= 0;
+                    cp_async8(as + mm * (BK + G_PAD) + kk, v ? Ap + om + ok - adj : Ap, v);
+                }
+            } else {
+#pragma unroll 2
+                for (int e = 0; e < EA; ++e) {
+                    const int idx = pt + e * NP;
+                    const int mm = idx % BM, kk = idx / BM;
+                    const int64_t om = offM_s[mm], ok = oka[kk];
+                    const bool v = (om | ok) >= 0;
+                    const int adj = (cca && (mm & kk & 1)) ? 2 : 0;
+                    cp_async8(as + mm + kk * (BM + G_PAD), v ? Ap + om + ok - adj : Ap, v);
+                }
+            }
+            if (bkf) {
+                const int kk = pt % BK;
+                const int64_t ok = okb[kk];
+#pragma unroll 2
+                for (int e = 0; e < EB; ++e) {
+                    const int nn = pt / BK + e * (NP / BK);
+                    const int64_t on = offN_s[nn];
+                    const bool v = (on | ok) >= 0;
+                    cp_async8(bs + nn * (BK + G_PAD) + kk, v ? Bp + on + ok : Bp, v);
+                }
+            } else {
+#pragma unroll 2
+                for (int e = 0; e < EB; ++e) {
+                    const int idx = pt + e * NP;
+                    const int nn = idx % BN, kk = idx / BN;
+                    const int64_t on = offN_s[nn], ok = okb[kk];
+                    const bool v = (on | ok) >= 0;
+                    cp_async8(bs + nn + kk * (BN + G_PAD), v ? Bp + on + ok : Bp, v);
+                }
+            }
+            mbar_arrive_cp_async(&full[ps.stage]);
+            ps.advance();
+            ktab ^= 1;
+            producer_sync();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, int ntiles,
                                                             const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
-                                                            double* __restrict__ C, double* __restrict__ ws,
-                                                            int* __restrict__ counter) {
+                                                            double* __restrict__ C, double* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + G_STAGES * G_STAGE_ELEMS;
     int64_t* offM_s = reinterpret_cast<int64_t*>(Bs + G_STAGES * G_STAGE_ELEMS);
     int64_t* offN_s = offM_s + G_MAXT;
     int64_t* offKa_s = offN_s + G_MAXT;
-    int64_t* offKb_s = offKa_s + G_KS * G_BK;
-    int* item_s = reinterpret_cast<int*>(offKb_s + G_KS * G_BK);
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) *item_s = atomicAdd(counter, 1);
-        __syncthreads();
-        const int item = *item_s;
-        if (item >= ntiles) break;
+    int64_t* offKb_s = offKa_s + 2 * G_BK;
+    uint64_t* full = reinterpret_cast<uint64_t*>(offKb_s + 2 * G_BK);
+    uint64_t* empty = full + G_STAGES;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&full[s], G_NPROD);     // one cp.async-completion arrive per producer thread
+            mbar_init(&empty[s], G_NCONS / 32); // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const bool producer = threadIdx.x >= G_NCONS;
+    // register re-balancing (warpgroup granular): the kernel launches with 96 regs/thread (640 threads);
+    // the producer warpgroup shrinks, the four consumer warpgroups grow (4*112 + 56 per SMSP fits 16K).
+    // (setmaxnreg variants measured slower or spilling: see DESIGN.md) if (producer) setmaxnreg.dec 56
+    // else setmaxnreg.inc 112
+    PipeState ps;
+    // static snake (boustrophedon) assignment of the LPT-sorted item list: both roles derive the same sequence
+    const int G = gridDim.x;
+    for (int round = 0;; ++round) {
+        const int item = round * G + ((round & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
+        if (round * G >= ntiles) break;
+        if (item >= ntiles) continue;
         const ItbTile tile = tiles[item];
         const ItbCBlk* cb = cblks + tile.cblk;
-        if (tile.cfg == 0) run_tile<128, 128>(tile, cb, pairs, A, B, C, ws, As, Bs, offM_s, offN_s, offKa_s, offKb_s);
-        else if (tile.cfg == 1) run_tile<64, 64>(tile, cb, pairs, A, B, C, ws, As, Bs, offM_s, offN_s, offKa_s, offKb_s);
-        else run_tile<32, 32>(tile, cb, pairs, A, B, C, ws, As, Bs, offM_s, offN_s, offKa_s, offKb_s);
+        if (producer) {
+            if (tile.cfg == 0) produce_tile<128, 128>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+            else if (tile.cfg == 1) produce_tile<64, 64>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+            else produce_tile<32, 32>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+        } else {
+            if (tile.cfg == 0) consume_tile<128, 128>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps);
+            else if (tile.cfg == 1) consume_tile<64, 64>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps);
+            else consume_tile<32, 32>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps);
+        }
     }
 }
 
@@ -623,7 +706,8 @@ cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* sou
     }
     int grid = num_sms;
     if (grid > ntiles) grid = ntiles;
-    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, ntiles, cblks, pairs, A, B, C, ws, counter);
+    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, ntiles, cblks, pairs, A, B, C, ws);
+    (void)counter;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {
