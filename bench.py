@@ -332,6 +332,30 @@ def main():
         if cls_ms[3] > 0:
             roof["streaming_class_gbs"] = sk_bytes / (cls_ms[3] * 1e-3) / 1e9
 
+    # ---- permute bandwidth (HBM-bound sibling task): reverse the 5 indices of the largest intermediate ----
+    perm_info = None
+    if rank == 0:
+        from itensor_b200.tensor import PermutePlan, permuted_struct
+
+        src = outs[0]  # T1 = phi*L : (s1,s2,r,k0,l')
+        D, perm = permuted_struct(src.struct, list(reversed(src.struct.inds)), flux=(0,))
+        pp = PermutePlan(src.struct, D, perm)
+        dst = ctx.empty(D.nreal)
+        best = 1e9
+        for it_ in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib().itb_permute_run(ctx.handle, pp._h, src.ptr, C.c_void_p(dst.data_ptr()), 1.0, 0.0, 0))
+            e1.record(); e1.synchronize()
+            if it_ > 0:
+                best = min(best, e0.elapsed_time(e1))
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        gbs = pp.bytes / (best * 1e-3) / 1e9
+        perm_info = {"what": "QDense permute, reverse 5 indices of T1=phi*L (fills all flux-allowed blocks)", "elements": int(src.struct.nelems),
+                     "bytes": int(pp.bytes), "ms": best, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm}
+        del dst
+
     # ---- CPU baseline: the reference itself on this box's host cores, bounded sample ----------------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -365,7 +389,7 @@ def main():
                        "l2": "flushed between timed iterations (256 MiB memset)", "sharding": "C blocks by l' sector" if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "permute": perm_info,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -18,6 +18,7 @@
 // Complex arithmetic arrives here already folded into a real problem by the planner (plan.cc).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tables.h"
 
@@ -480,8 +481,8 @@ struct SqPair {
     int32_t kbeg, K, n, fix;
 };
 
-template <int S>
-__global__ void __launch_bounds__(SQ_NT) bsc_skinny_smallk_kernel(const ItbSkinny* __restrict__ items, const ItbCBlk* __restrict__ cblks,
+template <int S, int SQ_KU, int MINB>
+__global__ void __launch_bounds__(SQ_NT, MINB) bsc_skinny_smallk_kernel(const ItbSkinny* __restrict__ items, const ItbCBlk* __restrict__ cblks,
                                                                   const ItbPair* __restrict__ pairs, const double* __restrict__ A,
                                                                   const double* __restrict__ B, double* __restrict__ C) {
     __shared__ __align__(32) double Ss[SQ_MAXK][S];
@@ -552,23 +553,35 @@ __global__ void __launch_bounds__(SQ_NT) bsc_skinny_smallk_kernel(const ItbSkinn
             int64_t offL[SQ_RPT];
 #pragma unroll
             for (int j = 0; j < SQ_RPT; ++j) offL[j] = valid[j] ? grp_off(it.row0 + r0 + tid + j * SQ_NT, P.ext, P.str, P.n) : 0;
-            for (int kk = 0; kk < P.K; ++kk) {
-                const int64_t ok = okl[P.kbeg + kk];
-                double x[SQ_RPT];
+            // SQ_KU k-columns x SQ_RPT rows of independent loads are issued before any FMA consumes them
+            for (int kk0 = 0; kk0 < P.K; kk0 += SQ_KU) {
+                double x[SQ_KU][SQ_RPT];
 #pragma unroll
-                for (int j = 0; j < SQ_RPT; ++j) {
-                    int64_t off = offL[j] + ok;
-                    if (P.fix) { // row parity == tid parity (row0, r0, j*SQ_NT are even)
-                        const int pq = (tid & 1) | ((kk & 1) << 1);
-                        if (pq == 3) off -= 2;
-                        x[j] = valid[j] ? Lp[off] : 0.0;
-                        if (pq == 2) x[j] = -x[j];
-                    } else x[j] = valid[j] ? Lp[off] : 0.0;
+                for (int u = 0; u < SQ_KU; ++u) {
+                    const int kk = kk0 + u;
+                    const bool kv = kk < P.K;
+                    const int64_t ok = kv ? okl[P.kbeg + kk] : 0;
+#pragma unroll
+                    for (int j = 0; j < SQ_RPT; ++j) {
+                        int64_t off = offL[j] + ok;
+                        double v = 0.0;
+                        if (P.fix) { // row parity == tid parity (row0, r0, j*SQ_NT are even)
+                            const int pq = (tid & 1) | ((kk & 1) << 1);
+                            if (pq == 3) off -= 2;
+                            if (kv && valid[j]) v = Lp[off];
+                            if (pq == 2) v = -v;
+                        } else if (kv && valid[j]) v = Lp[off];
+                        x[u][j] = v;
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < SQ_RPT; ++j)
+                for (int u = 0; u < SQ_KU; ++u) {
+                    const int kk = min(kk0 + u, P.K - 1); // x is zero past K
 #pragma unroll
-                    for (int s = 0; s < S; ++s) acc[j][s] = fma(x[j], Ss[P.kbeg + kk][s], acc[j][s]);
+                    for (int j = 0; j < SQ_RPT; ++j)
+#pragma unroll
+                        for (int s = 0; s < S; ++s) acc[j][s] = fma(x[u][j], Ss[P.kbeg + kk][s], acc[j][s]);
+                }
             }
         }
 #pragma unroll
@@ -719,8 +732,14 @@ cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* sou
 
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st) {
-    if (nq4 > 0) bsc_skinny_smallk_kernel<4><<<nq4, SQ_NT, 0, st>>>(q4, cblks, pairs, A, B, C);
-    if (nq8 > 0) bsc_skinny_smallk_kernel<8><<<nq8, SQ_NT, 0, st>>>(q8, cblks, pairs, A, B, C);
+    static int variant = -1; // tuning hook: ITB_SKINNY_VARIANT=0 (KU=1, 4 CTAs/SM) | 1 (KU=4, 3 CTAs/SM) | 2 (KU=2, 4 CTAs/SM)
+    if (variant < 0) { const char* e = getenv("ITB_SKINNY_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (nq4 > 0) {
+        if (variant == 1) bsc_skinny_smallk_kernel<4, 4, 3><<<nq4, SQ_NT, 0, st>>>(q4, cblks, pairs, A, B, C);
+        else if (variant == 2) bsc_skinny_smallk_kernel<4, 2, 4><<<nq4, SQ_NT, 0, st>>>(q4, cblks, pairs, A, B, C);
+        else bsc_skinny_smallk_kernel<4, 1, 4><<<nq4, SQ_NT, 0, st>>>(q4, cblks, pairs, A, B, C);
+    }
+    if (nq8 > 0) bsc_skinny_smallk_kernel<8, 1, 2><<<nq8, SQ_NT, 0, st>>>(q8, cblks, pairs, A, B, C);
     if (n > 0) bsc_skinny_kernel<<<n, SK_NT, 0, st>>>(items, cblks, pairs, A, B, C);
     return cudaGetLastError();
 }

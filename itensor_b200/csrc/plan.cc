@@ -345,11 +345,12 @@ int build_contract_tables(itb_contract_plan& P) {
                 }
             }
             P.dot_outs.push_back(o);
-        } else if (std::min(M, N) <= kSkinnyMax) {
+        } else if (std::min(M, N) <= kSkinnyMax && cb.ksum <= kSkinnyQMaxK) {
+            // HBM-bound streaming class: short side <= 8 and a short K loop (the MPO steps of H_eff*phi)
             P.class_flops[3] += cflops;
             const int long_is_n = (N > M) ? 1 : 0;
             const int64_t L = long_is_n ? N : M, Sh = long_is_n ? M : N;
-            if (cb.ksum <= kSkinnyQMaxK && cb.pair_end - cb.pair_begin <= kSkinnyQMaxPairs) {
+            if (cb.pair_end - cb.pair_begin <= kSkinnyQMaxPairs) {
                 auto& list = Sh <= 4 ? P.skinny_q4 : P.skinny_q8;
                 for (int64_t r0 = 0; r0 < L; r0 += kSkinnyQRows)
                     list.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyQRows, L - r0), long_is_n});
@@ -384,7 +385,7 @@ int build_contract_tables(itb_contract_plan& P) {
             const double nt = (double)((cb.M + T - 1) / T) * (double)((cb.N + T - 1) / T);
             total_work += nt * (double)chunks_of(cb) * (double)(T * T) / (128.0 * 128.0);
         }
-        const double cap_work = std::max(24.0, total_work / (kNumSMs * 4.0)); // <= 1/4 of a CTA's fair share
+        const double cap_work = std::max(32.0, total_work / (kNumSMs * 2.5)); // <= 0.4 of a CTA's fair share
         for (auto& tc : tile_cblks) {
             const int32_t c = tc.first; const int f = tc.second;
             const ItbCBlk& cb = P.cblks[c];
@@ -392,7 +393,7 @@ int build_contract_tables(itb_contract_plan& P) {
             const int64_t nch = chunks_of(cb);
             const double per_chunk = (double)(T * T) / (128.0 * 128.0);
             int64_t nsplit = (int64_t)std::ceil((double)nch * per_chunk / cap_work);
-            nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, nch / 8 > 0 ? nch / 8 : 1)); // >= 8 chunks per split
+            nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, nch / 16 > 0 ? nch / 16 : 1)); // >= 16 chunks per split
             const int64_t per = (nch + nsplit - 1) / nsplit;
             nsplit = (nch + per - 1) / per;
             for (int32_t tn = 0; tn < (cb.N + T - 1) / T; ++tn)

@@ -83,7 +83,7 @@ constexpr int kPermCopyChunk = 4096; // elements per work item, copy-like path
 constexpr int kPermTile = 32;        // tile edge, transposing path
 constexpr int kDotChunk = 8192;      // k-range per split-K item
 constexpr int kSkinnyRows = 1024;    // long-side rows per streaming item (4 per thread)
-constexpr int kSkinnyQRows = 2048;   // rows per item of the small-K fast path (2 batches of 4 rows/thread)
+constexpr int kSkinnyQRows = 8192;   // rows per item of the small-K fast path (8 batches of 4 rows/thread)
 constexpr int kSkinnyQMaxK = 64;     // sum of K over the pairs of a C block / max pairs for the fast path
 constexpr int kSkinnyQMaxPairs = 8;
 constexpr int kNumSMs = 148;         // B200: persistent grid size the split-K heuristic balances for
