@@ -1,0 +1,122 @@
+"""Host integer planning (libitb200.so, no device) vs the CPU oracle: block structure, offsets, index
+order and pair enumeration must be bit-exact. Also pins the reference's own integer KATs."""
+import numpy as np
+import pytest
+
+import itensor_b200 as itb
+from itensor_b200 import synth
+from itensor_b200.tensor import BlockStruct, Index, flux_blocks, permuted_struct
+from oracle import orc
+from util import assert_struct_equal
+
+F, Z = itb.ITB_F64, itb.ITB_C64
+
+
+def test_contract_structure_matches_oracle_random():
+    rng = np.random.default_rng(0)
+    nonempty = 0
+    for trial in range(400):
+        ra, rb = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+        nc = int(rng.integers(0, min(ra, rb) + 1))
+        A, B = synth.random_qn_pair(rng, ra, rb, nc, dtype_a=int(rng.integers(0, 2)), dtype_b=int(rng.integers(0, 2)))
+        P = itb.ContractPlan(A, B)
+        Cs, tr = orc.contract_structure(A, B)
+        assert_struct_equal(P.C, Cs)
+        assert np.array_equal(P.pairs(), tr)
+        nonempty += Cs.nelems > 0
+    assert nonempty > 100
+
+
+def test_flops_count():
+    """flops = sum_pairs 2*M*N*K, x2 real*cplx, x4 cplx*cplx"""
+    structs = synth.heff_chain([3, 9, 14, 8, 2])
+    phi, L = structs[0], structs[1]
+    P = itb.ContractPlan(phi, L)
+    tot = 0
+    for ia, ib, ic in P.pairs():
+        sa, sb = phi.block_shape(ia), L.block_shape(ib)
+        tot += 2 * np.prod(sa) * np.prod(sb) / sa[0]  # contracted index is phi's first (l), extent sa[0]
+    assert abs(P.flops - tot) < 1e-6 * tot
+    for da, db, mult in [(Z, F, 2), (F, Z, 2), (Z, Z, 4)]:
+        a = BlockStruct(phi.inds, phi.blocks, da)
+        b = BlockStruct(L.inds, L.blocks, db)
+        assert abs(itb.ContractPlan(a, b).flops - mult * tot) < 1e-6 * tot
+
+
+def test_heff_census_matches_survey():
+    """S=1/2 Heisenberg centre bond at m=400 (SURVEY 8a census: sectors 12,83,158,113,29,5):
+    60/102/106/60 pairs and 60/62/62/22 C blocks for the four LocalOp::product steps."""
+    structs = synth.heff_chain([12, 83, 158, 113, 29, 5])
+    s = structs[0]
+    pairs, cblocks = [], []
+    for t in structs[1:]:
+        P = itb.ContractPlan(s, t)
+        pairs.append(P.npairs)
+        cblocks.append(P.C.nblocks)
+        s = P.C
+    assert pairs == [60, 102, 106, 60]
+    assert cblocks == [60, 62, 62, 22]
+
+
+def test_block_deficient_kat():
+    """unittest/itensor_test.cc:2734-2765: A = a*prime(dag(a),i) has 4 blocks / 64 elements"""
+    i = Index(1, (2, 3, 4, 5, 6), ((0,), (1,), (2,), (1,), (3,)), 1)
+    l = Index(2, (3,), ((0,),), 1)
+    a_blocks = flux_blocks([i, l], (1,))
+    assert a_blocks.tolist() == [[1, 0], [3, 0]]
+    a = BlockStruct([i, l], a_blocks)
+    adag = BlockStruct([i.dag().prime(), l.dag()], a_blocks)
+    P = itb.ContractPlan(a, adag)
+    assert P.C.nblocks == 4 and P.C.nelems == 64
+    assert P.C.blocks.tolist() == [[1, 1], [3, 1], [1, 3], [3, 3]]  # last index most significant
+    assert P.C.offsets.tolist() == [0, 9, 24, 39]
+
+
+def test_flux_blocks_matches_oracle_incl_modular_qns():
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        r = int(rng.integers(1, 5))
+        nqn = int(rng.integers(1, 3))
+        mods = tuple(int(rng.choice([1, 2, 3, -2])) for _ in range(nqn))
+        inds = []
+        for j in range(r):
+            ns = int(rng.integers(1, 4))
+            qns = tuple(tuple(int(rng.integers(-2, 3)) for _ in range(nqn)) for _ in range(ns))
+            inds.append(Index(10 + j, tuple(int(v) for v in rng.integers(1, 4, ns)), qns, int(rng.choice([-1, 1])), mods))
+        flux = tuple(int(rng.integers(-2, 3)) for _ in range(nqn))
+        got, want = flux_blocks(inds, flux), orc.flux_blocks(inds, flux)
+        assert np.array_equal(got, want)
+        # sorted in the reference Block order (reverse lexicographic)
+        if len(got) > 1:
+            keys = [tuple(reversed(b)) for b in got.tolist()]
+            assert keys == sorted(keys)
+
+
+def test_permute_struct_fill_in_rule():
+    """QN permute allocates every flux-allowed block; dense/no-QN keeps the block list"""
+    rng = np.random.default_rng(5)
+    A, _ = synth.random_qn_pair(rng, 3, 1, 0, drop=0.6, max_sect=3)
+    new = [A.inds[2], A.inds[0], A.inds[1]]
+    D, perm = permuted_struct(A, new, flux=(0,))
+    assert perm == [1, 2, 0]
+    assert np.array_equal(D.blocks, orc.flux_blocks(new, (0,)))
+    assert D.nblocks >= A.nblocks
+    D2, _ = permuted_struct(A, new)  # no fill-in requested
+    assert D2.nblocks == A.nblocks
+
+
+def test_cblock_range_restriction():
+    """output-block sharding unit for multi-GPU: ranges partition the work, structure is unchanged"""
+    structs = synth.heff_chain([3, 9, 14, 8, 2])
+    P = itb.ContractPlan(structs[0], structs[1])
+    full = [P.info.n_gemm_tiles, P.info.n_skinny, P.info.n_dot]
+    fl_full = sum(P.info.class_flops)
+    nb = P.C.nblocks
+    parts, fl = [0, 0, 0], 0.0
+    for lo, hi in [(0, nb // 3), (nb // 3, 2 * nb // 3), (2 * nb // 3, nb)]:
+        P.set_cblock_range(lo, hi)
+        parts = [a + b for a, b in zip(parts, [P.info.n_gemm_tiles, P.info.n_skinny, P.info.n_dot])]
+        fl += sum(P.info.class_flops)
+    assert abs(fl - fl_full) < 1e-9 * fl_full
+    assert parts[2] == full[2] and parts[1] == full[1]
+    assert P.C.nblocks == nb
