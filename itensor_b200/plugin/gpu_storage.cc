@@ -1,0 +1,945 @@
+//
+// gpu_storage.cc — doTask overloads of DenseGPU<T> / QDenseGPU<T> (see gpu_storage.h).
+//
+// Host side only: label matching and result IndexSets come from the reference's own helpers
+// (computeLabels, contractIS, calcDiv, getBlockOffsets), the block tables and all arithmetic from the
+// C ABI in include/itb200.h. Citations name the reference routine each overload stands in for.
+//
+#include "itensor/itensor.h"
+#include "itensor/itdata/qutil.h"
+#include "itensor/tensor/contract.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <unordered_map>
+
+#include "itb200.h"
+
+namespace itensor {
+
+namespace gpu {
+
+static itb_ctx* g_ctx = nullptr;
+
+static void
+check(int rc, const char* what)
+    {
+    if(rc != ITB_OK) throw ITError(tinyformat::format("itensor_b200 (%s): %s",what,itb_last_error()));
+    }
+
+itb_ctx*
+context()
+    {
+    if(!g_ctx)
+        {
+        int dev = 0;
+        if(auto* e = std::getenv("ITB_DEVICE")) dev = std::atoi(e);
+        check(itb_ctx_create(dev,&g_ctx),"no CUDA device: DenseGPU/QDenseGPU have no CPU fallback");
+        }
+    return g_ctx;
+    }
+
+void
+synchronize() { check(itb_synchronize(context()),"synchronize"); }
+
+long
+launchCount() { return g_ctx ? long(itb_launch_count(g_ctx)) : 0; }
+
+Buffer::
+Buffer(size_t bytes) : bytes_(bytes)
+    {
+    check(itb_malloc(context(),bytes ? bytes : 1,&p_),"malloc");
+    }
+
+Buffer::
+Buffer(Buffer const& o) : bytes_(o.bytes_)
+    {
+    if(!o.p_) return;
+    check(itb_malloc(context(),bytes_ ? bytes_ : 1,&p_),"malloc");
+    check(itb_memcpy_d2d(context(),p_,o.p_,bytes_),"d2d");
+    }
+
+Buffer& Buffer::
+operator=(Buffer const& o)
+    {
+    if(this == &o) return *this;
+    Buffer tmp(o);
+    *this = std::move(tmp);
+    return *this;
+    }
+
+Buffer& Buffer::
+operator=(Buffer&& o) noexcept
+    {
+    if(this == &o) return *this;
+    if(p_ && g_ctx) itb_free(g_ctx,p_);
+    p_ = o.p_; bytes_ = o.bytes_;
+    o.p_ = nullptr; o.bytes_ = 0;
+    return *this;
+    }
+
+Buffer::
+~Buffer()
+    {
+    if(p_ && g_ctx) itb_free(g_ctx,p_);
+    }
+
+void Buffer::
+upload(void const* host, size_t bytes) { check(itb_memcpy_h2d(context(),p_,host,bytes),"h2d"); }
+
+void Buffer::
+download(void* host, size_t bytes) const { check(itb_memcpy_d2h(context(),host,p_,bytes),"d2h"); }
+
+void Buffer::
+zero() { check(itb_memset0(context(),p_,bytes_),"memset"); }
+
+} //namespace gpu
+
+using gpu::check;
+using gpu::context;
+
+const char* typeNameOf(QDenseGPUReal const&) { return "QDenseGPUReal"; }
+const char* typeNameOf(QDenseGPUCplx const&) { return "QDenseGPUCplx"; }
+const char* typeNameOf(DenseGPUReal const&) { return "DenseGPUReal"; }
+const char* typeNameOf(DenseGPUCplx const&) { return "DenseGPUCplx"; }
+
+template<typename T> int constexpr dtypeOf() { return std::is_same<T,Cplx>::value ? ITB_C64 : ITB_F64; }
+
+//
+// host <-> device
+//
+template<typename T>
+QDenseGPU<T>::
+QDenseGPU(QDense<T> const& h) : offsets(h.offsets), buf(h.store.size()*sizeof(T)), n(h.store.size())
+    {
+    // upload synchronously: the host vector may die right after this constructor
+    buf.upload(h.store.data(),n*sizeof(T));
+    gpu::synchronize();
+    }
+template QDenseGPU<Real>::QDenseGPU(QDense<Real> const&);
+template QDenseGPU<Cplx>::QDenseGPU(QDense<Cplx> const&);
+
+template<typename T>
+QDense<T> QDenseGPU<T>::
+toHost() const
+    {
+    auto h = QDense<T>(undef,offsets,n);
+    buf.download(h.store.data(),n*sizeof(T));
+    return h;
+    }
+template QDense<Real> QDenseGPU<Real>::toHost() const;
+template QDense<Cplx> QDenseGPU<Cplx>::toHost() const;
+
+template<typename T>
+DenseGPU<T>::
+DenseGPU(Dense<T> const& h) : buf(h.store.size()*sizeof(T)), n(h.store.size())
+    {
+    buf.upload(h.store.data(),n*sizeof(T));
+    gpu::synchronize();
+    }
+template DenseGPU<Real>::DenseGPU(Dense<Real> const&);
+template DenseGPU<Cplx>::DenseGPU(Dense<Cplx> const&);
+
+template<typename T>
+Dense<T> DenseGPU<T>::
+toHost() const
+    {
+    auto h = Dense<T>(undef,n);
+    buf.download(h.store.data(),n*sizeof(T));
+    return h;
+    }
+template Dense<Real> DenseGPU<Real>::toHost() const;
+template Dense<Cplx> DenseGPU<Cplx>::toHost() const;
+
+//
+// IndexSet + BlockOffsets -> itb_tensor_desc (the only thing that crosses the C boundary besides pointers)
+//
+struct Desc
+    {
+    std::vector<int32_t> nsect, blocks;
+    std::vector<int64_t> sect, offsets;
+    itb_tensor_desc d;
+
+    // block-sparse: sectors from Index::nblock()/blocksize0()
+    Desc(IndexSet const& is, BlockOffsets const& off, size_t nelems, int dtype)
+        {
+        auto r = order(is);
+        for(auto j : range(r))
+            {
+            nsect.push_back(is[j].nblock());
+            for(auto b : range(is[j].nblock())) sect.push_back(is[j].blocksize0(b));
+            }
+        for(auto const& bo : off)
+            {
+            for(auto j : range(r)) blocks.push_back(int32_t(bo.block[j]));
+            offsets.push_back(bo.offset);
+            }
+        finish(r,off.size(),nelems,dtype);
+        }
+
+    // dense: one sector per index, one block
+    Desc(IndexSet const& is, size_t nelems, int dtype)
+        {
+        auto r = order(is);
+        for(auto j : range(r))
+            {
+            nsect.push_back(1);
+            sect.push_back(dim(is[j]));
+            blocks.push_back(0);
+            }
+        offsets.push_back(0);
+        finish(r,1,nelems,dtype);
+        }
+
+    void
+    finish(long r, size_t nblocks, size_t nelems, int dtype)
+        {
+        if(nsect.empty()) nsect.push_back(0);
+        if(sect.empty()) sect.push_back(0);
+        if(blocks.empty()) blocks.push_back(0);
+        if(offsets.empty()) offsets.push_back(0);
+        d.order = int32_t(r);
+        d.dtype = dtype;
+        d.nsect = nsect.data();
+        d.sect = sect.data();
+        d.nblocks = int64_t(nblocks);
+        d.blocks = blocks.data();
+        d.offsets = offsets.data();
+        d.nelems = int64_t(nelems);
+        }
+
+    void
+    appendKey(std::string & k) const
+        {
+        k.append((const char*)&d.order,sizeof(int32_t)*2);
+        k.append((const char*)&d.nblocks,sizeof(int64_t));
+        k.append((const char*)nsect.data(),nsect.size()*sizeof(int32_t));
+        k.append((const char*)sect.data(),sect.size()*sizeof(int64_t));
+        k.append((const char*)blocks.data(),blocks.size()*sizeof(int32_t));
+        }
+    };
+
+//
+// Plan cache: inside davidson the same few contractions / permuted adds repeat with identical block
+// structure every iteration; the integer planning and table upload are done once per structure.
+//
+template<typename Plan, int (*Destroy)(Plan*)>
+class PlanCache
+    {
+    std::unordered_map<std::string,Plan*> map_;
+    std::deque<std::string> order_;
+    size_t cap_;
+    public:
+    explicit PlanCache(size_t cap) : cap_(cap) { }
+    Plan*
+    find(std::string const& key)
+        {
+        auto it = map_.find(key);
+        return it == map_.end() ? nullptr : it->second;
+        }
+    void
+    insert(std::string const& key, Plan* p)
+        {
+        if(map_.size() >= cap_)
+            {
+            auto old = order_.front();
+            order_.pop_front();
+            auto it = map_.find(old);
+            if(it != map_.end()) { Destroy(it->second); map_.erase(it); }
+            }
+        map_[key] = p;
+        order_.push_back(key);
+        }
+    };
+
+static PlanCache<itb_contract_plan,itb_contract_plan_destroy>&
+contractCache() { static PlanCache<itb_contract_plan,itb_contract_plan_destroy> c(256); return c; }
+static PlanCache<itb_permute_plan,itb_permute_plan_destroy>&
+permuteCache() { static PlanCache<itb_permute_plan,itb_permute_plan_destroy> c(256); return c; }
+
+static itb_contract_plan*
+getContractPlan(Desc const& dA, std::vector<int32_t> const& la, Desc const& dB, std::vector<int32_t> const& lb)
+    {
+    std::string key;
+    key.reserve(256);
+    dA.appendKey(key);
+    key.append((const char*)la.data(),la.size()*sizeof(int32_t));
+    key.push_back('|');
+    dB.appendKey(key);
+    key.append((const char*)lb.data(),lb.size()*sizeof(int32_t));
+    auto& cache = contractCache();
+    if(auto* p = cache.find(key)) return p;
+    itb_contract_plan* p = nullptr;
+    check(itb_contract_plan_create(&dA.d,la.data(),&dB.d,lb.data(),&p),"contract plan");
+    cache.insert(key,p);
+    return p;
+    }
+
+static itb_permute_plan*
+getPermutePlan(Desc const& dS, Desc const& dD, std::vector<int32_t> const& perm)
+    {
+    std::string key;
+    key.reserve(256);
+    dS.appendKey(key);
+    key.push_back('>');
+    dD.appendKey(key);
+    key.append((const char*)dD.offsets.data(),dD.offsets.size()*sizeof(int64_t));
+    key.append((const char*)perm.data(),perm.size()*sizeof(int32_t));
+    auto& cache = permuteCache();
+    if(auto* p = cache.find(key)) return p;
+    itb_permute_plan* p = nullptr;
+    check(itb_permute_plan_create(&dS.d,&dD.d,perm.data(),&p),"permute plan");
+    cache.insert(key,p);
+    return p;
+    }
+
+static std::vector<int32_t>
+toLabels(Labels const& L)
+    {
+    auto v = std::vector<int32_t>(L.size() > 0 ? L.size() : 1,0);
+    for(auto i : range(L.size())) v[i] = int32_t(L[i]);
+    return v;
+    }
+
+static std::vector<int32_t>
+toPerm(Permutation const& P, long r)
+    {
+    auto v = std::vector<int32_t>(r > 0 ? r : 1,0);
+    for(auto i : range(r)) v[i] = int32_t(P.dest(i));
+    return v;
+    }
+
+// block list + sizes -> BlockOffsets (QDense::updateOffsets(is,blocks), qdense.cc:186-211)
+static std::tuple<BlockOffsets,long>
+offsetsFor(IndexSet const& is, Blocks const& blocks)
+    {
+    auto bofs = BlockOffsets();
+    if(order(is)==0)
+        {
+        bofs.push_back(make_blof(Block(0),0));
+        return std::make_tuple(bofs,1l);
+        }
+    long tot = 0;
+    for(auto const& b : blocks)
+        {
+        long sz = 1;
+        for(auto j : range(order(is))) sz *= is[j].blocksize0(b[j]);
+        bofs.push_back(make_blof(b,tot));
+        tot += sz;
+        }
+    return std::make_tuple(bofs,tot);
+    }
+
+//
+// ---------------------------------------------------------------------------------------------
+//  QDenseGPU
+// ---------------------------------------------------------------------------------------------
+//
+
+// doTask(CalcDiv,QDense) qdense.cc:86-105
+template<typename T>
+QN
+doTask(CalcDiv const& C, QDenseGPU<T> const& D)
+    {
+    if(order(C.is)==0 || D.offsets.empty()) return QN{};
+    auto b = D.offsets.front().block;
+    auto block_ind = Block(order(C.is));
+    block_ind = b;
+    return calcDiv(C.is,block_ind);
+    }
+template QN doTask(CalcDiv const&,QDenseGPU<Real> const&);
+template QN doTask(CalcDiv const&,QDenseGPU<Cplx> const&);
+
+// doTask(NormNoScale,QDense) qdense.cc:409-417
+template<typename T>
+Real
+doTask(NormNoScale, QDenseGPU<T> const& d)
+    {
+    double out = 0;
+    check(itb_nrm2(context(),dtypeOf<T>(),int64_t(d.n),d.buf.data(),&out),"nrm2");
+    return out;
+    }
+template Real doTask(NormNoScale,QDenseGPU<Real> const&);
+template Real doTask(NormNoScale,QDenseGPU<Cplx> const&);
+
+// doTask(Mult<Real>,QDense) qdense.cc:303-311
+template<typename T>
+void
+doTask(Mult<Real> const& M, QDenseGPU<T>& d)
+    {
+    check(itb_scal(context(),dtypeOf<T>(),int64_t(d.n),d.buf.data(),M.x,0.),"scal");
+    }
+template void doTask(Mult<Real> const&,QDenseGPU<Real>&);
+template void doTask(Mult<Real> const&,QDenseGPU<Cplx>&);
+
+static void
+realToCplx(gpu::Buffer const& src, gpu::Buffer & dst, size_t n)
+    {
+    check(itb_real_to_cplx(context(),int64_t(n),src.data(),dst.data()),"real_to_cplx");
+    }
+
+// doTask(Mult<Cplx>,QDenseReal const&,ManageStore&) qdense.cc:314-325
+void
+doTask(Mult<Cplx> const& M, QDenseGPUReal const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<QDenseGPUCplx>(d.offsets,d.n);
+    realToCplx(d.buf,nd->buf,d.n);
+    check(itb_scal(context(),ITB_C64,int64_t(d.n),nd->buf.data(),M.x.real(),M.x.imag()),"scal");
+    }
+void
+doTask(Mult<Cplx> const& M, QDenseGPUCplx& d)
+    {
+    check(itb_scal(context(),ITB_C64,int64_t(d.n),d.buf.data(),M.x.real(),M.x.imag()),"scal");
+    }
+
+void
+doTask(MakeCplx const&, QDenseGPUCplx&) { }
+void
+doTask(MakeCplx const&, QDenseGPUReal const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<QDenseGPUCplx>(d.offsets,d.n);
+    realToCplx(d.buf,nd->buf,d.n);
+    }
+
+// doTask(Fill<T>,QDense) qdense.cc:356-373
+void
+doTask(Fill<Real> const& F, QDenseGPUReal& d)
+    {
+    check(itb_fill(context(),ITB_F64,int64_t(d.n),d.buf.data(),F.x,0.),"fill");
+    }
+void
+doTask(Fill<Cplx> const& F, QDenseGPUCplx& d)
+    {
+    check(itb_fill(context(),ITB_C64,int64_t(d.n),d.buf.data(),F.x.real(),F.x.imag()),"fill");
+    }
+void
+doTask(Fill<Real> const& F, QDenseGPUCplx const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<QDenseGPUReal>(d.offsets,d.n);
+    check(itb_fill(context(),ITB_F64,int64_t(d.n),nd->buf.data(),F.x,0.),"fill");
+    }
+void
+doTask(Fill<Cplx> const& F, QDenseGPUReal const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<QDenseGPUCplx>(d.offsets,d.n);
+    check(itb_fill(context(),ITB_C64,int64_t(d.n),nd->buf.data(),F.x.real(),F.x.imag()),"fill");
+    }
+
+void
+doTask(Conj, QDenseGPUCplx& d)
+    {
+    check(itb_conj(context(),int64_t(d.n),d.buf.data()),"conj");
+    }
+
+void
+doTask(TakeReal, QDenseGPUCplx const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<QDenseGPUReal>(d.offsets,d.n);
+    check(itb_take_part(context(),int64_t(d.n),d.buf.data(),nd->buf.data(),0),"take_real");
+    }
+void
+doTask(TakeImag, QDenseGPUReal& d)
+    {
+    check(itb_fill(context(),ITB_F64,int64_t(d.n),d.buf.data(),0.,0.),"fill");
+    }
+void
+doTask(TakeImag, QDenseGPUCplx const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<QDenseGPUReal>(d.offsets,d.n);
+    check(itb_take_part(context(),int64_t(d.n),d.buf.data(),nd->buf.data(),1),"take_imag");
+    }
+
+// QDense::getEltBlockOffset qdense.h:455-495 -> one element read back from the device
+template<typename T>
+static Cplx
+getEltGPU(GetElt& G, QDenseGPU<T> const& d)
+    {
+    auto r = long(G.inds.size());
+    double out[2] = {0.,0.};
+    if(r == 0)
+        {
+        if(d.n == 0) return Cplx(0.,0.);
+        check(itb_get_elt(context(),dtypeOf<T>(),d.buf.data(),0,out),"get_elt");
+        return Cplx(out[0],out[1]);
+        }
+    long eoff = 0, estr = 1;
+    auto block = Block(r);
+    for(auto i = 0; i < r; ++i)
+        {
+        auto& I = G.is[i];
+        long block_subind = 0, elt_subind = G.inds[i];
+        while(elt_subind >= I.blocksize0(block_subind))
+            {
+            elt_subind -= I.blocksize0(block_subind);
+            ++block_subind;
+            }
+        block[i] = block_subind;
+        eoff += elt_subind*estr;
+        estr *= I.blocksize0(block_subind);
+        }
+    auto boff = offsetOf(d.offsets,block);
+    if(boff < 0) return Cplx(0.,0.);
+    check(itb_get_elt(context(),dtypeOf<T>(),d.buf.data(),boff+eoff,out),"get_elt");
+    return Cplx(out[0],out[1]);
+    }
+Cplx doTask(GetElt& G, QDenseGPUReal const& d) { return getEltGPU(G,d); }
+Cplx doTask(GetElt& G, QDenseGPUCplx const& d) { return getEltGPU(G,d); }
+
+// doTask(Order,QDense) / permuteQDense qdense.cc:847-893: the result holds EVERY flux-allowed block
+template<typename T>
+void
+doTask(Order const& O, QDenseGPU<T>& dB)
+    {
+    auto const& Ais = O.is1();
+    auto r = order(Ais);
+    auto bind = IndexSetBuilder(r);
+    for(auto i : range(r)) bind.setIndex(O.perm().dest(i),Ais[i]);
+    auto Bis = bind.build();
+    auto div = doTask(CalcDiv{Ais},dB);
+    auto [bofs,size] = getBlockOffsets(Bis,div);
+    auto nB = QDenseGPU<T>(bofs,size);
+    auto dS = Desc(Ais,dB.offsets,dB.n,dtypeOf<T>());
+    auto dD = Desc(Bis,nB.offsets,nB.n,dtypeOf<T>());
+    auto* plan = getPermutePlan(dS,dD,toPerm(O.perm(),r));
+    check(itb_permute_run(context(),plan,dB.buf.data(),nB.buf.data(),1.,0.,0),"permute");
+    dB = std::move(nB);
+    }
+template void doTask(Order const&,QDenseGPU<Real>&);
+template void doTask(Order const&,QDenseGPU<Cplx>&);
+
+// doTask(Contract,QDense,QDense) qdense.cc:671-747 (+ getContractedOffsets, loopContractedBlocks, contract, gemm)
+template<typename VA, typename VB>
+static void
+contractQ(Contract& Con,
+          BlockOffsets const& Aoff, void const* Adata, size_t An,
+          BlockOffsets const& Boff, void const* Bdata, size_t Bn,
+          ManageStore& m)
+    {
+    using VC = common_type<VA,VB>;
+    Labels Lind, Rind, Cind;
+    computeLabels(Con.Lis,order(Con.Lis),Con.Ris,order(Con.Ris),Lind,Rind);
+    const bool sortResult = false;
+    contractIS(Con.Lis,Lind,Con.Ris,Rind,Con.Nis,Cind,sortResult);
+
+    auto dA = Desc(Con.Lis,Aoff,An,dtypeOf<VA>());
+    auto dB = Desc(Con.Ris,Boff,Bn,dtypeOf<VB>());
+    auto* plan = getContractPlan(dA,toLabels(Lind),dB,toLabels(Rind));
+    itb_contract_info info;
+    check(itb_contract_plan_info(plan,&info),"plan info");
+    auto rC = long(info.c_order);
+    auto cb = std::vector<int32_t>(size_t(info.c_nblocks*rC)+1);
+    auto co = std::vector<int64_t>(size_t(info.c_nblocks)+1);
+    itb_contract_plan_c_blocks(plan,cb.data());
+    itb_contract_plan_c_offsets(plan,co.data());
+    auto Coffsets = BlockOffsets();
+    Coffsets.reserve(info.c_nblocks);
+    for(auto c : range(info.c_nblocks))
+        {
+        auto b = Block(rC);
+        for(auto j : range(rC)) b[j] = cb[c*rC+j];
+        Coffsets.push_back(make_blof(b,co[c]));
+        }
+    auto* nd = m.makeNewData<QDenseGPU<VC>>(Coffsets,size_t(info.c_nelems));
+    check(itb_contract_run(context(),plan,Adata,Bdata,nd->buf.data()),"contract");
+    }
+
+template<typename VA, typename VB>
+void
+doTask(Contract& Con, QDenseGPU<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m)
+    {
+    contractQ<VA,VB>(Con,A.offsets,A.buf.data(),A.n,B.offsets,B.buf.data(),B.n,m);
+    }
+template<typename VA, typename VB>
+void
+doTask(Contract& Con, QDenseGPU<VA> const& A, QDense<VB> const& B, ManageStore& m)
+    {
+    auto gB = QDenseGPU<VB>(B); // upload the host operand
+    contractQ<VA,VB>(Con,A.offsets,A.buf.data(),A.n,gB.offsets,gB.buf.data(),gB.n,m);
+    }
+template<typename VA, typename VB>
+void
+doTask(Contract& Con, QDense<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m)
+    {
+    auto gA = QDenseGPU<VA>(A);
+    contractQ<VA,VB>(Con,gA.offsets,gA.buf.data(),gA.n,B.offsets,B.buf.data(),B.n,m);
+    }
+#define ITB_INST_CONTRACT(TA,TB) \
+template void doTask(Contract&,QDenseGPU<TA> const&,QDenseGPU<TB> const&,ManageStore&); \
+template void doTask(Contract&,QDenseGPU<TA> const&,QDense<TB> const&,ManageStore&); \
+template void doTask(Contract&,QDense<TA> const&,QDenseGPU<TB> const&,ManageStore&);
+ITB_INST_CONTRACT(Real,Real)
+ITB_INST_CONTRACT(Real,Cplx)
+ITB_INST_CONTRACT(Cplx,Real)
+ITB_INST_CONTRACT(Cplx,Cplx)
+#undef ITB_INST_CONTRACT
+
+// add(PlusEQ,QDense,QDense) qdense.cc:515-549:  A += alpha * permute(B)
+template<typename TA, typename TB>
+static void
+addQ(PlusEQ const& P, IndexSet const& isA, QDenseGPU<TA>& A, IndexSet const& isB, QDenseGPU<TB> const& B,
+     Permutation const& perm, Real alpha)
+    {
+    auto r = order(isA);
+    if(std::is_same<TA,TB>::value && isTrivial(perm) && A.offsets.size() == B.offsets.size() && A.n == B.n)
+        {
+        bool same = true;
+        for(auto i : range(A.offsets.size()))
+            if(A.offsets[i].block != B.offsets[i].block) { same = false; break; }
+        if(same) // daxpy fast path (qdense.cc:523-529)
+            {
+            check(itb_axpy(context(),dtypeOf<TA>(),int64_t(A.n),alpha,0.,B.buf.data(),A.buf.data()),"axpy");
+            return;
+            }
+        }
+    auto dS = Desc(isB,B.offsets,B.n,dtypeOf<TB>());
+    auto dD = Desc(isA,A.offsets,A.n,dtypeOf<TA>());
+    auto* plan = getPermutePlan(dS,dD,toPerm(perm,r));
+    check(itb_permute_run(context(),plan,B.buf.data(),A.buf.data(),alpha,0.,1),"permute-accumulate");
+    }
+
+// doTask(PlusEQ,QDense,QDense,ManageStore&) qdense.cc:551-668 (block-list merge, real->complex promotion)
+template<typename TA, typename TB>
+static void
+plusEqQ(PlusEQ const& P, QDenseGPU<TA> const& A, QDenseGPU<TB> const& B, ManageStore& m)
+    {
+    if(B.n == 0) return;
+    using TC = common_type<TA,TB>;
+    auto r = order(P.is1());
+    auto trivial = Permutation(r);
+
+    if(r == 0)
+        {
+        if(isReal(A) && isCplx(B))
+            {
+            auto* nA = m.makeNewData<QDenseGPUCplx>(A.offsets,A.n);
+            realToCplx(A.buf,nA->buf,A.n);
+            check(itb_axpy(context(),ITB_C64,1,P.alpha(),0.,B.buf.data(),nA->buf.data()),"axpy");
+            }
+        else
+            {
+            auto* mA = m.modifyData(A);
+            addQ(P,P.is1(),*mA,P.is2(),B,P.perm(),P.alpha());
+            }
+        return;
+        }
+
+    // permute and sort the blocks of B, then merge with A's (both sorted)
+    auto Bblockps = Blocks(B.offsets.size(),Block(r));
+    auto invperm = inverse(P.perm());
+    for(auto ib : range(B.offsets.size()))
+        for(auto i : range(r))
+            Bblockps[ib][i] = B.offsets[ib].block[invperm.dest(i)];
+    std::sort(Bblockps.begin(),Bblockps.end());
+    auto Cblocks = Blocks();
+    Cblocks.reserve(A.offsets.size()+B.offsets.size());
+    size_t ia = 0, ib = 0;
+    while(ia < A.offsets.size() && ib < B.offsets.size())
+        {
+        auto const& Ablock = A.offsets[ia].block;
+        auto const& Bblockp = Bblockps[ib];
+        if(Bblockp < Ablock) { Cblocks.push_back(Bblockp); ++ib; }
+        else if(Ablock < Bblockp) { Cblocks.push_back(Ablock); ++ia; }
+        else { Cblocks.push_back(Ablock); ++ia; ++ib; }
+        }
+    for(; ia < A.offsets.size(); ++ia) Cblocks.push_back(A.offsets[ia].block);
+    for(; ib < B.offsets.size(); ++ib) Cblocks.push_back(Bblockps[ib]);
+
+    if(A.offsets.size() < Cblocks.size())
+        {
+        // B has blocks A lacks: widen A's storage (zero-filled), copy A in, then accumulate B
+        auto [bofs,size] = offsetsFor(P.is1(),Cblocks);
+        auto* nA = m.makeNewData<QDenseGPU<TC>>(bofs,size_t(size));
+        auto dS = Desc(P.is1(),A.offsets,A.n,dtypeOf<TA>());
+        auto dD = Desc(P.is1(),nA->offsets,nA->n,dtypeOf<TC>());
+        auto* plan = getPermutePlan(dS,dD,toPerm(trivial,r));
+        check(itb_permute_run(context(),plan,A.buf.data(),nA->buf.data(),1.,0.,0),"widen");
+        addQ(P,P.is1(),*nA,P.is2(),B,P.perm(),P.alpha());
+        }
+    else if(isReal(A) && isCplx(B))
+        {
+        auto* nA = m.makeNewData<QDenseGPUCplx>(A.offsets,A.n);
+        realToCplx(A.buf,nA->buf,A.n);
+        addQ(P,P.is1(),*nA,P.is2(),B,P.perm(),P.alpha());
+        }
+    else
+        {
+        auto* mA = m.modifyData(A);
+        addQ(P,P.is1(),*mA,P.is2(),B,P.perm(),P.alpha());
+        }
+    }
+
+// real += complex is rejected by the reference's Adder (qdense.cc:513); addQ is only instantiated for legal pairs
+template<> void
+addQ<Real,Cplx>(PlusEQ const&, IndexSet const&, QDenseGPU<Real>&, IndexSet const&, QDenseGPU<Cplx> const&, Permutation const&, Real)
+    {
+    Error("itensor_b200: cannot accumulate a complex tensor into real storage");
+    }
+
+template<typename TA, typename TB>
+void
+doTask(PlusEQ const& P, QDenseGPU<TA> const& A, QDenseGPU<TB> const& B, ManageStore& m) { plusEqQ(P,A,B,m); }
+template<typename TA, typename TB>
+void
+doTask(PlusEQ const& P, QDenseGPU<TA> const& A, QDense<TB> const& B, ManageStore& m)
+    {
+    if(B.store.size() == 0) return;
+    auto gB = QDenseGPU<TB>(B);
+    plusEqQ(P,A,gB,m);
+    }
+template<typename TA, typename TB>
+void
+doTask(PlusEQ const& P, QDense<TA> const& A, QDenseGPU<TB> const& B, ManageStore& m)
+    {
+    // the accumulator is a host tensor: keep it on the host (reference path) with a downloaded B
+    doTask(P,A,B.toHost(),m);
+    }
+#define ITB_INST_PLUSEQ(TA,TB) \
+template void doTask(PlusEQ const&,QDenseGPU<TA> const&,QDenseGPU<TB> const&,ManageStore&); \
+template void doTask(PlusEQ const&,QDenseGPU<TA> const&,QDense<TB> const&,ManageStore&); \
+template void doTask(PlusEQ const&,QDense<TA> const&,QDenseGPU<TB> const&,ManageStore&);
+ITB_INST_PLUSEQ(Real,Real)
+ITB_INST_PLUSEQ(Real,Cplx)
+ITB_INST_PLUSEQ(Cplx,Real)
+ITB_INST_PLUSEQ(Cplx,Cplx)
+#undef ITB_INST_PLUSEQ
+
+//
+// ---------------------------------------------------------------------------------------------
+//  DenseGPU
+// ---------------------------------------------------------------------------------------------
+//
+template<typename T>
+Real
+doTask(NormNoScale, DenseGPU<T> const& d)
+    {
+    double out = 0;
+    check(itb_nrm2(context(),dtypeOf<T>(),int64_t(d.n),d.buf.data(),&out),"nrm2");
+    return out;
+    }
+template Real doTask(NormNoScale,DenseGPU<Real> const&);
+template Real doTask(NormNoScale,DenseGPU<Cplx> const&);
+
+template<typename T>
+void
+doTask(Mult<Real> const& M, DenseGPU<T>& d)
+    {
+    check(itb_scal(context(),dtypeOf<T>(),int64_t(d.n),d.buf.data(),M.x,0.),"scal");
+    }
+template void doTask(Mult<Real> const&,DenseGPU<Real>&);
+template void doTask(Mult<Real> const&,DenseGPU<Cplx>&);
+
+void
+doTask(Mult<Cplx> const& M, DenseGPUReal const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<DenseGPUCplx>(d.n);
+    realToCplx(d.buf,nd->buf,d.n);
+    check(itb_scal(context(),ITB_C64,int64_t(d.n),nd->buf.data(),M.x.real(),M.x.imag()),"scal");
+    }
+void
+doTask(Mult<Cplx> const& M, DenseGPUCplx& d)
+    {
+    check(itb_scal(context(),ITB_C64,int64_t(d.n),d.buf.data(),M.x.real(),M.x.imag()),"scal");
+    }
+void
+doTask(MakeCplx const&, DenseGPUCplx&) { }
+void
+doTask(MakeCplx const&, DenseGPUReal const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<DenseGPUCplx>(d.n);
+    realToCplx(d.buf,nd->buf,d.n);
+    }
+void
+doTask(Fill<Real> const& F, DenseGPUReal& d) { check(itb_fill(context(),ITB_F64,int64_t(d.n),d.buf.data(),F.x,0.),"fill"); }
+void
+doTask(Fill<Cplx> const& F, DenseGPUCplx& d) { check(itb_fill(context(),ITB_C64,int64_t(d.n),d.buf.data(),F.x.real(),F.x.imag()),"fill"); }
+void
+doTask(Fill<Real> const& F, DenseGPUCplx const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<DenseGPUReal>(d.n);
+    check(itb_fill(context(),ITB_F64,int64_t(d.n),nd->buf.data(),F.x,0.),"fill");
+    }
+void
+doTask(Fill<Cplx> const& F, DenseGPUReal const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<DenseGPUCplx>(d.n);
+    check(itb_fill(context(),ITB_C64,int64_t(d.n),nd->buf.data(),F.x.real(),F.x.imag()),"fill");
+    }
+void
+doTask(Conj, DenseGPUCplx& d) { check(itb_conj(context(),int64_t(d.n),d.buf.data()),"conj"); }
+void
+doTask(TakeReal, DenseGPUCplx const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<DenseGPUReal>(d.n);
+    check(itb_take_part(context(),int64_t(d.n),d.buf.data(),nd->buf.data(),0),"take_real");
+    }
+void
+doTask(TakeImag, DenseGPUReal& d) { check(itb_fill(context(),ITB_F64,int64_t(d.n),d.buf.data(),0.,0.),"fill"); }
+void
+doTask(TakeImag, DenseGPUCplx const& d, ManageStore& m)
+    {
+    auto* nd = m.makeNewData<DenseGPUReal>(d.n);
+    check(itb_take_part(context(),int64_t(d.n),d.buf.data(),nd->buf.data(),1),"take_imag");
+    }
+
+// doTask(GetElt,Dense) dense.cc:37-47
+Cplx
+doTask(GetElt const& g, DenseGPUReal const& d)
+    {
+    double out[2] = {0.,0.};
+    check(itb_get_elt(context(),ITB_F64,d.buf.data(),offset(g.is,g.inds),out),"get_elt");
+    return Cplx(out[0],0.);
+    }
+Cplx
+doTask(GetElt const& g, DenseGPUCplx const& d)
+    {
+    double out[2] = {0.,0.};
+    check(itb_get_elt(context(),ITB_C64,d.buf.data(),offset(g.is,g.inds),out),"get_elt");
+    return Cplx(out[0],out[1]);
+    }
+
+// doTask(Order,Dense) / permuteDense dense.cc:417-439
+template<typename T>
+void
+doTask(Order const& O, DenseGPU<T>& dA)
+    {
+    auto r = order(O.is1());
+    auto nB = DenseGPU<T>(dA.n);
+    auto dS = Desc(O.is1(),dA.n,dtypeOf<T>());
+    auto dD = Desc(O.is2(),nB.n,dtypeOf<T>());
+    auto* plan = getPermutePlan(dS,dD,toPerm(O.perm(),r));
+    check(itb_permute_run(context(),plan,dA.buf.data(),nB.buf.data(),1.,0.,0),"permute");
+    dA = std::move(nB);
+    }
+template void doTask(Order const&,DenseGPU<Real>&);
+template void doTask(Order const&,DenseGPU<Cplx>&);
+
+// doTask(Contract,Dense,Dense) dense.cc:262-330
+template<typename VA, typename VB>
+static void
+contractD(Contract& C, void const* Adata, size_t An, void const* Bdata, size_t Bn, ManageStore& m)
+    {
+    using VC = common_type<VA,VB>;
+    Labels Lind, Rind, Nind;
+    computeLabels(C.Lis,C.Lis.order(),C.Ris,C.Ris.order(),Lind,Rind);
+    auto wanted = C.Nis; // a caller may prescribe the result index order (dense.cc:287-303)
+    IndexSet natural;
+    contractIS(C.Lis,Lind,C.Ris,Rind,natural,Nind,false);
+    auto dA = Desc(C.Lis,An,dtypeOf<VA>());
+    auto dB = Desc(C.Ris,Bn,dtypeOf<VB>());
+    auto* plan = getContractPlan(dA,toLabels(Lind),dB,toLabels(Rind));
+    auto rsize = size_t(dim(natural));
+    auto* nd = m.makeNewData<DenseGPU<VC>>(rsize);
+    check(itb_contract_run(context(),plan,Adata,Bdata,nd->buf.data()),"contract");
+    if(!wanted)
+        {
+        C.Nis = natural;
+        return;
+        }
+    // permute the natural-order result into the prescribed order
+    auto r = order(natural);
+    auto P = Permutation(r);
+    calcPerm(natural,wanted,P);
+    if(isTrivial(P)) return;
+    auto out = DenseGPU<VC>(rsize);
+    auto dS = Desc(natural,rsize,dtypeOf<VC>());
+    auto dD = Desc(wanted,rsize,dtypeOf<VC>());
+    auto* pplan = getPermutePlan(dS,dD,toPerm(P,r));
+    check(itb_permute_run(context(),pplan,nd->buf.data(),out.buf.data(),1.,0.,0),"permute");
+    *nd = std::move(out);
+    }
+template<typename VA, typename VB>
+void
+doTask(Contract& C, DenseGPU<VA> const& A, DenseGPU<VB> const& B, ManageStore& m)
+    {
+    contractD<VA,VB>(C,A.buf.data(),A.n,B.buf.data(),B.n,m);
+    }
+template<typename VA, typename VB>
+void
+doTask(Contract& C, DenseGPU<VA> const& A, Dense<VB> const& B, ManageStore& m)
+    {
+    auto gB = DenseGPU<VB>(B);
+    contractD<VA,VB>(C,A.buf.data(),A.n,gB.buf.data(),gB.n,m);
+    }
+template<typename VA, typename VB>
+void
+doTask(Contract& C, Dense<VA> const& A, DenseGPU<VB> const& B, ManageStore& m)
+    {
+    auto gA = DenseGPU<VA>(A);
+    contractD<VA,VB>(C,gA.buf.data(),gA.n,B.buf.data(),B.n,m);
+    }
+#define ITB_INST_CONTRACT(TA,TB) \
+template void doTask(Contract&,DenseGPU<TA> const&,DenseGPU<TB> const&,ManageStore&); \
+template void doTask(Contract&,DenseGPU<TA> const&,Dense<TB> const&,ManageStore&); \
+template void doTask(Contract&,Dense<TA> const&,DenseGPU<TB> const&,ManageStore&);
+ITB_INST_CONTRACT(Real,Real)
+ITB_INST_CONTRACT(Real,Cplx)
+ITB_INST_CONTRACT(Cplx,Real)
+ITB_INST_CONTRACT(Cplx,Cplx)
+#undef ITB_INST_CONTRACT
+
+// doTask(PlusEQ,Dense,Dense) dense.cc:371-415
+template<typename TA, typename TB>
+static void
+addD(PlusEQ const& P, DenseGPU<TA>& A, DenseGPU<TB> const& B)
+    {
+    if(std::is_same<TA,TB>::value && isTrivial(P.perm()))
+        {
+        check(itb_axpy(context(),dtypeOf<TA>(),int64_t(A.n),P.alpha(),0.,B.buf.data(),A.buf.data()),"axpy");
+        return;
+        }
+    auto r = order(P.is1());
+    auto dS = Desc(P.is2(),B.n,dtypeOf<TB>());
+    auto dD = Desc(P.is1(),A.n,dtypeOf<TA>());
+    auto* plan = getPermutePlan(dS,dD,toPerm(P.perm(),r));
+    check(itb_permute_run(context(),plan,B.buf.data(),A.buf.data(),P.alpha(),0.,1),"permute-accumulate");
+    }
+template<> void
+addD<Real,Cplx>(PlusEQ const&, DenseGPU<Real>&, DenseGPU<Cplx> const&)
+    {
+    Error("itensor_b200: cannot accumulate a complex tensor into real storage");
+    }
+template<typename TA, typename TB>
+static void
+plusEqD(PlusEQ const& P, DenseGPU<TA> const& A, DenseGPU<TB> const& B, ManageStore& m)
+    {
+    if(isReal(A) && isCplx(B))
+        {
+        auto* nA = m.makeNewData<DenseGPUCplx>(A.n);
+        realToCplx(A.buf,nA->buf,A.n);
+        addD(P,*nA,B);
+        }
+    else
+        {
+        auto* mA = m.modifyData(A);
+        addD(P,*mA,B);
+        }
+    }
+template<typename TA, typename TB>
+void
+doTask(PlusEQ const& P, DenseGPU<TA> const& A, DenseGPU<TB> const& B, ManageStore& m) { plusEqD(P,A,B,m); }
+template<typename TA, typename TB>
+void
+doTask(PlusEQ const& P, DenseGPU<TA> const& A, Dense<TB> const& B, ManageStore& m)
+    {
+    auto gB = DenseGPU<TB>(B);
+    plusEqD(P,A,gB,m);
+    }
+template<typename TA, typename TB>
+void
+doTask(PlusEQ const& P, Dense<TA> const& A, DenseGPU<TB> const& B, ManageStore& m)
+    {
+    doTask(P,A,B.toHost(),m);
+    }
+#define ITB_INST_PLUSEQ(TA,TB) \
+template void doTask(PlusEQ const&,DenseGPU<TA> const&,DenseGPU<TB> const&,ManageStore&); \
+template void doTask(PlusEQ const&,DenseGPU<TA> const&,Dense<TB> const&,ManageStore&); \
+template void doTask(PlusEQ const&,Dense<TA> const&,DenseGPU<TB> const&,ManageStore&);
+ITB_INST_PLUSEQ(Real,Real)
+ITB_INST_PLUSEQ(Real,Cplx)
+ITB_INST_PLUSEQ(Cplx,Real)
+ITB_INST_PLUSEQ(Cplx,Cplx)
+#undef ITB_INST_PLUSEQ
+
+} //namespace itensor

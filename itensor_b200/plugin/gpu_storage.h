@@ -1,0 +1,281 @@
+//
+// gpu_storage.h — DenseGPU<T> / QDenseGPU<T>: ITensor storage types whose element data lives in B200 HBM.
+//
+// Drop-in through the reference's own storage plugin surface: the types are appended to StorageTypes
+// (itensor/itdata/storage_types.h:57-74, see INTEGRATION.md for the 3-line patch that
+// itensor_b200/plugin/Makefile applies to a build-directory copy) and every operation is a free
+// `doTask(Task, Storage...)` overload found by the dispatch in itensor/itdata/dotask.h:283-626.
+// All Index / QN / IndexSet bookkeeping stays in the reference's host code; these overloads only
+//   (1) turn IndexSet + BlockOffsets into the integer tables of include/itb200.h, and
+//   (2) call the extern "C" CUDA layer (libitb200.so). There is no CPU arithmetic in this file:
+//       if the CUDA library cannot create a context the first GPU task throws ITError.
+//
+// Hot-path tasks run on the device:
+//   Contract  (QDenseGPU x QDenseGPU, all four real/complex pairings; a host QDense operand is
+//              uploaded on the fly)                    replaces itensor/itdata/qdense.cc:671-747
+//   Order     (permute, fills in all flux-allowed blocks) replaces qdense.cc:847-893
+//   PlusEQ    (permuting accumulate, block-list merge, real->complex promotion) replaces qdense.cc:515-668
+//   NormNoScale, Mult<Real|Cplx>, Fill, Conj, MakeCplx, TakeReal/TakeImag, GetElt
+//   + integer-only tasks answered from the host-side block list: CalcDiv, NNZBlocks, NNZ, IsEmpty, ...
+// Everything else (combiners, Diag, SVD/eigh, element-wise apply/generate/set, I/O) is NOT on the hot
+// path (SURVEY §8f "next"): those overloads move the tensor to a host QDense/Dense and hand it to the
+// reference's own implementation, so results of svdBond etc. are host tensors that re-enter the device
+// the next time they meet a GPU tensor in a contraction.
+//
+#ifndef ITENSOR_B200_GPU_STORAGE_H
+#define ITENSOR_B200_GPU_STORAGE_H
+
+#include <memory>
+
+#include "itensor/itdata/dense.h"
+#include "itensor/itdata/qdense.h"
+#include "itensor/itdata/task_types.h"
+
+struct itb_ctx;
+
+namespace itensor {
+
+namespace gpu {
+
+// process-wide context on device $ITB_DEVICE (default 0); throws ITError when no device is usable
+itb_ctx* context();
+void synchronize();
+long launchCount();
+
+// RAII device buffer from the context's caching pool; copies are deep (device-to-device)
+class Buffer
+    {
+    void* p_ = nullptr;
+    size_t bytes_ = 0;
+    public:
+    Buffer() { }
+    explicit Buffer(size_t bytes);
+    Buffer(Buffer const& o);
+    Buffer(Buffer&& o) noexcept : p_(o.p_), bytes_(o.bytes_) { o.p_ = nullptr; o.bytes_ = 0; }
+    Buffer& operator=(Buffer const& o);
+    Buffer& operator=(Buffer&& o) noexcept;
+    ~Buffer();
+    void* data() const { return p_; }
+    size_t bytes() const { return bytes_; }
+    void upload(void const* host, size_t bytes);
+    void download(void* host, size_t bytes) const;
+    void zero();
+    };
+
+} //namespace gpu
+
+template<typename T>
+class QDenseGPU
+    {
+    public:
+    using value_type = T;
+
+    BlockOffsets offsets; // same host bookkeeping as QDense<T>::offsets (sorted block -> element offset)
+    gpu::Buffer buf;      // flat element data in HBM, laid out exactly like QDense<T>::store
+    size_t n = 0;         // number of stored elements
+
+    QDenseGPU() { }
+
+    // uninitialised device storage with the given block structure
+    QDenseGPU(BlockOffsets const& off, size_t size) : offsets(off), buf(size*sizeof(T)), n(size) { }
+
+    // upload
+    explicit QDenseGPU(QDense<T> const& h);
+
+    // download
+    QDense<T> toHost() const;
+
+    size_t size() const { return n; }
+    explicit operator bool() const { return n != 0 && !offsets.empty(); }
+    };
+
+template<typename T>
+class DenseGPU
+    {
+    public:
+    using value_type = T;
+
+    gpu::Buffer buf;
+    size_t n = 0;
+
+    DenseGPU() { }
+    explicit DenseGPU(size_t size) : buf(size*sizeof(T)), n(size) { }
+    explicit DenseGPU(Dense<T> const& h);
+    Dense<T> toHost() const;
+    size_t size() const { return n; }
+    explicit operator bool() const { return n != 0; }
+    };
+
+using QDenseGPUReal = QDenseGPU<Real>;
+using QDenseGPUCplx = QDenseGPU<Cplx>;
+using DenseGPUReal = DenseGPU<Real>;
+using DenseGPUCplx = DenseGPU<Cplx>;
+
+const char* typeNameOf(QDenseGPUReal const&);
+const char* typeNameOf(QDenseGPUCplx const&);
+const char* typeNameOf(DenseGPUReal const&);
+const char* typeNameOf(DenseGPUCplx const&);
+
+template<typename T> bool constexpr isReal(QDenseGPU<T> const&) { return std::is_same<T,Real>::value; }
+template<typename T> bool constexpr isCplx(QDenseGPU<T> const&) { return std::is_same<T,Cplx>::value; }
+template<typename T> bool constexpr isReal(DenseGPU<T> const&) { return std::is_same<T,Real>::value; }
+template<typename T> bool constexpr isCplx(DenseGPU<T> const&) { return std::is_same<T,Cplx>::value; }
+
+//
+// ---------------------------------------------------------------------------------------------
+//  QDenseGPU tasks
+// ---------------------------------------------------------------------------------------------
+//
+
+// integer-only tasks: answered from the host block list, no device access
+template<typename T> QN doTask(CalcDiv const& C, QDenseGPU<T> const& d);
+template<typename T> long doTask(NNZBlocks, QDenseGPU<T> const& d) { return long(d.offsets.size()); }
+template<typename T> long doTask(NNZ, QDenseGPU<T> const& d) { return long(d.n); }
+template<typename T> bool doTask(IsEmpty, QDenseGPU<T> const& d) { return d.offsets.empty(); }
+template<typename T> bool constexpr doTask(CheckComplex, QDenseGPU<T> const& d) { return isCplx(d); }
+auto constexpr inline doTask(StorageType const&, QDenseGPUReal const&) ->StorageType::Type { return StorageType::QDenseReal; }
+auto constexpr inline doTask(StorageType const&, QDenseGPUCplx const&) ->StorageType::Type { return StorageType::QDenseCplx; }
+
+// device tasks
+template<typename T> Real doTask(NormNoScale, QDenseGPU<T> const& d);
+template<typename T> void doTask(Mult<Real> const& M, QDenseGPU<T>& d);
+void doTask(Mult<Cplx> const& M, QDenseGPUReal const& d, ManageStore& m);
+void doTask(Mult<Cplx> const& M, QDenseGPUCplx& d);
+void doTask(MakeCplx const&, QDenseGPUCplx& d);
+void doTask(MakeCplx const&, QDenseGPUReal const& d, ManageStore& m);
+void doTask(Fill<Real> const& F, QDenseGPUReal& d);
+void doTask(Fill<Cplx> const& F, QDenseGPUCplx& d);
+void doTask(Fill<Real> const& F, QDenseGPUCplx const& d, ManageStore& m);
+void doTask(Fill<Cplx> const& F, QDenseGPUReal const& d, ManageStore& m);
+void inline doTask(Conj, QDenseGPUReal const&) { }
+void doTask(Conj, QDenseGPUCplx& d);
+void inline doTask(TakeReal, QDenseGPUReal const&) { }
+void doTask(TakeReal, QDenseGPUCplx const& d, ManageStore& m);
+void doTask(TakeImag, QDenseGPUReal& d);
+void doTask(TakeImag, QDenseGPUCplx const& d, ManageStore& m);
+Cplx doTask(GetElt& G, QDenseGPUReal const& d);
+Cplx doTask(GetElt& G, QDenseGPUCplx const& d);
+template<typename T> void doTask(Order const& O, QDenseGPU<T>& d);
+
+template<typename VA, typename VB>
+void doTask(Contract& Con, QDenseGPU<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m);
+template<typename VA, typename VB>
+void doTask(Contract& Con, QDenseGPU<VA> const& A, QDense<VB> const& B, ManageStore& m);
+template<typename VA, typename VB>
+void doTask(Contract& Con, QDense<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m);
+
+template<typename TA, typename TB>
+void doTask(PlusEQ const& P, QDenseGPU<TA> const& A, QDenseGPU<TB> const& B, ManageStore& m);
+template<typename TA, typename TB>
+void doTask(PlusEQ const& P, QDenseGPU<TA> const& A, QDense<TB> const& B, ManageStore& m);
+template<typename TA, typename TB>
+void doTask(PlusEQ const& P, QDense<TA> const& A, QDenseGPU<TB> const& B, ManageStore& m);
+
+//
+// Off-hot-path tasks: hand a host copy to the reference's own QDense implementation.
+//
+template<typename T> Cplx doTask(SumEls S, QDenseGPU<T> const& d) { return doTask(S,d.toHost()); }
+template<typename T> void doTask(PrintIT& P, QDenseGPU<T> const& d) { doTask(P,d.toHost()); }
+template<typename F, typename T>
+void doTask(VisitIT<F>& V, QDenseGPU<T> const& d) { doTask(V,d.toHost()); }
+template<typename F, typename T>
+void doTask(ApplyIT<F>& A, QDenseGPU<T>& d) { auto h = d.toHost(); doTask(A,h); d = QDenseGPU<T>(h); }
+template<typename T>
+void doTask(SetElt<Real>& S, QDenseGPU<T>& d) { auto h = d.toHost(); doTask(S,h); d = QDenseGPU<T>(h); }
+void inline doTask(SetElt<Cplx>& S, QDenseGPUCplx& d) { auto h = d.toHost(); doTask(S,h); d = QDenseGPUCplx(h); }
+template<typename F>
+void doTask(GenerateIT<F,Real>& G, QDenseGPUReal& d) { auto h = d.toHost(); doTask(G,h); d = QDenseGPUReal(h); }
+template<typename F>
+void doTask(GenerateIT<F,Cplx>& G, QDenseGPUCplx& d) { auto h = d.toHost(); doTask(G,h); d = QDenseGPUCplx(h); }
+// results below are host storage: they come back to the device when they next meet a GPU tensor
+template<typename V>
+void doTask(RemoveQNs& R, QDenseGPU<V> const& d, ManageStore& m) { doTask(R,d.toHost(),m); }
+template<typename T> bool doTask(IsDense, QDenseGPU<T> const&) { return true; }
+
+// contraction partners that are not on the hot path (combiners, diagonal tensors): via the host
+template<typename T> void doTask(Contract& C, QDenseGPU<T> const& d, QCombiner const& cmb, ManageStore& m) { doTask(C,d.toHost(),cmb,m); }
+template<typename T> void doTask(Contract& C, QCombiner const& cmb, QDenseGPU<T> const& d, ManageStore& m) { doTask(C,cmb,d.toHost(),m); }
+template<typename TA, typename TB>
+void doTask(Contract& C, QDenseGPU<TA> const& d, QDiag<TB> const& t, ManageStore& m) { doTask(C,d.toHost(),t,m); }
+template<typename TA, typename TB>
+void doTask(Contract& C, QDiag<TA> const& t, QDenseGPU<TB> const& d, ManageStore& m) { doTask(C,t,d.toHost(),m); }
+template<typename VA, typename VB>
+void doTask(NCProd& P, QDenseGPU<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m) { doTask(P,A.toHost(),B.toHost(),m); }
+
+//
+// ---------------------------------------------------------------------------------------------
+//  DenseGPU tasks (one block, no QNs): same kernels through the same C ABI
+// ---------------------------------------------------------------------------------------------
+//
+template<typename T> bool constexpr doTask(CheckComplex, DenseGPU<T> const& d) { return isCplx(d); }
+auto constexpr inline doTask(StorageType const&, DenseGPUReal const&) ->StorageType::Type { return StorageType::DenseReal; }
+auto constexpr inline doTask(StorageType const&, DenseGPUCplx const&) ->StorageType::Type { return StorageType::DenseCplx; }
+template<typename T> Real doTask(NormNoScale, DenseGPU<T> const& d);
+template<typename T> void doTask(Mult<Real> const& M, DenseGPU<T>& d);
+void doTask(Mult<Cplx> const& M, DenseGPUReal const& d, ManageStore& m);
+void doTask(Mult<Cplx> const& M, DenseGPUCplx& d);
+void doTask(MakeCplx const&, DenseGPUCplx& d);
+void doTask(MakeCplx const&, DenseGPUReal const& d, ManageStore& m);
+void doTask(Fill<Real> const& F, DenseGPUReal& d);
+void doTask(Fill<Cplx> const& F, DenseGPUCplx& d);
+void doTask(Fill<Real> const& F, DenseGPUCplx const& d, ManageStore& m);
+void doTask(Fill<Cplx> const& F, DenseGPUReal const& d, ManageStore& m);
+void inline doTask(Conj, DenseGPUReal const&) { }
+void doTask(Conj, DenseGPUCplx& d);
+void inline doTask(TakeReal, DenseGPUReal const&) { }
+void doTask(TakeReal, DenseGPUCplx const& d, ManageStore& m);
+void doTask(TakeImag, DenseGPUReal& d);
+void doTask(TakeImag, DenseGPUCplx const& d, ManageStore& m);
+Cplx doTask(GetElt const& G, DenseGPUReal const& d);
+Cplx doTask(GetElt const& G, DenseGPUCplx const& d);
+template<typename T> void doTask(Order const& O, DenseGPU<T>& d);
+template<typename VA, typename VB>
+void doTask(Contract& Con, DenseGPU<VA> const& A, DenseGPU<VB> const& B, ManageStore& m);
+template<typename VA, typename VB>
+void doTask(Contract& Con, DenseGPU<VA> const& A, Dense<VB> const& B, ManageStore& m);
+template<typename VA, typename VB>
+void doTask(Contract& Con, Dense<VA> const& A, DenseGPU<VB> const& B, ManageStore& m);
+template<typename TA, typename TB>
+void doTask(PlusEQ const& P, DenseGPU<TA> const& A, DenseGPU<TB> const& B, ManageStore& m);
+template<typename TA, typename TB>
+void doTask(PlusEQ const& P, DenseGPU<TA> const& A, Dense<TB> const& B, ManageStore& m);
+template<typename TA, typename TB>
+void doTask(PlusEQ const& P, Dense<TA> const& A, DenseGPU<TB> const& B, ManageStore& m);
+
+template<typename T> Cplx doTask(SumEls S, DenseGPU<T> const& d) { return doTask(S,d.toHost()); }
+template<typename T> void doTask(PrintIT& P, DenseGPU<T> const& d) { doTask(P,d.toHost()); }
+template<typename F, typename T>
+void doTask(VisitIT<F>& V, DenseGPU<T> const& d) { doTask(V,d.toHost()); }
+template<typename F, typename T>
+void doTask(ApplyIT<F>& A, DenseGPU<T> const& d, ManageStore& m) { doTask(A,d.toHost(),m); }
+template<typename E, typename T>
+void doTask(SetElt<E> const& S, DenseGPU<T> const& d, ManageStore& m) { doTask(S,d.toHost(),m); }
+// A dense combiner can be a pure relabelling that leaves the storage untouched (combiner.cc:55-155); the result
+// must still be a HOST tensor because the decompositions that follow take raw views of it (decomp.cc:60-68).
+template<typename T>
+void doTask(Contract& C, DenseGPU<T> const& d, Combiner const& cmb, ManageStore& m)
+    {
+    auto h = d.toHost();
+    doTask(C,h,cmb,m);
+    if(!m.newData()) m.makeNewData<Dense<T>>(std::move(h));
+    }
+template<typename T>
+void doTask(Contract& C, Combiner const& cmb, DenseGPU<T> const& d, ManageStore& m)
+    {
+    auto h = d.toHost();
+    doTask(C,cmb,h,m);
+    if(!m.newData()) m.makeNewData<Dense<T>>(std::move(h));
+    }
+template<typename TA, typename TB>
+void doTask(Contract& C, DenseGPU<TA> const& d, Diag<TB> const& t, ManageStore& m) { doTask(C,d.toHost(),t,m); }
+template<typename TA, typename TB>
+void doTask(Contract& C, Diag<TA> const& t, DenseGPU<TB> const& d, ManageStore& m) { doTask(C,t,d.toHost(),m); }
+
+// binary I/O (ITensor::write, LocalMPO disk spill): GPU storage is written in the host wire format
+// (StorageType QDenseReal/... above), so files read back as ordinary host tensors.
+template<typename T> void write(std::ostream& s, QDenseGPU<T> const& d) { write(s,d.toHost()); }
+template<typename T> void write(std::ostream& s, DenseGPU<T> const& d) { write(s,d.toHost()); }
+
+} //namespace itensor
+
+#endif

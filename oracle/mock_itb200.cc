@@ -1,0 +1,129 @@
+// mock_itb200.cc — HOST mock of the device half of the C ABI (include/itb200.h), backed by the oracle.
+//
+// TEST INFRASTRUCTURE ONLY. It exists so that the host-side logic of the storage plugin
+// (itensor_b200/plugin: dispatch, block bookkeeping, plan caching, ownership) can be exercised by
+// `pytest -m "not gpu"` in a container without a GPU. It is never linked into the product: the product
+// binaries link itensor_b200/libitb200.so, which fails loudly without a CUDA device.
+// The integer planner is the real one (itensor_b200/csrc/plan.cc, host-only); arithmetic is oracle.c.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "../itensor_b200/csrc/plan.h"
+
+extern "C" {
+struct orc_desc {
+    int32_t order, dtype;
+    const int32_t* nsect;
+    const int64_t* sect;
+    int64_t nblocks;
+    const int32_t* blocks;
+    const int64_t* offsets;
+    int64_t nelems;
+};
+int orc_contract_values(const orc_desc* A, const int32_t* labA, const double* Ad, const orc_desc* B, const int32_t* labB,
+                        const double* Bd, const orc_desc* C, const int64_t* triples, int64_t npairs, double* Cd);
+int orc_permute(const orc_desc* S, const double* Sd, const orc_desc* D, double* Dd, const int32_t* perm, double alpha_re,
+                double alpha_im, int accumulate);
+double orc_nrm2(int64_t n, const double* x);
+}
+
+struct itb_ctx { int64_t launches = 0; };
+
+static orc_desc to_orc(const itb::TensorStruct& t) {
+    static const int32_t zero32 = 0;
+    static const int64_t zero64 = 0;
+    orc_desc d;
+    d.order = t.order; d.dtype = t.dtype;
+    d.nsect = t.nsect.empty() ? &zero32 : t.nsect.data();
+    d.sect = t.sect.empty() ? &zero64 : t.sect.data();
+    d.nblocks = t.nblocks;
+    d.blocks = t.blocks.empty() ? &zero32 : t.blocks.data();
+    d.offsets = t.offsets.empty() ? &zero64 : t.offsets.data();
+    d.nelems = t.nelems;
+    return d;
+}
+
+extern "C" {
+void itb_contract_plan_release_device(itb_contract_plan*) {}
+void itb_permute_plan_release_device(itb_permute_plan*) {}
+const char* itb_version(void) { return "itb200 MOCK (oracle-backed, tests only)"; }
+int itb_device_count(void) { return 0; }
+int itb_ctx_create(int, itb_ctx** out) { *out = new itb_ctx(); return ITB_OK; }
+int itb_ctx_destroy(itb_ctx* c) { delete c; return ITB_OK; }
+void* itb_ctx_stream(itb_ctx*) { return nullptr; }
+int itb_ctx_set_stream(itb_ctx*, void*) { return ITB_OK; }
+int itb_synchronize(itb_ctx*) { return ITB_OK; }
+int64_t itb_launch_count(itb_ctx* c) { return c->launches; }
+int itb_malloc(itb_ctx*, size_t b, void** p) { *p = std::malloc(b ? b : 1); return *p ? ITB_OK : ITB_ERR_NOMEM; }
+int itb_free(itb_ctx*, void* p) { std::free(p); return ITB_OK; }
+int itb_memcpy_h2d(itb_ctx*, void* d, const void* s, size_t b) { std::memcpy(d, s, b); return ITB_OK; }
+int itb_memcpy_d2h(itb_ctx*, void* d, const void* s, size_t b) { std::memcpy(d, s, b); return ITB_OK; }
+int itb_memcpy_d2d(itb_ctx*, void* d, const void* s, size_t b) { std::memcpy(d, s, b); return ITB_OK; }
+int itb_memset0(itb_ctx*, void* d, size_t b) { std::memset(d, 0, b); return ITB_OK; }
+int itb_pool_trim(itb_ctx*) { return ITB_OK; }
+
+int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) {
+    if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK;
+    orc_desc a = to_orc(P->A), b = to_orc(P->B), cc = to_orc(P->C);
+    ++c->launches;
+    return orc_contract_values(&a, P->labA.data(), (const double*)A, &b, P->labB.data(), (const double*)B, &cc, P->triples.data(),
+                               (int64_t)P->triples.size() / 3, (double*)C) == 0 ? ITB_OK : ITB_ERR_INVALID;
+}
+int itb_contract_host(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) { return itb_contract_run(c, P, A, B, C); }
+int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) {
+    orc_desc s = to_orc(P->S), d = to_orc(P->D);
+    static const int32_t zero32 = 0;
+    ++c->launches;
+    return orc_permute(&s, (const double*)S, &d, (double*)D, P->perm.empty() ? &zero32 : P->perm.data(), ar, ai, acc) == 0 ? ITB_OK : ITB_ERR_INVALID;
+}
+int itb_permute_host(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) { return itb_permute_run(c, P, S, D, ar, ai, acc); }
+
+int itb_nrm2(itb_ctx* c, int32_t dt, int64_t n, const void* x, double* out) { ++c->launches; *out = orc_nrm2(dt == ITB_C64 ? 2 * n : n, (const double*)x); return ITB_OK; }
+int itb_scal(itb_ctx* c, int32_t dt, int64_t n, void* xv, double ar, double ai) {
+    double* x = (double*)xv; ++c->launches;
+    if (dt == ITB_F64) for (int64_t i = 0; i < n; ++i) x[i] *= ar;
+    else for (int64_t i = 0; i < n; ++i) { double r = x[2*i], im = x[2*i+1]; x[2*i] = ar*r - ai*im; x[2*i+1] = ar*im + ai*r; }
+    return ITB_OK;
+}
+int itb_axpy(itb_ctx* c, int32_t dt, int64_t n, double ar, double ai, const void* xv, void* yv) {
+    const double* x = (const double*)xv; double* y = (double*)yv; ++c->launches;
+    if (dt == ITB_F64) for (int64_t i = 0; i < n; ++i) y[i] += ar * x[i];
+    else for (int64_t i = 0; i < n; ++i) { y[2*i] += ar*x[2*i] - ai*x[2*i+1]; y[2*i+1] += ar*x[2*i+1] + ai*x[2*i]; }
+    return ITB_OK;
+}
+int itb_fill(itb_ctx* c, int32_t dt, int64_t n, void* xv, double re, double im) {
+    double* x = (double*)xv; ++c->launches;
+    if (dt == ITB_F64) for (int64_t i = 0; i < n; ++i) x[i] = re;
+    else for (int64_t i = 0; i < n; ++i) { x[2*i] = re; x[2*i+1] = im; }
+    return ITB_OK;
+}
+int itb_conj(itb_ctx* c, int64_t n, void* xv) { double* x = (double*)xv; ++c->launches; for (int64_t i = 0; i < n; ++i) x[2*i+1] = -x[2*i+1]; return ITB_OK; }
+int itb_real_to_cplx(itb_ctx* c, int64_t n, const void* xv, void* yv) {
+    const double* x = (const double*)xv; double* y = (double*)yv; ++c->launches;
+    for (int64_t i = 0; i < n; ++i) { y[2*i] = x[i]; y[2*i+1] = 0.0; }
+    return ITB_OK;
+}
+int itb_take_part(itb_ctx* c, int64_t n, const void* xv, void* yv, int imag) {
+    const double* x = (const double*)xv; double* y = (double*)yv; ++c->launches;
+    for (int64_t i = 0; i < n; ++i) y[i] = x[2*i + (imag ? 1 : 0)];
+    return ITB_OK;
+}
+int itb_get_elt(itb_ctx*, int32_t dt, const void* xv, int64_t off, double out[2]) {
+    const double* x = (const double*)xv;
+    if (dt == ITB_F64) { out[0] = x[off]; out[1] = 0; } else { out[0] = x[2*off]; out[1] = x[2*off+1]; }
+    return ITB_OK;
+}
+int itb_dot(itb_ctx*, int32_t dt, int64_t n, const void* xv, const void* yv, int conj_x, double out[2]) {
+    const double* x = (const double*)xv; const double* y = (const double*)yv;
+    out[0] = out[1] = 0;
+    if (dt == ITB_F64) for (int64_t i = 0; i < n; ++i) out[0] += x[i]*y[i];
+    else for (int64_t i = 0; i < n; ++i) { double xi = conj_x ? -x[2*i+1] : x[2*i+1]; out[0] += x[2*i]*y[2*i] - xi*y[2*i+1]; out[1] += x[2*i]*y[2*i+1] + xi*y[2*i]; }
+    return ITB_OK;
+}
+int itb_peak_fp64(itb_ctx*, int, int, double* t) { *t = 0; return ITB_ERR_UNSUPPORTED; }
+int itb_ctx_set_profile(itb_ctx*, int) { return ITB_OK; }
+int itb_contract_last_ms(itb_ctx*, float ms[5]) { for (int i = 0; i < 5; ++i) ms[i] = 0; return ITB_OK; }
+int itb_timer_start(itb_ctx*) { return ITB_OK; }
+int itb_timer_stop_ms(itb_ctx*, float* ms) { *ms = 0; return ITB_OK; }
+}
