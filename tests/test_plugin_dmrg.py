@@ -1,0 +1,78 @@
+"""The storage plugin end to end: the reference's UNMODIFIED DMRGWorker (itensor/mps/dmrg.h:336-467) on
+QDenseGPU / DenseGPU storage vs the same binary on host storage.
+
+  * CPU (`not gpu`): build/plugin/dmrg_driver_mock — plugin host logic (dispatch, block bookkeeping,
+    plan cache, PlusEQ block merge, permute fill-in, ownership) with the oracle-backed mock of the C ABI.
+  * GPU: build/plugin/dmrg_driver — the real libitb200.so kernels. Energies within 1e-10 for the
+    QN-conserving runs (north_star), truncation error and kept spectrum compared per bond.
+Both binaries are built where /root/reference exists (`__graft_entry__.build()`); they travel to the GPU box.
+"""
+import json
+import os
+import subprocess
+import sysconfig
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "build", "plugin", "dmrg_driver_mock")
+REAL = os.path.join(ROOT, "build", "plugin", "dmrg_driver")
+ENV = dict(os.environ, LD_LIBRARY_PATH=os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs") + ":" +
+           os.environ.get("LD_LIBRARY_PATH", ""), OPENBLAS_NUM_THREADS="1")
+SCHED = ["10,20,100,100,200", "1e-10", "2", "1e-7,1e-8,0"]  # sample/dmrg.cc:55-60
+
+
+def run(binary, model, N, qn, storage, sched=SCHED):
+    out = subprocess.run([binary, model, str(N), qn, storage] + sched, env=ENV, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().split("\n")[-1])
+
+
+def compare(g, c, etol, per_bond=True):
+    assert abs(g["energy"] - c["energy"]) <= etol, (g["energy"], c["energy"])
+    assert [s["maxlink"] for s in g["sweeps"]] == [s["maxlink"] for s in c["sweeps"]]
+    if per_bond:
+        tg, tc = np.array(g["last_sweep_truncerr"]), np.array(c["last_sweep_truncerr"])
+        assert tg.shape == tc.shape and np.allclose(tg, tc, rtol=1e-5, atol=1e-13)
+        sg, sc = np.array(g["centre_spectrum"]), np.array(c["centre_spectrum"])
+        assert sg.shape == sc.shape and np.allclose(sg, sc, rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.skipif(not os.path.exists(MOCK), reason="build/plugin/dmrg_driver_mock not built (needs /root/reference)")
+@pytest.mark.parametrize("model,N,qn", [("heis_half", 16, "qn"), ("heis_one", 10, "qn"), ("heis_half", 10, "dense")])
+def test_plugin_host_logic_on_mock_abi(model, N, qn):
+    g = run(MOCK, model, N, qn, "gpu", ["10,20,40", "1e-10", "2", "1e-7,1e-8,0"])
+    c = run(MOCK, model, N, qn, "cpu", ["10,20,40", "1e-10", "2", "1e-7,1e-8,0"])
+    assert g["gpu_launches"] > 500  # the GPU storage types really carried the run
+    compare(g, c, 1e-10 if qn == "qn" else 1e-8, per_bond=(qn == "qn"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REAL), reason="build/plugin/dmrg_driver not built")
+def test_dmrg_sample_config_energy_parity_on_gpu():
+    """BASELINE configs[0]: sample/dmrg.cc as-is (S=1, N=100, Sz QNs). Reference energy -138.9400860763."""
+    g = run(REAL, "heis_one", 100, "qn", "gpu")
+    c = run(REAL, "heis_one", 100, "qn", "cpu")
+    assert abs(c["energy"] - (-138.9400860763)) < 1e-9  # SURVEY F2 pin of the reference build
+    assert g["gpu_launches"] > 10000
+    compare(g, c, 1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REAL), reason="build/plugin/dmrg_driver not built")
+def test_dmrg_spin_half_parity_on_gpu():
+    g = run(REAL, "heis_half", 40, "qn", "gpu")
+    c = run(REAL, "heis_half", 40, "qn", "cpu")
+    compare(g, c, 1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REAL), reason="build/plugin/dmrg_driver not built")
+def test_dmrg_dense_storage_on_gpu():
+    """no-QN variant (DenseGPU): not reproducible to 1e-10 even CPU vs CPU (1.6e-6 across BLAS
+    thread counts), so only a loose bound is asserted and the value is reported."""
+    g = run(REAL, "heis_one", 12, "dense", "gpu", ["10,20,40,40,40,40", "1e-10", "2", "1e-7,1e-8,0"])
+    c = run(REAL, "heis_one", 12, "dense", "cpu", ["10,20,40,40,40,40", "1e-10", "2", "1e-7,1e-8,0"])
+    assert g["gpu_launches"] > 1000
+    assert abs(g["energy"] - c["energy"]) < 1e-4
