@@ -203,7 +203,11 @@ def main():
         from itensor_b200.shard import shard_chain
 
         shard = shard_chain(plans, world, rank)
-    my_flops = sum(p.info.class_flops[i] for p in plans for i in range(5))
+    max_share = 1.0
+    if shard is not None:
+        t = torch.tensor([shard.my_flops / shard.total_flops], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_share = float(t.item())
 
     pinned = [torch.from_numpy(np.ascontiguousarray(h).view(np.float64).reshape(-1)).pin_memory() for h in hosts]
     dts = [itb.QTensor(ctx, st, ctx.empty(st.nreal)) for st in structs]
@@ -215,6 +219,8 @@ def main():
 
     def step():
         cur = dts[0]
+        if shard is not None:
+            shard.zero_unowned(outs[-1].data)  # blocks of H*phi owned by other ranks must read as exact zeros
         for k, p in enumerate(plans):
             check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
             cur = outs[k]
@@ -386,7 +392,8 @@ def main():
             "config": {"workload": f"H_eff*phi (LocalOp::product: phi*L*W1*W2*R) S=1/2 Heisenberg N=100 centre bond, Sz QDense blocks, maxdim {args.m}",
                        "maxdim": args.m, "sectors": sizes, "d": 2, "mpo_link_sectors": [3, 1, 1],
                        "pairs_per_step": [int(p.npairs) for p in plans], "flops_per_step": total_flops,
-                       "l2": "flushed between timed iterations (256 MiB memset)", "sharding": "C blocks by l' sector" if world > 1 else "none"},
+                       "l2": "flushed between timed iterations (256 MiB memset)",
+                       "sharding": ("C blocks by l' sector, max rank share %.3f of flops" % (max_share,)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "permute": perm_info,

@@ -125,6 +125,9 @@ int itb_contract_plan_c_offsets(const itb_contract_plan* plan, int64_t* offsets 
 int itb_contract_plan_pairs(const itb_contract_plan* plan, int64_t* triples /*[npairs*3]*/);
 /* restrict execution to C blocks [first,last) — the output-block sharding unit for multi-GPU */
 int itb_contract_plan_set_cblock_range(itb_contract_plan* plan, int64_t first, int64_t last);
+/* general form: mask[c] != 0 selects C block c (c_nblocks entries); NULL selects all. Unselected C blocks
+ * are neither computed nor written (their storage is left untouched). */
+int itb_contract_plan_set_cblock_mask(itb_contract_plan* plan, const uint8_t* mask);
 
 /* blocks allowed by a total flux: sum_j dir[j]*qn(index j, sector) == flux (component-wise,
  * component c taken modulo |mod[c]| when |mod[c]|>1). qn: for index j, sector s, component c:

@@ -84,6 +84,7 @@ SYMBOLS = {
     "itb_contract_plan_c_offsets": (C.c_int, [_P, _I64P]),
     "itb_contract_plan_pairs": (C.c_int, [_P, _I64P]),
     "itb_contract_plan_set_cblock_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "itb_contract_plan_set_cblock_mask": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
     "itb_flux_blocks": (C.c_int64, [C.c_int32, _I32P, _I32P, C.c_int32, _I32P, _I32P, _I32P, _I32P, C.c_int64]),
     "itb_contract_run": (C.c_int, [_P, _P, _P, _P, _P]),
     "itb_contract_host": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -115,12 +116,16 @@ def lib() -> C.CDLL:
     """Load libitb200.so once; raise (never fall back) if it is missing."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = LIB_PATH
+        # tests only: ITB200_LIB_PATH points the bindings at the oracle-backed mock of the C ABI
+        # (oracle/_ref/libitb200_mock.so) to exercise host logic without a GPU; never set in production
+        path = os.environ.get("ITB200_LIB_PATH", path)
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). itensor_b200 has no CPU fallback."
             )
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError here == header/library mismatch
             fn.restype = res

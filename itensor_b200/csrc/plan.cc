@@ -240,7 +240,7 @@ int build_contract_tables(itb_contract_plan& P) {
         const int64_t ic = P.triples[3 * order[pos] + 2];
         int64_t end = pos;
         while (end < npairs && P.triples[3 * order[end] + 2] == ic) ++end;
-        if (ic < cb_first || ic >= cb_last) { pos = end; continue; }
+        if (ic < cb_first || ic >= cb_last || (!P.cb_mask.empty() && !P.cb_mask[ic])) { pos = end; continue; }
 
         ItbCBlk cbk;
         std::memset(&cbk, 0, sizeof(cbk));
@@ -584,6 +584,14 @@ int itb_contract_plan_set_cblock_range(itb_contract_plan* P, int64_t first, int6
     if (first < 0 || (last >= 0 && last < first) || last > P->C.nblocks) { set_error("set_cblock_range: bad range"); return ITB_ERR_INVALID; }
     P->cb_first = first;
     P->cb_last = last;
+    itb_contract_plan_release_device(P);
+    return build_contract_tables(*P);
+}
+
+int itb_contract_plan_set_cblock_mask(itb_contract_plan* P, const uint8_t* mask) {
+    if (!P) { set_error("set_cblock_mask: null"); return ITB_ERR_INVALID; }
+    if (mask) P->cb_mask.assign(mask, mask + P->C.nblocks);
+    else P->cb_mask.clear();
     itb_contract_plan_release_device(P);
     return build_contract_tables(*P);
 }

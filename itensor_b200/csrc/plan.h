@@ -39,6 +39,7 @@ struct itb_contract_plan {
     double flops = 0;
     double class_flops[5] = {0, 0, 0, 0, 0};
     int64_t cb_first = 0, cb_last = -1; // execution range of C blocks (sharding); -1 => all
+    std::vector<uint8_t> cb_mask;       // optional per-C-block selection (empty => all)
 
     // device-format tables (built by build_tables(), rebuilt when the range changes)
     bool tables_built = false;

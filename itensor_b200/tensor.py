@@ -179,6 +179,15 @@ class ContractPlan:
         check(lib().itb_contract_plan_set_cblock_range(self._h, first, last))
         check(lib().itb_contract_plan_info(self._h, C.byref(self.info)))
 
+    def set_cblock_mask(self, mask) -> None:
+        if mask is None:
+            check(lib().itb_contract_plan_set_cblock_mask(self._h, None))
+        else:
+            m = np.ascontiguousarray(mask, np.uint8)
+            assert m.shape == (self.C.nblocks,)
+            check(lib().itb_contract_plan_set_cblock_mask(self._h, m.ctypes.data_as(C.POINTER(C.c_uint8))))
+        check(lib().itb_contract_plan_info(self._h, C.byref(self.info)))
+
     def close(self):
         if self._h:
             lib().itb_contract_plan_destroy(self._h)

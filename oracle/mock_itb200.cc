@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../itensor_b200/csrc/plan.h"
 
@@ -67,8 +68,17 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK;
     orc_desc a = to_orc(P->A), b = to_orc(P->B), cc = to_orc(P->C);
     ++c->launches;
-    return orc_contract_values(&a, P->labA.data(), (const double*)A, &b, P->labB.data(), (const double*)B, &cc, P->triples.data(),
-                               (int64_t)P->triples.size() / 3, (double*)C) == 0 ? ITB_OK : ITB_ERR_INVALID;
+    // honour the C-block selection (multi-GPU sharding): only pairs of selected C blocks are executed
+    std::vector<int64_t> tr;
+    const int64_t last = P->cb_last < 0 ? P->C.nblocks : P->cb_last;
+    for (size_t p = 0; p + 2 < P->triples.size() + 0; p += 3) {
+        const int64_t ic = P->triples[p + 2];
+        if (ic < P->cb_first || ic >= last || (!P->cb_mask.empty() && !P->cb_mask[ic])) continue;
+        tr.insert(tr.end(), P->triples.begin() + p, P->triples.begin() + p + 3);
+    }
+    if (tr.empty()) return ITB_OK;
+    return orc_contract_values(&a, P->labA.data(), (const double*)A, &b, P->labB.data(), (const double*)B, &cc, tr.data(),
+                               (int64_t)tr.size() / 3, (double*)C) == 0 ? ITB_OK : ITB_ERR_INVALID;
 }
 int itb_contract_host(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) { return itb_contract_run(c, P, A, B, C); }
 int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) {
