@@ -21,9 +21,9 @@ cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, in
 cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
                        const double* A, const double* B, double* partial, double* C, cudaStream_t st);
 cudaError_t launch_peak(int which, int iters, double* out, int num_sms, cudaStream_t st);
-cudaError_t launch_permute(int src_cplx, int dst_cplx, const ItbPermBlk* bc, int nbc, int64_t items_c, const ItbPermBlk* bt, int nbt,
-                           int64_t items_t, const void* src, void* dst, double ar, double ai, int accum, cudaStream_t st,
-                           int* launches);
+cudaError_t launch_permute(int src_cplx, int dst_cplx, const ItbPermBlk* bc, const ItbPermChunk* chunks, int64_t items_c,
+                           const ItbPermTile* tiles, int64_t items_t, const void* src, void* dst, double ar, double ai, int accum,
+                           cudaStream_t st, int* launches);
 cudaError_t launch_scal(int cplx, int64_t n, void* x, double ar, double ai, int sms, cudaStream_t st);
 cudaError_t launch_axpy(int cplx, int64_t n, double ar, double ai, const void* x, void* y, int sms, cudaStream_t st);
 cudaError_t launch_fill(int cplx, int64_t n, void* x, double re, double im, int sms, cudaStream_t st);
@@ -49,7 +49,8 @@ struct DeviceTables {
     double* dot_partial = nullptr;
     int* counters = nullptr; // work-queue head
     const ItbPermBlk* pcopy = nullptr;
-    const ItbPermBlk* ptiled = nullptr;
+    const ItbPermChunk* pchunks = nullptr;
+    const ItbPermTile* ptiles = nullptr;
 };
 } // namespace itb
 
@@ -408,11 +409,13 @@ static int ensure_permute_tables(itb_ctx* c, itb_permute_plan* P) {
     auto* dev = new DeviceTables();
     Packer pk;
     const size_t o_c = pk.add(P->blks_copy.data(), P->blks_copy.size() * sizeof(ItbPermBlk));
-    const size_t o_t = pk.add(P->blks_tiled.data(), P->blks_tiled.size() * sizeof(ItbPermBlk));
+    const size_t o_ch = pk.add(P->chunk_items.data(), P->chunk_items.size() * sizeof(ItbPermChunk));
+    const size_t o_t = pk.add(P->tile_items.data(), P->tile_items.size() * sizeof(ItbPermTile));
     int rc = upload(c, pk, 0, dev);
     if (rc != ITB_OK) { delete dev; return rc; }
     dev->pcopy = (const ItbPermBlk*)((char*)dev->base + o_c);
-    dev->ptiled = (const ItbPermBlk*)((char*)dev->base + o_t);
+    dev->pchunks = (const ItbPermChunk*)((char*)dev->base + o_ch);
+    dev->ptiles = (const ItbPermTile*)((char*)dev->base + o_t);
     P->dev = dev;
     P->dev_ctx = c;
     return ITB_OK;
@@ -422,14 +425,22 @@ int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* dSrc, void* dDs
     if (!c || !P) { set_error("permute_run: null"); return ITB_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(c->device));
     if (P->S.dtype == ITB_F64 && P->D.dtype == ITB_F64 && ai != 0.0) { set_error("permute_run: complex alpha on a real destination"); return ITB_ERR_INVALID; }
-    if (!accumulate && P->need_zero && P->D.nelems > 0)
-        CUDA_TRY(cudaMemsetAsync(dDst, 0, (size_t)P->D.nelems * (P->D.dtype == ITB_C64 ? 16 : 8), c->stream));
+    if (!accumulate && P->need_zero && P->D.nelems > 0) {
+        // only the destination blocks without a source need zeros (permuteQDense fill-in)
+        const size_t es = P->D.dtype == ITB_C64 ? 16 : 8;
+        if (P->zero_ranges.size() <= 2 * 64) {
+            for (size_t i = 0; i + 1 < P->zero_ranges.size(); i += 2)
+                CUDA_TRY(cudaMemsetAsync((char*)dDst + (size_t)P->zero_ranges[i] * es, 0, (size_t)P->zero_ranges[i + 1] * es, c->stream));
+        } else {
+            CUDA_TRY(cudaMemsetAsync(dDst, 0, (size_t)P->D.nelems * es, c->stream));
+        }
+    }
     if (P->S.nblocks == 0) return ITB_OK;
     int rc = ensure_permute_tables(c, P);
     if (rc != ITB_OK) return rc;
     int launches = 0;
-    CUDA_TRY(launch_permute(P->S.dtype == ITB_C64, P->D.dtype == ITB_C64, P->dev->pcopy, (int)P->blks_copy.size(), P->items_copy,
-                            P->dev->ptiled, (int)P->blks_tiled.size(), P->items_tiled, dSrc, dDst, ar, ai, accumulate, c->stream, &launches));
+    CUDA_TRY(launch_permute(P->S.dtype == ITB_C64, P->D.dtype == ITB_C64, P->dev->pcopy, P->dev->pchunks, P->items_copy,
+                            P->dev->ptiles, P->items_tiled, dSrc, dDst, ar, ai, accumulate, c->stream, &launches));
     c->launches += launches;
     return ITB_OK;
 }

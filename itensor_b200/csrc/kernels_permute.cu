@@ -54,107 +54,110 @@ __device__ __forceinline__ int find_block(const ItbPermBlk* __restrict__ blks, i
 constexpr int PC_NT = 256, PC_CHUNK = 4096;
 
 template <bool CS, bool CD>
-__global__ void __launch_bounds__(PC_NT) perm_copy_kernel(const ItbPermBlk* __restrict__ blks, int nblk,
+__global__ void __launch_bounds__(PC_NT) perm_copy_kernel(const ItbPermBlk* __restrict__ blks, const ItbPermChunk* __restrict__ items,
                                                           const void* __restrict__ src_, void* __restrict__ dst_,
                                                           double ar, double ai, int accum) {
     using Op = ElemOp<CS, CD>;
     using S = typename Op::S; using D = typename Op::D;
     __shared__ ItbPermBlk sb;
-    const int64_t item = blockIdx.x;
-    if (threadIdx.x == 0) sb = blks[find_block(blks, nblk, item)];
+    const ItbPermChunk it = items[blockIdx.x];
+    if (threadIdx.x < (int)(sizeof(ItbPermBlk) / 8)) reinterpret_cast<int64_t*>(&sb)[threadIdx.x] = reinterpret_cast<const int64_t*>(blks + it.blk)[threadIdx.x];
     __syncthreads();
     const S* __restrict__ src = reinterpret_cast<const S*>(src_) + sb.s_off;
     D* __restrict__ dst = reinterpret_cast<D*>(dst_) + sb.d_off;
-    const int64_t e0 = (item - sb.item_begin) * PC_CHUNK;
+    const int64_t e0 = it.e0;
     const int n = sb.n;
-#pragma unroll 4
-    for (int i = 0; i < PC_CHUNK / PC_NT; ++i) {
-        const int64_t e = e0 + threadIdx.x + i * PC_NT;
-        if (e >= sb.nelem) break;
-        int64_t so = 0, rem = e;
+    constexpr int PER = PC_CHUNK / PC_NT, UB = 8; // UB independent loads in flight per thread
+#pragma unroll 1
+    for (int i0 = 0; i0 < PER; i0 += UB) {
+        S v[UB];
+        int64_t eo[UB];
 #pragma unroll
-        for (int d = 0; d < ITB_MAXG; ++d) {
-            if (d < n) {
-                if (d == n - 1) so += rem * sb.sstr[d];
-                else { const int64_t q = rem / sb.ext[d]; so += (rem - q * sb.ext[d]) * sb.sstr[d]; rem = q; }
+        for (int u = 0; u < UB; ++u) {
+            const int64_t e = e0 + threadIdx.x + (int64_t)(i0 + u) * PC_NT;
+            eo[u] = e;
+            v[u] = S();
+            if (e < sb.nelem) {
+                int64_t so = 0, rem = e;
+#pragma unroll
+                for (int d = 0; d < ITB_MAXG; ++d) {
+                    if (d < n) {
+                        if (d == n - 1) so += rem * sb.sstr[d];
+                        else { const int64_t q = rem / sb.ext[d]; so += (rem - q * sb.ext[d]) * sb.sstr[d]; rem = q; }
+                    }
+                }
+                v[u] = src[so];
             }
         }
-        const S v = src[so];
-        D old = D();
-        if (accum) old = dst[e];
-        dst[e] = Op::apply(v, old, ar, ai, accum);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            if (eo[u] < sb.nelem) {
+                D old = D();
+                if (accum) old = dst[eo[u]];
+                dst[eo[u]] = Op::apply(v[u], old, ar, ai, accum);
+            }
+        }
     }
 }
 
-constexpr int PT = 32, PT_ROWS = 8;
+// PT x PT tile per CTA (64 for 8-byte elements, 32 for 16-byte complex), 256 threads, every thread keeps
+// PT*PT/256 independent loads in flight before the tile is turned in shared memory.
+constexpr int PTN = 256;
 
-template <bool CS, bool CD>
-__global__ void __launch_bounds__(PT* PT_ROWS) perm_tile_kernel(const ItbPermBlk* __restrict__ blks, int nblk,
-                                                                const void* __restrict__ src_, void* __restrict__ dst_,
-                                                                double ar, double ai, int accum) {
+template <bool CS, bool CD, int PT>
+__global__ void __launch_bounds__(PTN) perm_tile_kernel(const ItbPermTile* __restrict__ items, const void* __restrict__ src_,
+                                                        void* __restrict__ dst_, double ar, double ai, int accum) {
     using Op = ElemOp<CS, CD>;
     using S = typename Op::S; using D = typename Op::D;
+    constexpr int ROWS = PTN / PT, PER = PT / ROWS; // rows covered per pass, passes
     __shared__ S tile[PT][PT + 1];
-    __shared__ ItbPermBlk sb;
-    __shared__ int64_t base_s, base_d;
-    __shared__ int t0_s, tT_s;
-    const int64_t item = blockIdx.x;
-    if (threadIdx.x == 0) {
-        sb = blks[find_block(blks, nblk, item)];
-        int64_t r = item - sb.item_begin;
-        t0_s = (int)(r % sb.tiles0); r /= sb.tiles0;
-        tT_s = (int)(r % sb.tilesT); r /= sb.tilesT;
-        int64_t bs = 0, bd = 0;
-        for (int d = 1; d < sb.n; ++d) {
-            if (d == sb.tdim) continue;
-            const int64_t i = r % sb.ext[d]; r /= sb.ext[d];
-            bs += i * sb.sstr[d]; bd += i * sb.dstr[d];
-        }
-        base_s = bs; base_d = bd;
-    }
-    __syncthreads();
-    const S* __restrict__ src = reinterpret_cast<const S*>(src_) + sb.s_off + base_s;
-    D* __restrict__ dst = reinterpret_cast<D*>(dst_) + sb.d_off + base_d;
+    const ItbPermTile it = items[blockIdx.x]; // one 48-byte record per CTA: no search, no index arithmetic
+    const S* __restrict__ src = reinterpret_cast<const S*>(src_) + it.s_base;
+    D* __restrict__ dst = reinterpret_cast<D*>(dst_) + it.d_base;
     const int tx = threadIdx.x % PT, ty = threadIdx.x / PT;
-    const int e0 = sb.ext[0], eT = sb.ext[sb.tdim];
-    const int64_t ss0 = sb.sstr[0], dsT = sb.dstr[sb.tdim];
-    // read: tx runs along the src-fastest dim (stride 1 in src)
+    // read: tx runs along the src-fastest dim (stride 1 in src); all PER loads issued before any store
     {
-        const int iT = tT_s * PT + tx;
+        S v[PER];
 #pragma unroll
-        for (int r = 0; r < PT / PT_ROWS; ++r) {
-            const int i0 = t0_s * PT + ty + r * PT_ROWS;
-            if (iT < eT && i0 < e0) tile[ty + r * PT_ROWS][tx] = src[(int64_t)iT + (int64_t)i0 * ss0];
+        for (int r = 0; r < PER; ++r) {
+            const int i0 = ty + r * ROWS;
+            v[r] = S();
+            if (tx < it.nT && i0 < it.n0) v[r] = src[(int64_t)tx + (int64_t)i0 * it.ss0];
         }
+#pragma unroll
+        for (int r = 0; r < PER; ++r) tile[ty + r * ROWS][tx] = v[r];
     }
     __syncthreads();
     // write: tx runs along the dst-fastest dim (stride 1 in dst)
-    {
-        const int i0 = t0_s * PT + tx;
+    if (accum) {
 #pragma unroll
-        for (int r = 0; r < PT / PT_ROWS; ++r) {
-            const int iT = tT_s * PT + ty + r * PT_ROWS;
-            if (iT < eT && i0 < e0) {
-                const int64_t o = (int64_t)i0 + (int64_t)iT * dsT;
-                D old = D();
-                if (accum) old = dst[o];
-                dst[o] = Op::apply(tile[tx][ty + r * PT_ROWS], old, ar, ai, accum);
+        for (int r = 0; r < PER; ++r) {
+            const int iT = ty + r * ROWS;
+            if (iT < it.nT && tx < it.n0) {
+                const int64_t o = (int64_t)tx + (int64_t)iT * it.dsT;
+                dst[o] = Op::apply(tile[tx][iT], dst[o], ar, ai, true);
             }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < PER; ++r) {
+            const int iT = ty + r * ROWS;
+            if (iT < it.nT && tx < it.n0) dst[(int64_t)tx + (int64_t)iT * it.dsT] = Op::apply(tile[tx][iT], D(), ar, ai, false);
         }
     }
 }
 
 template <bool CS, bool CD>
-static cudaError_t launch_t(const ItbPermBlk* bc, int nbc, int64_t items_c, const ItbPermBlk* bt, int nbt, int64_t items_t,
+static cudaError_t launch_t(const ItbPermBlk* bc, const ItbPermChunk* chunks, int64_t items_c, const ItbPermTile* tiles, int64_t items_t,
                             const void* src, void* dst, double ar, double ai, int accum, cudaStream_t st, int* launches) {
     if (items_c > 0) {
-        perm_copy_kernel<CS, CD><<<(unsigned)items_c, PC_NT, 0, st>>>(bc, nbc, src, dst, ar, ai, accum);
+        perm_copy_kernel<CS, CD><<<(unsigned)items_c, PC_NT, 0, st>>>(bc, chunks, src, dst, ar, ai, accum);
         ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     if (items_t > 0) {
-        perm_tile_kernel<CS, CD><<<(unsigned)items_t, PT * PT_ROWS, 0, st>>>(bt, nbt, src, dst, ar, ai, accum);
+        perm_tile_kernel<CS, CD, CS ? 32 : 64><<<(unsigned)items_t, PTN, 0, st>>>(tiles, src, dst, ar, ai, accum);
         ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -162,12 +165,12 @@ static cudaError_t launch_t(const ItbPermBlk* bc, int nbc, int64_t items_c, cons
     return cudaSuccess;
 }
 
-cudaError_t launch_permute(int src_cplx, int dst_cplx, const ItbPermBlk* bc, int nbc, int64_t items_c, const ItbPermBlk* bt,
-                           int nbt, int64_t items_t, const void* src, void* dst, double ar, double ai, int accum,
+cudaError_t launch_permute(int src_cplx, int dst_cplx, const ItbPermBlk* bc, const ItbPermChunk* chunks, int64_t items_c,
+                           const ItbPermTile* tiles, int64_t items_t, const void* src, void* dst, double ar, double ai, int accum,
                            cudaStream_t st, int* launches) {
-    if (src_cplx && dst_cplx) return launch_t<true, true>(bc, nbc, items_c, bt, nbt, items_t, src, dst, ar, ai, accum, st, launches);
-    if (!src_cplx && dst_cplx) return launch_t<false, true>(bc, nbc, items_c, bt, nbt, items_t, src, dst, ar, ai, accum, st, launches);
-    return launch_t<false, false>(bc, nbc, items_c, bt, nbt, items_t, src, dst, ar, ai, accum, st, launches);
+    if (src_cplx && dst_cplx) return launch_t<true, true>(bc, chunks, items_c, tiles, items_t, src, dst, ar, ai, accum, st, launches);
+    if (!src_cplx && dst_cplx) return launch_t<false, true>(bc, chunks, items_c, tiles, items_t, src, dst, ar, ai, accum, st, launches);
+    return launch_t<false, false>(bc, chunks, items_c, tiles, items_t, src, dst, ar, ai, accum, st, launches);
 }
 
 } // namespace itb

@@ -452,7 +452,7 @@ int build_permute_plan(itb_permute_plan& P) {
         for (int j = 0; j < r; ++j) key[j] = D.block(b)[j];
         dpos[key] = b;
     }
-    P.blks_copy.clear(); P.blks_tiled.clear();
+    P.blks_copy.clear(); P.blks_tiled.clear(); P.chunk_items.clear(); P.tile_items.clear();
     P.items_copy = P.items_tiled = 0;
     P.bytes = 0;
     std::vector<char> hit(D.nblocks, 0);
@@ -502,21 +502,54 @@ int build_permute_plan(itb_permute_plan& P) {
         pb.tdim = tdim;
         if (tdim == 0) {
             pb.item_begin = P.items_copy;
-            P.items_copy += (nelem + kPermCopyChunk - 1) / kPermCopyChunk;
+            const int64_t nch = (nelem + kPermCopyChunk - 1) / kPermCopyChunk;
+            for (int64_t c = 0; c < nch; ++c) P.chunk_items.push_back({(int32_t)P.blks_copy.size(), 0, c * kPermCopyChunk});
+            P.items_copy += nch;
             P.blks_copy.push_back(pb);
         } else {
-            pb.tiles0 = (pb.ext[0] + kPermTile - 1) / kPermTile;
-            pb.tilesT = (pb.ext[tdim] + kPermTile - 1) / kPermTile;
+            const int tile = (cs == 2) ? 32 : 64; // must match perm_tile_kernel's PT (kernels_permute.cu)
+            pb.tiles0 = (pb.ext[0] + tile - 1) / tile;
+            pb.tilesT = (pb.ext[tdim] + tile - 1) / tile;
             int64_t rest = 1;
             for (int d = 1; d < pb.n; ++d) if (d != tdim) rest *= pb.ext[d];
             pb.item_begin = P.items_tiled;
+            // enumerate tiles: dim-0 tiles fastest, then dim-T tiles, then the remaining dims (odometer)
+            std::vector<int64_t> idx(pb.n, 0);
+            for (int64_t rr = 0; rr < rest; ++rr) {
+                int64_t bs = 0, bd = 0;
+                for (int d = 1; d < pb.n; ++d) if (d != tdim) { bs += idx[d] * pb.sstr[d]; bd += idx[d] * pb.dstr[d]; }
+                for (int32_t tT = 0; tT < pb.tilesT; ++tT)
+                    for (int32_t t0 = 0; t0 < pb.tiles0; ++t0) {
+                        ItbPermTile it;
+                        it.s_base = pb.s_off + bs + (int64_t)tT * tile * pb.sstr[tdim] + (int64_t)t0 * tile * pb.sstr[0];
+                        it.d_base = pb.d_off + bd + (int64_t)tT * tile * pb.dstr[tdim] + (int64_t)t0 * tile * pb.dstr[0];
+                        it.ss0 = pb.sstr[0];
+                        it.dsT = pb.dstr[tdim];
+                        it.n0 = std::min<int32_t>(tile, pb.ext[0] - t0 * tile);
+                        it.nT = std::min<int32_t>(tile, pb.ext[tdim] - tT * tile);
+                        P.tile_items.push_back(it);
+                    }
+                for (int d = 1; d < pb.n; ++d) {
+                    if (d == tdim) continue;
+                    if (++idx[d] < pb.ext[d]) break;
+                    idx[d] = 0;
+                }
+            }
             P.items_tiled += (int64_t)pb.tiles0 * pb.tilesT * rest;
             P.blks_tiled.push_back(pb);
         }
         P.bytes += nelem * 8 * ((S.dtype == ITB_C64 ? 2 : 1) + (D.dtype == ITB_C64 ? 2 : 1));
     }
     P.need_zero = false;
-    for (auto h : hit) if (!h) P.need_zero = true;
+    P.zero_ranges.clear();
+    for (int64_t b = 0; b < D.nblocks; ++b) {
+        if (hit[b]) continue;
+        P.need_zero = true;
+        int64_t sz = 1;
+        for (int j = 0; j < r; ++j) sz *= D.ext(j, D.block(b)[j]);
+        if (!P.zero_ranges.empty() && P.zero_ranges[P.zero_ranges.size() - 2] + P.zero_ranges.back() == D.offsets[b]) P.zero_ranges.back() += sz;
+        else { P.zero_ranges.push_back(D.offsets[b]); P.zero_ranges.push_back(sz); }
+    }
     return ITB_OK;
 }
 

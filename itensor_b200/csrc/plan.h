@@ -67,7 +67,10 @@ struct itb_permute_plan {
     std::vector<ItbPermBlk> blks_copy;  // blocks whose src/dst fastest dims coincide
     std::vector<ItbPermBlk> blks_tiled; // blocks needing a shared-memory transpose
     int64_t items_copy = 0, items_tiled = 0;
+    std::vector<ItbPermChunk> chunk_items; // one per copy-path work item
+    std::vector<ItbPermTile> tile_items;   // one per transposing-path work item
     bool need_zero = false; // dst has blocks no src block maps to
+    std::vector<int64_t> zero_ranges; // (element offset, element count) of those blocks, merged when adjacent
     int64_t bytes = 0;
     itb::DeviceTables* dev = nullptr;
     void* dev_ctx = nullptr;

@@ -86,3 +86,13 @@ struct ItbPermBlk {
     int32_t cs;             // 2 if elements are complex pairs moved as units, else 1
     int32_t promote;        // 1: src real -> dst complex
 };
+// per-work-item records (one global load per CTA instead of a block search + index arithmetic)
+struct ItbPermTile { // transposing path: one PT x PT tile
+    int64_t s_base, d_base; // element offsets of the tile's origin in src / dst
+    int64_t ss0, dsT;       // src stride of the dst-fastest dim, dst stride of the src-fastest dim
+    int32_t n0, nT;         // valid extent of the tile along dst-fastest / src-fastest dim (<= PT)
+};
+struct ItbPermChunk { // copy-like path: PC_CHUNK consecutive dst elements of one block
+    int32_t blk, pad_;
+    int64_t e0;
+};
