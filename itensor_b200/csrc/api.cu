@@ -76,6 +76,8 @@ struct itb_ctx {
     double* h_result = nullptr; // pinned 4 doubles
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool profile = false;
+    cudaStream_t aux = nullptr;          // side stream: small streaming / split-K-dot launches overlap the tile kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float last_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t pev[10] = {};
 };
@@ -206,6 +208,9 @@ int itb_ctx_create(int device, itb_ctx** out) {
     CUDA_TRY(cudaMallocHost(&c->h_result, 8 * sizeof(double)));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *out = c;
     return ITB_OK;
 }
@@ -222,6 +227,9 @@ int itb_ctx_destroy(itb_ctx* c) {
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ITB_OK;
@@ -350,28 +358,45 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
         for (auto& e : c->pev) CUDA_TRY(cudaEventCreate(&e));
 #define PROF_BEGIN(i) do { if (c->profile) CUDA_TRY(cudaEventRecord(c->pev[2 * (i)], c->stream)); } while (0)
 #define PROF_END(i) do { if (c->profile) { CUDA_TRY(cudaEventRecord(c->pev[2 * (i) + 1], c->stream)); ran[i] = true; } } while (0)
-    if (!P->tiles.empty()) {
+    // The streaming and split-K-dot classes write disjoint C blocks; when the tile kernel also runs they go to
+    // the side stream FIRST (fork/join with events) so that their latency-bound CTAs overlap the persistent
+    // tile kernel instead of trailing it. In profile mode everything stays on one stream for per-class timing.
+    const bool has_tiles = !P->tiles.empty();
+    const bool has_stream = !P->skinny.empty() || !P->skinny_q4.empty() || !P->skinny_q8.empty();
+    const bool has_dots = !P->dots.empty();
+    const bool fork = has_tiles && (has_stream || has_dots) && !c->profile;
+    cudaStream_t side = fork ? c->aux : c->stream;
+    if (fork) {
+        CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+    }
+    auto launch_side = [&]() -> int {
+        if (has_stream) {
+            PROF_BEGIN(3);
+            CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->skinny_q4, (int)P->skinny_q4.size(), d->skinny_q8,
+                                   (int)P->skinny_q8.size(), d->cblks, d->pairs, A, B, C, side));
+            PROF_END(3);
+            c->launches += (P->skinny.empty() ? 0 : 1) + (P->skinny_q4.empty() ? 0 : 1) + (P->skinny_q8.empty() ? 0 : 1);
+        }
+        if (has_dots) {
+            PROF_BEGIN(4);
+            CUDA_TRY(launch_dot(d->dots, (int)P->dots.size(), d->dot_outs, (int)P->dot_outs.size(), d->cblks, d->pairs, A, B, d->dot_partial, C, side));
+            PROF_END(4);
+            c->launches += 2;
+        }
+        return ITB_OK;
+    };
+    if (fork) { rc = launch_side(); if (rc != ITB_OK) return rc; CUDA_TRY(cudaEventRecord(c->ev_join, c->aux)); }
+    if (has_tiles) {
         if (P->ws_slots > 0) { rc = ensure_ws(c, (size_t)P->ws_slots * ITB_WS_TILE); if (rc != ITB_OK) return rc; }
-        CUDA_TRY(cudaMemsetAsync(d->counters, 0, sizeof(int), c->stream));
         PROF_BEGIN(0);
         CUDA_TRY(launch_gemm(d->tiles, (int)P->tiles.size(), d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
                              d->counters, c->num_sms, c->stream));
         PROF_END(0);
         c->launches += P->splits.empty() ? 1 : 2;
     }
-    if (!P->skinny.empty() || !P->skinny_q4.empty() || !P->skinny_q8.empty()) {
-        PROF_BEGIN(3);
-        CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->skinny_q4, (int)P->skinny_q4.size(), d->skinny_q8,
-                               (int)P->skinny_q8.size(), d->cblks, d->pairs, A, B, C, c->stream));
-        PROF_END(3);
-        c->launches += (P->skinny.empty() ? 0 : 1) + (P->skinny_q4.empty() ? 0 : 1) + (P->skinny_q8.empty() ? 0 : 1);
-    }
-    if (!P->dots.empty()) {
-        PROF_BEGIN(4);
-        CUDA_TRY(launch_dot(d->dots, (int)P->dots.size(), d->dot_outs, (int)P->dot_outs.size(), d->cblks, d->pairs, A, B, d->dot_partial, C, c->stream));
-        PROF_END(4);
-        c->launches += 2;
-    }
+    if (fork) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    else { rc = launch_side(); if (rc != ITB_OK) return rc; }
 #undef PROF_BEGIN
 #undef PROF_END
     if (c->profile) {

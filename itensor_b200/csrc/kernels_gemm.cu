@@ -350,15 +350,18 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
     }
 }
 
-// C tile = sum of its split-K partials, in split order (deterministic)
+// C tile = sum of its split-K partials, in split order (deterministic). SR_PARTS CTAs per tile.
+constexpr int SR_PARTS = 8;
 __global__ void __launch_bounds__(256) bsc_splitk_reduce_kernel(const ItbSplitOut* __restrict__ outs, const ItbCBlk* __restrict__ cblks,
                                                                  const double* __restrict__ ws, double* __restrict__ C) {
-    const ItbSplitOut o = outs[blockIdx.x];
+    const ItbSplitOut o = outs[blockIdx.x / SR_PARTS];
+    const int part = blockIdx.x % SR_PARTS;
     const ItbCBlk* cb = cblks + o.cblk;
     const int T = o.cfg == 0 ? 128 : (o.cfg == 1 ? 64 : 32);
     const int M = cb->M, N = cb->N, m0 = o.tm * T, n0 = o.tn * T;
     double* __restrict__ Cp = C + cb->c_off;
-    for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+    const int per = T * T / SR_PARTS;
+    for (int e = part * per + threadIdx.x; e < (part + 1) * per; e += blockDim.x) {
         const int ml = e % T, nl = e / T;
         const int m = m0 + ml, n = n0 + nl;
         if (m >= M || n >= N) continue;
@@ -724,7 +727,7 @@ cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* sou
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {
-        bsc_splitk_reduce_kernel<<<nsouts, 256, 0, st>>>(souts, cblks, ws, C);
+        bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C);
         e = cudaGetLastError();
     }
     return e;

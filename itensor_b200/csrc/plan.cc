@@ -345,7 +345,7 @@ int build_contract_tables(itb_contract_plan& P) {
                 }
             }
             P.dot_outs.push_back(o);
-        } else if (std::min(M, N) <= kSkinnyMax && cb.ksum <= kSkinnyQMaxK) {
+        } else if (std::min(M, N) <= kSkinnyMax && cb.ksum <= kSkinnyQMaxK && M * N >= kSkinnyMinElems) {
             // HBM-bound streaming class: short side <= 8 and a short K loop (the MPO steps of H_eff*phi)
             P.class_flops[3] += cflops;
             const int long_is_n = (N > M) ? 1 : 0;

@@ -90,6 +90,7 @@ constexpr int kSkinnyRows = 1024;    // long-side rows per streaming item (4 per
 constexpr int kSkinnyQRows = 8192;   // rows per item of the small-K fast path (8 batches of 4 rows/thread)
 constexpr int kSkinnyQMaxK = 64;     // sum of K over the pairs of a C block / max pairs for the fast path
 constexpr int kSkinnyQMaxPairs = 8;
+constexpr int64_t kSkinnyMinElems = 0;       // (routing small streaming blocks into 32x32 tiles measured 8x slower: disabled)
 constexpr int kNumSMs = 148;         // B200: persistent grid size the split-K heuristic balances for
 constexpr int kSkinnyMax = 8;        // short side <= this -> streaming kernel
 constexpr int kDotMaxMN = 4;        // M*N <= this -> reduction kernel (scalar results, re/im pairs)
