@@ -156,6 +156,20 @@ int itb_permute_run(itb_ctx* ctx, itb_permute_plan* plan, const void* dSrc, void
 int itb_permute_host(itb_ctx* ctx, itb_permute_plan* plan, const void* hSrc, void* hDst,
                      double alpha_re, double alpha_im, int accumulate);
 
+/* Generic strided block copies (the kernel behind QCombiner combine/uncombine, itensor/itdata/qcombiner.cc:125-301,
+ * and any sub-block scatter/gather): item i copies an n-dim box  dst[d_off + sum_j i_j*dstr_j] = src[s_off + sum_j i_j*sstr_j].
+ * Offsets/strides in ELEMENTS of the respective dtype. The returned plan is run with itb_permute_run (alpha, accumulate
+ * as there; nothing is zero-filled — use itb_memset0 on the destination first if it needs zeros). */
+typedef struct itb_copy_item {
+    int64_t s_off, d_off;
+    int32_t n, pad_;
+    int64_t ext[ITB_MAX_ORDER];
+    int64_t sstr[ITB_MAX_ORDER];
+    int64_t dstr[ITB_MAX_ORDER];
+} itb_copy_item;
+int itb_blockcopy_plan_create(int64_t nitems, const itb_copy_item* items, int32_t src_dtype, int32_t dst_dtype,
+                              itb_permute_plan** out);
+
 /* ---- BLAS-1 style storage tasks (n counts ELEMENTS of the given dtype) -------------------- */
 int itb_nrm2(itb_ctx* ctx, int32_t dtype, int64_t n, const void* dX, double* out); /* syncs */
 int itb_scal(itb_ctx* ctx, int32_t dtype, int64_t n, void* dX, double alpha_re, double alpha_im);
@@ -168,6 +182,14 @@ int itb_take_part(itb_ctx* ctx, int64_t n, const void* dX, void* dY, int imag);
 int itb_get_elt(itb_ctx* ctx, int32_t dtype, const void* dX, int64_t offset, double out[2]); /* syncs */
 int itb_dot(itb_ctx* ctx, int32_t dtype, int64_t n, const void* dX, const void* dY, int conj_x,
             double out[2]); /* syncs */
+
+/* ---- per-block eigh / SVD for the svdBond path, host buffers in/out ------------------------ */
+/* LAPACK dsyev('V','U') / zheev semantics (itensor/tensor/lapack_wrap.cc:322-347,678-706): A (n x n, column-major)
+ * is overwritten by the eigenvectors, w receives the eigenvalues in ascending order. cuSOLVER syevd. */
+int itb_syevd_host(itb_ctx* ctx, int32_t dtype, int32_t n, void* hA, double* hW, int32_t* info);
+/* LAPACK gesdd(jobz='S') semantics (lapack_wrap.cc:365-486): thin SVD A = U diag(s) VT of an m x n column-major
+ * matrix (destroyed); U is m x l (ldu=m), VT is l x n (ldvt=l), l=min(m,n). cuSOLVER gesvd. */
+int itb_gesvd_host(itb_ctx* ctx, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement

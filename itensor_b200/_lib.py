@@ -89,6 +89,7 @@ SYMBOLS = {
     "itb_contract_run": (C.c_int, [_P, _P, _P, _P, _P]),
     "itb_contract_host": (C.c_int, [_P, _P, _P, _P, _P]),
     "itb_permute_plan_create": (C.c_int, [_DESCP, _DESCP, _I32P, C.POINTER(_P)]),
+    "itb_blockcopy_plan_create": (C.c_int, [C.c_int64, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "itb_permute_plan_destroy": (C.c_int, [_P]),
     "itb_permute_plan_bytes": (C.c_int64, [_P]),
     "itb_permute_run": (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_int]),
@@ -102,6 +103,8 @@ SYMBOLS = {
     "itb_take_part": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int]),
     "itb_get_elt": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _DP]),
     "itb_dot": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, C.c_int, _DP]),
+    "itb_syevd_host": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _DP, C.POINTER(C.c_int32)]),
+    "itb_gesvd_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _DP, _P, _P, C.POINTER(C.c_int32)]),
     "itb_peak_fp64": (C.c_int, [_P, C.c_int, C.c_int, _DP]),
     "itb_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "itb_contract_last_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

@@ -56,7 +56,15 @@ struct DeviceTables {
 
 using namespace itb;
 
+struct itb_solver;
+extern "C" {
+int itb_solver_create(void* stream, itb_solver** out);
+int itb_solver_syevd(itb_solver* s, int32_t dtype, int32_t n, void* hA, double* hW, int32_t* info);
+int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info);
+}
+
 struct itb_ctx {
+    itb_solver* solver = nullptr;
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -588,6 +596,24 @@ int itb_peak_fp64(itb_ctx* c, int which, int iters, double* tflops) {
     *tflops = flops / (ms * 1e-3) / 1e12;
     c->launches += 2;
     return ITB_OK;
+}
+
+static int ensure_solver(itb_ctx* c) {
+    if (c->solver) return ITB_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    return itb_solver_create((void*)c->stream, &c->solver);
+}
+int itb_syevd_host(itb_ctx* c, int32_t dtype, int32_t n, void* hA, double* hW, int32_t* info) {
+    int rc = ensure_solver(c);
+    if (rc != ITB_OK) return rc;
+    c->launches += 1;
+    return itb_solver_syevd(c->solver, dtype, n, hA, hW, info);
+}
+int itb_gesvd_host(itb_ctx* c, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info) {
+    int rc = ensure_solver(c);
+    if (rc != ITB_OK) return rc;
+    c->launches += 1;
+    return itb_solver_gesvd(c->solver, dtype, m, n, hA, hS, hU, hVT, info);
 }
 
 int itb_ctx_set_profile(itb_ctx* c, int profile) { c->profile = profile != 0; return ITB_OK; }

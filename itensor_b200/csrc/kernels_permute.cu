@@ -71,27 +71,32 @@ __global__ void __launch_bounds__(PC_NT) perm_copy_kernel(const ItbPermBlk* __re
 #pragma unroll 1
     for (int i0 = 0; i0 < PER; i0 += UB) {
         S v[UB];
-        int64_t eo[UB];
+        int64_t eo[UB]; // destination offset (or -1 past the end)
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int64_t e = e0 + threadIdx.x + (int64_t)(i0 + u) * PC_NT;
-            eo[u] = e;
+            eo[u] = -1;
             v[u] = S();
             if (e < sb.nelem) {
-                int64_t so = 0, rem = e;
+                int64_t so = 0, dof = 0, rem = e;
 #pragma unroll
                 for (int d = 0; d < ITB_MAXG; ++d) {
                     if (d < n) {
-                        if (d == n - 1) so += rem * sb.sstr[d];
-                        else { const int64_t q = rem / sb.ext[d]; so += (rem - q * sb.ext[d]) * sb.sstr[d]; rem = q; }
+                        if (d == n - 1) { so += rem * sb.sstr[d]; dof += rem * sb.dstr[d]; }
+                        else {
+                            const int64_t q = rem / sb.ext[d], i = rem - q * sb.ext[d];
+                            so += i * sb.sstr[d]; dof += i * sb.dstr[d];
+                            rem = q;
+                        }
                     }
                 }
                 v[u] = src[so];
+                eo[u] = dof;
             }
         }
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-            if (eo[u] < sb.nelem) {
+            if (eo[u] >= 0) {
                 D old = D();
                 if (accum) old = dst[eo[u]];
                 dst[eo[u]] = Op::apply(v[u], old, ar, ai, accum);

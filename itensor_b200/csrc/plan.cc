@@ -425,6 +425,89 @@ int build_contract_tables(itb_contract_plan& P) {
     return ITB_OK;
 }
 
+// ---- strided block copies (shared by permute plans and the generic block-copy plans) -------------------
+// One source block -> one destination (sub-)block, arbitrary strides on both sides. Dims are put in
+// destination order (smallest dst stride first), unit extents dropped, neighbours fused when contiguous in
+// BOTH tensors. If the src-fastest dim differs from the dst-fastest one the block goes to the shared-memory
+// transposing path (one record per tile), else to the direct path (one record per 4096-element chunk).
+struct CopyDim { int64_t ext, sstr, dstr; };
+
+static int add_copy_block(itb_permute_plan& P, int64_t s_off, int64_t d_off, std::vector<CopyDim> in, int cs, int promote) {
+    std::vector<CopyDim> dims;
+    std::stable_sort(in.begin(), in.end(), [](const CopyDim& x, const CopyDim& y) { return x.dstr < y.dstr; });
+    int64_t nelem = 1;
+    for (auto& d : in) {
+        nelem *= d.ext;
+        if (d.ext == 1) continue;
+        if (!dims.empty() && d.sstr == dims.back().sstr * dims.back().ext && d.dstr == dims.back().dstr * dims.back().ext) {
+            dims.back().ext *= d.ext;
+            continue;
+        }
+        dims.push_back(d);
+    }
+    if (nelem == 0) return ITB_OK;
+    if (dims.empty()) dims.push_back({1, 1, 1});
+    if ((int)dims.size() > ITB_MAXG) { set_error("permute: more than ITB_MAXG non-fusable indices"); return ITB_ERR_UNSUPPORTED; }
+    ItbPermBlk pb;
+    std::memset(&pb, 0, sizeof(pb));
+    pb.s_off = s_off;
+    pb.d_off = d_off;
+    pb.n = (int32_t)dims.size();
+    pb.nelem = nelem;
+    pb.cs = cs;
+    pb.promote = promote;
+    for (int d = 0; d < ITB_MAXG; ++d) pb.ext[d] = 1;
+    int tdim = 0;
+    for (size_t d = 0; d < dims.size(); ++d) {
+        if (dims[d].ext >= (1ll << 31)) { set_error("permute: fused extent exceeds 2^31"); return ITB_ERR_UNSUPPORTED; }
+        pb.ext[d] = (int32_t)dims[d].ext;
+        pb.sstr[d] = dims[d].sstr;
+        pb.dstr[d] = dims[d].dstr;
+        if (dims[d].sstr == 1) tdim = (int)d;
+    }
+    if (pb.dstr[0] != 1) tdim = 0; // destination not unit-stride along its fastest dim: direct path only
+    pb.tdim = tdim;
+    if (tdim == 0) {
+        pb.item_begin = P.items_copy;
+        const int64_t nch = (nelem + kPermCopyChunk - 1) / kPermCopyChunk;
+        for (int64_t c = 0; c < nch; ++c) P.chunk_items.push_back({(int32_t)P.blks_copy.size(), 0, c * kPermCopyChunk});
+        P.items_copy += nch;
+        P.blks_copy.push_back(pb);
+    } else {
+        const int tile = (cs == 2) ? 32 : 64; // must match perm_tile_kernel's PT (kernels_permute.cu)
+        pb.tiles0 = (pb.ext[0] + tile - 1) / tile;
+        pb.tilesT = (pb.ext[tdim] + tile - 1) / tile;
+        int64_t rest = 1;
+        for (int d = 1; d < pb.n; ++d) if (d != tdim) rest *= pb.ext[d];
+        pb.item_begin = P.items_tiled;
+        // enumerate tiles: dim-0 tiles fastest, then dim-T tiles, then the remaining dims (odometer)
+        std::vector<int64_t> idx(pb.n, 0);
+        for (int64_t rr = 0; rr < rest; ++rr) {
+            int64_t bs = 0, bd = 0;
+            for (int d = 1; d < pb.n; ++d) if (d != tdim) { bs += idx[d] * pb.sstr[d]; bd += idx[d] * pb.dstr[d]; }
+            for (int32_t tT = 0; tT < pb.tilesT; ++tT)
+                for (int32_t t0 = 0; t0 < pb.tiles0; ++t0) {
+                    ItbPermTile it;
+                    it.s_base = pb.s_off + bs + (int64_t)tT * tile * pb.sstr[tdim] + (int64_t)t0 * tile * pb.sstr[0];
+                    it.d_base = pb.d_off + bd + (int64_t)tT * tile * pb.dstr[tdim] + (int64_t)t0 * tile * pb.dstr[0];
+                    it.ss0 = pb.sstr[0];
+                    it.dsT = pb.dstr[tdim];
+                    it.n0 = std::min<int32_t>(tile, pb.ext[0] - t0 * tile);
+                    it.nT = std::min<int32_t>(tile, pb.ext[tdim] - tT * tile);
+                    P.tile_items.push_back(it);
+                }
+            for (int d = 1; d < pb.n; ++d) {
+                if (d == tdim) continue;
+                if (++idx[d] < pb.ext[d]) break;
+                idx[d] = 0;
+            }
+        }
+        P.items_tiled += (int64_t)pb.tiles0 * pb.tilesT * rest;
+        P.blks_tiled.push_back(pb);
+    }
+    return ITB_OK;
+}
+
 // ---- permute -------------------------------------------------------------------------------------
 int build_permute_plan(itb_permute_plan& P) {
     const TensorStruct &S = P.S, &D = P.D;
@@ -470,74 +553,10 @@ int build_permute_plan(itb_permute_plan& P) {
         const int64_t nelem = s;
         s = 1;
         for (int j = 0; j < r; ++j) { ds[j] = s; s *= D.ext(j, key[j]); }
-        // dims in dst order, unit dims dropped, neighbours fused when contiguous in src too
-        struct PD { int64_t ext, sstr, dstr; };
-        std::vector<PD> dims;
-        for (int j = 0; j < r; ++j) {
-            const int64_t e = D.ext(j, key[j]);
-            if (e == 1) continue;
-            const int64_t sst = ss[inv[j]];
-            if (!dims.empty() && sst == dims.back().sstr * dims.back().ext) { dims.back().ext *= e; continue; }
-            dims.push_back({e, sst, ds[j]});
-        }
-        if (dims.empty()) dims.push_back({1, 1, 1});
-        if ((int)dims.size() > ITB_MAXG) { set_error("permute: more than ITB_MAXG non-fusable indices"); return ITB_ERR_UNSUPPORTED; }
-        ItbPermBlk pb;
-        std::memset(&pb, 0, sizeof(pb));
-        pb.s_off = S.offsets[b];
-        pb.d_off = D.offsets[db];
-        pb.n = (int32_t)dims.size();
-        pb.nelem = nelem;
-        pb.cs = cs;
-        pb.promote = promote;
-        for (int d = 0; d < ITB_MAXG; ++d) pb.ext[d] = 1;
-        int tdim = 0;
-        for (size_t d = 0; d < dims.size(); ++d) {
-            if (dims[d].ext >= (1ll << 31)) { set_error("permute: fused extent exceeds 2^31"); return ITB_ERR_UNSUPPORTED; }
-            pb.ext[d] = (int32_t)dims[d].ext;
-            pb.sstr[d] = dims[d].sstr;
-            pb.dstr[d] = dims[d].dstr;
-            if (dims[d].sstr == 1) tdim = (int)d;
-        }
-        pb.tdim = tdim;
-        if (tdim == 0) {
-            pb.item_begin = P.items_copy;
-            const int64_t nch = (nelem + kPermCopyChunk - 1) / kPermCopyChunk;
-            for (int64_t c = 0; c < nch; ++c) P.chunk_items.push_back({(int32_t)P.blks_copy.size(), 0, c * kPermCopyChunk});
-            P.items_copy += nch;
-            P.blks_copy.push_back(pb);
-        } else {
-            const int tile = (cs == 2) ? 32 : 64; // must match perm_tile_kernel's PT (kernels_permute.cu)
-            pb.tiles0 = (pb.ext[0] + tile - 1) / tile;
-            pb.tilesT = (pb.ext[tdim] + tile - 1) / tile;
-            int64_t rest = 1;
-            for (int d = 1; d < pb.n; ++d) if (d != tdim) rest *= pb.ext[d];
-            pb.item_begin = P.items_tiled;
-            // enumerate tiles: dim-0 tiles fastest, then dim-T tiles, then the remaining dims (odometer)
-            std::vector<int64_t> idx(pb.n, 0);
-            for (int64_t rr = 0; rr < rest; ++rr) {
-                int64_t bs = 0, bd = 0;
-                for (int d = 1; d < pb.n; ++d) if (d != tdim) { bs += idx[d] * pb.sstr[d]; bd += idx[d] * pb.dstr[d]; }
-                for (int32_t tT = 0; tT < pb.tilesT; ++tT)
-                    for (int32_t t0 = 0; t0 < pb.tiles0; ++t0) {
-                        ItbPermTile it;
-                        it.s_base = pb.s_off + bs + (int64_t)tT * tile * pb.sstr[tdim] + (int64_t)t0 * tile * pb.sstr[0];
-                        it.d_base = pb.d_off + bd + (int64_t)tT * tile * pb.dstr[tdim] + (int64_t)t0 * tile * pb.dstr[0];
-                        it.ss0 = pb.sstr[0];
-                        it.dsT = pb.dstr[tdim];
-                        it.n0 = std::min<int32_t>(tile, pb.ext[0] - t0 * tile);
-                        it.nT = std::min<int32_t>(tile, pb.ext[tdim] - tT * tile);
-                        P.tile_items.push_back(it);
-                    }
-                for (int d = 1; d < pb.n; ++d) {
-                    if (d == tdim) continue;
-                    if (++idx[d] < pb.ext[d]) break;
-                    idx[d] = 0;
-                }
-            }
-            P.items_tiled += (int64_t)pb.tiles0 * pb.tilesT * rest;
-            P.blks_tiled.push_back(pb);
-        }
+        std::vector<CopyDim> dims;
+        for (int j = 0; j < r; ++j) dims.push_back({D.ext(j, key[j]), ss[inv[j]], ds[j]});
+        int rc2 = add_copy_block(P, S.offsets[b], D.offsets[db], dims, cs, promote);
+        if (rc2 != ITB_OK) return rc2;
         P.bytes += nelem * 8 * ((S.dtype == ITB_C64 ? 2 : 1) + (D.dtype == ITB_C64 ? 2 : 1));
     }
     P.need_zero = false;
@@ -641,6 +660,31 @@ int itb_permute_plan_create(const itb_tensor_desc* src, const itb_tensor_desc* d
         rc = build_permute_plan(*P);
     }
     if (rc != ITB_OK) { delete P; return rc; }
+    *out = P;
+    return ITB_OK;
+}
+int itb_blockcopy_plan_create(int64_t nitems, const itb_copy_item* items, int32_t src_dtype, int32_t dst_dtype,
+                              itb_permute_plan** out) {
+    if (!out || (nitems > 0 && !items)) { set_error("blockcopy_plan_create: null"); return ITB_ERR_INVALID; }
+    *out = nullptr;
+    if (src_dtype == ITB_C64 && dst_dtype == ITB_F64) { set_error("blockcopy: cannot demote complex to real"); return ITB_ERR_INVALID; }
+    auto* P = new itb_permute_plan();
+    P->S.dtype = src_dtype;
+    P->D.dtype = dst_dtype;
+    P->S.nblocks = nitems; // (only used to skip empty plans)
+    const int cs = src_dtype == ITB_C64 ? 2 : 1;
+    const int promote = (src_dtype == ITB_F64 && dst_dtype == ITB_C64) ? 1 : 0;
+    for (int64_t i = 0; i < nitems; ++i) {
+        const itb_copy_item& it = items[i];
+        if (it.n < 0 || it.n > ITB_MAX_ORDER) { delete P; set_error("blockcopy: bad item order"); return ITB_ERR_INVALID; }
+        std::vector<CopyDim> dims;
+        int64_t ne = 1;
+        for (int d = 0; d < it.n; ++d) { dims.push_back({it.ext[d], it.sstr[d], it.dstr[d]}); ne *= it.ext[d]; }
+        int rc = add_copy_block(*P, it.s_off, it.d_off, dims, cs, promote);
+        if (rc != ITB_OK) { delete P; return rc; }
+        P->bytes += ne * 8 * ((src_dtype == ITB_C64 ? 2 : 1) + (dst_dtype == ITB_C64 ? 2 : 1));
+    }
+    P->need_zero = false;
     *out = P;
     return ITB_OK;
 }

@@ -6,8 +6,11 @@
 // C ABI in include/itb200.h. Citations name the reference routine each overload stands in for.
 //
 #include "itensor/itensor.h"
+#include "itensor/decomp.h"
+#include "itensor/itdata/qcombiner.h"
 #include "itensor/itdata/qutil.h"
 #include "itensor/tensor/contract.h"
+#include "itensor/tensor/slicemat.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -704,6 +707,227 @@ ITB_INST_PLUSEQ(Real,Cplx)
 ITB_INST_PLUSEQ(Cplx,Real)
 ITB_INST_PLUSEQ(Cplx,Cplx)
 #undef ITB_INST_PLUSEQ
+
+//
+// QCombiner on the device. The index bookkeeping mirrors combine()/uncombine() (qcombiner.cc:125-301):
+// every stored block of d lands in (combine) / comes from (uncombine) a sub-range [start,end) of one
+// sector of the combined index; each such move is one strided box for itb_blockcopy.
+//
+static void
+runBlockCopy(std::vector<itb_copy_item> const& items, int dtype, void const* src, void* dst)
+    {
+    if(items.empty()) return;
+    itb_permute_plan* plan = nullptr;
+    check(itb_blockcopy_plan_create(int64_t(items.size()),items.data(),dtype,dtype,&plan),"blockcopy plan");
+    auto rc = itb_permute_run(context(),plan,src,dst,1.,0.,0);
+    itb_permute_plan_destroy(plan);
+    check(rc,"blockcopy");
+    }
+
+template<typename T>
+static void
+combineGPU(QDenseGPU<T> const& d, QCombiner const& C, IndexSet const& dis, IndexSet const& Cis, IndexSet& Nis, ManageStore& m)
+    {
+    auto dr = order(dis);
+    auto ncomb = order(Cis)-1;
+    auto nr = dr-ncomb+1;
+    auto dperm = Labels(dr,-1);
+    auto uncomb_dest = ncomb;
+    for(auto i : range(dr))
+        {
+        auto jc = indexPosition(Cis,dis[i]);
+        if(jc >= 0) dperm[i] = jc-1;
+        else        dperm[i] = uncomb_dest++;
+        }
+    auto combined = [&dperm,ncomb](long i) { return dperm[i] < long(ncomb); };
+    auto newind = IndexSetBuilder(nr);
+    newind.nextIndex(Cis[0]);
+    for(auto i : range(dr)) if(!combined(i)) newind.nextIndex(dis[i]);
+    Nis = newind.build();
+
+    auto [bofs,size] = getBlockOffsets(Nis,doTask(CalcDiv{dis},d));
+    auto& nd = *m.makeNewData<QDenseGPU<T>>(bofs,size_t(size));
+    nd.buf.zero();
+
+    auto items = std::vector<itb_copy_item>();
+    items.reserve(d.offsets.size());
+    auto nblock = Block(nr);
+    auto cblock = Block(ncomb);
+    for(auto const& io : d.offsets)
+        {
+        size_t nu = 1;
+        for(auto i : range(dr))
+            {
+            if(combined(i)) cblock[dperm[i]] = io.block[i];
+            else            nblock[nu++] = io.block[i];
+            }
+        size_t start = 0, end = 0;
+        std::tie(nblock[0],start,end) = C.getBlockRange(cblock);
+        auto doff = offsetOf(nd.offsets,nblock);
+        if(doff < 0) Error("itensor_b200: combine target block missing");
+        // destination strides of the new block (column-major) and of the fused group inside dim 0
+        auto nstr = std::vector<long>(nr,1);
+        for(auto j : range(1,nr)) nstr[j] = nstr[j-1]*Nis[j-1].blocksize0(nblock[j-1]);
+        auto cstr = std::vector<long>(ncomb,1);
+        for(auto p : range(1,ncomb)) cstr[p] = cstr[p-1]*Cis[p].blocksize0(cblock[p-1]);
+        itb_copy_item it;
+        std::memset(&it,0,sizeof(it));
+        it.s_off = io.offset;
+        it.d_off = doff+long(start);
+        it.n = int32_t(dr);
+        long sstr = 1;
+        size_t un = 1;
+        for(auto i : range(dr))
+            {
+            auto e = dis[i].blocksize0(io.block[i]);
+            it.ext[i] = e;
+            it.sstr[i] = sstr;
+            it.dstr[i] = combined(i) ? cstr[dperm[i]] : nstr[un++];
+            sstr *= e;
+            }
+        items.push_back(it);
+        }
+    runBlockCopy(items,dtypeOf<T>(),d.buf.data(),nd.buf.data());
+    }
+
+template<typename T>
+static void
+uncombineGPU(QDenseGPU<T> const& d, QCombiner const& C, IndexSet const& dis, IndexSet const& Cis, IndexSet& Nis, ManageStore& m)
+    {
+    auto& cind = Cis[0];
+    auto dr = order(dis);
+    auto cr = order(Cis);
+    auto ncomb = cr-1;
+    auto nr = dr-1+ncomb;
+    decltype(dr) jc = 0;
+    auto newind = IndexSetBuilder(nr);
+    for(auto n : range(dr))
+        {
+        if(dis[n] == cind)
+            {
+            jc = n;
+            for(auto k : range(1,cr)) newind.nextIndex(Cis[k]);
+            }
+        else newind.nextIndex(dis[n]);
+        }
+    Nis = newind.build();
+
+    auto [bofs,size] = getBlockOffsets(Nis,doTask(CalcDiv{dis},d));
+    auto& nd = *m.makeNewData<QDenseGPU<T>>(bofs,size_t(size));
+    nd.buf.zero();
+
+    auto items = std::vector<itb_copy_item>();
+    auto nblock = Block(nr);
+    for(auto const& io : d.offsets)
+        {
+        auto n = io.block[jc];
+        auto sstrs = std::vector<long>(dr,1);
+        for(auto i : range(1,dr)) sstrs[i] = sstrs[i-1]*dis[i-1].blocksize0(io.block[i-1]);
+        for(auto oo : range(C.store_))
+            {
+            auto& br = C.store_[oo];
+            if(long(br.block) != long(n)) continue;
+            auto o = oo;
+            for(auto k : range(ncomb-1))
+                {
+                nblock[jc+k] = o % Cis[1+k].nblock();
+                o = (o-nblock[jc+k])/Cis[1+k].nblock();
+                }
+            nblock[jc+ncomb-1] = o;
+            for(auto k : range(jc)) nblock[k] = io.block[k];
+            for(auto k : range(1+jc,dr)) nblock[ncomb+k-1] = io.block[k];
+            auto doff = offsetOf(nd.offsets,nblock);
+            if(doff < 0) Error("itensor_b200: uncombine target block missing");
+            auto nstr = std::vector<long>(nr,1);
+            for(auto j : range(1,nr)) nstr[j] = nstr[j-1]*Nis[j-1].blocksize0(nblock[j-1]);
+            itb_copy_item it;
+            std::memset(&it,0,sizeof(it));
+            it.s_off = io.offset+long(br.start)*sstrs[jc];
+            it.d_off = doff;
+            int q = 0;
+            for(auto i : range(dr))
+                {
+                if(i == jc)
+                    {
+                    long sub = sstrs[jc];
+                    for(auto k : range(ncomb))
+                        {
+                        auto e = Cis[1+k].blocksize0(nblock[jc+k]);
+                        it.ext[q] = e;
+                        it.sstr[q] = sub;
+                        it.dstr[q] = nstr[jc+k];
+                        sub *= e;
+                        ++q;
+                        }
+                    }
+                else
+                    {
+                    auto ni = i < jc ? i : i+ncomb-1;
+                    it.ext[q] = dis[i].blocksize0(io.block[i]);
+                    it.sstr[q] = sstrs[i];
+                    it.dstr[q] = nstr[ni];
+                    ++q;
+                    }
+                }
+            it.n = q;
+            if(q > ITB_MAX_ORDER) Error("itensor_b200: uncombine order too large");
+            items.push_back(it);
+            }
+        }
+    runBlockCopy(items,dtypeOf<T>(),d.buf.data(),nd.buf.data());
+    }
+
+template<typename T>
+void
+doTask(Contract& C, QDenseGPU<T> const& d, QCombiner const& cmb, ManageStore& m)
+    {
+    if(hasIndex(C.Lis,C.Ris[0])) uncombineGPU(d,cmb,C.Lis,C.Ris,C.Nis,m);
+    else                         combineGPU(d,cmb,C.Lis,C.Ris,C.Nis,m);
+    }
+template<typename T>
+void
+doTask(Contract& C, QCombiner const& cmb, QDenseGPU<T> const& d, ManageStore& m)
+    {
+    if(hasIndex(C.Ris,C.Lis[0])) uncombineGPU(d,cmb,C.Ris,C.Lis,C.Nis,m);
+    else                         combineGPU(d,cmb,C.Ris,C.Lis,C.Nis,m);
+    }
+template void doTask(Contract&,QDenseGPU<Real> const&,QCombiner const&,ManageStore&);
+template void doTask(Contract&,QDenseGPU<Cplx> const&,QCombiner const&,ManageStore&);
+template void doTask(Contract&,QCombiner const&,QDenseGPU<Real> const&,ManageStore&);
+template void doTask(Contract&,QCombiner const&,QDenseGPU<Cplx> const&,ManageStore&);
+
+// doTask(GetBlocks,QDense) decomp.cc:84-113: matrix views of the blocks of an order-2 tensor for the per-block
+// LAPACK loops of diagHImpl / svdImpl. The views point into a host snapshot of the device data.
+template<typename T>
+std::vector<Ord2Block<T>>
+doTask(GetBlocks<T> const& G, QDenseGPU<T> const& d)
+    {
+    if(G.is.order() != 2) Error("doTask(GetBlocks,QDenseGPU) only supports 2-index tensors");
+    d.mirror = std::make_shared<std::vector<T>>(d.n);
+    d.buf.download(d.mirror->data(),d.n*sizeof(T));
+    auto res = std::vector<Ord2Block<T>>{d.offsets.size()};
+    size_t n = 0;
+    for(auto const& dio : d.offsets)
+        {
+        auto& R = res[n++];
+        auto nrow = G.is[0].blocksize0(dio.block[0]);
+        auto ncol = G.is[1].blocksize0(dio.block[1]);
+        R.i1 = dio.block[0];
+        R.i2 = dio.block[1];
+        R.M = makeMatRef(d.mirror->data()+dio.offset,d.n-dio.offset,nrow,ncol);
+        }
+    if(G.transpose)
+        {
+        for(auto& R : res)
+            {
+            R.M = transpose(R.M);
+            std::swap(R.i1,R.i2);
+            }
+        }
+    return res;
+    }
+template std::vector<Ord2Block<Real>> doTask(GetBlocks<Real> const&,QDenseGPU<Real> const&);
+template std::vector<Ord2Block<Cplx>> doTask(GetBlocks<Cplx> const&,QDenseGPU<Cplx> const&);
 
 //
 // ---------------------------------------------------------------------------------------------

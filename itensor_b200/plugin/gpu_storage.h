@@ -73,6 +73,9 @@ class QDenseGPU
     BlockOffsets offsets; // same host bookkeeping as QDense<T>::offsets (sorted block -> element offset)
     gpu::Buffer buf;      // flat element data in HBM, laid out exactly like QDense<T>::store
     size_t n = 0;         // number of stored elements
+    // host snapshot handed out as raw matrix views by GetBlocks (per-block eigh/SVD, decomp.cc:84-113);
+    // refreshed on every GetBlocks call, never used as a compute fallback
+    mutable std::shared_ptr<std::vector<T>> mirror;
 
     QDenseGPU() { }
 
@@ -192,9 +195,17 @@ template<typename V>
 void doTask(RemoveQNs& R, QDenseGPU<V> const& d, ManageStore& m) { doTask(R,d.toHost(),m); }
 template<typename T> bool doTask(IsDense, QDenseGPU<T> const&) { return true; }
 
-// contraction partners that are not on the hot path (combiners, diagonal tensors): via the host
-template<typename T> void doTask(Contract& C, QDenseGPU<T> const& d, QCombiner const& cmb, ManageStore& m) { doTask(C,d.toHost(),cmb,m); }
-template<typename T> void doTask(Contract& C, QCombiner const& cmb, QDenseGPU<T> const& d, ManageStore& m) { doTask(C,cmb,d.toHost(),m); }
+// QN combiner (index fusion) on the device: block scatter/gather through the strided block-copy kernel
+// (replaces combine()/uncombine(), itensor/itdata/qcombiner.cc:125-301); the result stays in HBM.
+template<typename T> void doTask(Contract& C, QDenseGPU<T> const& d, QCombiner const& cmb, ManageStore& m);
+template<typename T> void doTask(Contract& C, QCombiner const& cmb, QDenseGPU<T> const& d, ManageStore& m);
+
+// per-block matrix views for the host-side eigh/SVD loops (decomp.cc:84-113): views into a host snapshot
+template<typename T> struct GetBlocks;
+template<typename T> struct Ord2Block;
+template<typename T> std::vector<Ord2Block<T>> doTask(GetBlocks<T> const& G, QDenseGPU<T> const& d);
+
+// contraction partners that are not on the hot path (diagonal tensors): via the host
 template<typename TA, typename TB>
 void doTask(Contract& C, QDenseGPU<TA> const& d, QDiag<TB> const& t, ManageStore& m) { doTask(C,d.toHost(),t,m); }
 template<typename TA, typename TB>

@@ -81,11 +81,32 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void
                                (int64_t)tr.size() / 3, (double*)C) == 0 ? ITB_OK : ITB_ERR_INVALID;
 }
 int itb_contract_host(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) { return itb_contract_run(c, P, A, B, C); }
+// executes the CANONICAL copy blocks of the plan (so the host mock also exercises the planner's dim sorting,
+// fusing and sub-block addressing); zero-fill of sourceless destination blocks as in api.cu
+static void mock_copy_block(const ItbPermBlk& b, const double* S, double* D, int scs, int dcs, double ar, double ai, int acc) {
+    int64_t idx[ITB_MAXG] = {0};
+    for (int64_t e = 0; e < b.nelem; ++e) {
+        int64_t so = b.s_off, dof = b.d_off;
+        for (int d = 0; d < b.n; ++d) { so += idx[d] * b.sstr[d]; dof += idx[d] * b.dstr[d]; }
+        const double vr = S[so * scs], vi = scs == 2 ? S[so * scs + 1] : 0.0;
+        const double rr = ar * vr - ai * vi, ri = ar * vi + ai * vr;
+        if (dcs == 2) {
+            if (acc) { D[2 * dof] += rr; D[2 * dof + 1] += ri; } else { D[2 * dof] = rr; D[2 * dof + 1] = ri; }
+        } else {
+            if (acc) D[dof] += rr; else D[dof] = rr;
+        }
+        for (int d = 0; d < b.n; ++d) { if (++idx[d] < b.ext[d]) break; idx[d] = 0; }
+    }
+}
 int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) {
-    orc_desc s = to_orc(P->S), d = to_orc(P->D);
-    static const int32_t zero32 = 0;
+    const int scs = P->S.dtype == ITB_C64 ? 2 : 1, dcs = P->D.dtype == ITB_C64 ? 2 : 1;
     ++c->launches;
-    return orc_permute(&s, (const double*)S, &d, (double*)D, P->perm.empty() ? &zero32 : P->perm.data(), ar, ai, acc) == 0 ? ITB_OK : ITB_ERR_INVALID;
+    if (!acc && P->need_zero)
+        for (size_t i = 0; i + 1 < P->zero_ranges.size(); i += 2)
+            std::memset((double*)D + P->zero_ranges[i] * dcs, 0, sizeof(double) * (size_t)P->zero_ranges[i + 1] * dcs);
+    for (auto& b : P->blks_copy) mock_copy_block(b, (const double*)S, (double*)D, scs, dcs, ar, ai, acc);
+    for (auto& b : P->blks_tiled) mock_copy_block(b, (const double*)S, (double*)D, scs, dcs, ar, ai, acc);
+    return ITB_OK;
 }
 int itb_permute_host(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) { return itb_permute_run(c, P, S, D, ar, ai, acc); }
 
@@ -131,6 +152,8 @@ int itb_dot(itb_ctx*, int32_t dt, int64_t n, const void* xv, const void* yv, int
     else for (int64_t i = 0; i < n; ++i) { double xi = conj_x ? -x[2*i+1] : x[2*i+1]; out[0] += x[2*i]*y[2*i] - xi*y[2*i+1]; out[1] += x[2*i]*y[2*i+1] + xi*y[2*i]; }
     return ITB_OK;
 }
+int itb_syevd_host(itb_ctx*, int32_t, int32_t, void*, double*, int32_t*) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
+int itb_gesvd_host(itb_ctx*, int32_t, int32_t, int32_t, void*, double*, void*, void*, int32_t*) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
 int itb_peak_fp64(itb_ctx*, int, int, double* t) { *t = 0; return ITB_ERR_UNSUPPORTED; }
 int itb_ctx_set_profile(itb_ctx*, int) { return ITB_OK; }
 int itb_contract_last_ms(itb_ctx*, float ms[5]) { for (int i = 0; i < 5; ++i) ms[i] = 0; return ITB_OK; }

@@ -20,11 +20,14 @@ MOCK = os.path.join(ROOT, "build", "plugin", "dmrg_driver_mock")
 REAL = os.path.join(ROOT, "build", "plugin", "dmrg_driver")
 ENV = dict(os.environ, LD_LIBRARY_PATH=os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs") + ":" +
            os.environ.get("LD_LIBRARY_PATH", ""), OPENBLAS_NUM_THREADS="1")
+MOCK_ENV = dict(ENV, ITB_SOLVER_MIN_N="1000000000")  # the mock ABI has no device solver: keep eigh/SVD on host LAPACK
+GPU_ENV = dict(ENV, ITB_SOLVER_MIN_N="24")            # push even small blocks through cuSOLVER in the parity tests
 SCHED = ["10,20,100,100,200", "1e-10", "2", "1e-7,1e-8,0"]  # sample/dmrg.cc:55-60
 
 
 def run(binary, model, N, qn, storage, sched=SCHED):
-    out = subprocess.run([binary, model, str(N), qn, storage] + sched, env=ENV, capture_output=True, text=True, timeout=1200)
+    env = MOCK_ENV if binary == MOCK else GPU_ENV
+    out = subprocess.run([binary, model, str(N), qn, storage] + sched, env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0, out.stderr[-2000:]
     return json.loads(out.stdout.strip().split("\n")[-1])
 
@@ -65,6 +68,18 @@ def test_dmrg_spin_half_parity_on_gpu():
     g = run(REAL, "heis_half", 40, "qn", "gpu")
     c = run(REAL, "heis_half", 40, "qn", "cpu")
     compare(g, c, 1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REAL), reason="build/plugin/dmrg_driver not built")
+def test_dmrg_svd_path_on_gpu():
+    """cutoff 0 + noise 0 switches svdBond from the density-matrix/eigh path to the SVD path (SURVEY F5,
+    mps_impl.h:50): both decompositions, the device combiner and cuSOLVER are exercised. Converged run
+    (10 sweeps at maxdim 60), so the 1e-10 bar applies."""
+    sched = ["10,20,40,60,60,60,60,60,60,60", "1e-10,1e-10,1e-10,0,0,0,0,0,0,0", "3", "1e-7,1e-8,0"]
+    g = run(REAL, "heis_half", 30, "qn", "gpu", sched)
+    c = run(REAL, "heis_half", 30, "qn", "cpu", sched)
+    compare(g, c, 1e-10, per_bond=False)
 
 
 @pytest.mark.gpu
