@@ -10,6 +10,7 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/itb200.h"
@@ -27,6 +28,8 @@ struct itb_solver {
     void* d_work = nullptr; size_t work_bytes = 0;
     int* d_info = nullptr;
     cudaStream_t stream = nullptr;
+    gesvdjInfo_t jinfo = nullptr;
+    int svd_method = 1; // 0: gesvd (QR iteration), 1: gesvdj (one-sided Jacobi) — ITB_SVD_METHOD
 };
 
 #define S_TRY(expr)                                                                         \
@@ -81,6 +84,10 @@ int itb_solver_create(void* stream, itb_solver** out) {
     CS_TRY(cusolverDnCreate(&s->h));
     CS_TRY(cusolverDnSetStream(s->h, s->stream));
     S_TRY(cudaMalloc((void**)&s->d_info, sizeof(int)));
+    CS_TRY(cusolverDnCreateGesvdjInfo(&s->jinfo));
+    CS_TRY(cusolverDnXgesvdjSetTolerance(s->jinfo, 1e-15));
+    CS_TRY(cusolverDnXgesvdjSetMaxSweeps(s->jinfo, 100));
+    if (const char* e = getenv("ITB_SVD_METHOD")) s->svd_method = atoi(e);
     *out = s;
     return ITB_OK;
 }
@@ -111,7 +118,39 @@ int itb_solver_syevd(itb_solver* s, int32_t dtype, int32_t n, void* hA, double* 
 // thin SVD, LAPACK gesdd(jobz='S') semantics: A (m x n, column-major, host; destroyed) = U diag(S) VT with
 // U m x l (ldu = m), VT l x n (ldvt = l), l = min(m,n). cuSOLVER gesvd needs m >= n, so wide blocks are
 // factorised through their (conjugate) transpose on the device.
+// one-sided Jacobi SVD (gesvdj): any m,n; returns V (n x l), so VT = V^H needs one transpose (+ conjugation)
+static int solver_gesvdj(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info) {
+    const size_t es = dtype == ITB_C64 ? 16 : 8;
+    const int l = std::min(m, n);
+    int rc = grow(&s->d_a, &s->a_bytes, (size_t)m * n * es); if (rc) return rc;
+    rc = grow(&s->d_b, &s->b_bytes, (size_t)m * l * es); if (rc) return rc; // U
+    rc = grow(&s->d_c, &s->c_bytes, (size_t)n * l * es * 2); if (rc) return rc; // V, then VT behind it
+    rc = grow(&s->d_w, &s->w_bytes, (size_t)l * 8 + 64); if (rc) return rc;
+    S_TRY(cudaMemcpyAsync(s->d_a, hA, (size_t)m * n * es, cudaMemcpyHostToDevice, s->stream));
+    int lwork = 0;
+    if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj_bufferSize(s->h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)s->d_a, m, (double*)s->d_w, (double*)s->d_b, m, (double*)s->d_c, n, &lwork, s->jinfo));
+    else CS_TRY(cusolverDnZgesvdj_bufferSize(s->h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)s->d_a, m, (double*)s->d_w, (cuDoubleComplex*)s->d_b, m, (cuDoubleComplex*)s->d_c, n, &lwork, s->jinfo));
+    rc = grow(&s->d_work, &s->work_bytes, (size_t)lwork * es); if (rc) return rc;
+    if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj(s->h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)s->d_a, m, (double*)s->d_w, (double*)s->d_b, m, (double*)s->d_c, n, (double*)s->d_work, lwork, s->d_info, s->jinfo));
+    else CS_TRY(cusolverDnZgesvdj(s->h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)s->d_a, m, (double*)s->d_w, (cuDoubleComplex*)s->d_b, m, (cuDoubleComplex*)s->d_c, n, (cuDoubleComplex*)s->d_work, lwork, s->d_info, s->jinfo));
+    char* vt = (char*)s->d_c + (size_t)n * l * es;
+    if (dtype == ITB_F64) launch_transpose<double>((const double*)s->d_c, (double*)vt, n, l, s->stream);
+    else {
+        launch_transpose<double2>((const double2*)s->d_c, (double2*)vt, n, l, s->stream);
+        conj_inplace_kernel<<<148, 256, 0, s->stream>>>((double2*)vt, (size_t)n * l);
+    }
+    int hinfo = 0;
+    S_TRY(cudaMemcpyAsync(hU, s->d_b, (size_t)m * l * es, cudaMemcpyDeviceToHost, s->stream));
+    S_TRY(cudaMemcpyAsync(hVT, vt, (size_t)l * n * es, cudaMemcpyDeviceToHost, s->stream));
+    S_TRY(cudaMemcpyAsync(hS, s->d_w, (size_t)l * 8, cudaMemcpyDeviceToHost, s->stream));
+    S_TRY(cudaMemcpyAsync(&hinfo, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    S_TRY(cudaStreamSynchronize(s->stream));
+    *info = hinfo;
+    return ITB_OK;
+}
+
 int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info) {
+    if (s->svd_method == 1) return solver_gesvdj(s, dtype, m, n, hA, hS, hU, hVT, info);
     const size_t es = dtype == ITB_C64 ? 16 : 8;
     const int l = std::min(m, n);
     const bool wide = m < n;

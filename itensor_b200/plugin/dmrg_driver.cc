@@ -120,7 +120,11 @@ main(int argc, char* argv[])
         toGPU(psi);
         }
 
+#ifdef DRIVER_VERBOSE
+    auto args = Args("Quiet",true);
+#else
     auto args = Args("Silent",true);
+#endif
     auto t0 = std::chrono::steady_clock::now();
     auto PH = LocalMPO(H,args);
     auto obs = TimingObserver(psi,args);

@@ -20,11 +20,46 @@
 
 #include "itb200.h"
 
+#include <chrono>
+#include <map>
+
 namespace itensor {
 
 namespace gpu {
 
 static itb_ctx* g_ctx = nullptr;
+
+// ITB_PROFILE=1: host wall time and call counts per plugin entry point, printed at exit (the storage-level
+// counterpart of the reference's -DCOLLECT_TIMES section timers, itensor/util/timers.h)
+struct Prof
+    {
+    struct Rec { double secs = 0; long calls = 0; };
+    std::map<std::string,Rec> recs;
+    bool on = false;
+    Prof() { if(auto* e = std::getenv("ITB_PROFILE")) on = std::atoi(e) != 0; }
+    ~Prof()
+        {
+        if(!on) return;
+        std::fprintf(stderr,"[itensor_b200 profile] %-28s %10s %12s\n","entry","calls","seconds");
+        for(auto& kv : recs) std::fprintf(stderr,"[itensor_b200 profile] %-28s %10ld %12.4f\n",kv.first.c_str(),kv.second.calls,kv.second.secs);
+        }
+    };
+static Prof& prof() { static Prof p; return p; }
+struct Scope
+    {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit Scope(const char* n) : name(n), on(prof().on) { if(on) t0 = std::chrono::steady_clock::now(); }
+    ~Scope()
+        {
+        if(!on) return;
+        auto& r = prof().recs[name];
+        r.secs += std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
+        r.calls += 1;
+        }
+    };
+#define ITB_SCOPE(name) gpu::Scope itb_scope_(name)
 
 static void
 check(int rc, const char* what)
@@ -117,6 +152,7 @@ template<typename T>
 QDenseGPU<T>::
 QDenseGPU(QDense<T> const& h) : offsets(h.offsets), buf(h.store.size()*sizeof(T)), n(h.store.size())
     {
+    ITB_SCOPE("upload QDense");
     // upload synchronously: the host vector may die right after this constructor
     buf.upload(h.store.data(),n*sizeof(T));
     gpu::synchronize();
@@ -128,6 +164,7 @@ template<typename T>
 QDense<T> QDenseGPU<T>::
 toHost() const
     {
+    ITB_SCOPE("download QDense");
     auto h = QDense<T>(undef,offsets,n);
     buf.download(h.store.data(),n*sizeof(T));
     return h;
@@ -360,6 +397,7 @@ template<typename T>
 Real
 doTask(NormNoScale, QDenseGPU<T> const& d)
     {
+    ITB_SCOPE("NormNoScale");
     double out = 0;
     check(itb_nrm2(context(),dtypeOf<T>(),int64_t(d.n),d.buf.data(),&out),"nrm2");
     return out;
@@ -459,6 +497,7 @@ template<typename T>
 static Cplx
 getEltGPU(GetElt& G, QDenseGPU<T> const& d)
     {
+    ITB_SCOPE("GetElt");
     auto r = long(G.inds.size());
     double out[2] = {0.,0.};
     if(r == 0)
@@ -495,6 +534,7 @@ template<typename T>
 void
 doTask(Order const& O, QDenseGPU<T>& dB)
     {
+    ITB_SCOPE("Order");
     auto const& Ais = O.is1();
     auto r = order(Ais);
     auto bind = IndexSetBuilder(r);
@@ -522,6 +562,7 @@ contractQ(Contract& Con,
     {
     using VC = common_type<VA,VB>;
     Labels Lind, Rind, Cind;
+    ITB_SCOPE("Contract QDenseGPU");
     computeLabels(Con.Lis,order(Con.Lis),Con.Ris,order(Con.Ris),Lind,Rind);
     const bool sortResult = false;
     contractIS(Con.Lis,Lind,Con.Ris,Rind,Con.Nis,Cind,sortResult);
@@ -607,6 +648,7 @@ template<typename TA, typename TB>
 static void
 plusEqQ(PlusEQ const& P, QDenseGPU<TA> const& A, QDenseGPU<TB> const& B, ManageStore& m)
     {
+    ITB_SCOPE("PlusEQ");
     if(B.n == 0) return;
     using TC = common_type<TA,TB>;
     auto r = order(P.is1());
@@ -728,6 +770,7 @@ template<typename T>
 static void
 combineGPU(QDenseGPU<T> const& d, QCombiner const& C, IndexSet const& dis, IndexSet const& Cis, IndexSet& Nis, ManageStore& m)
     {
+    ITB_SCOPE("combine");
     auto dr = order(dis);
     auto ncomb = order(Cis)-1;
     auto nr = dr-ncomb+1;
@@ -794,6 +837,7 @@ template<typename T>
 static void
 uncombineGPU(QDenseGPU<T> const& d, QCombiner const& C, IndexSet const& dis, IndexSet const& Cis, IndexSet& Nis, ManageStore& m)
     {
+    ITB_SCOPE("uncombine");
     auto& cind = Cis[0];
     auto dr = order(dis);
     auto cr = order(Cis);
@@ -902,6 +946,7 @@ template<typename T>
 std::vector<Ord2Block<T>>
 doTask(GetBlocks<T> const& G, QDenseGPU<T> const& d)
     {
+    ITB_SCOPE("GetBlocks");
     if(G.is.order() != 2) Error("doTask(GetBlocks,QDenseGPU) only supports 2-index tensors");
     d.mirror = std::make_shared<std::vector<T>>(d.n);
     d.buf.download(d.mirror->data(),d.n*sizeof(T));
