@@ -35,7 +35,7 @@ void zgesdd_wrapper_host(char* jobz, LAPACK_INT* m, LAPACK_INT* n, Cplx* A, LAPA
 // thresholds (block dimension from which a call goes to the device); measured on B200 (profiles/README.md):
 // cuSOLVER syevd beats host LAPACK from n~256 (1024: 17 ms vs 90 ms); gesvd/gesvdj lose to host gesdd on DMRG
 // blocks up to several hundred, so the SVD path is opt-in. First use of each cuSOLVER kernel pays seconds of
-// lazy module loading (CUDA_MODULE_LOADING=EAGER moves that to start-up).
+// lazy module loading (a few seconds per process; do not use CUDA_MODULE_LOADING=EAGER: measured 277 s).
 static long
 envLong(const char* name, long dflt)
     {

@@ -8,7 +8,7 @@ SCHED_G="10,20,100,200,400,800,1200,1600,2000,2000"
 SCHED_C="10,20,100,200,400,800"
 OPENBLAS_NUM_THREADS=8 timeout 1500 $D heis_half 100 qn cpu $SCHED_C 0 2 1e-7,1e-8,1e-10 $OUT/dmrg2000_cpu.json > /dev/null 2> $OUT/dmrg2000_cpu.err &
 CPU_PID=$!
-CUDA_MODULE_LOADING=EAGER ITB_PROFILE=1 OPENBLAS_NUM_THREADS=4 timeout 1500 $D heis_half 100 qn gpu $SCHED_G 0 2 1e-7,1e-8,1e-10 $OUT/dmrg2000_gpu.json > /dev/null 2> $OUT/dmrg2000_gpu.err
+ITB_PROFILE=1 OPENBLAS_NUM_THREADS=4 timeout 1500 $D heis_half 100 qn gpu $SCHED_G 0 2 1e-7,1e-8,1e-10 $OUT/dmrg2000_gpu.json > /dev/null 2> $OUT/dmrg2000_gpu.err
 wait $CPU_PID
 python - <<PY
 import json
