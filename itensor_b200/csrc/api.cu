@@ -86,6 +86,8 @@ struct itb_ctx {
     bool profile = false;
     cudaStream_t aux = nullptr;          // side stream: small streaming / split-K-dot launches overlap the tile kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_staging = nullptr;    // completion of the last table upload out of the pinned staging buffer
+    bool staging_busy = false;
     float last_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t pev[10] = {};
 };
@@ -159,7 +161,7 @@ static int ensure_ws(itb_ctx* c, size_t doubles) {
 }
 static int ensure_staging(itb_ctx* c, size_t bytes) {
     if (c->staging_bytes >= bytes) return ITB_OK;
-    if (c->staging) { CUDA_TRY(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->staging); c->staging = nullptr; }
+    if (c->staging) { CUDA_TRY(cudaStreamSynchronize(c->stream)); c->staging_busy = false; cudaFreeHost(c->staging); c->staging = nullptr; }
     size_t nb = std::max<size_t>(bytes, 1u << 20);
     CUDA_TRY(cudaMallocHost(&c->staging, nb));
     c->staging_bytes = nb;
@@ -219,6 +221,7 @@ int itb_ctx_create(int device, itb_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_staging, cudaEventDisableTiming));
     *out = c;
     return ITB_OK;
 }
@@ -306,11 +309,13 @@ static int upload(itb_ctx* c, Packer& pk, size_t extra_dev_bytes, DeviceTables* 
     if (pk.total) {
         rc = ensure_staging(c, pk.total);
         if (rc != ITB_OK) return rc;
-        // the staging buffer may still be in flight from a previous upload
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        // the staging buffer may still be in flight from the previous upload: wait for THAT copy only
+        if (c->staging_busy) { CUDA_TRY(cudaEventSynchronize(c->ev_staging)); c->staging_busy = false; }
         for (size_t i = 0; i < pk.parts.size(); ++i)
             if (pk.parts[i].second) std::memcpy((char*)c->staging + pk.offs[i], pk.parts[i].first, pk.parts[i].second);
         CUDA_TRY(cudaMemcpyAsync(dev->base, c->staging, pk.total, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_staging, c->stream));
+        c->staging_busy = true;
     }
     return ITB_OK;
 }
