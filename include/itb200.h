@@ -1,7 +1,7 @@
 /*
  * itb200.h — C ABI of the B200-native block-sparse contraction path (libitb200.so).
  *
- * This is the thin `extern "C"` layer that the storage-type plugin (itensor_b200/plugin/*.h:
+ * This is the thin `extern "C"` layer that the storage-type plugin (itensor_b200/plugin/gpu_storage.h:
  * DenseGPU<T>, QDenseGPU<T> and their doTask overloads) calls. Plain pointers and sizes only.
  * All Index / QN / TagSet bookkeeping stays in the caller; what crosses this boundary is
  *   - integer block structure (sector sizes, block coordinates, element offsets), and
@@ -128,6 +128,14 @@ int itb_contract_plan_set_cblock_range(itb_contract_plan* plan, int64_t first, i
 /* general form: mask[c] != 0 selects C block c (c_nblocks entries); NULL selects all. Unselected C blocks
  * are neither computed nor written (their storage is left untouched). */
 int itb_contract_plan_set_cblock_mask(itb_contract_plan* plan, const uint8_t* mask);
+/* introspection of the device work lists (tests, schedule analysis). Tile items of the DMMA kernel in queue
+ * order, 8 int32 each: {C block (position in the plan's executed C-block list), m0, n0, tile_m, tile_n,
+ * chunk_begin, chunk_end, ws_slot}; executed C blocks, 4 int64 each: {M, N, ksum, npairs} (real-expanded dims).
+ * All return the item count and write at most cap items (out may be NULL). */
+int64_t itb_contract_plan_tiles(const itb_contract_plan* plan, int32_t* out, int64_t cap);
+int64_t itb_contract_plan_cblks(const itb_contract_plan* plan, int64_t* out, int64_t cap);
+/* stream-K partition: CTA b of the persistent grid owns tile items [cta_begin[b], cta_begin[b+1]) */
+int64_t itb_contract_plan_cta_begin(const itb_contract_plan* plan, int32_t* out, int64_t cap);
 
 /* blocks allowed by a total flux: sum_j dir[j]*qn(index j, sector) == flux (component-wise,
  * component c taken modulo |mod[c]| when |mod[c]|>1). qn: for index j, sector s, component c:
@@ -197,6 +205,8 @@ int itb_gesvd_host(itb_ctx* ctx, int32_t dtype, int32_t m, int32_t n, void* hA, 
  * (same order as itb_contract_info.class_flops; 0 for classes that did not launch). */
 int itb_ctx_set_profile(itb_ctx* ctx, int profile);
 int itb_contract_last_ms(itb_ctx* ctx, float ms[5]);
+/* profile mode: clock64 span of every CTA of the last DMMA tile-kernel launch (schedule calibration); returns the count */
+int64_t itb_contract_last_cta_cycles(itb_ctx* ctx, int64_t* out, int64_t cap);
 /* bare DMMA (mma.sync f64) and DFMA issue loops, no memory traffic; returns TFLOP/s */
 int itb_peak_fp64(itb_ctx* ctx, int which /*0=dmma m8n8k4, 1=dfma, 2=dmma m16n8k8*/, int iters, double* tflops);
 /* device-side timing on the context's stream (CUDA events) */

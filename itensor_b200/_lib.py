@@ -85,6 +85,9 @@ SYMBOLS = {
     "itb_contract_plan_pairs": (C.c_int, [_P, _I64P]),
     "itb_contract_plan_set_cblock_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "itb_contract_plan_set_cblock_mask": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    "itb_contract_plan_tiles": (C.c_int64, [_P, _I32P, C.c_int64]),
+    "itb_contract_plan_cta_begin": (C.c_int64, [_P, _I32P, C.c_int64]),
+    "itb_contract_plan_cblks": (C.c_int64, [_P, _I64P, C.c_int64]),
     "itb_flux_blocks": (C.c_int64, [C.c_int32, _I32P, _I32P, C.c_int32, _I32P, _I32P, _I32P, _I32P, C.c_int64]),
     "itb_contract_run": (C.c_int, [_P, _P, _P, _P, _P]),
     "itb_contract_host": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -107,6 +110,7 @@ SYMBOLS = {
     "itb_gesvd_host": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _DP, _P, _P, C.POINTER(C.c_int32)]),
     "itb_peak_fp64": (C.c_int, [_P, C.c_int, C.c_int, _DP]),
     "itb_ctx_set_profile": (C.c_int, [_P, C.c_int]),
+    "itb_contract_last_cta_cycles": (C.c_int64, [_P, _I64P, C.c_int64]),
     "itb_contract_last_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "itb_timer_start": (C.c_int, [_P]),
     "itb_timer_stop_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),

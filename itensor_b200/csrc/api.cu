@@ -13,8 +13,9 @@
 #include "plan.h"
 
 namespace itb {
-cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks,
-                        const ItbPair* pairs, const double* A, const double* B, double* C, double* ws, int* counter, int num_sms,
+cudaError_t launch_gemm(const ItbTile* tiles, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+                        const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
+                        long long* cta_cycles,
                         cudaStream_t st);
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st);
@@ -40,6 +41,7 @@ struct DeviceTables {
     const ItbPair* pairs = nullptr;
     const ItbCBlk* cblks = nullptr;
     const ItbTile* tiles = nullptr;
+    const int32_t* cta_begin = nullptr;
     const ItbSplitOut* splits = nullptr;
     const ItbSkinny* skinny = nullptr;
     const ItbSkinny* skinny_q4 = nullptr;
@@ -89,6 +91,8 @@ struct itb_ctx {
     cudaEvent_t ev_staging = nullptr;    // completion of the last table upload out of the pinned staging buffer
     bool staging_busy = false;
     float last_ms[5] = {0, 0, 0, 0, 0};
+    long long* d_cta_cycles = nullptr;   // profile mode: per-CTA clock64 span of the last tile-kernel launch
+    std::vector<long long> h_cta_cycles;
     cudaEvent_t pev[10] = {};
 };
 
@@ -330,6 +334,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     const size_t o_cblk = pk.add(P->cblks.data(), P->cblks.size() * sizeof(ItbCBlk));
     const size_t o_tiles = pk.add(P->tiles.data(), P->tiles.size() * sizeof(ItbTile));
     const size_t o_splits = pk.add(P->splits.data(), P->splits.size() * sizeof(ItbSplitOut));
+    const size_t o_cta = pk.add(P->cta_begin.data(), P->cta_begin.size() * sizeof(int32_t));
     const size_t o_sk = pk.add(P->skinny.data(), P->skinny.size() * sizeof(ItbSkinny));
     const size_t o_sq4 = pk.add(P->skinny_q4.data(), P->skinny_q4.size() * sizeof(ItbSkinny));
     const size_t o_sq8 = pk.add(P->skinny_q8.data(), P->skinny_q8.size() * sizeof(ItbSkinny));
@@ -344,6 +349,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     dev->cblks = (const ItbCBlk*)(b + o_cblk);
     dev->tiles = (const ItbTile*)(b + o_tiles);
     dev->splits = (const ItbSplitOut*)(b + o_splits);
+    dev->cta_begin = (const int32_t*)(b + o_cta);
     dev->skinny = (const ItbSkinny*)(b + o_sk);
     dev->skinny_q4 = (const ItbSkinny*)(b + o_sq4);
     dev->skinny_q8 = (const ItbSkinny*)(b + o_sq8);
@@ -403,8 +409,15 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     if (has_tiles) {
         if (P->ws_slots > 0) { rc = ensure_ws(c, (size_t)P->ws_slots * ITB_WS_TILE); if (rc != ITB_OK) return rc; }
         PROF_BEGIN(0);
-        CUDA_TRY(launch_gemm(d->tiles, (int)P->tiles.size(), d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
-                             d->counters, c->num_sms, c->stream));
+        // the grid is the planner's partition width (one CTA per B200 SM); CTAs whose share is empty exit at once
+        const int grid = (int)P->cta_begin.size() - 1;
+        if (c->profile && !c->d_cta_cycles) CUDA_TRY(cudaMalloc(&c->d_cta_cycles, 1024 * sizeof(long long)));
+        CUDA_TRY(launch_gemm(d->tiles, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
+                             A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
+        if (c->profile) {
+            c->h_cta_cycles.assign(grid, 0);
+            CUDA_TRY(cudaMemcpyAsync(c->h_cta_cycles.data(), c->d_cta_cycles, grid * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        }
         PROF_END(0);
         c->launches += P->splits.empty() ? 1 : 2;
     }
@@ -622,6 +635,10 @@ int itb_gesvd_host(itb_ctx* c, int32_t dtype, int32_t m, int32_t n, void* hA, do
 }
 
 int itb_ctx_set_profile(itb_ctx* c, int profile) { c->profile = profile != 0; return ITB_OK; }
+int64_t itb_contract_last_cta_cycles(itb_ctx* c, int64_t* out, int64_t cap) {
+    for (int64_t i = 0; out && i < (int64_t)c->h_cta_cycles.size() && i < cap; ++i) out[i] = c->h_cta_cycles[i];
+    return (int64_t)c->h_cta_cycles.size();
+}
 int itb_contract_last_ms(itb_ctx* c, float ms[5]) {
     for (int i = 0; i < 5; ++i) ms[i] = c->last_ms[i];
     return ITB_OK;

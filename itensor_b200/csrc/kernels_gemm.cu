@@ -30,6 +30,15 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// warp-uniformly predicated DMMA (straight-line code: no branch per fragment on edge tiles)
+__device__ __forceinline__ void dmma884_if(double& d0, double& d1, double a, double b, int on) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %4, 0;\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n\t}"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b), "r"(on));
+}
+
 // offset of linear index idx within an index group (extents fastest-first)
 __device__ __forceinline__ int64_t grp_off(int idx, const int32_t* __restrict__ ext, const int64_t* __restrict__ str, int n) {
     int64_t o = 0;
@@ -62,8 +71,9 @@ __device__ __forceinline__ int64_t grp_off(int idx, const int32_t* __restrict__ 
 // interleave freely and the epilogue of one tile overlaps the loads of the next.
 constexpr int G_NCONS = 512, G_NPROD = 128, G_NT = G_NCONS + G_NPROD;
 constexpr int G_STAGES = 4, G_BK = ITB_BK, G_PAD = 4, G_MAXT = 128;
+constexpr int G_KT = 1024; // k offsets per shared table fill (per operand)
 constexpr int G_STAGE_ELEMS = G_MAXT * (G_BK + G_PAD); // per operand per stage (covers both layouts)
-constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT + 2 * 2 * G_BK) * 8 + 2 * G_STAGES * 8 + 16;
+constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT) * 8 + (size_t)(2 * G_KT) * 4 + 2 * G_STAGES * 8 + 16;
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -101,10 +111,13 @@ struct PipeState { // position in the stage ring; identical sequence on both sid
 
 // inner K loop of one block pair with the shared-memory layout of both operands fixed at compile time
 // (all fragment addresses become immediates off one base register per operand)
-template <int BM, int BN, bool AKF, bool BKF>
+// EDGE: the warp owns fewer than FM x FN valid 8x8 fragments (tile overhanging the C block): fragments that lie
+// entirely outside are neither loaded nor multiplied. Rows/columns of a partially valid fragment that fall
+// outside only ever see their own (unwritten) C rows/columns, so the operands need no zero fill along m and n.
+template <int BM, int BN, bool AKF, bool BKF, bool EDGE>
 __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2], int nchunks, int sgn, int wm0, int wn0, int g, int t4,
-                                             int lane, const double* As, const double* Bs, uint64_t* full, uint64_t* empty,
-                                             PipeState& ps) {
+                                             int lane, int fmv, int fnv, const double* As, const double* Bs, uint64_t* full,
+                                             uint64_t* empty, PipeState& ps) {
     constexpr int BK = G_BK, FM = BM / 32, FN = BN / 32;
     constexpr int sAm = AKF ? (BK + G_PAD) : 1, sAk = AKF ? 1 : (BM + G_PAD);
     constexpr int sBn = BKF ? (BK + G_PAD) : 1, sBk = BKF ? 1 : (BN + G_PAD);
@@ -115,7 +128,7 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
         const double* bs = Bs + ps.stage * G_STAGE_ELEMS + b_base;
 #pragma unroll
         for (int ks = 0; ks < BK / 4; ++ks) {
-            double fa[FM], fb[FN];
+            double fa[FM], fb[FN]; // (fragments outside an edge tile are loaded anyway: the addresses stay inside the stage)
 #pragma unroll
             for (int i = 0; i < FM; ++i) {
                 const double v = as[i * 8 * sAm + ks * 4 * sAk];
@@ -126,7 +139,10 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
 #pragma unroll
             for (int i = 0; i < FM; ++i)
 #pragma unroll
-                for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                for (int j = 0; j < FN; ++j) {
+                    if (EDGE) dmma884_if(acc[i][j][0], acc[i][j][1], fa[i], fb[j], (i < fmv) & (j < fnv));
+                    else dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[ps.stage]);
@@ -137,15 +153,19 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
 template <int BM, int BN>
 __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
                                              double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
-                                             uint64_t* full, uint64_t* empty, PipeState& ps) {
+                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute) {
     constexpr int BK = G_BK;
     constexpr int WM = BM / 4, WN = BN / 4, FM = WM / 8, FN = WN / 8;
     static_assert(FM >= 1 && FN >= 1, "tile too small for a 4x4 warp grid");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int wm0 = (warp & 3) * WM, wn0 = (warp >> 2) * WN;
+    // warp w runs on SMSP w&3: (wm,wn) = ((w ^ (w>>2)) & 3, w>>2) puts one warp of every warp-row and of every
+    // warp-column on each SMSP, so fragment skipping on edge tiles unloads all four tensor pipes evenly
+    const int wm0 = ((warp ^ (warp >> 2)) & 3) * WM, wn0 = (warp >> 2) * WN;
     const int M = cb->M, N = cb->N;
-    const int m0 = tile.tm * BM, n0 = tile.tn * BN;
+    const int m0 = tile.m0, n0 = tile.n0;
+    const int fmv = min(FM, max(0, (M - m0 - wm0 + 7) >> 3)), fnv = min(FN, max(0, (N - n0 - wn0 + 7) >> 3));
+    const bool edge = fmv < FM || fnv < FN;
 
     double acc[FM][FN][2];
 #pragma unroll
@@ -163,12 +183,27 @@ __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk*
         const int flags = pr->flags;
         // sign of the A' = [[Ar,-Ai],[Ai,Ar]] expansion, applied when the fragment is read (row even, col odd)
         const int sgn = ((flags & ITB_PF_CCA) && !(g & 1) && (t4 & 1)) ? (int)0x80000000 : 0;
-        switch (flags & (ITB_PF_A_KFAST | ITB_PF_B_KFAST)) {
-            case 0: consume_pair<BM, BN, false, false>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
-            case ITB_PF_A_KFAST: consume_pair<BM, BN, true, false>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
-            case ITB_PF_B_KFAST: consume_pair<BM, BN, false, true>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
-            default: consume_pair<BM, BN, true, true>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, As, Bs, full, empty, ps); break;
+        if (fmv == 0 || fnv == 0 || dbg_nocompute) { // nothing of this warp's sub-tile is inside the C block: keep the ring moving
+            // (dbg_nocompute: producer-rate measurement, tools/tile_calib.py --nocompute; results are garbage)
+            for (int kc = c0; kc < c1; ++kc) {
+                mbar_wait(&full[ps.stage], ps.phase);
+                if (lane == 0) mbar_arrive(&empty[ps.stage]);
+                ps.advance();
+            }
+            continue;
         }
+#define ITB_CONSUME(AKF, BKF)                                                                                                     \
+    do {                                                                                                                          \
+        if (edge) consume_pair<BM, BN, AKF, BKF, true>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, fmv, fnv, As, Bs, full, empty, ps); \
+        else consume_pair<BM, BN, AKF, BKF, false>(acc, c1 - c0, sgn, wm0, wn0, g, t4, lane, fmv, fnv, As, Bs, full, empty, ps);     \
+    } while (0)
+        switch (flags & (ITB_PF_A_KFAST | ITB_PF_B_KFAST)) {
+            case 0: ITB_CONSUME(false, false); break;
+            case ITB_PF_A_KFAST: ITB_CONSUME(true, false); break;
+            case ITB_PF_B_KFAST: ITB_CONSUME(false, true); break;
+            default: ITB_CONSUME(true, true); break;
+        }
+#undef ITB_CONSUME
     }
     // ---- epilogue: each C element is written exactly once (or one partial per split) ----------------------
     if (tile.ws_slot < 0) {
@@ -198,30 +233,133 @@ __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk*
     }
 }
 
+// Producer side of one block pair with both operand layouts fixed at compile time. Everything that does not change
+// along K lives in registers for the whole pair: the row (m / n) offsets of the elements this thread gathers — one
+// offset when the operand's fastest index is m/n (thread = one row, walks k), ROWS/8 offsets when it is k
+// (thread = one k column, walks rows). The k offsets of up to G_KT consecutive k sit in a shared table that is
+// refilled every G_KT/BK chunks, so a chunk costs one broadcast LDS + one 64-bit add + one LDGSTS per element and
+// no barrier among the producers.
+template <int ROWS, bool KF>
+struct OperandGather {
+    static constexpr int BK = G_BK, NP = G_NPROD;
+    static constexpr int E = ROWS * BK / NP;                     // elements per thread per chunk
+    static constexpr int NR = KF ? E : 1;                        // row offsets held in registers
+    const double* base;                                          // block base
+    int roff[NR];                                                // row offset inside the block (< 2^31, planner-checked); -1: row outside the C block
+    int soff;                                                    // shared-memory element offset of this thread's first element in a stage
+    int k0;                                                      // first k column (within a chunk) of this thread
+    bool odd_row;                                                // parity of the row(s): complex*complex fix-up
+    __device__ __forceinline__ void init(int pt, const double* b, const int64_t* off_s) {
+        base = b;
+        if (KF) { // k column fixed, rows pt/BK + e*(NP/BK)
+            k0 = pt % BK;
+            odd_row = (pt / BK) & 1; // NP/BK is even
+            soff = (pt / BK) * (BK + G_PAD) + k0;
+#pragma unroll
+            for (int e = 0; e < NR; ++e) roff[e] = (int)off_s[pt / BK + e * (NP / BK)];
+        } else { // row fixed, k columns pt/ROWS + e*(NP/ROWS)
+            const int r = pt % ROWS;
+            k0 = pt / ROWS;
+            odd_row = r & 1;
+            roff[0] = (int)off_s[r];
+            soff = r + k0 * (ROWS + G_PAD);
+        }
+    }
+    // issue this thread's share of one chunk; ktab: k offsets of the chunk's BK columns (0 past K: the address stays
+    // valid and the copy zero-fills; kleft = K - first k of the chunk). All table reads happen BEFORE the first copy
+    // is issued: the cp.async statements are ordered memory operations for the compiler, so interleaving them with
+    // the table loads would serialise one shared-memory round trip per element.
+    template <bool CCA>
+    __device__ __forceinline__ void issue(double* stage, const int* ktab, int kleft) const {
+        if (KF) {
+            const int ok = ktab[k0];
+            const bool v = k0 < kleft;
+            const double* col = base + ok - ((CCA && v && (k0 & 1) && odd_row) ? 2 : 0);
+#pragma unroll
+            for (int e = 0; e < NR; ++e)
+                if (roff[e] >= 0) cp_async8(stage + soff + e * (NP / BK) * (BK + G_PAD), col + roff[e], v);
+        } else {
+            constexpr int STEP = NP / ROWS; // k columns between two elements of this thread (1, 2 or 4)
+            int ok[E];
+            if (STEP == 1) { // 16 consecutive table entries: four 128-bit loads
+#pragma unroll
+                for (int q = 0; q < E / 4; ++q) {
+                    const int4 t = reinterpret_cast<const int4*>(ktab)[q];
+                    ok[4 * q] = t.x; ok[4 * q + 1] = t.y; ok[4 * q + 2] = t.z; ok[4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) ok[e] = ktab[k0 + e * STEP];
+            }
+            if (roff[0] >= 0) {
+                const double* row = base + roff[0];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int kk = k0 + e * STEP;
+                    const bool v = kk < kleft;
+                    const int adj = (CCA && v && (kk & 1) && odd_row) ? 2 : 0;
+                    cp_async8(stage + soff + e * STEP * (ROWS + G_PAD), row + ok[e] - adj, v);
+                }
+            }
+        }
+    }
+};
+
+template <int BM, int BN, bool AKF, bool BKF>
+__device__ __forceinline__ void produce_pair(const ItbPair* __restrict__ pr, int c0, int c1, const double* __restrict__ Ap,
+                                             const double* __restrict__ Bp, double* As, double* Bs, const int64_t* offM_s,
+                                             const int64_t* offN_s, int* ktabA, int* ktabB, uint64_t* full, uint64_t* empty,
+                                             PipeState& ps) {
+    constexpr int BK = G_BK, NP = G_NPROD;
+    const int pt = threadIdx.x - G_NCONS;
+    const int K = pr->K;
+    const bool cca = pr->flags & ITB_PF_CCA;
+    OperandGather<BM, AKF> ga;
+    OperandGather<BN, BKF> gb;
+    ga.init(pt, Ap, offM_s);
+    gb.init(pt, Bp, offN_s);
+    for (int kb = c0; kb < c1; kb += G_KT / BK) {
+        const int ke = min(c1, kb + G_KT / BK);
+        if (kb > c0) producer_sync(); // everyone is done with the previous table
+        for (int i = pt; i < (ke - kb) * BK; i += NP) {
+            const int k = kb * BK + i;
+            ktabA[i] = (k < K) ? (int)grp_off(k, pr->k_ext, pr->ak_str, pr->k_n) : 0; // < 2^31: planner-checked block size
+            ktabB[i] = (k < K) ? (int)grp_off(k, pr->k_ext, pr->bk_str, pr->k_n) : 0;
+        }
+        producer_sync();
+        for (int kc = kb; kc < ke; ++kc) {
+            mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+            double* as = As + ps.stage * G_STAGE_ELEMS;
+            double* bs = Bs + ps.stage * G_STAGE_ELEMS;
+            const int* ta = ktabA + (kc - kb) * BK;
+            const int* tb = ktabB + (kc - kb) * BK;
+            const int kleft = K - kc * BK;
+            if (cca) ga.template issue<true>(as, ta, kleft);
+            else ga.template issue<false>(as, ta, kleft);
+            gb.template issue<false>(bs, tb, kleft);
+            mbar_arrive_cp_async(&full[ps.stage]);
+            ps.advance();
+        }
+    }
+}
+
 template <int BM, int BN>
 __device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
                                              const double* __restrict__ A, const double* __restrict__ B, double* As, double* Bs,
-                                             int64_t* offM_s, int64_t* offN_s, int64_t* offKa_s, int64_t* offKb_s, uint64_t* full,
+                                             int64_t* offM_s, int64_t* offN_s, int* ktabA, int* ktabB, uint64_t* full,
                                              uint64_t* empty, PipeState& ps) {
     constexpr int BK = G_BK, NP = G_NPROD;
-    constexpr int EA = BM * BK / NP, EB = BN * BK / NP;
     const int pt = threadIdx.x - G_NCONS; // 0..G_NPROD-1
     const int M = cb->M, N = cb->N;
-    const int m0 = tile.tm * BM, n0 = tile.tn * BN;
+    const int m0 = tile.m0, n0 = tile.n0;
     int gchunk = 0;
-    int ktab = 0; // double-buffered k-offset table
     for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
         const ItbPair* pr = pairs + p;
-        const int K = pr->K;
-        const int nk = (K + BK - 1) / BK;
+        const int nk = (pr->K + BK - 1) / BK;
         const int c0 = max(tile.chunk_begin - gchunk, 0), c1 = min(tile.chunk_end - gchunk, nk);
         gchunk += nk;
         if (c0 >= c1) continue;
         const int flags = pr->flags;
-        const bool cca = flags & ITB_PF_CCA, akf = flags & ITB_PF_A_KFAST, bkf = flags & ITB_PF_B_KFAST;
-        const double* __restrict__ Ap = A + pr->a_off;
-        const double* __restrict__ Bp = B + pr->b_off;
-
         producer_sync(); // every producer is done reading the previous pair's tables
         for (int i = pt; i < BM + BN; i += NP) {
             if (i < BM) {
@@ -232,89 +370,32 @@ __device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk*
                 offN_s[i - BM] = (n < N) ? grp_off(n, pr->n_ext, pr->bn_str, pr->n_n) : -1;
             }
         }
-        auto fill_ktab = [&](int c, int slot) {
-            if (pt < 2 * BK) {
-                const int kk = pt % BK, k = c * BK + kk;
-                int64_t* dst = (pt < BK ? offKa_s : offKb_s) + slot * BK + kk;
-                *dst = (k < K) ? grp_off(k, pr->k_ext, pt < BK ? pr->ak_str : pr->bk_str, pr->k_n) : -1;
-            }
-        };
-        fill_ktab(c0, ktab);
         producer_sync();
-
-        // m-fast mapping: idx = pt + e*NP, row mm = idx % BM, column kk = idx / BM
-        // k-fast mapping: column kk = pt % BK, row mm = pt / BK + e*(NP/BK)
-        // (p,q) parity of the complex fold: m-fast: p = pt&1 (BM, NP even), q = kk&1 varies with e -> handled per e;
-        //                                   k-fast: q = pt&1, p = (pt/BK + 4e)&1 = (pt/BK)&1
-        for (int kc = c0; kc < c1; ++kc) {
-            if (kc + 1 < c1) fill_ktab(kc + 1, ktab ^ 1); // visible after this iteration's producer_sync
-            mbar_wait(&empty[ps.stage], ps.phase ^ 1);
-            double* as = As + ps.stage * G_STAGE_ELEMS;
-            double* bs = Bs + ps.stage * G_STAGE_ELEMS;
-            const int64_t* oka = offKa_s + ktab * BK;
-            const int64_t* okb = offKb_s + ktab * BK;
-            if (akf) {
-                const int kk = pt % BK;
-                const int64_t ok = oka[kk];
-                const int adj = (cca && (kk & 1) && ((pt / BK) & 1)) ? 2 : 0;
-#pragma unroll 2
-                for (int e = 0; e < EA; ++e) {
-                    const int mm = pt / BK + e * (NP / BK);
-                    const int64_t om = offM_s[mm];
-                    const bool v = (om | ok) >= 0;
-                    cp_async8(as + mm * (BK + G_PAD) + kk, v ? Ap + om + ok - adj : Ap, v);
-                }
-            } else {
-#pragma unroll 2
-                for (int e = 0; e < EA; ++e) {
-                    const int idx = pt + e * NP;
-                    const int mm = idx % BM, kk = idx / BM;
-                    const int64_t om = offM_s[mm], ok = oka[kk];
-                    const bool v = (om | ok) >= 0;
-                    const int adj = (cca && (mm & kk & 1)) ? 2 : 0;
-                    cp_async8(as + mm + kk * (BM + G_PAD), v ? Ap + om + ok - adj : Ap, v);
-                }
-            }
-            if (bkf) {
-                const int kk = pt % BK;
-                const int64_t ok = okb[kk];
-#pragma unroll 2
-                for (int e = 0; e < EB; ++e) {
-                    const int nn = pt / BK + e * (NP / BK);
-                    const int64_t on = offN_s[nn];
-                    const bool v = (on | ok) >= 0;
-                    cp_async8(bs + nn * (BK + G_PAD) + kk, v ? Bp + on + ok : Bp, v);
-                }
-            } else {
-#pragma unroll 2
-                for (int e = 0; e < EB; ++e) {
-                    const int idx = pt + e * NP;
-                    const int nn = idx % BN, kk = idx / BN;
-                    const int64_t on = offN_s[nn], ok = okb[kk];
-                    const bool v = (on | ok) >= 0;
-                    cp_async8(bs + nn + kk * (BN + G_PAD), v ? Bp + on + ok : Bp, v);
-                }
-            }
-            mbar_arrive_cp_async(&full[ps.stage]);
-            ps.advance();
-            ktab ^= 1;
-            producer_sync();
+        const double* __restrict__ Ap = A + pr->a_off;
+        const double* __restrict__ Bp = B + pr->b_off;
+        switch (flags & (ITB_PF_A_KFAST | ITB_PF_B_KFAST)) {
+            case 0: produce_pair<BM, BN, false, false>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
+            case ITB_PF_A_KFAST: produce_pair<BM, BN, true, false>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
+            case ITB_PF_B_KFAST: produce_pair<BM, BN, false, true>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
+            default: produce_pair<BM, BN, true, true>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
         }
     }
 }
 
-__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, int ntiles,
+__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, const int32_t* __restrict__ cta_begin,
                                                             const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
-                                                            double* __restrict__ C, double* __restrict__ ws) {
+                                                            double* __restrict__ C, double* __restrict__ ws,
+                                                            long long* __restrict__ cta_cycles, int dbg_nocompute) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long t_begin = cta_cycles ? clock64() : 0;
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + G_STAGES * G_STAGE_ELEMS;
     int64_t* offM_s = reinterpret_cast<int64_t*>(Bs + G_STAGES * G_STAGE_ELEMS);
     int64_t* offN_s = offM_s + G_MAXT;
-    int64_t* offKa_s = offN_s + G_MAXT;
-    int64_t* offKb_s = offKa_s + 2 * G_BK;
-    uint64_t* full = reinterpret_cast<uint64_t*>(offKb_s + 2 * G_BK);
+    int* offKa_s = reinterpret_cast<int*>(offN_s + G_MAXT); // 16-byte aligned: read as int4 by the producers
+    int* offKb_s = offKa_s + G_KT;
+    uint64_t* full = reinterpret_cast<uint64_t*>(offKb_s + G_KT);
     uint64_t* empty = full + G_STAGES;
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
@@ -330,12 +411,10 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
     // (setmaxnreg variants measured slower or spilling: see DESIGN.md) if (producer) setmaxnreg.dec 56
     // else setmaxnreg.inc 112
     PipeState ps;
-    // static snake (boustrophedon) assignment of the LPT-sorted item list: both roles derive the same sequence
-    const int G = gridDim.x;
-    for (int round = 0;; ++round) {
-        const int item = round * G + ((round & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x);
-        if (round * G >= ntiles) break;
-        if (item >= ntiles) continue;
+    // the host planner hands every CTA a contiguous range of (tile, K-chunk range) items of equal modelled cost
+    // (stream-K partition, plan.cc); both roles walk it in the same order
+    const int item_end = cta_begin[blockIdx.x + 1];
+    for (int item = cta_begin[blockIdx.x]; item < item_end; ++item) {
         const ItbTile tile = tiles[item];
         const ItbCBlk* cb = cblks + tile.cblk;
         if (producer) {
@@ -343,11 +422,12 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
             else if (tile.cfg == 1) produce_tile<64, 64>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
             else produce_tile<32, 32>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
         } else {
-            if (tile.cfg == 0) consume_tile<128, 128>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps);
-            else if (tile.cfg == 1) consume_tile<64, 64>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps);
-            else consume_tile<32, 32>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps);
+            if (tile.cfg == 0) consume_tile<128, 128>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            else if (tile.cfg == 1) consume_tile<64, 64>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            else consume_tile<32, 32>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
         }
     }
+    if (cta_cycles && threadIdx.x == 0) cta_cycles[blockIdx.x] = clock64() - t_begin; // schedule calibration (profile mode)
 }
 
 // C tile = sum of its split-K partials, in split order (deterministic). SR_PARTS CTAs per tile.
@@ -358,7 +438,7 @@ __global__ void __launch_bounds__(256) bsc_splitk_reduce_kernel(const ItbSplitOu
     const int part = blockIdx.x % SR_PARTS;
     const ItbCBlk* cb = cblks + o.cblk;
     const int T = o.cfg == 0 ? 128 : (o.cfg == 1 ? 64 : 32);
-    const int M = cb->M, N = cb->N, m0 = o.tm * T, n0 = o.tn * T;
+    const int M = cb->M, N = cb->N, m0 = o.m0, n0 = o.n0;
     double* __restrict__ Cp = C + cb->c_off;
     const int per = T * T / SR_PARTS;
     for (int e = part * per + threadIdx.x; e < (part + 1) * per; e += blockDim.x) {
@@ -711,19 +791,18 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) 
 }
 
 // ---- launchers (called from api.cu) ---------------------------------------------------------------------
-cudaError_t launch_gemm(const ItbTile* tiles, int ntiles, const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks,
-                        const ItbPair* pairs, const double* A, const double* B, double* C, double* ws, int* counter, int num_sms,
-                        cudaStream_t st) {
+cudaError_t launch_gemm(const ItbTile* tiles, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+                        const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
+                        long long* cta_cycles, cudaStream_t st) {
+    static int nocompute = -1; // ITB_DEBUG_NOCOMPUTE=1: consumers skip the DMMA work (measures the producers' gather rate)
+    if (nocompute < 0) { const char* e = getenv("ITB_DEBUG_NOCOMPUTE"); nocompute = e ? atoi(e) : 0; }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(bsc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    int grid = num_sms;
-    if (grid > ntiles) grid = ntiles;
-    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, ntiles, cblks, pairs, A, B, C, ws);
-    (void)counter;
+    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, cta_begin, cblks, pairs, A, B, C, ws, cta_cycles, nocompute);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {

@@ -18,6 +18,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -212,6 +214,60 @@ static void canon(std::vector<Dim>& g, bool two) {
     g.swap(out);
 }
 
+// ---- cycle model of the DMMA tile kernel (per BK=16 K-chunk of one tile, per SM) -----------------------------
+// Consumer warp w sits at (wm,wn) = ((w ^ (w>>2)) & 3, w>>2) of a 4x4 grid and runs on SMSP w&3, so every SMSP
+// holds one warp of each warp-row and each warp-column. Warps skip 8x8 fragments that lie entirely outside the
+// valid part of an edge tile, so the tensor-pipe time of a chunk is 4 k-steps x 16 cycles x the fragment
+// products of the busiest SMSP; below that the producers (gather + barriers) set a floor per configuration.
+// Constants measured on B200 (tools/tile_calib.py, tools/sched_fit.py; profiles/README.md): a full 128x128 chunk
+// takes 4550 cycles (1.11 x its 4096 DMMA cycles); the four producer warps need ~2950 cycles to gather a 128x128
+// chunk from cold operands however few of its rows are valid (8-byte LDGSTS path), 1700 for 64x64, 1050 for 32x32,
+// which is what an edge tile costs. On top: ~4000 cycles per item plus ~3500 per block pair it walks.
+// Least-squares fit of measured per-CTA cycles on the maxdim-2000 H_eff workload (tools/sched_fit.py): a 128x128
+// chunk costs 2466 + 0.54 x (DMMA cycles of the busiest SMSP), i.e. 4680 full and ~3150 for a 34-wide edge.
+static double g_tile_floor[ITB_NCFG] = {2950.0, 1700.0, 1050.0};
+static double kTileOverhead[ITB_NCFG] = {1200.0, 8000.0, 5300.0};
+static double kPairOverhead = 4300.0;
+static const double kDmmaSlack = 1.11;
+static int kForceCfg = -1;
+static const int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this
+static void read_tile_env() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (const char* e = getenv("ITB_TILE_FLOOR")) sscanf(e, "%lf,%lf,%lf", &g_tile_floor[0], &g_tile_floor[1], &g_tile_floor[2]);
+    if (const char* e = getenv("ITB_TILE_OVERHEAD")) sscanf(e, "%lf,%lf,%lf,%lf", &kTileOverhead[0], &kTileOverhead[1], &kTileOverhead[2], &kPairOverhead);
+    if (const char* e = getenv("ITB_FORCE_CFG")) kForceCfg = atoi(e);
+}
+static double chunk_cycles(int f, int64_t vm, int64_t vn) {
+    const int WM = kTileM[f] / 4, WN = kTileN[f] / 4, FM = WM / 8, FN = WN / 8;
+    int fm[4], fn[4];
+    for (int i = 0; i < 4; ++i) {
+        fm[i] = (int)std::max<int64_t>(0, std::min<int64_t>(FM, (vm - i * WM + 7) / 8));
+        fn[i] = (int)std::max<int64_t>(0, std::min<int64_t>(FN, (vn - i * WN + 7) / 8));
+    }
+    int worst = 0;
+    for (int s = 0; s < 4; ++s) {
+        int sum = 0;
+        for (int j = 0; j < 4; ++j) sum += fm[s ^ j] * fn[j];
+        worst = std::max(worst, sum);
+    }
+    if (f == ITB_CFG_BIG) return 2466.0 + 0.54 * 64.0 * worst;
+    return std::max(kDmmaSlack * 64.0 * worst, g_tile_floor[f]);
+}
+static double cblk_cost(int f, int64_t M, int64_t N, double nch, int npairs) {
+    const int TM = kTileM[f], TN = kTileN[f];
+    double cost = 0;
+    // full tiles + the (up to) three distinct edge shapes
+    const int64_t fm = M / TM, fn = N / TN, rm = M % TM, rn = N % TN;
+    const double ovh = kTileOverhead[f] + kPairOverhead * npairs;
+    cost += (double)fm * fn * (chunk_cycles(f, TM, TN) * nch + ovh);
+    if (rm) cost += (double)fn * (chunk_cycles(f, rm, TN) * nch + ovh);
+    if (rn) cost += (double)fm * (chunk_cycles(f, TM, rn) * nch + ovh);
+    if (rm && rn) cost += chunk_cycles(f, rm, rn) * nch + ovh;
+    return cost;
+}
+
 int build_contract_tables(itb_contract_plan& P) {
     const TensorStruct &A = P.A, &B = P.B, &C = P.C;
     const int rA = A.order, rB = B.order;
@@ -223,7 +279,7 @@ int build_contract_tables(itb_contract_plan& P) {
     const int64_t csA = cA ? 2 : 1, csB = cB ? 2 : 1, csC = (cA || cB) ? 2 : 1;
 
     P.pairs.clear(); P.cblks.clear(); P.skinny.clear(); P.skinny_q4.clear(); P.skinny_q8.clear(); P.dots.clear(); P.dot_outs.clear();
-    P.tiles.clear(); P.splits.clear(); P.ws_slots = 0;
+    P.tiles.clear(); P.splits.clear(); P.ws_slots = 0; P.cta_begin.clear();
     P.ndot_slots = 0;
 
     const int64_t npairs = (int64_t)P.triples.size() / 3;
@@ -305,7 +361,10 @@ int build_contract_tables(itb_contract_plan& P) {
             for (size_t d = 0; d < gk.size(); ++d) { pr.k_ext[d] = (int32_t)gk[d].ext; pr.ak_str[d] = gk[d].sa; pr.bk_str[d] = gk[d].sb; }
             pr.m_n = (int32_t)gm.size(); pr.n_n = (int32_t)gn.size(); pr.k_n = (int32_t)gk.size();
             const int64_t Kr = k * ((cA && cB) ? 2 : 1);
-            if (Kr >= (1ll << 31) || m * 2 >= (1ll << 31) || n * 2 >= (1ll << 31)) {
+            int64_t abl = csA, bbl = csB; // real elements of the two blocks: device row offsets are 32-bit
+            for (int i = 0; i < rA; ++i) abl *= A.ext(i, ab[i]);
+            for (int j = 0; j < rB; ++j) bbl *= B.ext(j, bb[j]);
+            if (Kr >= (1ll << 31) || m * 2 >= (1ll << 31) || n * 2 >= (1ll << 31) || abl >= (1ll << 31) || bbl >= (1ll << 31)) {
                 set_error("contract: block dimension exceeds 2^31");
                 return ITB_ERR_UNSUPPORTED;
             }
@@ -327,6 +386,12 @@ int build_contract_tables(itb_contract_plan& P) {
     }
 
     // ---- classify C blocks into kernel work lists --------------------------------------------------
+    read_tile_env();
+    auto chunks_of = [&](const ItbCBlk& cb) {
+        int64_t n = 0;
+        for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) n += (P.pairs[p].K + ITB_BK - 1) / ITB_BK;
+        return n;
+    };
     for (double& f : P.class_flops) f = 0;
     std::vector<std::pair<int32_t, int>> tile_cblks; // (C block, tile config)
     for (int32_t c = 0; c < (int32_t)P.cblks.size(); ++c) {
@@ -359,68 +424,89 @@ int build_contract_tables(itb_contract_plan& P) {
                     P.skinny.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyRows, L - r0), long_is_n});
             }
         } else {
-            // pick the tile config with the least padded work (bigger tiles run more efficiently)
+            // pick the tile config with the least modelled cycles (tile_cost below)
             int best = 0; double bestc = 1e300;
-            static const double eff[ITB_NCFG] = {1.0, 0.8, 0.5};
             for (int f = 0; f < ITB_NCFG; ++f) {
-                const double tm = (double)((M + kTileM[f] - 1) / kTileM[f]), tn = (double)((N + kTileN[f] - 1) / kTileN[f]);
-                const double cost = tm * tn * kTileM[f] * kTileN[f] / eff[f];
+                const double cost = cblk_cost(f, M, N, (double)chunks_of(cb), cb.pair_end - cb.pair_begin);
                 if (cost < bestc) { bestc = cost; best = f; }
             }
+            if (kForceCfg >= 0) best = kForceCfg;
             P.class_flops[best] += cflops;
             tile_cblks.push_back({c, best});
         }
     }
-    // ---- tile items with split-K: cap the K-chunks per item so that the persistent grid balances ---------
+    // ---- tile items: stream-K partition of the tile list over the persistent grid -------------------------
+    // Every CTA of the kNumSMs-wide grid gets the same modelled cycle count: the tile list (C-block order, so
+    // neighbouring items share operand panels in L2) is cut at K-chunk boundaries wherever a CTA's share is
+    // full. A tile cut into several pieces writes partial sums to workspace slots which
+    // bsc_splitk_reduce_kernel adds in piece order (deterministic); at most kNumSMs-1 tiles are cut.
     {
-        auto chunks_of = [&](const ItbCBlk& cb) {
-            int64_t n = 0;
-            for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) n += (P.pairs[p].K + ITB_BK - 1) / ITB_BK;
-            return n;
-        };
-        double total_work = 0; // in units of 128x128x16 chunk-tiles
-        for (auto& tc : tile_cblks) {
-            const ItbCBlk& cb = P.cblks[tc.first];
-            const int T = kTileM[tc.second];
-            const double nt = (double)((cb.M + T - 1) / T) * (double)((cb.N + T - 1) / T);
-            total_work += nt * (double)chunks_of(cb) * (double)(T * T) / (128.0 * 128.0);
-        }
-        const double cap_work = std::max(32.0, total_work / (kNumSMs * 2.5)); // <= 0.4 of a CTA's fair share
+        struct Proto { int32_t c, m0, n0, f; int64_t nch; double w; int np; };
+        std::vector<Proto> protos;
+        double total = 0;
         for (auto& tc : tile_cblks) {
             const int32_t c = tc.first; const int f = tc.second;
             const ItbCBlk& cb = P.cblks[c];
-            const int T = kTileM[f];
+            const int TM = kTileM[f], TN = kTileN[f];
             const int64_t nch = chunks_of(cb);
-            const double per_chunk = (double)(T * T) / (128.0 * 128.0);
-            int64_t nsplit = (int64_t)std::ceil((double)nch * per_chunk / cap_work);
-            nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, nch / 16 > 0 ? nch / 16 : 1)); // >= 16 chunks per split
-            const int64_t per = (nch + nsplit - 1) / nsplit;
-            nsplit = (nch + per - 1) / per;
-            for (int32_t tn = 0; tn < (cb.N + T - 1) / T; ++tn)
-                for (int32_t tm = 0; tm < (cb.M + T - 1) / T; ++tm) {
-                    if (nsplit == 1) {
-                        P.tiles.push_back({c, tm, tn, f, 0, (int32_t)nch, -1, 0});
-                    } else {
-                        P.splits.push_back({c, tm, tn, f, (int32_t)P.ws_slots, (int32_t)nsplit, {0, 0}});
-                        for (int64_t q = 0; q < nsplit; ++q)
-                            P.tiles.push_back({c, tm, tn, f, (int32_t)(q * per), (int32_t)std::min<int64_t>(nch, (q + 1) * per), (int32_t)P.ws_slots++, 0});
-                    }
+            for (int32_t n0 = 0; n0 < cb.N; n0 += TN)
+                for (int32_t m0 = 0; m0 < cb.M; m0 += TM) {
+                    const double w = chunk_cycles(f, std::min<int64_t>(TM, cb.M - m0), std::min<int64_t>(TN, cb.N - n0));
+                    protos.push_back({c, m0, n0, f, nch, w, cb.pair_end - cb.pair_begin});
+                    total += w * (double)nch + kTileOverhead[f] + kPairOverhead * (cb.pair_end - cb.pair_begin);
                 }
         }
+        const int G = kNumSMs;
+        P.cta_begin.assign(G + 1, 0);
+        // pieces cost an extra epilogue/prologue each; spread that too (<= G-1 cuts)
+        double target = total / G, assigned = 0;
+        int b = 0; double load = 0;
+        auto close_cta = [&]() { // re-derive the share from what is left so that rounding never piles up on the last CTA
+            if (b < G - 1) { ++b; P.cta_begin[b] = (int32_t)P.tiles.size(); load = 0; target = std::max(0.0, total - assigned) / (G - b); }
+        };
+        for (auto& t : protos) {
+            // fixed cost of a piece: item prologue/epilogue + one table rebuild per block pair it walks
+            auto piece_ovh = [&](int64_t take) { return kTileOverhead[t.f] + kPairOverhead * std::ceil((double)t.np * (double)take / (double)t.nch); };
+            int64_t c0 = 0;
+            std::vector<std::pair<int64_t, int64_t>> pieces;
+            while (c0 < t.nch) {
+                const int64_t rem = t.nch - c0;
+                const double space = target - load - piece_ovh(t.nch - c0);
+                const int64_t fit = (int64_t)std::floor(space / t.w);
+                int64_t take;
+                if (b == G - 1 || fit >= rem) take = rem;
+                else if (fit >= kMinPiece && rem - fit >= kMinPiece) take = fit; // cut here, a viable piece stays behind
+                else {
+                    // no clean cut: either close this CTA short of its share or overshoot with the smallest viable piece
+                    const int64_t x = (rem - std::max<int64_t>(fit, 0) < kMinPiece || rem < 2 * kMinPiece) ? rem : kMinPiece;
+                    const double over = (double)x * t.w - space, under = target - load;
+                    if (load > 0 && under <= over) { close_cta(); continue; }
+                    take = x;
+                }
+                if (take <= 0) { close_cta(); continue; }
+                if (!pieces.empty()) total += kTileOverhead[t.f] + kPairOverhead; // every extra piece pays its own prologue/epilogue
+                pieces.push_back({c0, c0 + take});
+                // ws slots are fixed up below once the number of pieces is known
+                P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)(c0 + take), -1, 0});
+                load += (double)take * t.w + piece_ovh(take);
+                assigned += (double)take * t.w + piece_ovh(take);
+                c0 += take;
+                if (load >= target - 0.5 * t.w) close_cta();
+            }
+            if (pieces.size() > 1) {
+                P.splits.push_back({t.c, t.m0, t.n0, t.f, (int32_t)P.ws_slots, (int32_t)pieces.size(), {0, 0}});
+                for (size_t q = 0; q < pieces.size(); ++q) P.tiles[P.tiles.size() - pieces.size() + q].ws_slot = (int32_t)P.ws_slots++;
+            }
+        }
+        for (int g = b + 1; g <= G; ++g) P.cta_begin[g] = (int32_t)P.tiles.size();
     }
-    // longest-processing-time-first: heavy items to the front of the persistent queue
-    std::stable_sort(P.tiles.begin(), P.tiles.end(), [&](const ItbTile& x, const ItbTile& y) {
-        const double wx = (double)(x.chunk_end - x.chunk_begin) * kTileM[x.cfg] * kTileN[x.cfg];
-        const double wy = (double)(y.chunk_end - y.chunk_begin) * kTileM[y.cfg] * kTileN[y.cfg];
-        return wx > wy;
-    });
     std::stable_sort(P.skinny.begin(), P.skinny.end(), [&](const ItbSkinny& x, const ItbSkinny& y) {
         return P.cblks[x.cblk].ksum * (P.cblks[x.cblk].M + P.cblks[x.cblk].N) > P.cblks[y.cblk].ksum * (P.cblks[y.cblk].M + P.cblks[y.cblk].N);
     });
     P.table_bytes = (int64_t)(P.pairs.size() * sizeof(ItbPair) + P.cblks.size() * sizeof(ItbCBlk) +
                               (P.skinny.size() + P.skinny_q4.size() + P.skinny_q8.size()) * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
                               P.dot_outs.size() * sizeof(ItbDotOut) + P.tiles.size() * sizeof(ItbTile) +
-                              P.splits.size() * sizeof(ItbSplitOut));
+                              P.splits.size() * sizeof(ItbSplitOut) + P.cta_begin.size() * sizeof(int32_t));
     P.tables_built = true;
     return ITB_OK;
 }
@@ -630,6 +716,30 @@ int itb_contract_plan_c_sect(const itb_contract_plan* P, int64_t* v) { std::copy
 int itb_contract_plan_c_blocks(const itb_contract_plan* P, int32_t* v) { std::copy(P->C.blocks.begin(), P->C.blocks.end(), v); return ITB_OK; }
 int itb_contract_plan_c_offsets(const itb_contract_plan* P, int64_t* v) { std::copy(P->C.offsets.begin(), P->C.offsets.end(), v); return ITB_OK; }
 int itb_contract_plan_pairs(const itb_contract_plan* P, int64_t* v) { std::copy(P->triples.begin(), P->triples.end(), v); return ITB_OK; }
+
+int64_t itb_contract_plan_tiles(const itb_contract_plan* P, int32_t* out, int64_t cap) {
+    if (!P) return ITB_ERR_INVALID;
+    for (int64_t i = 0; out && i < (int64_t)P->tiles.size() && i < cap; ++i) {
+        const ItbTile& t = P->tiles[i];
+        const int32_t v[8] = {t.cblk, t.m0, t.n0, kTileM[t.cfg], kTileN[t.cfg], t.chunk_begin, t.chunk_end, t.ws_slot};
+        std::copy(v, v + 8, out + 8 * i);
+    }
+    return (int64_t)P->tiles.size();
+}
+int64_t itb_contract_plan_cta_begin(const itb_contract_plan* P, int32_t* out, int64_t cap) {
+    if (!P) return ITB_ERR_INVALID;
+    for (int64_t i = 0; out && i < (int64_t)P->cta_begin.size() && i < cap; ++i) out[i] = P->cta_begin[i];
+    return (int64_t)P->cta_begin.size();
+}
+int64_t itb_contract_plan_cblks(const itb_contract_plan* P, int64_t* out, int64_t cap) {
+    if (!P) return ITB_ERR_INVALID;
+    for (int64_t i = 0; out && i < (int64_t)P->cblks.size() && i < cap; ++i) {
+        const ItbCBlk& c = P->cblks[i];
+        const int64_t v[4] = {c.M, c.N, c.ksum, c.pair_end - c.pair_begin};
+        std::copy(v, v + 4, out + 4 * i);
+    }
+    return (int64_t)P->cblks.size();
+}
 
 int itb_contract_plan_set_cblock_range(itb_contract_plan* P, int64_t first, int64_t last) {
     if (!P) { set_error("set_cblock_range: null"); return ITB_ERR_INVALID; }

@@ -45,7 +45,8 @@ struct itb_contract_plan {
     bool tables_built = false;
     std::vector<ItbPair> pairs;
     std::vector<ItbCBlk> cblks;
-    std::vector<ItbTile> tiles;       // every tile class in one persistent queue (LPT order)
+    std::vector<ItbTile> tiles;       // every tile class in one list; CTA b of the persistent grid owns [cta_begin[b], cta_begin[b+1])
+    std::vector<int32_t> cta_begin;   // kNumSMs+1 entries (stream-K partition: equal modelled cycles per CTA)
     std::vector<ItbSplitOut> splits;  // split-K tiles to be reduced from the workspace
     int64_t ws_slots = 0;
     std::vector<ItbSkinny> skinny;    // generic streaming items

@@ -45,7 +45,7 @@ struct ItbCBlk {
 };
 
 struct ItbTile { // work item of the persistent DMMA tile kernel
-    int32_t cblk, tm, tn;
+    int32_t cblk, m0, n0; // C block and origin of the tile inside it (real-expanded rows / columns)
     int32_t cfg;         // tile configuration (ITB_CFG_*: 128x128 / 64x64 / 32x32)
     int32_t chunk_begin; // range of BK-chunks of the C block's concatenated K loop (split-K)
     int32_t chunk_end;
@@ -53,7 +53,7 @@ struct ItbTile { // work item of the persistent DMMA tile kernel
     int32_t pad_;
 };
 struct ItbSplitOut { // split-K tile: C tile = sum of workspace slots [ws_slot0, ws_slot0+nsplit) in order
-    int32_t cblk, tm, tn, cfg, ws_slot0, nsplit, pad_[2];
+    int32_t cblk, m0, n0, cfg, ws_slot0, nsplit, pad_[2];
 };
 #define ITB_BK 16              // K-chunk of the tile kernel
 #define ITB_WS_TILE (128 * 128) // doubles per workspace slot
