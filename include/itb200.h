@@ -134,6 +134,8 @@ int itb_contract_plan_set_cblock_mask(itb_contract_plan* plan, const uint8_t* ma
  * All return the item count and write at most cap items (out may be NULL). */
 int64_t itb_contract_plan_tiles(const itb_contract_plan* plan, int32_t* out, int64_t cap);
 int64_t itb_contract_plan_cblks(const itb_contract_plan* plan, int64_t* out, int64_t cap);
+/* row groups of the streaming class, 4 int64 each: {input slots, output slots, long-side dims, rows} */
+int64_t itb_contract_plan_rowgroups(const itb_contract_plan* plan, int64_t* out, int64_t cap);
 /* stream-K partition: CTA b of the persistent grid owns tile items [cta_begin[b], cta_begin[b+1]) */
 int64_t itb_contract_plan_cta_begin(const itb_contract_plan* plan, int32_t* out, int64_t cap);
 

@@ -21,6 +21,8 @@ cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, in
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st);
 cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
                        const double* A, const double* B, double* partial, double* C, cudaStream_t st);
+cudaError_t launch_rowgroups(const ItbRgItem* items, int nitems, const ItbRowGroup* groups, const ItbRgIn* ins, const int64_t* outs,
+                             const ItbRgW* wents, int max_nout, const double* A, const double* B, double* C, cudaStream_t st);
 cudaError_t launch_peak(int which, int iters, double* out, int num_sms, cudaStream_t st);
 cudaError_t launch_permute(int src_cplx, int dst_cplx, const ItbPermBlk* bc, const ItbPermChunk* chunks, int64_t items_c,
                            const ItbPermTile* tiles, int64_t items_t, const void* src, void* dst, double ar, double ai, int accum,
@@ -43,6 +45,12 @@ struct DeviceTables {
     const ItbTile* tiles = nullptr;
     const int32_t* cta_begin = nullptr;
     const ItbSplitOut* splits = nullptr;
+    const ItbRowGroup* rgroups = nullptr;
+    const ItbRgIn* rg_in = nullptr;
+    const int64_t* rg_out = nullptr;
+    const ItbRgW* rg_w = nullptr;
+    const ItbRgItem* rg_items = nullptr;
+    int rg_max_nout = 0;
     const ItbSkinny* skinny = nullptr;
     const ItbSkinny* skinny_q4 = nullptr;
     const ItbSkinny* skinny_q8 = nullptr;
@@ -335,6 +343,11 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     const size_t o_tiles = pk.add(P->tiles.data(), P->tiles.size() * sizeof(ItbTile));
     const size_t o_splits = pk.add(P->splits.data(), P->splits.size() * sizeof(ItbSplitOut));
     const size_t o_cta = pk.add(P->cta_begin.data(), P->cta_begin.size() * sizeof(int32_t));
+    const size_t o_rg = pk.add(P->rgroups.data(), P->rgroups.size() * sizeof(ItbRowGroup));
+    const size_t o_rgi = pk.add(P->rg_in.data(), P->rg_in.size() * sizeof(ItbRgIn));
+    const size_t o_rgo = pk.add(P->rg_out.data(), P->rg_out.size() * sizeof(int64_t));
+    const size_t o_rgw = pk.add(P->rg_w.data(), P->rg_w.size() * sizeof(ItbRgW));
+    const size_t o_rgit = pk.add(P->rg_items.data(), P->rg_items.size() * sizeof(ItbRgItem));
     const size_t o_sk = pk.add(P->skinny.data(), P->skinny.size() * sizeof(ItbSkinny));
     const size_t o_sq4 = pk.add(P->skinny_q4.data(), P->skinny_q4.size() * sizeof(ItbSkinny));
     const size_t o_sq8 = pk.add(P->skinny_q8.data(), P->skinny_q8.size() * sizeof(ItbSkinny));
@@ -350,6 +363,13 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     dev->tiles = (const ItbTile*)(b + o_tiles);
     dev->splits = (const ItbSplitOut*)(b + o_splits);
     dev->cta_begin = (const int32_t*)(b + o_cta);
+    dev->rgroups = (const ItbRowGroup*)(b + o_rg);
+    dev->rg_in = (const ItbRgIn*)(b + o_rgi);
+    dev->rg_out = (const int64_t*)(b + o_rgo);
+    dev->rg_w = (const ItbRgW*)(b + o_rgw);
+    dev->rg_items = (const ItbRgItem*)(b + o_rgit);
+    dev->rg_max_nout = 0;
+    for (auto& g : P->rgroups) dev->rg_max_nout = std::max(dev->rg_max_nout, (int)g.nout);
     dev->skinny = (const ItbSkinny*)(b + o_sk);
     dev->skinny_q4 = (const ItbSkinny*)(b + o_sq4);
     dev->skinny_q8 = (const ItbSkinny*)(b + o_sq8);
@@ -381,7 +401,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     // the side stream FIRST (fork/join with events) so that their latency-bound CTAs overlap the persistent
     // tile kernel instead of trailing it. In profile mode everything stays on one stream for per-class timing.
     const bool has_tiles = !P->tiles.empty();
-    const bool has_stream = !P->skinny.empty() || !P->skinny_q4.empty() || !P->skinny_q8.empty();
+    const bool has_stream = !P->skinny.empty() || !P->skinny_q4.empty() || !P->skinny_q8.empty() || !P->rg_items.empty();
     const bool has_dots = !P->dots.empty();
     const bool fork = has_tiles && (has_stream || has_dots) && !c->profile;
     cudaStream_t side = fork ? c->aux : c->stream;
@@ -392,6 +412,8 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     auto launch_side = [&]() -> int {
         if (has_stream) {
             PROF_BEGIN(3);
+            CUDA_TRY(launch_rowgroups(d->rg_items, (int)P->rg_items.size(), d->rgroups, d->rg_in, d->rg_out, d->rg_w, d->rg_max_nout, A, B, C, side));
+            c->launches += P->rg_items.empty() ? 0 : 1;
             CUDA_TRY(launch_skinny(d->skinny, (int)P->skinny.size(), d->skinny_q4, (int)P->skinny_q4.size(), d->skinny_q8,
                                    (int)P->skinny_q8.size(), d->cblks, d->pairs, A, B, C, side));
             PROF_END(3);

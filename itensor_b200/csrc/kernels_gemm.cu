@@ -682,6 +682,93 @@ __global__ void __launch_bounds__(SQ_NT, MINB) bsc_skinny_smallk_kernel(const It
     }
 }
 
+// ---- row-group streaming kernel ------------------------------------------------------------------------------
+// The MPO steps of H_eff*phi as a stream: for every long-side row l of a row group (tables.h) load the nin inputs
+// x_j once (coalesced across the warp: the long side's fastest dim is A's fastest dim), multiply by the small dense
+// operator W (nin x nout, assembled from B in shared memory, zeros where no block pair couples j and o) and store
+// the nout outputs (coalesced: C is contiguous in l). Bound by HBM: 8*(nnz(A)+nnz(C)) bytes per contraction.
+constexpr int RG_NT = 256;
+template <int NOUT, int RG_RPT, int JB, int MINB>
+__global__ void __launch_bounds__(RG_NT, MINB) bsc_rowgroup_kernel(const ItbRgItem* __restrict__ items, const ItbRowGroup* __restrict__ groups,
+                                                             const ItbRgIn* __restrict__ ins, const int64_t* __restrict__ outs,
+                                                             const ItbRgW* __restrict__ wents, const double* __restrict__ A,
+                                                             const double* __restrict__ B, double* __restrict__ C) {
+    __shared__ __align__(16) double W[ITB_RG_MAXIN][NOUT];
+    __shared__ ItbRgIn in_s[ITB_RG_MAXIN];
+    __shared__ int64_t out_s[NOUT];
+    const ItbRgItem it = items[blockIdx.x];
+    const ItbRowGroup* __restrict__ gp = groups + it.group;
+    const int tid = threadIdx.x;
+    const int nin = gp->nin, nout = gp->nout;
+    for (int i = tid; i < ITB_RG_MAXIN * NOUT; i += RG_NT) (&W[0][0])[i] = 0.0;
+    if (tid < nin) in_s[tid] = ins[gp->in_begin + tid];
+    if (tid < nout) out_s[tid] = outs[gp->out_begin + tid];
+    __syncthreads();
+    {
+        const int wb = gp->w_begin, wc = gp->w_count;
+        for (int i = tid; i < wc; i += RG_NT) {
+            const ItbRgW e = wents[wb + i];
+            W[e.j][e.o] = B[e.b_off];
+        }
+    }
+    __syncthreads();
+    const int e0 = gp->ext[0], e1 = gp->ext[1];
+    for (int r0 = tid; r0 < it.rows; r0 += RG_NT * RG_RPT) {
+        int i0[RG_RPT], i1[RG_RPT], i2[RG_RPT];
+        bool valid[RG_RPT];
+#pragma unroll
+        for (int q = 0; q < RG_RPT; ++q) {
+            const int r = r0 + q * RG_NT;
+            valid[q] = r < it.rows;
+            int l = it.row0 + (valid[q] ? r : 0);
+            const int a = l / e0;
+            i0[q] = l - a * e0;
+            const int b = a / e1;
+            i1[q] = a - b * e1;
+            i2[q] = b;
+        }
+        double y[RG_RPT][NOUT];
+#pragma unroll
+        for (int q = 0; q < RG_RPT; ++q)
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) y[q][o] = 0.0;
+        for (int j0 = 0; j0 < nin; j0 += JB) { // JB inputs x RG_RPT rows of independent loads in flight
+            double x[JB][RG_RPT];
+#pragma unroll
+            for (int u = 0; u < JB; ++u) {
+                const int j = min(j0 + u, nin - 1);
+                const ItbRgIn& in = in_s[j];
+#pragma unroll
+                for (int q = 0; q < RG_RPT; ++q) {
+                    const int64_t off = in.base + (int64_t)i0[q] * in.str[0] + (int64_t)i1[q] * in.str[1] + (int64_t)i2[q] * in.str[2];
+                    x[u][q] = (valid[q] && j0 + u < nin) ? A[off] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < JB; ++u) {
+                const int j = min(j0 + u, nin - 1);
+#pragma unroll
+                for (int o = 0; o < NOUT; o += 2) {
+                    const double2 w = *reinterpret_cast<const double2*>(&W[j][o]);
+#pragma unroll
+                    for (int q = 0; q < RG_RPT; ++q) {
+                        y[q][o] = fma(x[u][q], w.x, y[q][o]);
+                        y[q][o + 1] = fma(x[u][q], w.y, y[q][o + 1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RG_RPT; ++q) {
+            if (!valid[q]) continue;
+            const int64_t l = it.row0 + r0 + q * RG_NT;
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o)
+                if (o < nout) C[out_s[o] + l] = y[q][o];
+        }
+    }
+}
+
 // ---- split-K reduction kernel: M*N <= 4 ---------------------------------------------------------------
 constexpr int DOT_NT = 256;
 
@@ -823,6 +910,16 @@ cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, in
     }
     if (nq8 > 0) bsc_skinny_smallk_kernel<8, 1, 2><<<nq8, SQ_NT, 0, st>>>(q8, cblks, pairs, A, B, C);
     if (n > 0) bsc_skinny_kernel<<<n, SK_NT, 0, st>>>(items, cblks, pairs, A, B, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rowgroups(const ItbRgItem* items, int nitems, const ItbRowGroup* groups, const ItbRgIn* ins, const int64_t* outs,
+                             const ItbRgW* wents, int max_nout, const double* A, const double* B, double* C, cudaStream_t st) {
+    if (nitems <= 0) return cudaSuccess;
+    // rows per thread in flight shrink as the accumulator tile grows (<= 64 registers of accumulators + loads)
+    if (max_nout <= 4) bsc_rowgroup_kernel<4, 4, 2, 3><<<nitems, RG_NT, 0, st>>>(items, groups, ins, outs, wents, A, B, C);
+    else if (max_nout <= 8) bsc_rowgroup_kernel<8, 2, 4, 3><<<nitems, RG_NT, 0, st>>>(items, groups, ins, outs, wents, A, B, C);
+    else bsc_rowgroup_kernel<ITB_RG_MAXOUT, 1, 4, 3><<<nitems, RG_NT, 0, st>>>(items, groups, ins, outs, wents, A, B, C);
     return cudaGetLastError();
 }
 

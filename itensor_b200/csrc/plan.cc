@@ -230,6 +230,7 @@ static double kTileOverhead[ITB_NCFG] = {1200.0, 8000.0, 5300.0};
 static double kPairOverhead = 4300.0;
 static const double kDmmaSlack = 1.11;
 static int kForceCfg = -1;
+static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static const int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this
 static void read_tile_env() {
     static bool done = false;
@@ -238,6 +239,7 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_TILE_FLOOR")) sscanf(e, "%lf,%lf,%lf", &g_tile_floor[0], &g_tile_floor[1], &g_tile_floor[2]);
     if (const char* e = getenv("ITB_TILE_OVERHEAD")) sscanf(e, "%lf,%lf,%lf,%lf", &kTileOverhead[0], &kTileOverhead[1], &kTileOverhead[2], &kPairOverhead);
     if (const char* e = getenv("ITB_FORCE_CFG")) kForceCfg = atoi(e);
+    if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
 }
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
     const int WM = kTileM[f] / 4, WN = kTileN[f] / 4, FM = WM / 8, FN = WN / 8;
@@ -280,6 +282,7 @@ int build_contract_tables(itb_contract_plan& P) {
 
     P.pairs.clear(); P.cblks.clear(); P.skinny.clear(); P.skinny_q4.clear(); P.skinny_q8.clear(); P.dots.clear(); P.dot_outs.clear();
     P.tiles.clear(); P.splits.clear(); P.ws_slots = 0; P.cta_begin.clear();
+    P.rgroups.clear(); P.rg_in.clear(); P.rg_out.clear(); P.rg_w.clear(); P.rg_items.clear();
     P.ndot_slots = 0;
 
     const int64_t npairs = (int64_t)P.triples.size() / 3;
@@ -291,6 +294,7 @@ int build_contract_tables(itb_contract_plan& P) {
     const int64_t cb_first = P.cb_first, cb_last = (P.cb_last < 0 ? C.nblocks : P.cb_last);
 
     std::vector<int64_t> strA(rA), strB(rB);
+    std::vector<int64_t> pair_ia; // A block of every entry of P.pairs (host only)
     int64_t pos = 0;
     while (pos < npairs) {
         const int64_t ic = P.triples[3 * order[pos] + 2];
@@ -374,6 +378,7 @@ int build_contract_tables(itb_contract_plan& P) {
             pr.flags = flags;
             cbk.ksum += Kr;
             P.pairs.push_back(pr);
+            pair_ia.push_back(ia);
         }
         cbk.pair_end = (int32_t)P.pairs.size();
         cbk.c_off = C.offsets[ic] * csC;
@@ -394,6 +399,33 @@ int build_contract_tables(itb_contract_plan& P) {
     };
     for (double& f : P.class_flops) f = 0;
     std::vector<std::pair<int32_t, int>> tile_cblks; // (C block, tile config)
+    std::vector<int32_t> rg_cands;                   // streaming C blocks eligible for the row-group kernel
+    std::vector<int32_t> stream_cands;               // skinny C blocks (streaming class unless they are too few to matter)
+    auto to_tiles = [&](int32_t c) {                 // tile class: pick the config with the least modelled cycles
+        const ItbCBlk& cb = P.cblks[c];
+        int best = 0; double bestc = 1e300;
+        for (int f = 0; f < ITB_NCFG; ++f) {
+            const double cost = cblk_cost(f, cb.M, cb.N, (double)chunks_of(cb), cb.pair_end - cb.pair_begin);
+            if (cost < bestc) { bestc = cost; best = f; }
+        }
+        if (kForceCfg >= 0) best = kForceCfg;
+        P.class_flops[best] += 2.0 * (double)cb.M * (double)cb.N * (double)cb.ksum;
+        tile_cblks.push_back({c, best});
+    };
+    auto push_skinny = [&](int32_t c) {              // C-stationary streaming kernels (one C block at a time)
+        const ItbCBlk& cb = P.cblks[c];
+        const int64_t M = cb.M, N = cb.N;
+        const int long_is_n = (N > M) ? 1 : 0;
+        const int64_t L = long_is_n ? N : M, Sh = long_is_n ? M : N;
+        if (cb.pair_end - cb.pair_begin <= kSkinnyQMaxPairs) {
+            auto& list = Sh <= 4 ? P.skinny_q4 : P.skinny_q8;
+            for (int64_t r0 = 0; r0 < L; r0 += kSkinnyQRows)
+                list.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyQRows, L - r0), long_is_n});
+        } else {
+            for (int64_t r0 = 0; r0 < L; r0 += kSkinnyRows)
+                P.skinny.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyRows, L - r0), long_is_n});
+        }
+    };
     for (int32_t c = 0; c < (int32_t)P.cblks.size(); ++c) {
         const ItbCBlk& cb = P.cblks[c];
         const int64_t M = cb.M, N = cb.N;
@@ -412,27 +444,127 @@ int build_contract_tables(itb_contract_plan& P) {
             P.dot_outs.push_back(o);
         } else if (std::min(M, N) <= kSkinnyMax && cb.ksum <= kSkinnyQMaxK && M * N >= kSkinnyMinElems) {
             // HBM-bound streaming class: short side <= 8 and a short K loop (the MPO steps of H_eff*phi)
-            P.class_flops[3] += cflops;
-            const int long_is_n = (N > M) ? 1 : 0;
-            const int64_t L = long_is_n ? N : M, Sh = long_is_n ? M : N;
-            if (cb.pair_end - cb.pair_begin <= kSkinnyQMaxPairs) {
-                auto& list = Sh <= 4 ? P.skinny_q4 : P.skinny_q8;
-                for (int64_t r0 = 0; r0 < L; r0 += kSkinnyQRows)
-                    list.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyQRows, L - r0), long_is_n});
-            } else {
-                for (int64_t r0 = 0; r0 < L; r0 += kSkinnyRows)
-                    P.skinny.push_back({c, (int32_t)r0, (int32_t)std::min<int64_t>(kSkinnyRows, L - r0), long_is_n});
-            }
+            stream_cands.push_back(c);
         } else {
-            // pick the tile config with the least modelled cycles (tile_cost below)
-            int best = 0; double bestc = 1e300;
-            for (int f = 0; f < ITB_NCFG; ++f) {
-                const double cost = cblk_cost(f, M, N, (double)chunks_of(cb), cb.pair_end - cb.pair_begin);
-                if (cost < bestc) { bestc = cost; best = f; }
+            to_tiles(c);
+        }
+    }
+    {
+        int64_t stream_elems = 0;
+        for (int32_t c : stream_cands) stream_elems += (int64_t)P.cblks[c].M * P.cblks[c].N;
+        const bool ride = !tile_cblks.empty() && stream_elems < kStreamMinTotal;
+        for (int32_t c : stream_cands) {
+            if (ride) { to_tiles(c); continue; }
+            const ItbCBlk& cb = P.cblks[c];
+            P.class_flops[3] += 2.0 * (double)cb.M * (double)cb.N * (double)cb.ksum;
+            if (!cA && !cB && cb.M >= cb.N && kUseRowGroups) rg_cands.push_back(c); // row-group kernel (below); else C-stationary kernels
+            else push_skinny(c);
+        }
+    }
+    // ---- row groups: streaming C blocks that share their long-side (A-uncontracted) block coordinates ----------
+    if (!rg_cands.empty()) {
+        std::vector<int> uncA; // A's uncontracted indices, in order (they lead the C index list)
+        for (int i = 0; i < rA; ++i) if (AtoB[i] < 0) uncA.push_back(i);
+        auto host_off = [](int64_t idx, const int32_t* ext, const int64_t* str, int n) {
+            int64_t o = 0;
+            for (int d = 0; d < n; ++d) {
+                if (d == n - 1) { o += idx * str[d]; break; }
+                o += (idx % ext[d]) * str[d];
+                idx /= ext[d];
             }
-            if (kForceCfg >= 0) best = kForceCfg;
-            P.class_flops[best] += cflops;
-            tile_cblks.push_back({c, best});
+            return o;
+        };
+        std::map<std::vector<int32_t>, std::vector<int32_t>> by_key;
+        std::vector<std::vector<int32_t>> key_order;
+        for (int32_t c : rg_cands) {
+            const int32_t* ab = A.block(pair_ia[P.cblks[c].pair_begin]);
+            std::vector<int32_t> key;
+            for (int i : uncA) key.push_back(ab[i]);
+            auto it = by_key.find(key);
+            if (it == by_key.end()) { key_order.push_back(key); by_key[key] = {c}; }
+            else it->second.push_back(c);
+        }
+        for (auto& key : key_order) {
+            const std::vector<int32_t>& cs = by_key[key];
+            // long-side dims (unit extents dropped), strides per A block of the group
+            std::vector<int64_t> A_blocks;
+            for (int32_t c : cs)
+                for (int32_t p = P.cblks[c].pair_begin; p < P.cblks[c].pair_end; ++p)
+                    if (std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) == A_blocks.end()) A_blocks.push_back(pair_ia[p]);
+            struct LDim { int64_t ext; std::vector<int64_t> str; };
+            std::vector<LDim> ld;
+            for (size_t u = 0; u < uncA.size(); ++u) {
+                const int64_t e = A.ext(uncA[u], key[u]);
+                if (e == 1) continue;
+                LDim d{e, {}};
+                for (int64_t ia : A_blocks) {
+                    int64_t st = 1;
+                    for (int i = 0; i < uncA[u]; ++i) st *= A.ext(i, A.block(ia)[i]);
+                    d.str.push_back(st);
+                }
+                bool fused = false;
+                if (!ld.empty()) {
+                    bool ok = true;
+                    for (size_t q = 0; q < A_blocks.size(); ++q) ok = ok && d.str[q] == ld.back().str[q] * ld.back().ext;
+                    if (ok) { ld.back().ext *= e; fused = true; }
+                }
+                if (!fused) ld.push_back(d);
+            }
+            int64_t L = 1;
+            for (auto& d : ld) L *= d.ext;
+            bool eligible = (int)ld.size() <= ITB_RG_MAXL && L < (1ll << 31);
+            for (int32_t c : cs) eligible = eligible && P.cblks[c].N <= ITB_RG_MAXOUT && P.cblks[c].ksum <= ITB_RG_MAXIN && P.cblks[c].M == L;
+            if (!eligible) { for (int32_t c : cs) push_skinny(c); continue; }
+            if (ld.empty()) ld.push_back({1, std::vector<int64_t>(A_blocks.size(), 0)});
+            // sub-groups of whole C blocks: <= ITB_RG_MAXOUT output slots and <= ITB_RG_MAXIN input slots each
+            size_t ci = 0;
+            while (ci < cs.size()) {
+                ItbRowGroup g;
+                std::memset(&g, 0, sizeof(g));
+                g.nL = (int32_t)ld.size();
+                for (int d = 0; d < ITB_RG_MAXL; ++d) g.ext[d] = d < g.nL ? (int32_t)ld[d].ext : 1;
+                g.L = L;
+                g.in_begin = (int32_t)P.rg_in.size(); g.out_begin = (int32_t)P.rg_out.size(); g.w_begin = (int32_t)P.rg_w.size();
+                std::map<int64_t, int32_t> slot_of; // A element offset of (block, k) -> input slot
+                while (ci < cs.size()) {
+                    const ItbCBlk& cb = P.cblks[cs[ci]];
+                    // input slots this C block would add
+                    std::vector<int64_t> fresh;
+                    for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p)
+                        for (int32_t k = 0; k < P.pairs[p].K; ++k) {
+                            const int64_t ae = P.pairs[p].a_off + host_off(k, P.pairs[p].k_ext, P.pairs[p].ak_str, P.pairs[p].k_n);
+                            if (!slot_of.count(ae) && std::find(fresh.begin(), fresh.end(), ae) == fresh.end()) fresh.push_back(ae);
+                        }
+                    if (g.nout > 0 && (g.nout + cb.N > ITB_RG_MAXOUT || g.nin + (int)fresh.size() > ITB_RG_MAXIN)) break;
+                    for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
+                        const ItbPair& pr = P.pairs[p];
+                        const size_t qa = std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) - A_blocks.begin();
+                        for (int32_t k = 0; k < pr.K; ++k) {
+                            const int64_t ae = pr.a_off + host_off(k, pr.k_ext, pr.ak_str, pr.k_n);
+                            auto it = slot_of.find(ae);
+                            if (it == slot_of.end()) {
+                                ItbRgIn in;
+                                std::memset(&in, 0, sizeof(in));
+                                in.base = ae;
+                                for (int d = 0; d < g.nL; ++d) in.str[d] = ld[d].str[qa];
+                                it = slot_of.emplace(ae, g.nin++).first;
+                                P.rg_in.push_back(in);
+                            }
+                            const int64_t bk = pr.b_off + host_off(k, pr.k_ext, pr.bk_str, pr.k_n);
+                            for (int32_t n = 0; n < cb.N; ++n)
+                                P.rg_w.push_back({it->second, g.nout + n, bk + host_off(n, pr.n_ext, pr.bn_str, pr.n_n)});
+                        }
+                    }
+                    for (int32_t n = 0; n < cb.N; ++n) P.rg_out.push_back(cb.c_off + (int64_t)n * cb.c_ns);
+                    g.nout += cb.N;
+                    ++ci;
+                }
+                g.w_count = (int32_t)P.rg_w.size() - g.w_begin;
+                const int32_t gi = (int32_t)P.rgroups.size();
+                P.rgroups.push_back(g);
+                for (int64_t r0 = 0; r0 < L; r0 += kRowGroupRows)
+                    P.rg_items.push_back({gi, (int32_t)r0, (int32_t)std::min<int64_t>(kRowGroupRows, L - r0), 0});
+            }
         }
     }
     // ---- tile items: stream-K partition of the tile list over the persistent grid -------------------------
@@ -503,7 +635,9 @@ int build_contract_tables(itb_contract_plan& P) {
     std::stable_sort(P.skinny.begin(), P.skinny.end(), [&](const ItbSkinny& x, const ItbSkinny& y) {
         return P.cblks[x.cblk].ksum * (P.cblks[x.cblk].M + P.cblks[x.cblk].N) > P.cblks[y.cblk].ksum * (P.cblks[y.cblk].M + P.cblks[y.cblk].N);
     });
-    P.table_bytes = (int64_t)(P.pairs.size() * sizeof(ItbPair) + P.cblks.size() * sizeof(ItbCBlk) +
+    P.table_bytes = (int64_t)(P.rgroups.size() * sizeof(ItbRowGroup) + P.rg_in.size() * sizeof(ItbRgIn) + P.rg_out.size() * 8 +
+                              P.rg_w.size() * sizeof(ItbRgW) + P.rg_items.size() * sizeof(ItbRgItem)) +
+                    (int64_t)(P.pairs.size() * sizeof(ItbPair) + P.cblks.size() * sizeof(ItbCBlk) +
                               (P.skinny.size() + P.skinny_q4.size() + P.skinny_q8.size()) * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
                               P.dot_outs.size() * sizeof(ItbDotOut) + P.tiles.size() * sizeof(ItbTile) +
                               P.splits.size() * sizeof(ItbSplitOut) + P.cta_begin.size() * sizeof(int32_t));
@@ -704,7 +838,7 @@ int itb_contract_plan_info(const itb_contract_plan* P, itb_contract_info* o) {
     o->npairs = (int64_t)P->triples.size() / 3;
     o->flops = P->flops;
     o->n_gemm_tiles = (int64_t)P->tiles.size();
-    o->n_skinny = (int64_t)(P->skinny.size() + P->skinny_q4.size() + P->skinny_q8.size());
+    o->n_skinny = (int64_t)(P->skinny.size() + P->skinny_q4.size() + P->skinny_q8.size() + P->rg_items.size());
     o->n_dot = (int64_t)P->dots.size();
     o->table_bytes = P->table_bytes;
     for (int i = 0; i < 5; ++i) o->class_flops[i] = P->class_flops[i];
@@ -730,6 +864,15 @@ int64_t itb_contract_plan_cta_begin(const itb_contract_plan* P, int32_t* out, in
     if (!P) return ITB_ERR_INVALID;
     for (int64_t i = 0; out && i < (int64_t)P->cta_begin.size() && i < cap; ++i) out[i] = P->cta_begin[i];
     return (int64_t)P->cta_begin.size();
+}
+int64_t itb_contract_plan_rowgroups(const itb_contract_plan* P, int64_t* out, int64_t cap) {
+    if (!P) return ITB_ERR_INVALID;
+    for (int64_t i = 0; out && i < (int64_t)P->rgroups.size() && i < cap; ++i) {
+        const ItbRowGroup& g = P->rgroups[i];
+        const int64_t v[4] = {g.nin, g.nout, g.nL, g.L};
+        std::copy(v, v + 4, out + 4 * i);
+    }
+    return (int64_t)P->rgroups.size();
 }
 int64_t itb_contract_plan_cblks(const itb_contract_plan* P, int64_t* out, int64_t cap) {
     if (!P) return ITB_ERR_INVALID;

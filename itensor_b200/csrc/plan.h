@@ -52,6 +52,11 @@ struct itb_contract_plan {
     std::vector<ItbSkinny> skinny;    // generic streaming items
     std::vector<ItbSkinny> skinny_q4; // small-K fast path, short side <= 4
     std::vector<ItbSkinny> skinny_q8; // small-K fast path, short side <= 8
+    std::vector<ItbRowGroup> rgroups; // row-group streaming class (see tables.h)
+    std::vector<ItbRgIn> rg_in;
+    std::vector<int64_t> rg_out;      // output slot bases (REAL-element offsets into C)
+    std::vector<ItbRgW> rg_w;
+    std::vector<ItbRgItem> rg_items;
     std::vector<ItbDot> dots;
     std::vector<ItbDotOut> dot_outs;
     int64_t ndot_slots = 0;
@@ -91,8 +96,12 @@ constexpr int kSkinnyRows = 1024;    // long-side rows per streaming item (4 per
 constexpr int kSkinnyQRows = 8192;   // rows per item of the small-K fast path (8 batches of 4 rows/thread)
 constexpr int kSkinnyQMaxK = 64;     // sum of K over the pairs of a C block / max pairs for the fast path
 constexpr int kSkinnyQMaxPairs = 8;
-constexpr int64_t kSkinnyMinElems = 0;       // (routing small streaming blocks into 32x32 tiles measured 8x slower: disabled)
+constexpr int64_t kSkinnyMinElems = 0;
+constexpr int64_t kStreamMinTotal = 262144;  // when a contraction also has tile work and its skinny C blocks hold fewer elements than this in
+                                             // total, they ride the tile queue (a few thousand cycles each, spread over all CTAs by the stream-K
+                                             // partition) instead of paying latency-bound launches of their own
 constexpr int kNumSMs = 148;         // B200: persistent grid size the split-K heuristic balances for
 constexpr int kSkinnyMax = 8;        // short side <= this -> streaming kernel
+constexpr int kRowGroupRows = 4096;  // long-side rows per work item of the row-group streaming kernel
 constexpr int kDotMaxMN = 4;        // M*N <= this -> reduction kernel (scalar results, re/im pairs)
 } // namespace itb

@@ -60,6 +60,29 @@ struct ItbSplitOut { // split-K tile: C tile = sum of workspace slots [ws_slot0,
 struct ItbSkinny { // work item of the streaming kernel: rows [row0,row0+rows) of the long side
     int32_t cblk, row0, rows, long_is_n; // long_is_n: 1 -> threads run over n, short side is m
 };
+// ---- row-group streaming class -----------------------------------------------------------------------------
+// HBM-bound contractions of a large operand A with tiny operator blocks B (the MPO steps of H_eff*phi): all A blocks
+// that share their uncontracted ("long side") block coordinates feed all C blocks with those coordinates. One row
+// group = those blocks; for every long-side row l
+//     y[o] = sum_j x[j] * W[j][o],   x[j] = A[in_base_j + sum_d i_d*in_str_j[d]],   C[out_base_o + l] = y[o]
+// where (i_0..i_{nL-1}) decomposes l over ext[]. Input slot j = (A block, k), output slot o = (C block, n); W is
+// assembled in shared memory from B through w entries. Every element of A is read once and every element of C
+// written once per row group (the C-stationary kernels re-read an A block once per C block it feeds).
+#define ITB_RG_MAXIN 32
+#define ITB_RG_MAXOUT 16
+#define ITB_RG_MAXL 3
+struct ItbRowGroup {
+    int32_t nin, nout, nL, pad_;
+    int32_t ext[ITB_RG_MAXL];
+    int32_t in_begin, out_begin; // into the slot tables
+    int32_t w_begin, w_count;    // into the W entry table
+    int32_t pad2_;
+    int64_t L;                   // rows
+};
+struct ItbRgIn { int64_t base; int64_t str[ITB_RG_MAXL]; }; // REAL-element offsets into A
+struct ItbRgW { int32_t j, o; int64_t b_off; };              // W[j][o] = B[b_off]
+struct ItbRgItem { int32_t group, row0, rows, pad_; };
+
 struct ItbDot { // work item of the split-K reduction kernel
     int32_t cblk, pair, k0, klen;
     int32_t slot; // partial-sum slot (row in the partial buffer, 16 doubles each)

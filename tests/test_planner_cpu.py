@@ -118,5 +118,7 @@ def test_cblock_range_restriction():
         parts = [a + b for a, b in zip(parts, [P.info.n_gemm_tiles, P.info.n_skinny, P.info.n_dot])]
         fl += sum(P.info.class_flops)
     assert abs(fl - fl_full) < 1e-9 * fl_full
-    assert parts[2] == full[2] and parts[1] == full[1]
+    # (whether skinny C blocks stream or ride the tile queue is decided per executed range, so only the split-K
+    # dot items and the flops are additive)
+    assert parts[2] == full[2]
     assert P.C.nblocks == nb
