@@ -69,6 +69,9 @@ using namespace itb;
 struct itb_solver;
 extern "C" {
 int itb_solver_create(void* stream, itb_solver** out);
+}
+void itb_warm_library_pages(); // solver.cu: background read of the cuSOLVER/cuBLAS shared objects
+extern "C" {
 int itb_solver_syevd(itb_solver* s, int32_t dtype, int32_t n, void* hA, double* hW, int32_t* info);
 int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info);
 }
@@ -234,6 +237,7 @@ int itb_ctx_create(int device, itb_ctx** out) {
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_staging, cudaEventDisableTiming));
+    itb_warm_library_pages();
     *out = c;
     return ITB_OK;
 }

@@ -32,6 +32,7 @@ struct SweepRecord { double energy = 0, seconds = 0, maxtrunc = 0; int maxlink =
 class TimingObserver : public DMRGObserver
     {
     MPS const& psi_;
+    MPS* pin_ = nullptr; // GPU runs: site tensors are re-pinned in HBM after every bond update
     std::chrono::steady_clock::time_point t0_;
     double maxtrunc_ = 0;
     int N_;
@@ -40,7 +41,7 @@ class TimingObserver : public DMRGObserver
     std::vector<double> lastTrunc;   // per bond, last completed half sweep pair
     std::vector<double> centreSpec;  // kept spectrum at the centre bond, last sweep (right-to-left pass)
 
-    TimingObserver(MPS const& psi, Args const& args) : DMRGObserver(psi,args), psi_(psi), N_(length(psi))
+    TimingObserver(MPS& psi, Args const& args, bool pin) : DMRGObserver(psi,args), psi_(psi), pin_(pin ? &psi : nullptr), N_(length(psi))
         {
         t0_ = std::chrono::steady_clock::now();
         }
@@ -51,6 +52,7 @@ class TimingObserver : public DMRGObserver
         auto b = args.getInt("AtBond");
         auto ha = args.getInt("HalfSweep");
         auto terr = args.getReal("Truncerr",0.);
+        if(pin_) { pinToGPU(*pin_,b); pinToGPU(*pin_,b+1); }
         if(b == 1 && ha == 1) { maxtrunc_ = 0; lastTrunc.assign(2*(N_-1),0.); }
         maxtrunc_ = std::max(maxtrunc_,terr);
         auto slot = (ha == 1) ? (b-1) : (N_-1)+(N_-1-b);
@@ -127,7 +129,7 @@ main(int argc, char* argv[])
 #endif
     auto t0 = std::chrono::steady_clock::now();
     auto PH = LocalMPO(H,args);
-    auto obs = TimingObserver(psi,args);
+    auto obs = TimingObserver(psi,args,useGPU);
     auto energy = DMRGWorker(psi,PH,sweeps,obs,args);
     if(useGPU) gpu::synchronize();
     auto total = std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();

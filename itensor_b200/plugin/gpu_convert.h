@@ -73,6 +73,22 @@ toGPU(MPSLike & psi)
     {
     for(auto j : range1(length(psi))) psi.ref(j) = toGPU(psi(j));
     }
+// Re-pin one site tensor in HBM without disturbing the orthogonality bookkeeping (ref() widens the limits).
+// svdBond's factors come out of the reference's host-side per-block loops as host storage; a DMRG observer
+// calls this for sites b, b+1 after every bond update (dmrg.h:445 obs.measure) so that the next
+// phi = A(b)*A(b+1), H_eff*phi and the Davidson vector algebra all run on device-resident data.
+template<class MPSLike>
+void
+pinToGPU(MPSLike & psi, int j)
+    {
+    if(j < 1 || j > length(psi) || onGPU(psi(j))) return;
+    auto l = psi.leftLim();
+    auto r = psi.rightLim();
+    psi.ref(j) = toGPU(psi(j));
+    psi.leftLim(l);
+    psi.rightLim(r);
+    }
+
 template<class MPSLike>
 void
 toCPU(MPSLike & psi)

@@ -29,14 +29,15 @@ namespace gpu {
 
 static itb_ctx* g_ctx = nullptr;
 
-// ITB_PROFILE=1: host wall time and call counts per plugin entry point, printed at exit (the storage-level
+// ITB_PROFILE=1 (2: with device synchronisation): host wall time and call counts per plugin entry point, printed at exit (the storage-level
 // counterpart of the reference's -DCOLLECT_TIMES section timers, itensor/util/timers.h)
 struct Prof
     {
     struct Rec { double secs = 0; long calls = 0; };
     std::map<std::string,Rec> recs;
     bool on = false;
-    Prof() { if(auto* e = std::getenv("ITB_PROFILE")) on = std::atoi(e) != 0; }
+    bool sync = false; // ITB_PROFILE=2: synchronise the device around every entry so that GPU time lands in the entry that queued it
+    Prof() { if(auto* e = std::getenv("ITB_PROFILE")) { on = std::atoi(e) != 0; sync = std::atoi(e) >= 2; } }
     ~Prof()
         {
         if(!on) return;
@@ -50,10 +51,16 @@ struct Scope
     const char* name;
     std::chrono::steady_clock::time_point t0;
     bool on;
-    explicit Scope(const char* n) : name(n), on(prof().on) { if(on) t0 = std::chrono::steady_clock::now(); }
+    explicit Scope(const char* n) : name(n), on(prof().on)
+        {
+        if(!on) return;
+        if(prof().sync && g_ctx) itb_synchronize(g_ctx);
+        t0 = std::chrono::steady_clock::now();
+        }
     ~Scope()
         {
         if(!on) return;
+        if(prof().sync && g_ctx) itb_synchronize(g_ctx);
         auto& r = prof().recs[name];
         r.secs += std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
         r.calls += 1;
