@@ -201,6 +201,27 @@ int itb_syevd_host(itb_ctx* ctx, int32_t dtype, int32_t n, void* hA, double* hW,
  * matrix (destroyed); U is m x l (ldu=m), VT is l x n (ldvt=l), l=min(m,n). cuSOLVER gesvd. */
 int itb_gesvd_host(itb_ctx* ctx, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info);
 
+/* 1 once the device solvers can be used without first-touch stalls. cuSOLVER / cuBLAS load their kernels lazily; on a
+ * box whose page cache is cold the context therefore reads those shared objects sequentially in a background thread
+ * (started by itb_ctx_create, ITB_WARM_LIBS=0 disables). Callers keep small-matrix work on host LAPACK until this
+ * returns 1 (plugin/lapack_gpu.cc, plugin/svd_gpu.cc). */
+int itb_solver_ready(void);
+
+/* Device-resident batched SVD of the blocks of an order-2 block-sparse tensor (svdOrd2 / svdImpl QN loop,
+ * itensor/svd.cc:169-422, on QDenseGPU storage): block b is an m[b] x n[b] column-major matrix at ELEMENT offset
+ * a_off[b] of the device buffer dA (not modified). A_b = U_b diag(s_b) V_b^H with l_b = min(m,n) singular values in
+ * descending order. U and V stay on the device inside the batch object; the caller reads the singular values back
+ * (itb_svd_batch_values: concatenated in block order, synchronises), decides the truncation on the host and copies
+ * the kept leading columns into the new tensors with itb_svd_batch_copy_u / _v (device to device, ordered on the
+ * context's stream). cuSOLVER Xgesvdp (polar decomposition) for min(m,n) >= 96, gesvdj below, 4 concurrent streams. */
+typedef struct itb_svd_batch itb_svd_batch;
+int itb_svd_batch_run(itb_ctx* ctx, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* m, const int32_t* n,
+                      const void* dA, itb_svd_batch** out);
+int itb_svd_batch_values(itb_svd_batch* batch, double* hS);
+int itb_svd_batch_copy_u(itb_svd_batch* batch, int64_t block, int32_t ncols, void* dDst);           /* m x ncols */
+int itb_svd_batch_copy_v(itb_svd_batch* batch, int64_t block, int32_t ncols, void* dDst, int conj); /* n x ncols */
+int itb_svd_batch_destroy(itb_svd_batch* batch);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement
  * only). itb_contract_last_ms then returns the device time of the last run by kernel class

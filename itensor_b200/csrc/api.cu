@@ -67,6 +67,7 @@ struct DeviceTables {
 using namespace itb;
 
 struct itb_solver;
+struct itb_svd_batch;
 extern "C" {
 int itb_solver_create(void* stream, itb_solver** out);
 }
@@ -74,6 +75,8 @@ void itb_warm_library_pages(); // solver.cu: background read of the cuSOLVER/cuB
 extern "C" {
 int itb_solver_syevd(itb_solver* s, int32_t dtype, int32_t n, void* hA, double* hW, int32_t* info);
 int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info);
+int itb_solver_svd_batch_run(itb_solver* s, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* m, const int32_t* n,
+                             const void* dA, itb_svd_batch** out);
 }
 
 struct itb_ctx {
@@ -658,6 +661,15 @@ int itb_gesvd_host(itb_ctx* c, int32_t dtype, int32_t m, int32_t n, void* hA, do
     if (rc != ITB_OK) return rc;
     c->launches += 1;
     return itb_solver_gesvd(c->solver, dtype, m, n, hA, hS, hU, hVT, info);
+}
+
+int itb_svd_batch_run(itb_ctx* c, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* m, const int32_t* n,
+                      const void* dA, itb_svd_batch** out) {
+    if (!c || !out || nblocks < 0) { set_error("svd_batch_run: bad arguments"); return ITB_ERR_INVALID; }
+    int rc = ensure_solver(c);
+    if (rc != ITB_OK) return rc;
+    c->launches += nblocks;
+    return itb_solver_svd_batch_run(c->solver, dtype, nblocks, a_off, m, n, dA, out);
 }
 
 int itb_ctx_set_profile(itb_ctx* c, int profile) { c->profile = profile != 0; return ITB_OK; }

@@ -15,6 +15,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,7 @@
 namespace itb {
 void set_error(const std::string& msg);
 }
+extern "C" const char* itb_last_error(void);
 
 struct itb_solver {
     cusolverDnHandle_t h = nullptr;
@@ -43,6 +45,7 @@ struct itb_solver {
     cusolverDnParams_t params = nullptr;
     void* h_work = nullptr; size_t h_work_bytes = 0;
     double last_err_sigma = 0;
+    struct itb_svd_lanes* lanes = nullptr; // streams + handles of the device-resident batched SVD
 };
 
 #define S_TRY(expr)                                                                         \
@@ -101,12 +104,13 @@ static int collect_cuda_libs(struct dl_phdr_info* info, size_t, void* data) {
     if (n && (strstr(n, "libcusolver") || strstr(n, "libcublas"))) v->push_back(n);
     return 0;
 }
+static std::atomic<int> g_warm_state{0}; // 0: not started, 1: reading, 2: done (or disabled)
+extern "C" int itb_solver_ready(void) { return g_warm_state.load() == 2 ? 1 : 0; }
 void itb_warm_library_pages() {
-    static bool started = false;
-    if (started) return;
-    started = true;
+    int expected = 0;
+    if (!g_warm_state.compare_exchange_strong(expected, 1)) return;
     const char* e = getenv("ITB_WARM_LIBS");
-    if (e && atoi(e) == 0) return;
+    if (e && atoi(e) == 0) { g_warm_state = 2; return; }
     std::vector<std::string> libs;
     dl_iterate_phdr(collect_cuda_libs, &libs);
     std::thread([libs]() {
@@ -124,6 +128,7 @@ void itb_warm_library_pages() {
         if (getenv("ITB_PROFILE"))
             fprintf(stderr, "[itensor_b200] read %zu MB of cuSOLVER/cuBLAS pages in %.1f s\n", total >> 20,
                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        g_warm_state = 2;
     }).detach();
 }
 
@@ -288,6 +293,188 @@ int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* h
     S_TRY(cudaMemcpyAsync(&hinfo, s->d_info, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     S_TRY(cudaStreamSynchronize(s->stream));
     *info = hinfo;
+    return ITB_OK;
+}
+
+
+// ---- device-resident batched SVD of the blocks of an order-2 block-sparse tensor (svdOrd2 on QDenseGPU) ---------------
+// All blocks of one tensor are factorised from the tensor's device buffer, spread over a few streams (a single
+// 700^2 polar SVD leaves most of a B200 idle), and U / V stay on the device: the caller reads back only the singular
+// values (the truncation decision is host logic), then copies the kept columns straight into the new U and V
+// tensors. Large blocks use the polar-decomposition solver (Xgesvdp), small ones one-sided Jacobi (gesvdj).
+constexpr int SVD_LANES = 4;
+struct SvdLane {
+    cudaStream_t st = nullptr;
+    cusolverDnHandle_t h = nullptr;
+    cusolverDnParams_t params = nullptr;
+    gesvdjInfo_t jinfo = nullptr;
+    void* d_work = nullptr; size_t work_bytes = 0;
+    void* d_a = nullptr; size_t a_bytes = 0; // private copy of the block (the solvers destroy their input)
+    void* h_work = nullptr; size_t h_work_bytes = 0;
+    int* d_info = nullptr;
+    cudaEvent_t done = nullptr;
+};
+struct itb_svd_lanes {
+    SvdLane lane[SVD_LANES];
+    cudaEvent_t ready = nullptr;
+    bool init = false;
+};
+} // extern "C" (reopened below)
+
+struct itb_svd_batch {
+    int32_t dtype = ITB_F64;
+    int64_t nblocks = 0;
+    std::vector<int32_t> m, n, l;
+    std::vector<size_t> u_off, v_off, s_off; // byte offsets of U_b (m x l), V_b (n x l); element offset of s_b
+    void* d_uv = nullptr;                    // all U and V
+    double* d_s = nullptr;                   // all singular values
+    int64_t ns = 0;
+    itb_svd_lanes* lanes = nullptr;
+    cudaStream_t main = nullptr;
+    // asynchronous execution: one host thread per busy lane, joined by itb_svd_batch_values / _destroy
+    std::vector<int64_t> a_off;
+    std::vector<int64_t> mine[SVD_LANES];
+    std::vector<std::thread> threads;
+    int lane_rc[SVD_LANES] = {0, 0, 0, 0};
+    std::string lane_err[SVD_LANES];
+    bool joined = false;
+};
+
+static int svd_batch_join(itb_svd_batch* B) {
+    if (B->joined) return ITB_OK;
+    for (auto& t : B->threads) t.join();
+    B->threads.clear();
+    B->joined = true;
+    for (int q = 0; q < SVD_LANES; ++q)
+        if (B->lane_rc[q]) { itb::set_error(B->lane_err[q]); return B->lane_rc[q]; }
+    // everything queued on the context's stream from here on sees the finished factorisations
+    for (auto& ln : B->lanes->lane) { S_TRY(cudaEventRecord(ln.done, ln.st)); S_TRY(cudaStreamWaitEvent(B->main, ln.done, 0)); }
+    return ITB_OK;
+}
+
+static int lanes_init(itb_svd_lanes* L) {
+    if (L->init) return ITB_OK;
+    for (auto& ln : L->lane) {
+        S_TRY(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        CS_TRY(cusolverDnCreate(&ln.h));
+        CS_TRY(cusolverDnSetStream(ln.h, ln.st));
+        CS_TRY(cusolverDnCreateParams(&ln.params));
+        CS_TRY(cusolverDnCreateGesvdjInfo(&ln.jinfo));
+        CS_TRY(cusolverDnXgesvdjSetTolerance(ln.jinfo, 1e-15));
+        CS_TRY(cusolverDnXgesvdjSetMaxSweeps(ln.jinfo, 100));
+        S_TRY(cudaMalloc((void**)&ln.d_info, sizeof(int)));
+        S_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+    }
+    S_TRY(cudaEventCreateWithFlags(&L->ready, cudaEventDisableTiming));
+    L->init = true;
+    return ITB_OK;
+}
+
+static int svd_one(SvdLane& ln, int32_t dtype, int m, int n, const void* dA, double* dS, void* dU, void* dV) {
+    const size_t es = dtype == ITB_C64 ? 16 : 8;
+    const cudaDataType dt = dtype == ITB_C64 ? CUDA_C_64F : CUDA_R_64F;
+    int rc = grow(&ln.d_a, &ln.a_bytes, (size_t)m * n * es); if (rc) return rc;
+    S_TRY(cudaMemcpyAsync(ln.d_a, dA, (size_t)m * n * es, cudaMemcpyDeviceToDevice, ln.st));
+    static int min_polar = -1;
+    if (min_polar < 0) { const char* e = getenv("ITB_SVD_POLAR_MIN_N"); min_polar = e ? atoi(e) : 96; }
+    if (std::min(m, n) >= min_polar) {
+        size_t wd = 0, wh = 0;
+        double err_sigma = 0;
+        CS_TRY(cusolverDnXgesvdp_bufferSize(ln.h, ln.params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, dt, ln.d_a, m, CUDA_R_64F, dS, dt, dU, m, dt, dV, n, dt, &wd, &wh));
+        rc = grow(&ln.d_work, &ln.work_bytes, wd + 256); if (rc) return rc;
+        if (ln.h_work_bytes < wh) { free(ln.h_work); ln.h_work = malloc(wh + 64); ln.h_work_bytes = wh; }
+        CS_TRY(cusolverDnXgesvdp(ln.h, ln.params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, dt, ln.d_a, m, CUDA_R_64F, dS, dt, dU, m, dt, dV, n, dt,
+                                 ln.d_work, wd, ln.h_work, wh, ln.d_info, &err_sigma));
+    } else {
+        int lwork = 0;
+        if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)ln.d_a, m, dS, (double*)dU, m, (double*)dV, n, &lwork, ln.jinfo));
+        else CS_TRY(cusolverDnZgesvdj_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)ln.d_a, m, dS, (cuDoubleComplex*)dU, m, (cuDoubleComplex*)dV, n, &lwork, ln.jinfo));
+        rc = grow(&ln.d_work, &ln.work_bytes, (size_t)lwork * es + 256); if (rc) return rc;
+        if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)ln.d_a, m, dS, (double*)dU, m, (double*)dV, n, (double*)ln.d_work, lwork, ln.d_info, ln.jinfo));
+        else CS_TRY(cusolverDnZgesvdj(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)ln.d_a, m, dS, (cuDoubleComplex*)dU, m, (cuDoubleComplex*)dV, n, (cuDoubleComplex*)ln.d_work, lwork, ln.d_info, ln.jinfo));
+    }
+    return ITB_OK;
+}
+
+extern "C" {
+
+int itb_solver_svd_batch_run(itb_solver* s, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* m, const int32_t* n,
+                             const void* dA, itb_svd_batch** out) {
+    if (!s->lanes) s->lanes = new itb_svd_lanes();
+    int rc = lanes_init(s->lanes); if (rc) return rc;
+    const size_t es = dtype == ITB_C64 ? 16 : 8;
+    auto* B = new itb_svd_batch();
+    B->dtype = dtype; B->nblocks = nblocks; B->lanes = s->lanes; B->main = s->stream;
+    size_t bytes = 0; int64_t ns = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        const int l = std::min(m[b], n[b]);
+        B->m.push_back(m[b]); B->n.push_back(n[b]); B->l.push_back(l);
+        B->u_off.push_back(bytes); bytes += ((size_t)m[b] * l * es + 255) & ~(size_t)255;
+        B->v_off.push_back(bytes); bytes += ((size_t)n[b] * l * es + 255) & ~(size_t)255;
+        B->s_off.push_back((size_t)ns); ns += l;
+    }
+    B->ns = ns;
+    // stream-ordered allocations on the context's stream: the lanes only start after the `ready` event below
+    if (cudaMallocAsync(&B->d_uv, bytes + 256, s->stream) != cudaSuccess || cudaMallocAsync((void**)&B->d_s, (size_t)ns * 8 + 256, s->stream) != cudaSuccess) {
+        itb::set_error("svd batch: out of device memory"); delete B; return ITB_ERR_NOMEM;
+    }
+    // the tensor was produced on the context's stream
+    S_TRY(cudaEventRecord(s->lanes->ready, s->stream));
+    for (auto& ln : s->lanes->lane) S_TRY(cudaStreamWaitEvent(ln.st, s->lanes->ready, 0));
+    // largest blocks first onto the least loaded lane; one host thread drives each lane (the polar solver
+    // synchronises with the host inside the call, so lanes only overlap when they are issued concurrently). The
+    // call returns at once: the caller overlaps its own host work and collects with itb_svd_batch_values.
+    std::vector<int64_t> order(nblocks);
+    for (int64_t b = 0; b < nblocks; ++b) order[b] = b;
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return (double)m[x] * n[x] * std::min(m[x], n[x]) > (double)m[y] * n[y] * std::min(m[y], n[y]); });
+    double load[SVD_LANES] = {0, 0, 0, 0};
+    B->a_off.assign(a_off, a_off + nblocks);
+    static int nlanes = -1; // ITB_SVD_LANES=1..4 (measurement)
+    if (nlanes < 0) { const char* e = getenv("ITB_SVD_LANES"); nlanes = e ? std::max(1, std::min(SVD_LANES, atoi(e))) : SVD_LANES; }
+    for (int64_t b : order) {
+        int best = 0;
+        for (int q = 1; q < nlanes; ++q) if (load[q] < load[best]) best = q;
+        load[best] += (double)m[b] * n[b] * std::min(m[b], n[b]) + 2e7;
+        B->mine[best].push_back(b);
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto work = [B, dev, dA, es, dtype](int q) {
+        cudaSetDevice(dev);
+        for (int64_t b : B->mine[q]) {
+            const int r = svd_one(B->lanes->lane[q], dtype, B->m[b], B->n[b], (const char*)dA + (size_t)B->a_off[b] * es, B->d_s + B->s_off[b],
+                                  (char*)B->d_uv + B->u_off[b], (char*)B->d_uv + B->v_off[b]);
+            if (r) { B->lane_rc[q] = r; B->lane_err[q] = itb_last_error(); return; }
+        }
+    };
+    for (int q = 0; q < SVD_LANES; ++q) if (!B->mine[q].empty()) B->threads.emplace_back(work, q);
+    *out = B;
+    return ITB_OK;
+}
+int itb_svd_batch_values(itb_svd_batch* B, double* hS) { // joins the lanes, syncs
+    int rc = svd_batch_join(B); if (rc) return rc;
+    S_TRY(cudaMemcpyAsync(hS, B->d_s, (size_t)B->ns * 8, cudaMemcpyDeviceToHost, B->main));
+    S_TRY(cudaStreamSynchronize(B->main));
+    return ITB_OK;
+}
+// first ncols columns of U_b (m x ncols, contiguous) / of V_b (n x ncols; conj != 0: complex conjugate) to dDst
+int itb_svd_batch_copy_u(itb_svd_batch* B, int64_t b, int32_t ncols, void* dDst) {
+    const size_t es = B->dtype == ITB_C64 ? 16 : 8;
+    S_TRY(cudaMemcpyAsync(dDst, (char*)B->d_uv + B->u_off[b], (size_t)B->m[b] * ncols * es, cudaMemcpyDeviceToDevice, B->main));
+    return ITB_OK;
+}
+int itb_svd_batch_copy_v(itb_svd_batch* B, int64_t b, int32_t ncols, void* dDst, int conj) {
+    const size_t es = B->dtype == ITB_C64 ? 16 : 8;
+    S_TRY(cudaMemcpyAsync(dDst, (char*)B->d_uv + B->v_off[b], (size_t)B->n[b] * ncols * es, cudaMemcpyDeviceToDevice, B->main));
+    if (conj && B->dtype == ITB_C64) conj_inplace_kernel<<<148, 256, 0, B->main>>>((double2*)dDst, (size_t)B->n[b] * ncols);
+    return ITB_OK;
+}
+int itb_svd_batch_destroy(itb_svd_batch* B) {
+    if (!B) return ITB_OK;
+    svd_batch_join(B);
+    cudaFreeAsync(B->d_uv, B->main); // ordered after the column copies queued on the same stream
+    cudaFreeAsync(B->d_s, B->main);
+    delete B;
     return ITB_OK;
 }
 

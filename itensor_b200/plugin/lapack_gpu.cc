@@ -78,7 +78,7 @@ checkSolver(int rc, const char* what)
 void
 dsyev_wrapper(char jobz, char uplo, LAPACK_INT n, LAPACK_REAL* A, LAPACK_REAL* eigs, LAPACK_INT& info)
     {
-    if(n < eighMinN() || jobz != 'V' || uplo != 'U')
+    if(n < eighMinN() || jobz != 'V' || uplo != 'U' || !itb_solver_ready())
         {
         SolverScope sc(1);
         dsyev_wrapper_host(jobz,uplo,n,A,eigs,info);
@@ -99,7 +99,7 @@ dsyev_wrapper(char jobz, char uplo, LAPACK_INT n, LAPACK_REAL* A, LAPACK_REAL* e
 LAPACK_INT
 zheev_wrapper(LAPACK_INT N, Cplx* A, LAPACK_REAL* d)
     {
-    if(N < eighMinN()) { SolverScope sc(1); return zheev_wrapper_host(N,A,d); }
+    if(N < eighMinN() || !itb_solver_ready()) { SolverScope sc(1); return zheev_wrapper_host(N,A,d); }
     SolverScope sc(0);
     int32_t inf = 0;
     checkSolver(itb_syevd_host(gpu::context(),ITB_C64,N,A,d,&inf),"heevd");
@@ -109,7 +109,7 @@ zheev_wrapper(LAPACK_INT N, Cplx* A, LAPACK_REAL* d)
 void
 dgesdd_wrapper(char* jobz, LAPACK_INT* m, LAPACK_INT* n, LAPACK_REAL* A, LAPACK_REAL* s, LAPACK_REAL* u, LAPACK_REAL* vt, LAPACK_INT* info)
     {
-    if(std::min(*m,*n) < svdMinN() || *jobz != 'S')
+    if(std::min(*m,*n) < svdMinN() || *jobz != 'S' || !itb_solver_ready())
         {
         SolverScope sc(3);
         dgesdd_wrapper_host(jobz,m,n,A,s,u,vt,info);
@@ -124,7 +124,7 @@ dgesdd_wrapper(char* jobz, LAPACK_INT* m, LAPACK_INT* n, LAPACK_REAL* A, LAPACK_
 void
 zgesdd_wrapper(char* jobz, LAPACK_INT* m, LAPACK_INT* n, Cplx* A, LAPACK_REAL* s, Cplx* u, Cplx* vt, LAPACK_INT* info)
     {
-    if(std::min(*m,*n) < svdMinN() || *jobz != 'S')
+    if(std::min(*m,*n) < svdMinN() || *jobz != 'S' || !itb_solver_ready())
         {
         SolverScope sc(3);
         zgesdd_wrapper_host(jobz,m,n,A,s,u,vt,info);

@@ -154,6 +154,12 @@ int itb_dot(itb_ctx*, int32_t dt, int64_t n, const void* xv, const void* yv, int
 }
 int itb_syevd_host(itb_ctx*, int32_t, int32_t, void*, double*, int32_t*) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
 int itb_gesvd_host(itb_ctx*, int32_t, int32_t, int32_t, void*, double*, void*, void*, int32_t*) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
+int itb_svd_batch_run(itb_ctx*, int32_t, int64_t, const int64_t*, const int32_t*, const int32_t*, const void*, itb_svd_batch**) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
+int itb_solver_ready(void) { return 0; }
+int itb_svd_batch_values(itb_svd_batch*, double*) { return ITB_ERR_UNSUPPORTED; }
+int itb_svd_batch_copy_u(itb_svd_batch*, int64_t, int32_t, void*) { return ITB_ERR_UNSUPPORTED; }
+int itb_svd_batch_copy_v(itb_svd_batch*, int64_t, int32_t, void*, int) { return ITB_ERR_UNSUPPORTED; }
+int itb_svd_batch_destroy(itb_svd_batch*) { return ITB_OK; }
 int itb_peak_fp64(itb_ctx*, int, int, double* t) { *t = 0; return ITB_ERR_UNSUPPORTED; }
 int itb_ctx_set_profile(itb_ctx*, int) { return ITB_OK; }
 int64_t itb_contract_last_cta_cycles(itb_ctx*, int64_t*, int64_t) { return 0; }

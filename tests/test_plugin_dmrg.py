@@ -20,8 +20,9 @@ MOCK = os.path.join(ROOT, "build", "plugin", "dmrg_driver_mock")
 REAL = os.path.join(ROOT, "build", "plugin", "dmrg_driver")
 ENV = dict(os.environ, LD_LIBRARY_PATH=os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs") + ":" +
            os.environ.get("LD_LIBRARY_PATH", ""), OPENBLAS_NUM_THREADS="1")
-MOCK_ENV = dict(ENV, ITB_EIGH_MIN_N="1000000000", ITB_SVD_MIN_N="1000000000")  # the mock ABI has no device solver: keep eigh/SVD on host LAPACK
-GPU_ENV = dict(ENV, ITB_EIGH_MIN_N="24", ITB_SVD_MIN_N="24")            # push even small blocks through cuSOLVER in the parity tests
+MOCK_ENV = dict(ENV, ITB_EIGH_MIN_N="1000000000", ITB_SVD_MIN_N="1000000000", ITB_SVD_DEVICE="0")  # the mock ABI has no device solver: keep eigh/SVD on host LAPACK
+# push even small blocks through cuSOLVER in the parity tests (ITB_WARM_LIBS=0: device solvers usable at once)
+GPU_ENV = dict(ENV, ITB_EIGH_MIN_N="24", ITB_SVD_MIN_N="24", ITB_SVD_DEVICE_MIN_N="24", ITB_WARM_LIBS="0")
 SCHED = ["10,20,100,100,200", "1e-10", "2", "1e-7,1e-8,0"]  # sample/dmrg.cc:55-60
 
 
