@@ -366,6 +366,15 @@ static int lanes_init(itb_svd_lanes* L) {
         S_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
     }
     S_TRY(cudaEventCreateWithFlags(&L->ready, cudaEventDisableTiming));
+    { // keep the stream-ordered pool's memory cached across bonds (default: released at every synchronisation,
+      // i.e. ~100 MB of U/V scratch unmapped and remapped per SVD)
+        int dev = 0;
+        cudaMemPool_t pool;
+        S_TRY(cudaGetDevice(&dev));
+        S_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = ~0ull;
+        S_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     L->init = true;
     return ITB_OK;
 }

@@ -127,6 +127,15 @@ svdBlocksGPU(ITensor const& A, QDenseGPU<T> const& d, Index const& uI, Index con
         }
     Lap lap;
     svdProf().calls += 1;
+    // small blocks come to the host first (these synchronous copies must not queue behind the device solvers) ...
+    auto hbuf = std::vector<std::vector<T>>(host_blocks.size());
+    for(auto i : range(host_blocks.size()))
+        {
+        auto b = host_blocks[i];
+        hbuf[i].resize(size_t(mm[b])*nn[b]);
+        checkSvd(itb_memcpy_d2h(gpu::context(),hbuf[i].data(),static_cast<const char*>(d.buf.data())+size_t(off[b])*sizeof(T),hbuf[i].size()*sizeof(T)),"svd block download");
+        }
+    // ... then the device batch starts (asynchronous, one host thread per lane) ...
     BatchGuard batch;
     if(!dev_blocks.empty())
         {
@@ -140,19 +149,14 @@ svdBlocksGPU(ITensor const& A, QDenseGPU<T> const& d, Index const& uI, Index con
     auto sval = std::vector<Real>(size_t(first[nb]));
     auto Uh = std::vector<Mat<T>>(nb);
     auto Vh = std::vector<Mat<T>>(nb);
-    if(!host_blocks.empty())
+    // ... and the host factorises its share meanwhile (no CUDA calls in this loop)
+    for(auto i : range(host_blocks.size()))
         {
-        auto hostargs = args;
-        std::vector<T> tmp;
-        for(auto b : host_blocks)
-            {
-            tmp.resize(size_t(mm[b])*nn[b]);
-            checkSvd(itb_memcpy_d2h(gpu::context(),tmp.data(),static_cast<const char*>(d.buf.data())+size_t(off[b])*sizeof(T),tmp.size()*sizeof(T)),"svd block download");
-            auto S = makeMatRef(tmp.data(),tmp.size(),mm[b],nn[b]);
-            Vector dv;
-            SVD(S,Uh[b],dv,Vh[b],hostargs);
-            for(auto i : range(dv.size())) sval[first[b]+i] = dv(i);
-            }
+        auto b = host_blocks[i];
+        auto S = makeMatRef(hbuf[i].data(),hbuf[i].size(),mm[b],nn[b]);
+        Vector dv;
+        SVD(S,Uh[b],dv,Vh[b],args);
+        for(auto j : range(dv.size())) sval[first[b]+j] = dv(j);
         }
     lap.mark(1);
     if(batch.b)
