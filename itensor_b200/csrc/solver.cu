@@ -241,7 +241,14 @@ static int solver_gesvdp(itb_solver* s, int32_t dtype, int32_t m, int32_t n, voi
 
 int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* hA, double* hS, void* hU, void* hVT, int32_t* info) {
     if (s->svd_method == 1) return solver_gesvdj(s, dtype, m, n, hA, hS, hU, hVT, info);
-    if (s->svd_method == 2) return solver_gesvdp(s, dtype, m, n, hA, hS, hU, hVT, info);
+    if (s->svd_method == 2) {
+        // the polar solver needs a numerically full-rank, not-too-small matrix: small blocks go to Jacobi directly and a
+        // failed polar iteration (exactly rank-deficient input) is redone with Jacobi from the untouched host copy
+        if (std::min(m, n) < 96) return solver_gesvdj(s, dtype, m, n, hA, hS, hU, hVT, info);
+        const int rc = solver_gesvdp(s, dtype, m, n, hA, hS, hU, hVT, info);
+        if (rc == ITB_OK && *info == 0) return rc;
+        return solver_gesvdj(s, dtype, m, n, hA, hS, hU, hVT, info);
+    }
     const size_t es = dtype == ITB_C64 ? 16 : 8;
     const int l = std::min(m, n);
     const bool wide = m < n;
@@ -386,15 +393,28 @@ static int svd_one(SvdLane& ln, int32_t dtype, int m, int n, const void* dA, dou
     S_TRY(cudaMemcpyAsync(ln.d_a, dA, (size_t)m * n * es, cudaMemcpyDeviceToDevice, ln.st));
     static int min_polar = -1;
     if (min_polar < 0) { const char* e = getenv("ITB_SVD_POLAR_MIN_N"); min_polar = e ? atoi(e) : 96; }
-    if (std::min(m, n) >= min_polar) {
+    bool jacobi = std::min(m, n) < min_polar;
+    if (!jacobi) {
         size_t wd = 0, wh = 0;
         double err_sigma = 0;
         CS_TRY(cusolverDnXgesvdp_bufferSize(ln.h, ln.params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, dt, ln.d_a, m, CUDA_R_64F, dS, dt, dU, m, dt, dV, n, dt, &wd, &wh));
         rc = grow(&ln.d_work, &ln.work_bytes, wd + 256); if (rc) return rc;
         if (ln.h_work_bytes < wh) { free(ln.h_work); ln.h_work = malloc(wh + 64); ln.h_work_bytes = wh; }
-        CS_TRY(cusolverDnXgesvdp(ln.h, ln.params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, dt, ln.d_a, m, CUDA_R_64F, dS, dt, dU, m, dt, dV, n, dt,
-                                 ln.d_work, wd, ln.h_work, wh, ln.d_info, &err_sigma));
-    } else {
+        const cusolverStatus_t st = cusolverDnXgesvdp(ln.h, ln.params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, dt, ln.d_a, m, CUDA_R_64F, dS, dt, dU, m, dt, dV, n, dt,
+                                                      ln.d_work, wd, ln.h_work, wh, ln.d_info, &err_sigma);
+        int hinfo = 0;
+        if (st == CUSOLVER_STATUS_SUCCESS) {
+            S_TRY(cudaMemcpyAsync(&hinfo, ln.d_info, sizeof(int), cudaMemcpyDeviceToHost, ln.st));
+            S_TRY(cudaStreamSynchronize(ln.st));
+        }
+        if (st != CUSOLVER_STATUS_SUCCESS || hinfo != 0) {
+            // the polar iteration needs a numerically full-rank matrix: redo exactly rank-deficient blocks with Jacobi
+            (void)cudaGetLastError();
+            S_TRY(cudaMemcpyAsync(ln.d_a, dA, (size_t)m * n * es, cudaMemcpyDeviceToDevice, ln.st));
+            jacobi = true;
+        }
+    }
+    if (jacobi) {
         int lwork = 0;
         if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)ln.d_a, m, dS, (double*)dU, m, (double*)dV, n, &lwork, ln.jinfo));
         else CS_TRY(cusolverDnZgesvdj_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)ln.d_a, m, dS, (cuDoubleComplex*)dU, m, (cuDoubleComplex*)dV, n, &lwork, ln.jinfo));

@@ -3,6 +3,8 @@
 //
 //   dmrg_driver <model> <N> <qn|dense> <cpu|gpu> <maxdims> <cutoffs> <niters> <noises> [json-out]
 //     model   : heis_half | heis_one        (sample/dmrg.cc Hamiltonian, Neel product start)
+//               hubbard                     (sample/hubbard_2d.cc: Nx x Ny cylinder, t=1, U=8 or $HUBBARD_U, Nf and Sz
+//                                            conserved, seeded randomMPS start; <N> is written NxxNy, e.g. 16x4)
 //     lists   : comma separated, one entry per sweep (last entry repeats)
 // Prints one JSON line: final energy, per-sweep energy / wall seconds / max truncation error / max link
 // dimension, per-bond truncation errors of the last sweep and the kept density-matrix spectrum at the
@@ -81,11 +83,21 @@ main(int argc, char* argv[])
     {
     if(argc < 9)
         {
-        println("usage: dmrg_driver <heis_half|heis_one> <N> <qn|dense> <cpu|gpu> <maxdims> <cutoffs> <niters> <noises> [json-out]");
+        println("usage: dmrg_driver <heis_half|heis_one|hubbard> <N|NxxNy> <qn|dense> <cpu|gpu> <maxdims> <cutoffs> <niters> <noises> [json-out]");
         return 2;
         }
     auto model = std::string(argv[1]);
     int N = std::atoi(argv[2]);
+    int Nx = 0, Ny = 0;
+    if(model == "hubbard")
+        {
+        auto a = std::string(argv[2]);
+        auto x = a.find('x');
+        if(x == std::string::npos) { println("hubbard: <N> must be NxxNy"); return 2; }
+        Nx = std::atoi(a.substr(0,x).c_str());
+        Ny = std::atoi(a.substr(x+1).c_str());
+        N = Nx*Ny;
+        }
     bool qn = std::string(argv[3]) == "qn";
     bool useGPU = std::string(argv[4]) == "gpu";
     auto maxdim = parseList(argv[5]), cutoff = parseList(argv[6]), niter = parseList(argv[7]), noise = parseList(argv[8]);
@@ -94,18 +106,41 @@ main(int argc, char* argv[])
 
     SiteSet sites;
     if(model == "heis_half") sites = SpinHalf(N,{"ConserveQNs=",qn});
+    else if(model == "hubbard") sites = Electron(N,{"ConserveQNs=",qn});
     else sites = SpinOne(N,{"ConserveQNs=",qn});
     auto ampo = AutoMPO(sites);
-    for(auto j : range1(N-1))
+    if(model == "hubbard")
         {
-        ampo += 0.5,"S+",j,"S-",j+1;
-        ampo += 0.5,"S-",j,"S+",j+1;
-        ampo +=     "Sz",j,"Sz",j+1;
+        // sample/hubbard_2d.cc:19-35: nearest-neighbour hopping on a cylinder plus on-site repulsion
+        Real U = 8., t = 1.;
+        if(auto* e = std::getenv("HUBBARD_U")) U = std::atof(e);
+        for(auto bnd : squareLattice(Nx,Ny,{"YPeriodic=",true}))
+            for(auto* sp : {"up","dn"})
+                {
+                auto cd = std::string("Cdag")+sp, c = std::string("C")+sp;
+                ampo += -t,cd,bnd.s1,c,bnd.s2;
+                ampo += -t,cd,bnd.s2,c,bnd.s1;
+                }
+        for(auto j : range1(N)) ampo += U,"Nupdn",j;
+        }
+    else
+        {
+        for(auto j : range1(N-1))
+            {
+            ampo += 0.5,"S+",j,"S-",j+1;
+            ampo += 0.5,"S-",j,"S+",j+1;
+            ampo +=     "Sz",j,"Sz",j+1;
+            }
         }
     auto H = toMPO(ampo);
     auto state = InitState(sites);
     for(auto i : range1(N)) state.set(i,i%2==1 ? "Up" : "Dn");
     auto psi = MPS(state);
+    if(model == "hubbard")
+        {
+        seedRNG(1); // randomMPS is unseeded otherwise (mps.cc:281-287)
+        psi = randomMPS(state);
+        }
 
     auto sweeps = Sweeps(nsweep);
     for(int s = 1; s <= nsweep; ++s)

@@ -58,6 +58,10 @@ toCPU(ITensor const& T)
     return out;
     }
 
+// (non-const lvalues would otherwise pick the MPS/MPO template below)
+ITensor inline toGPU(ITensor & T) { return toGPU(static_cast<ITensor const&>(T)); }
+ITensor inline toCPU(ITensor & T) { return toCPU(static_cast<ITensor const&>(T)); }
+
 bool inline
 onGPU(ITensor const& T)
     {

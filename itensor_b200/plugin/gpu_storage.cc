@@ -1091,6 +1091,158 @@ doTask(Order const& O, DenseGPU<T>& dA)
 template void doTask(Order const&,DenseGPU<Real>&);
 template void doTask(Order const&,DenseGPU<Cplx>&);
 
+// Dense combiner (combiner.cc:55-178) with the tensor resident in HBM
+template<typename T>
+static void
+combineDenseGPU(DenseGPU<T> const& d, IndexSet const& dis, IndexSet const& Cis, IndexSet& Nis, ManageStore& m)
+    {
+    auto const& cind = Cis[0];
+    auto dr = long(order(dis));
+    auto cr = long(order(Cis));
+    auto jc = indexPosition(dis,cind);
+    if(jc >= 0) // the tensor carries the combined index: put the original indices back in its place
+        {
+        auto nb = IndexSetBuilder(dr+cr-2);
+        for(auto j : range(dr))
+            {
+            if(j == jc) { for(auto k : range(1,cr)) nb.nextIndex(Cis[k]); }
+            else nb.nextIndex(dis[j]);
+            }
+        Nis = nb.build();
+        return;
+        }
+    // positions of the indices to fuse
+    auto pos = std::vector<long>(cr-1);
+    for(auto k : range(1,cr))
+        {
+        pos[k-1] = indexPosition(dis,Cis[k]);
+        if(pos[k-1] < 0)
+            {
+            println("IndexSet of dense tensor = \n",dis);
+            println("IndexSet of combiner/delta = \n",Cis);
+            Error("Combiner: missing index (no contracted indices in combiner-tensor product)");
+            }
+        }
+    bool in_place = true;
+    for(auto k : range(1,cr-1)) if(pos[k] != pos[k-1]+1) in_place = false;
+    if(in_place)
+        {
+        auto nb = IndexSetBuilder(dr+2-cr);
+        for(auto j : range(pos[0])) nb.nextIndex(dis[j]);
+        nb.nextIndex(cind);
+        for(auto j : range(pos[0]+cr-1,dr)) nb.nextIndex(dis[j]);
+        Nis = nb.build();
+        return;
+        }
+    // fused indices to the front in combiner order, the others behind them in their old order
+    auto P = Permutation(dr);
+    auto taken = std::vector<bool>(dr,false);
+    long dest = 0;
+    for(auto k : range(cr-1)) { P.setFromTo(pos[k],dest++); taken[pos[k]] = true; }
+    auto nb = IndexSetBuilder(dr+2-cr);
+    nb.nextIndex(cind);
+    for(auto j : range(dr))
+        if(!taken[j]) { P.setFromTo(j,dest++); nb.nextIndex(dis[j]); }
+    Nis = nb.build();
+    auto pb = IndexSetBuilder(dr);
+    for(auto j : range(dr)) pb.setIndex(P.dest(j),dis[j]);
+    auto pis = pb.build();
+    auto* nd = m.makeNewData<DenseGPU<T>>(d.n);
+    auto dS = Desc(dis,d.n,dtypeOf<T>());
+    auto dD = Desc(pis,d.n,dtypeOf<T>());
+    auto* plan = getPermutePlan(dS,dD,toPerm(P,dr));
+    check(itb_permute_run(context(),plan,d.buf.data(),nd->buf.data(),1.,0.,0),"combiner permute");
+    }
+template<typename T>
+void
+doTask(Contract& C, DenseGPU<T> const& d, Combiner const& cmb, ManageStore& m)
+    {
+    combineDenseGPU(d,C.Lis,C.Ris,C.Nis,m);
+    }
+template<typename T>
+void
+doTask(Contract& C, Combiner const& cmb, DenseGPU<T> const& d, ManageStore& m)
+    {
+    combineDenseGPU(d,C.Ris,C.Lis,C.Nis,m);
+    if(!m.newData()) m.assignPointerRtoL();
+    }
+template void doTask(Contract&,DenseGPU<Real> const&,Combiner const&,ManageStore&);
+template void doTask(Contract&,DenseGPU<Cplx> const&,Combiner const&,ManageStore&);
+template void doTask(Contract&,Combiner const&,DenseGPU<Real> const&,ManageStore&);
+template void doTask(Contract&,Combiner const&,DenseGPU<Cplx> const&,ManageStore&);
+
+template<typename VA, typename VB>
+static void contractD(Contract& C, void const* Adata, size_t An, void const* Bdata, size_t Bn, ManageStore& m);
+
+// An order-2 diagonal tensor with exactly one index contracted scales the slices of the dense tensor along that index
+// and renames it. On the device this is the dense contraction with the diagonal written out as a (tiny) matrix: the
+// n^2 zeros cost nothing next to keeping the big operand in HBM.
+template<typename T>
+static bool
+scalesOneIndex(IndexSet const& tis, Labels const& lab) { return order(tis) == 2 && ((lab[0] < 0) != (lab[1] < 0)); }
+template<typename T>
+static DenseGPU<T>
+diagAsMatrix(Diag<T> const& t, IndexSet const& tis)
+    {
+    auto n0 = size_t(dim(tis[0])), n1 = size_t(dim(tis[1]));
+    auto h = Dense<T>(n0*n1,T(0.));
+    for(auto i : range(std::min(n0,n1))) h.store[i+n0*i] = t.allSame() ? t.val : t.store[i];
+    return DenseGPU<T>(h);
+    }
+
+// Diag x Dense (diag.cc:128-207): is the diagonal tensor a unit delta over two equal-size indices of which exactly
+// one is contracted? Then the product only renames that index.
+template<typename T>
+static bool
+renamesOneIndex(Diag<T> const& t, IndexSet const& tis, Labels const& lab)
+    {
+    if(order(tis) != 2 || !t.allSame() || !(t.val == 1.) || dim(tis[0]) != dim(tis[1])) return false;
+    return (lab[0] < 0) != (lab[1] < 0);
+    }
+template<typename TA, typename TB>
+void
+doTask(Contract& C, DenseGPU<TA> const& d, Diag<TB> const& t, ManageStore& m)
+    {
+    Labels Lind, Rind;
+    computeLabels(C.Lis,order(C.Lis),C.Ris,order(C.Ris),Lind,Rind);
+    if(renamesOneIndex(t,C.Ris,Rind)) { contractISReplaceIndex(C.Lis,Lind,C.Ris,Rind,C.Nis); return; } // storage untouched
+    if(scalesOneIndex<TB>(C.Ris,Rind))
+        {
+        auto g = diagAsMatrix(t,C.Ris);
+        contractD<TA,TB>(C,d.buf.data(),d.n,g.buf.data(),g.n,m);
+        return;
+        }
+    doTask(C,d.toHost(),t,m);
+    }
+template<typename TA, typename TB>
+void
+doTask(Contract& C, Diag<TA> const& t, DenseGPU<TB> const& d, ManageStore& m)
+    {
+    Labels Lind, Rind;
+    computeLabels(C.Lis,order(C.Lis),C.Ris,order(C.Ris),Lind,Rind);
+    if(renamesOneIndex(t,C.Lis,Lind))
+        {
+        contractISReplaceIndex(C.Ris,Rind,C.Lis,Lind,C.Nis);
+        m.makeNewData<DenseGPU<TB>>(d); // the result owns a (device) copy of the dense operand, as diag.cc:192 does
+        return;
+        }
+    if(scalesOneIndex<TA>(C.Lis,Lind))
+        {
+        auto g = diagAsMatrix(t,C.Lis);
+        contractD<TA,TB>(C,g.buf.data(),g.n,d.buf.data(),d.n,m);
+        return;
+        }
+    doTask(C,t,d.toHost(),m);
+    }
+#define ITB_INST_DIAG(TA,TB) \
+template void doTask(Contract&,DenseGPU<TA> const&,Diag<TB> const&,ManageStore&); \
+template void doTask(Contract&,Diag<TA> const&,DenseGPU<TB> const&,ManageStore&);
+ITB_INST_DIAG(Real,Real)
+ITB_INST_DIAG(Real,Cplx)
+ITB_INST_DIAG(Cplx,Real)
+ITB_INST_DIAG(Cplx,Cplx)
+#undef ITB_INST_DIAG
+
 // doTask(Contract,Dense,Dense) dense.cc:262-330
 template<typename VA, typename VB>
 static void

@@ -261,26 +261,16 @@ template<typename F, typename T>
 void doTask(ApplyIT<F>& A, DenseGPU<T> const& d, ManageStore& m) { doTask(A,d.toHost(),m); }
 template<typename E, typename T>
 void doTask(SetElt<E> const& S, DenseGPU<T> const& d, ManageStore& m) { doTask(S,d.toHost(),m); }
-// A dense combiner can be a pure relabelling that leaves the storage untouched (combiner.cc:55-155); the result
-// must still be a HOST tensor because the decompositions that follow take raw views of it (decomp.cc:60-68).
-template<typename T>
-void doTask(Contract& C, DenseGPU<T> const& d, Combiner const& cmb, ManageStore& m)
-    {
-    auto h = d.toHost();
-    doTask(C,h,cmb,m);
-    if(!m.newData()) m.makeNewData<Dense<T>>(std::move(h));
-    }
-template<typename T>
-void doTask(Contract& C, Combiner const& cmb, DenseGPU<T> const& d, ManageStore& m)
-    {
-    auto h = d.toHost();
-    doTask(C,cmb,h,m);
-    if(!m.newData()) m.makeNewData<Dense<T>>(std::move(h));
-    }
-template<typename TA, typename TB>
-void doTask(Contract& C, DenseGPU<TA> const& d, Diag<TB> const& t, ManageStore& m) { doTask(C,d.toHost(),t,m); }
-template<typename TA, typename TB>
-void doTask(Contract& C, Diag<TA> const& t, DenseGPU<TB> const& d, ManageStore& m) { doTask(C,t,d.toHost(),m); }
+// Dense combiner on the device (combiner.cc:55-178): combining is a relabelling when the fused indices already sit
+// together in combiner order, otherwise one device permute brings them to the front; uncombining is always a
+// relabelling. The result stays in HBM; the decompositions that follow reach it through svdOrd2 / diag_hermitian
+// (plugin/svd_gpu.cc), not through raw host views.
+template<typename T> void doTask(Contract& C, DenseGPU<T> const& d, Combiner const& cmb, ManageStore& m);
+template<typename T> void doTask(Contract& C, Combiner const& cmb, DenseGPU<T> const& d, ManageStore& m);
+// Diag x Dense (diag.cc:128-207): a delta that replaces one index is metadata only (the storage is shared / copied
+// on the device); everything else (scaling by a diagonal, traces) goes through the reference's host code.
+template<typename TA, typename TB> void doTask(Contract& C, DenseGPU<TA> const& d, Diag<TB> const& t, ManageStore& m);
+template<typename TA, typename TB> void doTask(Contract& C, Diag<TA> const& t, DenseGPU<TB> const& d, ManageStore& m);
 
 // binary I/O (ITensor::write, LocalMPO disk spill): GPU storage is written in the host wire format
 // (StorageType QDenseReal/... above), so files read back as ordinary host tensors.

@@ -289,6 +289,71 @@ svdBlocksGPU(ITensor const& A, QDenseGPU<T> const& d, Index const& uI, Index con
     return Spectrum(std::move(probs),{"Truncerr",truncerr});
     }
 
+// dense (no-QN) branch of svdImpl (svd.cc:88-166) on a DenseGPU tensor: one device SVD, truncate() on the host,
+// kept columns copied into new DenseGPU factors
+template<typename T>
+Spectrum
+svdDenseGPU(ITensor const& A, DenseGPU<T> const& d, Index const& uI, Index const& vI,
+            ITensor & U, ITensor & D, ITensor & V, Args const& args)
+    {
+    auto do_truncate = args.getBool("Truncate");
+    auto cutoff = args.getReal("Cutoff",MIN_CUT);
+    auto maxdim = args.getInt("MaxDim",args.getInt("Maxm",MAX_DIM));
+    auto mindim = args.getInt("MinDim",args.getInt("Minm",1));
+    auto doRelCutoff = args.getBool("DoRelCutoff",true);
+    auto absoluteCutoff = args.getBool("AbsoluteCutoff",false);
+    auto litagset = getTagSet(args,"LeftTags","Link,U");
+    auto ritagset = getTagSet(args,"RightTags","Link,V");
+    if(litagset == ritagset) Error("In SVD, must specify different tags for the new left and right indices (with Args 'LeftTags' and 'RightTags')");
+
+    auto const& is = A.inds();
+    const bool transposed = !(uI == is.front()); // stored matrix S is dim(is[0]) x dim(is[1]); M = S or S^T (decomp.cc:70-79)
+    int64_t off = 0;
+    int32_t mm = int32_t(dim(is[0])), nn = int32_t(dim(is[1]));
+    BatchGuard batch;
+    checkSvd(itb_svd_batch_run(gpu::context(),dtypeFor<T>(),1,&off,&mm,&nn,d.buf.data(),&batch.b),"svd (dense)");
+    auto l = long(std::min(mm,nn));
+    auto sval = std::vector<Real>(size_t(l));
+    checkSvd(itb_svd_batch_values(batch.b,sval.data()),"svd values");
+
+    auto probs = Vector(l);
+    for(auto j : range(l)) probs(j) = sval[j]*sval[j];
+    Real truncerr = 0, cut_lo = -1, cut_hi = -1;
+    int ndegen = 1;
+    long k = l;
+    if(do_truncate)
+        {
+        std::tie(truncerr,cut_lo,cut_hi,ndegen) = truncate(probs,maxdim,mindim,cutoff,absoluteCutoff,doRelCutoff,args);
+        k = long(probs.size());
+        }
+    auto uL = Index(k,litagset);
+    auto vL = Index(k,ritagset);
+    auto Ug = DenseGPU<T>(size_t(dim(uI))*size_t(k));
+    auto Vg = DenseGPU<T>(size_t(dim(vI))*size_t(k));
+    // S = Us diag(s) Vs^H; the reference keeps U = U_M and V = conj(V_M) of M = U_M s V_M^H (svd.cc:100-103)
+    if(!transposed)
+        {
+        checkSvd(itb_svd_batch_copy_u(batch.b,0,int32_t(k),Ug.buf.data()),"svd copy U");
+        checkSvd(itb_svd_batch_copy_v(batch.b,0,int32_t(k),Vg.buf.data(),1),"svd copy V");
+        }
+    else
+        {
+        checkSvd(itb_svd_batch_copy_v(batch.b,0,int32_t(k),Ug.buf.data(),1),"svd copy U");
+        checkSvd(itb_svd_batch_copy_u(batch.b,0,int32_t(k),Vg.buf.data()),"svd copy V");
+        }
+    Real signfix = (A.scale().sign() == -1) ? -1 : +1;
+    D = ITensor({uL,vL},Diag<Real>{sval.begin(),sval.begin()+k},A.scale()*signfix);
+    U = ITensor({uI,uL},std::move(Ug),LogNum(signfix));
+    V = ITensor({vI,vL},std::move(Vg));
+    auto DD = Vector(k);
+    for(auto j : range(k)) DD(j) = sval[j]*sval[j];
+#ifdef USESCALE
+    if(A.scale().isFiniteReal()) DD *= sqr(A.scale().real0());
+    else println("Warning: scale not finite real after svd");
+#endif
+    return Spectrum(std::move(DD),{"Truncerr",truncerr});
+    }
+
 // find out whether A is one of the HBM-resident block-sparse storage types
 struct SvdDispatch
     {
@@ -296,6 +361,8 @@ struct SvdDispatch
     Spectrum& spec; bool& done;
     void operator()(QDenseGPUReal const& d) { spec = svdBlocksGPU<Real>(A,d,uI,vI,U,D,V,args); done = true; }
     void operator()(QDenseGPUCplx const& d) { spec = svdBlocksGPU<Cplx>(A,d,uI,vI,U,D,V,args); done = true; }
+    void operator()(DenseGPUReal const& d) { spec = svdDenseGPU<Real>(A,d,uI,vI,U,D,V,args); done = true; }
+    void operator()(DenseGPUCplx const& d) { spec = svdDenseGPU<Cplx>(A,d,uI,vI,U,D,V,args); done = true; }
     template<typename S> void operator()(S const&) { }
     };
 
@@ -306,7 +373,7 @@ svdOrd2(ITensor const& A, Index const& uI, Index const& vI, ITensor & U, ITensor
     {
     static const bool device_svd = [] { auto* e = std::getenv("ITB_SVD_DEVICE"); return !(e && std::atoi(e) == 0); }();
     const bool plain = !args.getBool("ComputeQNs",false) && !args.getBool("ShowEigs",false);
-    if(device_svd && plain && A.store() && A.order() == 2 && onGPU(A) && hasQNs(A))
+    if(device_svd && plain && A.store() && A.order() == 2 && onGPU(A))
         {
         auto a = args;
         if(!a.defined("MaxDim") && a.defined("Maxm")) a.add("MaxDim",a.getInt("Maxm"));
@@ -316,8 +383,29 @@ svdOrd2(ITensor const& A, Index const& uI, Index const& vI, ITensor & U, ITensor
         applyFunc(SvdDispatch{A,uI,vI,U,D,V,a,spec,done},A.store());
         if(done) return spec;
         }
-    // the reference's path (host storage; GPU storage reaches its per-block loops through GetBlocks / ToMatRefc views)
+    // the reference's path (host storage; QDenseGPU reaches its per-block loops through GetBlocks views; dense GPU
+    // storage has no raw host view, so it is downloaded)
+    if(A.store() && onGPU(A) && !hasQNs(A)) return svdOrd2_host(toCPU(A),uI,vI,U,D,V,args);
     return svdOrd2_host(A,uI,vI,U,D,V,args);
+    }
+
+// diag_hermitian (hermitian.cc:429-440) likewise: hermitian.cc is compiled with -Ddiag_hermitian=diag_hermitian_host.
+// Block-sparse GPU tensors go through the reference's per-block loop (GetBlocks views; blocks >= 256 are diagonalised
+// by cuSOLVER behind the LAPACK boundary). A dense GPU tensor has no raw host view (ToMatRefc is private to
+// decomp.cc), so it is diagonalised from a host copy and the eigenvectors return to HBM.
+Spectrum
+diag_hermitian_host(ITensor H, ITensor & U, ITensor & D, Args const& args);
+
+Spectrum
+diag_hermitian(ITensor H, ITensor & U, ITensor & D, Args const& args)
+    {
+    if(H.store() && onGPU(H) && !hasQNs(H))
+        {
+        auto spec = diag_hermitian_host(toCPU(H),U,D,args);
+        U = toGPU(U);
+        return spec;
+        }
+    return diag_hermitian_host(H,U,D,args);
     }
 
 } //namespace itensor

@@ -44,7 +44,7 @@ def compare(g, c, etol, per_bond=True):
 
 
 @pytest.mark.skipif(not os.path.exists(MOCK), reason="build/plugin/dmrg_driver_mock not built (needs /root/reference)")
-@pytest.mark.parametrize("model,N,qn", [("heis_half", 16, "qn"), ("heis_one", 10, "qn"), ("heis_half", 10, "dense")])
+@pytest.mark.parametrize("model,N,qn", [("heis_half", 16, "qn"), ("heis_one", 10, "qn"), ("heis_half", 10, "dense"), ("hubbard", "4x2", "qn")])
 def test_plugin_host_logic_on_mock_abi(model, N, qn):
     g = run(MOCK, model, N, qn, "gpu", ["10,20,40", "1e-10", "2", "1e-7,1e-8,0"])
     c = run(MOCK, model, N, qn, "cpu", ["10,20,40", "1e-10", "2", "1e-7,1e-8,0"])
@@ -92,3 +92,61 @@ def test_dmrg_dense_storage_on_gpu():
     c = run(REAL, "heis_one", 12, "dense", "cpu", ["10,20,40,40,40,40", "1e-10", "2", "1e-7,1e-8,0"])
     assert g["gpu_launches"] > 1000
     assert abs(g["energy"] - c["energy"]) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REAL), reason="build/plugin/dmrg_driver not built")
+def test_dmrg_hubbard_cylinder_parity_on_gpu():
+    """BASELINE configs[2]'s model at a size the CPU finishes in seconds: sample/hubbard_2d.cc on a 4x3 cylinder, U=8,
+    (Nf,Sz) blocks (two QN components, fermionic MPO of bond dimension ~14), seeded randomMPS start."""
+    sched = ["20,60,100,100,200,200", "1e-8", "2", "1e-7,1e-8,1e-10,0"]
+    g = run(REAL, "hubbard", "4x3", "qn", "gpu", sched)
+    c = run(REAL, "hubbard", "4x3", "qn", "cpu", sched)
+    assert g["gpu_launches"] > 10000
+    compare(g, c, 1e-9, per_bond=False)
+
+
+TRG = os.path.join(ROOT, "build", "plugin", "trg_driver")
+
+
+def run_trg(maxdim, topscale, storage):
+    out = subprocess.run([TRG, str(maxdim), str(topscale), storage], env=GPU_ENV, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().split("\n")[-1])
+
+
+@pytest.mark.skipif(not os.path.exists(TRG), reason="build/plugin/trg_driver not built (needs /root/reference)")
+def test_trg_reference_value_on_host_storage():
+    """sample/trg.cc as-is (maxdim 20, 20 scales): kappa = 2.717050813029 (SURVEY 8c pin of the reference build)."""
+    c = run_trg(20, 20, "cpu")
+    assert abs(c["kappa"] - 2.717050813029) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(TRG), reason="build/plugin/trg_driver not built")
+def test_trg_dense_path_on_gpu():
+    """BASELINE configs[4]: dense TRG. delta() renames, dense combiners, factor()'s SVD and the four-tensor contraction
+    all stay on DenseGPU storage; kappa must match the host run of the same binary."""
+    g = run_trg(20, 20, "gpu")
+    c = run_trg(20, 20, "cpu")
+    assert g["result_on_gpu"] and g["gpu_launches"] > 200
+    assert abs(g["kappa"] - c["kappa"]) < 1e-10
+    assert abs(g["kappa"] - 2.717050813029) < 1e-10
+
+
+OPS_MOCK = os.path.join(ROOT, "build", "plugin", "dense_ops_check_mock")
+OPS_REAL = os.path.join(ROOT, "build", "plugin", "dense_ops_check")
+
+
+@pytest.mark.skipif(not os.path.exists(OPS_MOCK), reason="build/plugin/dense_ops_check_mock not built (needs /root/reference)")
+def test_dense_combiner_delta_diag_overloads_on_mock_abi():
+    """DenseGPU x Combiner / delta / Diag against the reference's host products of the same ITensors"""
+    out = subprocess.run([OPS_MOCK], env=MOCK_ENV, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all dense-ops cases ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(OPS_REAL), reason="build/plugin/dense_ops_check not built")
+def test_dense_combiner_delta_diag_overloads_on_gpu():
+    out = subprocess.run([OPS_REAL], env=GPU_ENV, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all dense-ops cases ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
