@@ -64,6 +64,35 @@ main()
         same("partial trace with delta(j,jj)",S*delta(j,jj),toGPU(S)*delta(j,jj),false);
         }
         }
+    // svd / factor of a dense GPU tensor (device svdOrd2): reconstruction, spectrum and truncation vs the host run.
+    // (skipped on the mock ABI, which has no device solver: ITB_SVD_DEVICE=0)
+    if(!(std::getenv("ITB_SVD_DEVICE") && std::atoi(std::getenv("ITB_SVD_DEVICE")) == 0))
+        {
+        auto a = Index(6,"a"), b = Index(5,"b"), c = Index(7,"c"), e = Index(4,"e");
+        for(int cplx = 0; cplx < 2; ++cplx)
+            {
+            auto T = cplx ? randomITensorC(a,b,c,e) : randomITensor(a,b,c,e);
+            auto G = toGPU(T);
+            for(int pass = 0; pass < 3; ++pass)
+                {
+                // pass 0: U = (a,b) leading indices; pass 1: U = (c,a) scattered (stored matrix is transposed / permuted);
+                // pass 2: truncated to 9 singular values
+                ITensor Uh(a,b), Dh, Vh, Ug(a,b), Dg, Vg;
+                if(pass == 1) { Uh = ITensor(c,a); Ug = ITensor(c,a); }
+                auto args = pass == 2 ? Args("MaxDim",9,"Cutoff",0.) : Args::global();
+                auto sh = svd(T,Uh,Dh,Vh,args);
+                auto sg = svd(G,Ug,Dg,Vg,args);
+                auto rec_h = Uh*Dh*Vh, rec_g = toCPU(Ug)*Dg*toCPU(Vg);
+                auto dspec = 0.;
+                for(auto n : range1(std::min(sh.numEigsKept(),sg.numEigsKept()))) dspec = std::max(dspec,std::fabs(sh.eig(n)-sg.eig(n)));
+                auto ok = onGPU(Ug) && onGPU(Vg) && sh.numEigsKept() == sg.numEigsKept() && dspec <= 1e-12*sh.eig(1)
+                          && norm(rec_h-rec_g) <= 1e-11*norm(T) && std::fabs(sh.truncerr()-sg.truncerr()) <= 1e-12;
+                printfln("svd dense %s pass %d: kept %d/%d  |dspec| %.1e  |rec_h-rec_g| %.1e  truncerr %.3e/%.3e  %s",cplx ? "cplx" : "real",pass,
+                         sg.numEigsKept(),sh.numEigsKept(),dspec,norm(rec_h-rec_g),sg.truncerr(),sh.truncerr(),ok ? "ok" : "FAIL");
+                if(!ok) ++failures;
+                }
+            }
+        }
     if(failures) { printfln("%d case(s) FAILED",failures); return 1; }
     println("all dense-ops cases ok");
     return 0;

