@@ -48,7 +48,9 @@ def workload(m: int, nsect: int, dtype: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe). The timed region of this bench
+    is ~15 ms, shorter than one nvidia-smi loop period, so the sampler polls NVML in-process (nvidia_ml_py) every
+    millisecond from a thread; nvidia-smi -lms is the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -57,8 +59,26 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines = []
+        self.samples = []  # (sm_mhz, reasons bitmask)
+        self.nvml = None
+        self.stop_flag = False
+        self.max_mhz = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.device]) if vis and vis.split(",")[self.device].isdigit() else self.device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -67,11 +87,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
+            sm = [s for s, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml polled every 1 ms during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +138,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def measure_dgemm_peak(torch, dev, n=8192, reps=6):
@@ -332,8 +378,14 @@ def main():
         lib().itb_peak_fp64(ctx.handle, 0, 4096, C.byref(dmma))
         dfma = C.c_double()
         lib().itb_peak_fp64(ctx.handle, 1, 4096, C.byref(dfma))
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tp) and args.m == 2000 and args.nsect == 9 and not args.complex and world == 1:
+            tj = json.load(open(tp))["bsc_gemm_kernel"]
+            traffic = float(np.mean(tj["per_launch_bytes"]))  # DRAM bytes per launch (mean of the step-1 and step-4 launches)
+            traffic_src = "profiles/r02_traffic.json (ncu --set full of this command; algorithmic bytes per launch %.3g)" % float(np.mean(tj["algorithmic_bytes_per_launch"]))
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                "traffic": None, "kernel": "bsc_gemm_kernel (persistent DMMA tiles 128/64/32, split-K)",
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "bsc_gemm_kernel (persistent warp-specialised DMMA tiles 128/64/32, stream-K partition)",
                 "peak_source": "measured in this run: torch.matmul fp64 8192^3 best of 6 (MEASURED_PEAKS.json has no FP64 entry)",
                 "launches_per_step": n_launch, "ms_per_step": {"tile_kernel": float(cls_ms[0]), "streaming_kernel": float(cls_ms[3]), "dot_kernel": float(cls_ms[4])},
                 "flops_per_step_by_class": {"tile128": float(cls_fl[0]), "tile64": float(cls_fl[1]), "tile32": float(cls_fl[2]),
