@@ -229,6 +229,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version banner)
         dist.init_process_group("nccl", device_id=dev)
     ctx = itb.Context(local)
     dtype = ITB_C64 if args.complex else ITB_F64

@@ -199,19 +199,32 @@ struct Dim {
     int64_t sa, sb; // strides (REAL units) in the tensors that carry this dim (sb unused for M/N)
 };
 
+// index-group scratch without heap traffic (the planner runs once per new block structure, i.e. at every DMRG bond)
+struct DimList {
+    Dim d[ITB_MAX_ORDER + 2];
+    int n = 0;
+    void push_back(const Dim& x) { d[n++] = x; }
+    void push_front(const Dim& x) { for (int i = n; i > 0; --i) d[i] = d[i - 1]; d[0] = x; ++n; }
+    size_t size() const { return (size_t)n; }
+    Dim& operator[](size_t i) { return d[i]; }
+    const Dim* begin() const { return d; }
+    const Dim* end() const { return d + n; }
+};
+
 // drop unit dims, then fuse neighbours that are contiguous in every tensor carrying the group
-static void canon(std::vector<Dim>& g, bool two) {
-    std::vector<Dim> out;
-    for (auto& d : g) {
+static void canon(DimList& g, bool two) {
+    int o = 0;
+    for (int i = 0; i < g.n; ++i) {
+        const Dim d = g.d[i];
         if (d.ext == 1) continue;
-        if (!out.empty()) {
-            Dim& l = out.back();
-            bool ok = (d.sa == l.sa * l.ext) && (!two || d.sb == l.sb * l.ext);
+        if (o > 0) {
+            Dim& l = g.d[o - 1];
+            const bool ok = (d.sa == l.sa * l.ext) && (!two || d.sb == l.sb * l.ext);
             if (ok) { l.ext *= d.ext; continue; }
         }
-        out.push_back(d);
+        g.d[o++] = d;
     }
-    g.swap(out);
+    g.n = o;
 }
 
 // ---- cycle model of the DMMA tile kernel (per BK=16 K-chunk of one tile, per SM) -----------------------------
@@ -315,7 +328,7 @@ int build_contract_tables(itb_contract_plan& P) {
             for (int i = 0; i < rA; ++i) { strA[i] = s; s *= A.ext(i, ab[i]); }
             s = csB;
             for (int j = 0; j < rB; ++j) { strB[j] = s; s *= B.ext(j, bb[j]); }
-            std::vector<Dim> gm, gk, gn;
+            DimList gm, gk, gn;
             // which operand-fastest (non-unit) index is contracted?
             int fa = -1, fb = -1;
             for (int i = 0; i < rA && fa < 0; ++i) if (A.ext(i, ab[i]) > 1) fa = i;
@@ -342,13 +355,13 @@ int build_contract_tables(itb_contract_plan& P) {
             // ---- complex folding: prepend a pseudo-dim of extent 2 (re,im) -------------------------
             int flags = 0;
             if (cA && cB) { // [Cr;Ci] = [[Ar,-Ai],[Ai,Ar]] [Br;Bi]
-                gm.insert(gm.begin(), {2, 1, 0});
-                gk.insert(gk.begin(), {2, 1, 1});
+                gm.push_front({2, 1, 0});
+                gk.push_front({2, 1, 1});
                 flags |= ITB_PF_CCA;
             } else if (cA) { // rows of A doubled: C'(2m+p,n) = sum_k A(m,k).comp(p) B(k,n)
-                gm.insert(gm.begin(), {2, 1, 0});
+                gm.push_front({2, 1, 0});
             } else if (cB) { // columns of B doubled: C'(m,2n+q) = sum_k A(m,k) B(k,n).comp(q)
-                gn.insert(gn.begin(), {2, 1, 0});
+                gn.push_front({2, 1, 0});
             }
             canon(gm, false); canon(gk, true); canon(gn, false);
             if (gm.size() > ITB_MAXG || gk.size() > ITB_MAXG || gn.size() > ITB_MAXG) {

@@ -57,13 +57,35 @@ main()
         same("diag scaling D*T",Dg*T,Dg*G);
         same("diag vs dense matrix",T*D,G*Dg);
         }
-        // trace over two indices of equal size goes through the reference's host code (result small, host)
+        // partial trace over two indices of equal size, and the full trace down to a scalar
         {
         auto jj = Index(4,"jj");
         auto S = cplx ? randomITensorC(j,jj,k) : randomITensor(j,jj,k);
-        same("partial trace with delta(j,jj)",S*delta(j,jj),toGPU(S)*delta(j,jj),false);
+        same("partial trace with delta(j,jj)",S*delta(j,jj),toGPU(S)*delta(j,jj));
+        same("partial trace, delta on the left",delta(j,jj)*S,delta(j,jj)*toGPU(S));
+        auto S2 = cplx ? randomITensorC(j,jj) : randomITensor(j,jj);
+        auto th = eltC(S2*delta(j,jj)), tg = eltC(toGPU(S2)*delta(j,jj));
+        auto ok = std::abs(th-tg) <= 1e-13*std::max(1.,std::abs(th));
+        printfln("%-44s |diff| %.2e  %s","full trace to a scalar",std::abs(th-tg),ok ? "ok" : "FAIL");
+        if(!ok) ++failures;
         }
         }
+    // QDiag x QDenseGPU (svdBond's A *= D): the diagonal factor of a host SVD against the device-resident factors
+    {
+    auto I = Index(QN({"Sz",-1}),3,QN({"Sz",0}),4,QN({"Sz",1}),2,Out,"I");
+    auto J = Index(QN({"Sz",-1}),2,QN({"Sz",0}),5,QN({"Sz",1}),3,Out,"J");
+    auto K = Index(QN({"Sz",-1}),2,QN({"Sz",1}),2,Out,"K");
+    for(int cplx = 0; cplx < 2; ++cplx)
+        {
+        auto T = cplx ? randomITensorC(QN({"Sz",0}),I,dag(J),K) : randomITensor(QN({"Sz",0}),I,dag(J),K);
+        ITensor U(I,K), D, V;
+        svd(T,U,D,V,{"MaxDim",6});
+        same("QDiag: V*D",V*D,toGPU(V)*D);
+        same("QDiag: D*V",D*V,D*toGPU(V));
+        same("QDiag: U*D",U*D,toGPU(U)*D);
+        same("QDiag: U*D*V",U*D*V,toGPU(U)*D*toGPU(V));
+        }
+    }
     // svd / factor of a dense GPU tensor (device svdOrd2): reconstruction, spectrum and truncation vs the host run.
     // (skipped on the mock ABI, which has no device solver: ITB_SVD_DEVICE=0)
     if(!(std::getenv("ITB_SVD_DEVICE") && std::atoi(std::getenv("ITB_SVD_DEVICE")) == 0))

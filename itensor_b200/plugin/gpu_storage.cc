@@ -626,6 +626,85 @@ ITB_INST_CONTRACT(Cplx,Real)
 ITB_INST_CONTRACT(Cplx,Cplx)
 #undef ITB_INST_CONTRACT
 
+// QDiag written out as a block-sparse matrix: diagonal position i of an order-2 QDiag over (I0,I1) lies in block
+// (sector of i in I0, sector of i in I1) at the in-sector positions; the blocks it touches become dense matrices.
+template<typename T>
+static QDenseGPU<T>
+qdiagAsMatrix(QDiag<T> const& t, IndexSet const& tis)
+    {
+    auto n = std::min(dim(tis[0]),dim(tis[1]));
+    struct Hit { long s0, s1, p0, p1; };
+    auto hits = std::vector<Hit>(n);
+    long s0 = 0, s1 = 0, b0 = 0, b1 = 0; // current sectors and their first positions
+    for(auto i : range(n))
+        {
+        while(i >= b0+tis[0].blocksize0(s0)) { b0 += tis[0].blocksize0(s0); ++s0; }
+        while(i >= b1+tis[1].blocksize0(s1)) { b1 += tis[1].blocksize0(s1); ++s1; }
+        hits[i] = Hit{s0,s1,i-b0,i-b1};
+        }
+    // unique blocks in the reference's order (last index most significant, qdense.cc:60-65)
+    auto blocks = std::vector<std::pair<long,long>>();
+    for(auto& h : hits) blocks.emplace_back(h.s1,h.s0);
+    std::sort(blocks.begin(),blocks.end());
+    blocks.erase(std::unique(blocks.begin(),blocks.end()),blocks.end());
+    auto offs = BlockOffsets();
+    auto start = std::map<std::pair<long,long>,long>();
+    long size = 0;
+    for(auto& b : blocks)
+        {
+        auto blk = Block(2);
+        blk[0] = b.second; blk[1] = b.first;
+        offs.push_back(make_blof(blk,size));
+        start[b] = size;
+        size += tis[0].blocksize0(b.second)*tis[1].blocksize0(b.first);
+        }
+    auto h = QDense<T>();
+    h.offsets = offs;
+    h.store.assign(size_t(size),T(0.));
+    for(auto i : range(n))
+        {
+        auto& x = hits[i];
+        h.store[size_t(start[{x.s1,x.s0}] + x.p0 + x.p1*tis[0].blocksize0(x.s0))] = t.allSame() ? t.val : t.store[i];
+        }
+    return QDenseGPU<T>(h);
+    }
+template<typename TA, typename TB>
+void
+doTask(Contract& C, QDenseGPU<TA> const& d, QDiag<TB> const& t, ManageStore& m)
+    {
+    Labels Lind, Rind;
+    computeLabels(C.Lis,order(C.Lis),C.Ris,order(C.Ris),Lind,Rind);
+    if(order(C.Ris) == 2 && (Rind[0] < 0 || Rind[1] < 0))
+        {
+        auto g = qdiagAsMatrix(t,C.Ris);
+        contractQ<TA,TB>(C,d.offsets,d.buf.data(),d.n,g.offsets,g.buf.data(),g.n,m);
+        return;
+        }
+    doTask(C,d.toHost(),t,m);
+    }
+template<typename TA, typename TB>
+void
+doTask(Contract& C, QDiag<TA> const& t, QDenseGPU<TB> const& d, ManageStore& m)
+    {
+    Labels Lind, Rind;
+    computeLabels(C.Lis,order(C.Lis),C.Ris,order(C.Ris),Lind,Rind);
+    if(order(C.Lis) == 2 && (Lind[0] < 0 || Lind[1] < 0))
+        {
+        auto g = qdiagAsMatrix(t,C.Lis);
+        contractQ<TA,TB>(C,g.offsets,g.buf.data(),g.n,d.offsets,d.buf.data(),d.n,m);
+        return;
+        }
+    doTask(C,t,d.toHost(),m);
+    }
+#define ITB_INST_QDIAG(TA,TB) \
+template void doTask(Contract&,QDenseGPU<TA> const&,QDiag<TB> const&,ManageStore&); \
+template void doTask(Contract&,QDiag<TA> const&,QDenseGPU<TB> const&,ManageStore&);
+ITB_INST_QDIAG(Real,Real)
+ITB_INST_QDIAG(Real,Cplx)
+ITB_INST_QDIAG(Cplx,Real)
+ITB_INST_QDIAG(Cplx,Cplx)
+#undef ITB_INST_QDIAG
+
 // add(PlusEQ,QDense,QDense) qdense.cc:515-549:  A += alpha * permute(B)
 template<typename TA, typename TB>
 static void
@@ -1174,12 +1253,13 @@ template void doTask(Contract&,Combiner const&,DenseGPU<Cplx> const&,ManageStore
 template<typename VA, typename VB>
 static void contractD(Contract& C, void const* Adata, size_t An, void const* Bdata, size_t Bn, ManageStore& m);
 
-// An order-2 diagonal tensor with exactly one index contracted scales the slices of the dense tensor along that index
-// and renames it. On the device this is the dense contraction with the diagonal written out as a (tiny) matrix: the
-// n^2 zeros cost nothing next to keeping the big operand in HBM.
+// An order-2 diagonal tensor with one index contracted scales the slices of the dense tensor along that index and
+// renames it; with both contracted it takes a (weighted) partial trace (TRG's normalisation, sample/src/trg.h:58). On
+// the device both are the dense contraction with the diagonal written out as a (tiny) matrix: the n^2 zeros cost
+// nothing next to keeping the big operand in HBM.
 template<typename T>
 static bool
-scalesOneIndex(IndexSet const& tis, Labels const& lab) { return order(tis) == 2 && ((lab[0] < 0) != (lab[1] < 0)); }
+scalesOneIndex(IndexSet const& tis, Labels const& lab) { return order(tis) == 2 && (lab[0] < 0 || lab[1] < 0); }
 template<typename T>
 static DenseGPU<T>
 diagAsMatrix(Diag<T> const& t, IndexSet const& tis)

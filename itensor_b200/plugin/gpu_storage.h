@@ -205,11 +205,11 @@ template<typename T> struct GetBlocks;
 template<typename T> struct Ord2Block;
 template<typename T> std::vector<Ord2Block<T>> doTask(GetBlocks<T> const& G, QDenseGPU<T> const& d);
 
-// contraction partners that are not on the hot path (diagonal tensors): via the host
-template<typename TA, typename TB>
-void doTask(Contract& C, QDenseGPU<TA> const& d, QDiag<TB> const& t, ManageStore& m) { doTask(C,d.toHost(),t,m); }
-template<typename TA, typename TB>
-void doTask(Contract& C, QDiag<TA> const& t, QDenseGPU<TB> const& d, ManageStore& m) { doTask(C,t,d.toHost(),m); }
+// QDiag x QDense (qdiag.cc:352-566): an order-2 diagonal tensor with a contracted index (svdBond's A *= D,
+// mps_impl.h:63-64) is written out as block-diagonal QDense matrices and contracted on the device, so the site tensor
+// stays in HBM; any other diagonal product runs the reference's host code on a host copy.
+template<typename TA, typename TB> void doTask(Contract& C, QDenseGPU<TA> const& d, QDiag<TB> const& t, ManageStore& m);
+template<typename TA, typename TB> void doTask(Contract& C, QDiag<TA> const& t, QDenseGPU<TB> const& d, ManageStore& m);
 template<typename VA, typename VB>
 void doTask(NCProd& P, QDenseGPU<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m) { doTask(P,A.toHost(),B.toHost(),m); }
 

@@ -122,3 +122,82 @@ def test_cblock_range_restriction():
     # dot items and the flops are additive)
     assert parts[2] == full[2]
     assert P.C.nblocks == nb
+
+
+def _introspect(P):
+    import ctypes as C
+
+    from itensor_b200._lib import lib
+
+    n = lib().itb_contract_plan_tiles(P._h, None, 0)
+    t = np.zeros((n, 8), np.int32)
+    lib().itb_contract_plan_tiles(P._h, t.ctypes.data_as(C.POINTER(C.c_int32)), n)
+    nc = lib().itb_contract_plan_cblks(P._h, None, 0)
+    c = np.zeros((nc, 4), np.int64)
+    lib().itb_contract_plan_cblks(P._h, c.ctypes.data_as(C.POINTER(C.c_int64)), nc)
+    ng = lib().itb_contract_plan_cta_begin(P._h, None, 0)
+    g = np.zeros(ng, np.int32)
+    lib().itb_contract_plan_cta_begin(P._h, g.ctypes.data_as(C.POINTER(C.c_int32)), ng)
+    nr = lib().itb_contract_plan_rowgroups(P._h, None, 0)
+    r = np.zeros((nr, 4), np.int64)
+    lib().itb_contract_plan_rowgroups(P._h, r.ctypes.data_as(C.POINTER(C.c_int64)), nr)
+    return t, c, g, r
+
+
+@pytest.mark.parametrize("sizes,dtype", [([6, 47, 214, 507, 634, 418, 145, 27, 3], F), ([12, 83, 158, 113, 29, 5], F),
+                                         ([3, 9, 14, 8, 2], Z), ([40, 70, 33], F)])
+def test_stream_k_partition_covers_every_tile_once(sizes, dtype):
+    """The DMMA tile queue: every (C block, tile) of the tile class appears with K-chunk ranges that partition its
+    chunk loop exactly (pieces of a cut tile carry consecutive workspace slots, in order), the per-CTA ranges partition
+    the item list, and the modelled work is balanced."""
+    structs = synth.heff_chain(sizes, dtype=dtype)
+    s = structs[0]
+    for tt in structs[1:]:
+        P = itb.ContractPlan(s, tt)
+        s = P.C
+        t, c, g, r = _introspect(P)
+        if len(t) == 0:
+            continue
+        assert g[0] == 0 and g[-1] == len(t) and np.all(np.diff(g) >= 0) and len(g) == 149
+        by_tile = {}
+        for i, (cb, m0, n0, tm, tn, c0, c1, slot) in enumerate(t.tolist()):
+            assert 0 <= m0 < c[cb, 0] and 0 <= n0 < c[cb, 1] and m0 % tm == 0 and n0 % tn == 0 and c1 > c0 >= 0
+            by_tile.setdefault((cb, m0, n0, tm, tn), []).append((i, c0, c1, slot))
+        covered = {}
+        for (cb, m0, n0, tm, tn), pieces in by_tile.items():
+            pieces.sort(key=lambda p: p[1])
+            assert pieces[0][1] == 0
+            for a, b in zip(pieces, pieces[1:]):
+                assert a[2] == b[1] and b[0] == a[0] + 1 and b[3] == a[3] + 1  # consecutive chunks, items and slots
+            if len(pieces) == 1:
+                assert pieces[0][3] == -1  # an uncut tile writes C directly
+            else:
+                assert all(p[3] >= 0 for p in pieces)
+            covered.setdefault(cb, {"nch": pieces[-1][2], "area": 0})
+            assert covered[cb]["nch"] == pieces[-1][2]  # every tile of a C block walks the same K loop
+            covered[cb]["area"] += min(tm, c[cb, 0] - m0) * min(tn, c[cb, 1] - n0)
+        for cb, v in covered.items():
+            assert v["area"] == c[cb, 0] * c[cb, 1]  # tiles tile the block exactly
+        if P.flops > 1e9:  # enough work to balance: no CTA carries more than 1.5x the mean chunk-area
+            w = np.array([(c1 - c0) * tm * tn for _, _, _, tm, tn, c0, c1, _ in t.tolist()], float)
+            load = np.array([w[g[b]:g[b + 1]].sum() for b in range(148)])
+            assert load.max() <= 1.5 * load.mean()
+
+
+def test_row_groups_read_every_input_once():
+    """Streaming class (MPO steps of H_eff*phi): the row groups' input slots x rows account for every element of A
+    exactly once and their output slots x rows for every element of C exactly once."""
+    structs = synth.heff_chain([6, 47, 214, 507, 634, 418, 145, 27, 3])
+    s = structs[0]
+    seen = 0
+    for k, tt in enumerate(structs[1:]):
+        P = itb.ContractPlan(s, tt)
+        t, c, g, r = _introspect(P)
+        if k in (1, 2):  # *W1, *W2
+            assert len(r) > 0 and len(t) == 0
+            assert int((r[:, 0] * r[:, 3]).sum()) == s.nelems
+            assert int((r[:, 1] * r[:, 3]).sum()) == P.C.nelems
+            assert r[:, 0].max() <= 32 and r[:, 1].max() <= 16 and r[:, 2].max() <= 3
+            seen += 1
+        s = P.C
+    assert seen == 2
