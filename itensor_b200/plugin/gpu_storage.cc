@@ -304,7 +304,7 @@ class PlanCache
 // Davidson repeats the same handful of structures many times at one bond; across bonds and sweeps the sector sizes
 // keep changing, so a larger cache only grows the table pool: measured on the Hubbard 16x4 run, 4096 entries cost
 // 25.9 s inside Contract against 13.9 s with 16 (every retained plan's device tables are a fresh cudaMalloc instead of
-// a recycled pool block). 256 entries; ITB_PLAN_CACHE overrides.
+// a recycled pool block). 32 entries; ITB_PLAN_CACHE overrides.
 static size_t
 planCacheCap(size_t dflt)
     {
@@ -312,9 +312,9 @@ planCacheCap(size_t dflt)
     return dflt;
     }
 static PlanCache<itb_contract_plan,itb_contract_plan_destroy>&
-contractCache() { static PlanCache<itb_contract_plan,itb_contract_plan_destroy> c(planCacheCap(256)); return c; }
+contractCache() { static PlanCache<itb_contract_plan,itb_contract_plan_destroy> c(planCacheCap(32)); return c; }
 static PlanCache<itb_permute_plan,itb_permute_plan_destroy>&
-permuteCache() { static PlanCache<itb_permute_plan,itb_permute_plan_destroy> c(planCacheCap(256)); return c; }
+permuteCache() { static PlanCache<itb_permute_plan,itb_permute_plan_destroy> c(planCacheCap(32)); return c; }
 
 static itb_contract_plan*
 getContractPlan(Desc const& dA, std::vector<int32_t> const& la, Desc const& dB, std::vector<int32_t> const& lb)
