@@ -410,20 +410,27 @@ def main():
         src = outs[0]  # T1 = phi*L : (s1,s2,r,k0,l')
         D, perm = permuted_struct(src.struct, list(reversed(src.struct.inds)), flux=(0,))
         pp = PermutePlan(src.struct, D, perm)
-        dst = ctx.empty(D.nreal)
+        # four permutes back to back into alternating destinations inside one event pair: the 254 MB moved per permute
+        # exceed the 126 MB L2 (no flush needed between them) and the ~5 us of launch/event latency that a single
+        # 50 us kernel would carry is amortised
+        dsts = [ctx.empty(D.nreal), ctx.empty(D.nreal)]
+        reps_in = 4
         best = 1e9
-        for it_ in range(6):
+        for it_ in range(4):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            check(lib().itb_permute_run(ctx.handle, pp._h, src.ptr, C.c_void_p(dst.data_ptr()), 1.0, 0.0, 0))
+            for q in range(reps_in):
+                check(lib().itb_permute_run(ctx.handle, pp._h, src.ptr, C.c_void_p(dsts[q & 1].data_ptr()), 1.0, 0.0, 0))
             e1.record(); e1.synchronize()
             if it_ > 0:
-                best = min(best, e0.elapsed_time(e1))
+                best = min(best, e0.elapsed_time(e1) / reps_in)
+        dst = dsts[0]
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         gbs = pp.bytes / (best * 1e-3) / 1e9
         perm_info = {"what": "QDense permute, reverse 5 indices of T1=phi*L (fills all flux-allowed blocks)", "elements": int(src.struct.nelems),
-                     "bytes": int(pp.bytes), "ms": best, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm}
+                     "bytes": int(pp.bytes), "ms": best, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm,
+                     "timing": "mean of 4 back-to-back permutes (alternating destinations, 254 MB each > L2) per CUDA-event pair, best of 3"}
         del dst
 
     # ---- CPU baseline: the reference itself on this box's host cores, bounded sample ----------------

@@ -119,6 +119,11 @@ __global__ void __launch_bounds__(PTN) perm_tile_kernel(const ItbPermTile* __res
     const ItbPermTile it = items[blockIdx.x]; // one 48-byte record per CTA: no search, no index arithmetic
     const S* __restrict__ src = reinterpret_cast<const S*>(src_) + it.s_base;
     D* __restrict__ dst = reinterpret_cast<D*>(dst_) + it.d_base;
+    if (it.nT < 0) { // zero-fill item: n0 contiguous destination elements no source block maps to (permuteQDense fill-in)
+        if (!accum) // (an accumulating pass leaves blocks without a source untouched)
+            for (int e = threadIdx.x; e < it.n0; e += PTN) dst[e] = D();
+        return;
+    }
     const int tx = threadIdx.x % PT, ty = threadIdx.x / PT;
     // read: tx runs along the src-fastest dim (stride 1 in src); all PER loads issued before any store
     {

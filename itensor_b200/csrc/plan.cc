@@ -802,6 +802,26 @@ int build_permute_plan(itb_permute_plan& P) {
         if (!P.zero_ranges.empty() && P.zero_ranges[P.zero_ranges.size() - 2] + P.zero_ranges.back() == D.offsets[b]) P.zero_ranges.back() += sz;
         else { P.zero_ranges.push_back(D.offsets[b]); P.zero_ranges.push_back(sz); }
     }
+    // Small fill-ins ride the transposing kernel's item list as zero-fill items (no extra launches); a destination
+    // that is mostly fill-in keeps the memset path (need_zero stays set).
+    {
+        int64_t zero_elems = 0;
+        for (size_t i = 1; i < P.zero_ranges.size(); i += 2) zero_elems += P.zero_ranges[i];
+        if (P.need_zero && P.items_tiled > 0 && zero_elems <= (int64_t)4096 * 256) {
+            for (size_t i = 0; i + 1 < P.zero_ranges.size(); i += 2)
+                for (int64_t e = 0; e < P.zero_ranges[i + 1]; e += 4096) {
+                    ItbPermTile it;
+                    std::memset(&it, 0, sizeof(it));
+                    it.d_base = P.zero_ranges[i] + e;
+                    it.n0 = (int32_t)std::min<int64_t>(4096, P.zero_ranges[i + 1] - e);
+                    it.nT = -1;
+                    P.tile_items.push_back(it);
+                    ++P.items_tiled;
+                }
+            P.need_zero = false;
+            P.zero_in_items = true;
+        }
+    }
     return ITB_OK;
 }
 

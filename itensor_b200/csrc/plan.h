@@ -75,7 +75,8 @@ struct itb_permute_plan {
     int64_t items_copy = 0, items_tiled = 0;
     std::vector<ItbPermChunk> chunk_items; // one per copy-path work item
     std::vector<ItbPermTile> tile_items;   // one per transposing-path work item
-    bool need_zero = false; // dst has blocks no src block maps to
+    bool need_zero = false; // dst has blocks no src block maps to (memset path)
+    bool zero_in_items = false; // ... and they are zero-fill items of the tile kernel instead (skipped when accumulating)
     std::vector<int64_t> zero_ranges; // (element offset, element count) of those blocks, merged when adjacent
     int64_t bytes = 0;
     itb::DeviceTables* dev = nullptr;

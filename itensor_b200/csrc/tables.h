@@ -113,7 +113,8 @@ struct ItbPermBlk {
 struct ItbPermTile { // transposing path: one PT x PT tile
     int64_t s_base, d_base; // element offsets of the tile's origin in src / dst
     int64_t ss0, dsT;       // src stride of the dst-fastest dim, dst stride of the src-fastest dim
-    int32_t n0, nT;         // valid extent of the tile along dst-fastest / src-fastest dim (<= PT)
+    int32_t n0, nT;         // valid extent of the tile along dst-fastest / src-fastest dim (<= PT);
+                            // nT < 0: zero-fill item, n0 (<= 4096) contiguous elements at d_base
 };
 struct ItbPermChunk { // copy-like path: PC_CHUNK consecutive dst elements of one block
     int32_t blk, pad_;

@@ -101,7 +101,7 @@ static void mock_copy_block(const ItbPermBlk& b, const double* S, double* D, int
 int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) {
     const int scs = P->S.dtype == ITB_C64 ? 2 : 1, dcs = P->D.dtype == ITB_C64 ? 2 : 1;
     ++c->launches;
-    if (!acc && P->need_zero)
+    if (!acc && (P->need_zero || P->zero_in_items))
         for (size_t i = 0; i + 1 < P->zero_ranges.size(); i += 2)
             std::memset((double*)D + P->zero_ranges[i] * dcs, 0, sizeof(double) * (size_t)P->zero_ranges[i + 1] * dcs);
     for (auto& b : P->blks_copy) mock_copy_block(b, (const double*)S, (double*)D, scs, dcs, ar, ai, acc);
