@@ -124,69 +124,129 @@ int build_contract_plan(itb_contract_plan& P) {
     if (rC > ITB_MAX_ORDER) { set_error("contract: result order too large"); return ITB_ERR_UNSUPPORTED; }
     C.order = rC;
 
-    // ---- pair enumeration: bucket B blocks by contracted coordinates --------------------------
+    // ---- pair enumeration + C block list ----------------------------------------------------------
     std::vector<int> contA, contB;
     for (int i = 0; i < rA; ++i)
         if (AtoB[i] >= 0) { contA.push_back(i); contB.push_back(AtoB[i]); }
-    std::unordered_map<std::vector<int32_t>, std::vector<int64_t>, VecHash> bucket;
-    std::vector<int32_t> key(contA.size());
-    for (int64_t b = 0; b < B.nblocks; ++b) {
-        for (size_t c = 0; c < contB.size(); ++c) key[c] = B.block(b)[contB[c]];
-        bucket[key].push_back(b);
-    }
+    // Fast path: block coordinates packed into one 64-bit key per tuple (sector counts are small, so the C tuple
+    // almost always fits). The LAST index goes to the most significant bits, which makes integer order the
+    // reference's block order (qdense.cc:60-65). Same pairs in the same order as the generic path below.
+    auto bits_for = [](int32_t n) { int b = 1; while ((1ll << b) < n) ++b; return b; };
+    int cbits = 0, kbits = 0;
+    std::vector<int> c_shift(rC, 0), c_width(rC, 0);
+    for (int j = 0; j < rC; ++j) { c_shift[j] = cbits; c_width[j] = bits_for(C.nsect[j]); cbits += c_width[j]; }
+    std::vector<int> k_shift(contA.size(), 0);
+    for (size_t c = 0; c < contA.size(); ++c) { k_shift[c] = kbits; kbits += bits_for(A.nsect[contA[c]]); }
     struct PairRec { int64_t a, b; std::vector<int32_t> cb; };
-    std::vector<PairRec> recs;
-    std::vector<int32_t> cb(rC);
-    for (int64_t a = 0; a < A.nblocks; ++a) {
-        for (size_t c = 0; c < contA.size(); ++c) key[c] = A.block(a)[contA[c]];
-        auto it = bucket.find(key);
-        if (it == bucket.end()) continue;
-        for (int i = 0; i < rA; ++i)
-            if (AtoC[i] >= 0) cb[AtoC[i]] = A.block(a)[i];
-        for (int64_t b : it->second) {
-            for (int j = 0; j < rB; ++j)
-                if (BtoC[j] >= 0) cb[BtoC[j]] = B.block(b)[j];
-            recs.push_back({a, b, cb});
-        }
-    }
-    // ---- C block list: sort + unique by the reference ordering, prefix-sum offsets ------------
-    std::vector<std::vector<int32_t>> cblocks;
-    cblocks.reserve(recs.size());
-    for (auto& r : recs) cblocks.push_back(r.cb);
-    std::sort(cblocks.begin(), cblocks.end(),
-              [rC](const std::vector<int32_t>& x, const std::vector<int32_t>& y) { return block_less(x.data(), y.data(), rC); });
-    cblocks.erase(std::unique(cblocks.begin(), cblocks.end()), cblocks.end());
-    C.nblocks = (int64_t)cblocks.size();
-    C.blocks.resize(C.nblocks * rC);
-    C.offsets.resize(C.nblocks);
+    std::vector<PairRec> recs;           // generic path
+    struct PackedRec { int64_t a, b; uint64_t ck; };
+    std::vector<PackedRec> precs;        // fast path
     std::unordered_map<std::vector<int32_t>, int64_t, VecHash> cpos;
-    int64_t off = 0;
-    for (int64_t c = 0; c < C.nblocks; ++c) {
-        int64_t sz = 1;
-        for (int j = 0; j < rC; ++j) {
-            C.blocks[c * rC + j] = cblocks[c][j];
-            sz *= C.ext(j, cblocks[c][j]);
+    std::vector<uint64_t> ckeys;         // fast path: sorted unique C keys
+    const bool packed = cbits <= 63 && kbits <= 63;
+    if (packed) {
+        std::vector<std::pair<uint64_t, int64_t>> bkeys(B.nblocks); // (contracted key, B block), sorted: B order kept inside a key
+        for (int64_t b = 0; b < B.nblocks; ++b) {
+            uint64_t k = 0;
+            for (size_t c = 0; c < contB.size(); ++c) k |= (uint64_t)B.block(b)[contB[c]] << k_shift[c];
+            bkeys[b] = {k, b};
         }
-        C.offsets[c] = off;
-        off += sz;
-        cpos[cblocks[c]] = c;
+        std::sort(bkeys.begin(), bkeys.end());
+        std::vector<uint64_t> bpart(B.nblocks); // C-key contribution of every B block
+        for (int64_t b = 0; b < B.nblocks; ++b) {
+            uint64_t k = 0;
+            for (int j = 0; j < rB; ++j)
+                if (BtoC[j] >= 0) k |= (uint64_t)B.block(b)[j] << c_shift[BtoC[j]];
+            bpart[b] = k;
+        }
+        precs.reserve((size_t)A.nblocks * 2);
+        for (int64_t a = 0; a < A.nblocks; ++a) {
+            uint64_t k = 0, apart = 0;
+            for (size_t c = 0; c < contA.size(); ++c) k |= (uint64_t)A.block(a)[contA[c]] << k_shift[c];
+            for (int i = 0; i < rA; ++i)
+                if (AtoC[i] >= 0) apart |= (uint64_t)A.block(a)[i] << c_shift[AtoC[i]];
+            auto lo = std::lower_bound(bkeys.begin(), bkeys.end(), std::make_pair(k, (int64_t)-1));
+            for (auto it = lo; it != bkeys.end() && it->first == k; ++it) precs.push_back({a, it->second, apart | bpart[it->second]});
+        }
+        ckeys.reserve(precs.size());
+        for (auto& r : precs) ckeys.push_back(r.ck);
+        std::sort(ckeys.begin(), ckeys.end());
+        ckeys.erase(std::unique(ckeys.begin(), ckeys.end()), ckeys.end());
+        C.nblocks = (int64_t)ckeys.size();
+        C.blocks.resize(C.nblocks * rC);
+        C.offsets.resize(C.nblocks);
+        int64_t off = 0;
+        for (int64_t c = 0; c < C.nblocks; ++c) {
+            int64_t sz = 1;
+            for (int j = 0; j < rC; ++j) {
+                const int32_t v = (int32_t)((ckeys[c] >> c_shift[j]) & ((1ull << c_width[j]) - 1));
+                C.blocks[c * rC + j] = v;
+                sz *= C.ext(j, v);
+            }
+            C.offsets[c] = off;
+            off += sz;
+        }
+        C.nelems = off;
+    } else {
+        std::unordered_map<std::vector<int32_t>, std::vector<int64_t>, VecHash> bucket;
+        std::vector<int32_t> key(contA.size());
+        for (int64_t b = 0; b < B.nblocks; ++b) {
+            for (size_t c = 0; c < contB.size(); ++c) key[c] = B.block(b)[contB[c]];
+            bucket[key].push_back(b);
+        }
+        std::vector<int32_t> cb(rC);
+        for (int64_t a = 0; a < A.nblocks; ++a) {
+            for (size_t c = 0; c < contA.size(); ++c) key[c] = A.block(a)[contA[c]];
+            auto it = bucket.find(key);
+            if (it == bucket.end()) continue;
+            for (int i = 0; i < rA; ++i)
+                if (AtoC[i] >= 0) cb[AtoC[i]] = A.block(a)[i];
+            for (int64_t b : it->second) {
+                for (int j = 0; j < rB; ++j)
+                    if (BtoC[j] >= 0) cb[BtoC[j]] = B.block(b)[j];
+                recs.push_back({a, b, cb});
+            }
+        }
+        // C block list: sort + unique by the reference ordering, prefix-sum offsets
+        std::vector<std::vector<int32_t>> cblocks;
+        cblocks.reserve(recs.size());
+        for (auto& r : recs) cblocks.push_back(r.cb);
+        std::sort(cblocks.begin(), cblocks.end(),
+                  [rC](const std::vector<int32_t>& x, const std::vector<int32_t>& y) { return block_less(x.data(), y.data(), rC); });
+        cblocks.erase(std::unique(cblocks.begin(), cblocks.end()), cblocks.end());
+        C.nblocks = (int64_t)cblocks.size();
+        C.blocks.resize(C.nblocks * rC);
+        C.offsets.resize(C.nblocks);
+        int64_t off = 0;
+        for (int64_t c = 0; c < C.nblocks; ++c) {
+            int64_t sz = 1;
+            for (int j = 0; j < rC; ++j) {
+                C.blocks[c * rC + j] = cblocks[c][j];
+                sz *= C.ext(j, cblocks[c][j]);
+            }
+            C.offsets[c] = off;
+            off += sz;
+            cpos[cblocks[c]] = c;
+        }
+        C.nelems = off;
     }
-    C.nelems = off;
+    const size_t nrec = packed ? precs.size() : recs.size();
     // ---- triples + flops -----------------------------------------------------------------------
-    P.triples.resize(recs.size() * 3);
+    P.triples.resize(nrec * 3);
     P.flops = 0;
     const double cmul = (A.dtype == ITB_C64 ? 2.0 : 1.0) * (B.dtype == ITB_C64 ? 2.0 : 1.0);
-    for (size_t p = 0; p < recs.size(); ++p) {
-        P.triples[3 * p + 0] = recs[p].a;
-        P.triples[3 * p + 1] = recs[p].b;
-        P.triples[3 * p + 2] = cpos[recs[p].cb];
+    for (size_t p = 0; p < nrec; ++p) {
+        const int64_t ra = packed ? precs[p].a : recs[p].a, rb = packed ? precs[p].b : recs[p].b;
+        P.triples[3 * p + 0] = ra;
+        P.triples[3 * p + 1] = rb;
+        P.triples[3 * p + 2] = packed ? (int64_t)(std::lower_bound(ckeys.begin(), ckeys.end(), precs[p].ck) - ckeys.begin()) : cpos[recs[p].cb];
         double m = 1, n = 1, k = 1;
         for (int i = 0; i < rA; ++i) {
-            double e = (double)A.ext(i, A.block(recs[p].a)[i]);
+            double e = (double)A.ext(i, A.block(ra)[i]);
             if (AtoB[i] >= 0) k *= e; else m *= e;
         }
         for (int j = 0; j < rB; ++j)
-            if (BtoA[j] < 0) n *= (double)B.ext(j, B.block(recs[p].b)[j]);
+            if (BtoA[j] < 0) n *= (double)B.ext(j, B.block(rb)[j]);
         P.flops += 2.0 * m * n * k * cmul;
     }
     P.tables_built = false;
@@ -487,20 +547,32 @@ int build_contract_tables(itb_contract_plan& P) {
             }
             return o;
         };
-        std::map<std::vector<int32_t>, std::vector<int32_t>> by_key;
-        std::vector<std::vector<int32_t>> key_order;
-        for (int32_t c : rg_cands) {
-            const int32_t* ab = A.block(pair_ia[P.cblks[c].pair_begin]);
-            std::vector<int32_t> key;
-            for (int i : uncA) key.push_back(ab[i]);
-            auto it = by_key.find(key);
-            if (it == by_key.end()) { key_order.push_back(key); by_key[key] = {c}; }
-            else it->second.push_back(c);
+        // candidates sorted by their long-side coordinates (first appearance order of the groups is kept)
+        std::vector<std::vector<int32_t>> cand_key(rg_cands.size());
+        for (size_t i = 0; i < rg_cands.size(); ++i) {
+            const int32_t* ab = A.block(pair_ia[P.cblks[rg_cands[i]].pair_begin]);
+            cand_key[i].reserve(uncA.size());
+            for (int u : uncA) cand_key[i].push_back(ab[u]);
         }
-        for (auto& key : key_order) {
-            const std::vector<int32_t>& cs = by_key[key];
+        std::vector<size_t> ord(rg_cands.size());
+        std::iota(ord.begin(), ord.end(), (size_t)0);
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return cand_key[x] < cand_key[y]; });
+        std::vector<std::pair<size_t, std::vector<int32_t>>> groups; // (first candidate position, members)
+        for (size_t q = 0; q < ord.size();) {
+            size_t e = q;
+            std::vector<int32_t> members;
+            size_t first = ord[q];
+            while (e < ord.size() && cand_key[ord[e]] == cand_key[ord[q]]) { members.push_back(rg_cands[ord[e]]); first = std::min(first, ord[e]); ++e; }
+            groups.push_back({first, std::move(members)});
+            q = e;
+        }
+        std::sort(groups.begin(), groups.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+        std::vector<int64_t> A_blocks;
+        for (auto& grp : groups) {
+            const std::vector<int32_t>& cs = grp.second;
+            const std::vector<int32_t>& key = cand_key[grp.first];
             // long-side dims (unit extents dropped), strides per A block of the group
-            std::vector<int64_t> A_blocks;
+            A_blocks.clear();
             for (int32_t c : cs)
                 for (int32_t p = P.cblks[c].pair_begin; p < P.cblks[c].pair_end; ++p)
                     if (std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) == A_blocks.end()) A_blocks.push_back(pair_ia[p]);
@@ -510,6 +582,7 @@ int build_contract_tables(itb_contract_plan& P) {
                 const int64_t e = A.ext(uncA[u], key[u]);
                 if (e == 1) continue;
                 LDim d{e, {}};
+                d.str.reserve(A_blocks.size());
                 for (int64_t ia : A_blocks) {
                     int64_t st = 1;
                     for (int i = 0; i < uncA[u]; ++i) st *= A.ext(i, A.block(ia)[i]);
@@ -521,7 +594,7 @@ int build_contract_tables(itb_contract_plan& P) {
                     for (size_t q = 0; q < A_blocks.size(); ++q) ok = ok && d.str[q] == ld.back().str[q] * ld.back().ext;
                     if (ok) { ld.back().ext *= e; fused = true; }
                 }
-                if (!fused) ld.push_back(d);
+                if (!fused) ld.push_back(std::move(d));
             }
             int64_t L = 1;
             for (auto& d : ld) L *= d.ext;
@@ -538,7 +611,8 @@ int build_contract_tables(itb_contract_plan& P) {
                 for (int d = 0; d < ITB_RG_MAXL; ++d) g.ext[d] = d < g.nL ? (int32_t)ld[d].ext : 1;
                 g.L = L;
                 g.in_begin = (int32_t)P.rg_in.size(); g.out_begin = (int32_t)P.rg_out.size(); g.w_begin = (int32_t)P.rg_w.size();
-                std::map<int64_t, int32_t> slot_of; // A element offset of (block, k) -> input slot
+                std::vector<std::pair<int64_t, int32_t>> slot_of; // A element offset of (block, k) -> input slot (<= ITB_RG_MAXIN entries)
+                auto find_slot = [&](int64_t ae) { for (auto& kv : slot_of) if (kv.first == ae) return kv.second; return (int32_t)-1; };
                 while (ci < cs.size()) {
                     const ItbCBlk& cb = P.cblks[cs[ci]];
                     // input slots this C block would add
@@ -546,7 +620,7 @@ int build_contract_tables(itb_contract_plan& P) {
                     for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p)
                         for (int32_t k = 0; k < P.pairs[p].K; ++k) {
                             const int64_t ae = P.pairs[p].a_off + host_off(k, P.pairs[p].k_ext, P.pairs[p].ak_str, P.pairs[p].k_n);
-                            if (!slot_of.count(ae) && std::find(fresh.begin(), fresh.end(), ae) == fresh.end()) fresh.push_back(ae);
+                            if (find_slot(ae) < 0 && std::find(fresh.begin(), fresh.end(), ae) == fresh.end()) fresh.push_back(ae);
                         }
                     if (g.nout > 0 && (g.nout + cb.N > ITB_RG_MAXOUT || g.nin + (int)fresh.size() > ITB_RG_MAXIN)) break;
                     for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
@@ -554,18 +628,19 @@ int build_contract_tables(itb_contract_plan& P) {
                         const size_t qa = std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) - A_blocks.begin();
                         for (int32_t k = 0; k < pr.K; ++k) {
                             const int64_t ae = pr.a_off + host_off(k, pr.k_ext, pr.ak_str, pr.k_n);
-                            auto it = slot_of.find(ae);
-                            if (it == slot_of.end()) {
+                            int32_t slot = find_slot(ae);
+                            if (slot < 0) {
                                 ItbRgIn in;
                                 std::memset(&in, 0, sizeof(in));
                                 in.base = ae;
                                 for (int d = 0; d < g.nL; ++d) in.str[d] = ld[d].str[qa];
-                                it = slot_of.emplace(ae, g.nin++).first;
+                                slot = g.nin++;
+                                slot_of.push_back({ae, slot});
                                 P.rg_in.push_back(in);
                             }
                             const int64_t bk = pr.b_off + host_off(k, pr.k_ext, pr.bk_str, pr.k_n);
                             for (int32_t n = 0; n < cb.N; ++n)
-                                P.rg_w.push_back({it->second, g.nout + n, bk + host_off(n, pr.n_ext, pr.bn_str, pr.n_n)});
+                                P.rg_w.push_back({slot, g.nout + n, bk + host_off(n, pr.n_ext, pr.bn_str, pr.n_n)});
                         }
                     }
                     for (int32_t n = 0; n < cb.N; ++n) P.rg_out.push_back(cb.c_off + (int64_t)n * cb.c_ns);
