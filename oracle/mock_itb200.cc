@@ -4,7 +4,9 @@
 // (itensor_b200/plugin: dispatch, block bookkeeping, plan caching, ownership) can be exercised by
 // `pytest -m "not gpu"` in a container without a GPU. It is never linked into the product: the product
 // binaries link itensor_b200/libitb200.so, which fails loudly without a CUDA device.
-// The integer planner is the real one (itensor_b200/csrc/plan.cc, host-only); arithmetic is oracle.c.
+// The integer planner is the real one (itensor_b200/csrc/plan.cc, host-only); arithmetic is oracle.c, or — with
+// ITB_MOCK_TABLES=1 — a sequential walk of the planner's DEVICE tables (emu_contract below), which is how the tables
+// the GPU kernels consume are validated on CPU.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +47,130 @@ static orc_desc to_orc(const itb::TensorStruct& t) {
     return d;
 }
 
+// ---- table-walking executor (ITB_MOCK_TABLES=1) -------------------------------------------------------------------
+// Executes a contraction from the DEVICE tables the planner built (pairs, C blocks, stream-K tile items and their
+// split-K reduction, row groups, C-stationary streaming items, split-K dot items) with the addressing rules of the
+// sm_100a kernels (kernels_gemm.cu), sequentially on the host. tests/test_tables_emulation_cpu.py compares the result
+// with the oracle, so that every table the GPU kernels consume is checked in `pytest -m "not gpu"`.
+static int64_t emu_off(int64_t idx, const int32_t* ext, const int64_t* str, int n) {
+    int64_t o = 0;
+    for (int d = 0; d < n; ++d) {
+        if (d == n - 1) { o += idx * str[d]; break; }
+        o += (idx % ext[d]) * str[d];
+        idx /= ext[d];
+    }
+    return o;
+}
+static double emu_a(const ItbPair& pr, const double* A, int64_t m, int64_t k) { // A'(m,k) incl. the complex*complex fold
+    int64_t off = pr.a_off + emu_off(m, pr.m_ext, pr.am_str, pr.m_n) + emu_off(k, pr.k_ext, pr.ak_str, pr.k_n);
+    if (pr.flags & ITB_PF_CCA) {
+        const int pq = (int)(m & 1) | ((int)(k & 1) << 1);
+        if (pq == 3) off -= 2;
+        const double v = A[off];
+        return pq == 2 ? -v : v;
+    }
+    return A[off];
+}
+static double emu_b(const ItbPair& pr, const double* B, int64_t k, int64_t n) {
+    return B[pr.b_off + emu_off(k, pr.k_ext, pr.bk_str, pr.k_n) + emu_off(n, pr.n_ext, pr.bn_str, pr.n_n)];
+}
+static int64_t emu_c(const ItbCBlk& cb, int64_t m, int64_t n) { return cb.c_off + m * cb.c_ms + (n & cb.c_nmask) + (n >> cb.c_nshift) * cb.c_ns; }
+static const int kEmuTile[3] = {128, 64, 32};
+
+static int emu_contract(itb_contract_plan* P, const double* A, const double* B, double* C) {
+    if (!P->tables_built) { int rc = itb::build_contract_tables(*P); if (rc != ITB_OK) return rc; }
+    // tile class: items in CTA order; pieces of a cut tile go to workspace slots and are summed in slot order
+    std::vector<std::vector<double>> ws((size_t)P->ws_slots);
+    const int G = (int)P->cta_begin.size() - 1;
+    for (int b = 0; b < G; ++b)
+        for (int i = P->cta_begin[b]; i < P->cta_begin[b + 1]; ++i) {
+            const ItbTile& t = P->tiles[i];
+            const ItbCBlk& cb = P->cblks[t.cblk];
+            const int T = kEmuTile[t.cfg];
+            std::vector<double> acc((size_t)T * T, 0.0);
+            int64_t gchunk = 0;
+            for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
+                const ItbPair& pr = P->pairs[p];
+                const int64_t nk = (pr.K + ITB_BK - 1) / ITB_BK;
+                const int64_t c0 = std::max<int64_t>(t.chunk_begin - gchunk, 0), c1 = std::min<int64_t>(t.chunk_end - gchunk, nk);
+                gchunk += nk;
+                for (int64_t k = c0 * ITB_BK; k < std::min<int64_t>(c1 * ITB_BK, pr.K); ++k)
+                    for (int ml = 0; ml < T && t.m0 + ml < cb.M; ++ml) {
+                        const double a = emu_a(pr, A, t.m0 + ml, k);
+                        for (int nl = 0; nl < T && t.n0 + nl < cb.N; ++nl) acc[(size_t)ml + (size_t)T * nl] += a * emu_b(pr, B, k, t.n0 + nl);
+                    }
+            }
+            if (t.ws_slot < 0) {
+                for (int ml = 0; ml < T && t.m0 + ml < cb.M; ++ml)
+                    for (int nl = 0; nl < T && t.n0 + nl < cb.N; ++nl) C[emu_c(cb, t.m0 + ml, t.n0 + nl)] = acc[(size_t)ml + (size_t)T * nl];
+            } else ws[(size_t)t.ws_slot] = std::move(acc);
+        }
+    for (auto& o : P->splits) {
+        const ItbCBlk& cb = P->cblks[o.cblk];
+        const int T = kEmuTile[o.cfg];
+        for (int ml = 0; ml < T && o.m0 + ml < cb.M; ++ml)
+            for (int nl = 0; nl < T && o.n0 + nl < cb.N; ++nl) {
+                double sum = 0;
+                for (int q = 0; q < o.nsplit; ++q) {
+                    if (ws[(size_t)o.ws_slot0 + q].empty()) return ITB_ERR_INVALID; // a slot nobody wrote
+                    sum += ws[(size_t)o.ws_slot0 + q][(size_t)ml + (size_t)T * nl];
+                }
+                C[emu_c(cb, o.m0 + ml, o.n0 + nl)] = sum;
+            }
+    }
+    // row groups
+    for (auto& it : P->rg_items) {
+        const ItbRowGroup& g = P->rgroups[it.group];
+        std::vector<double> W((size_t)g.nin * g.nout, 0.0);
+        for (int32_t w = g.w_begin; w < g.w_begin + g.w_count; ++w) W[(size_t)P->rg_w[w].j * g.nout + P->rg_w[w].o] = B[P->rg_w[w].b_off];
+        for (int64_t l = it.row0; l < (int64_t)it.row0 + it.rows; ++l) {
+            const int64_t a = l / g.ext[0], i0 = l - a * g.ext[0], b2 = a / g.ext[1], i1 = a - b2 * g.ext[1], i2 = b2;
+            for (int o = 0; o < g.nout; ++o) {
+                double y = 0;
+                for (int j = 0; j < g.nin; ++j) {
+                    const ItbRgIn& in = P->rg_in[g.in_begin + j];
+                    y += A[in.base + i0 * in.str[0] + i1 * in.str[1] + i2 * in.str[2]] * W[(size_t)j * g.nout + o];
+                }
+                C[P->rg_out[g.out_begin + o] + l] = y;
+            }
+        }
+    }
+    // C-stationary streaming items
+    auto skinny = [&](const std::vector<ItbSkinny>& items) {
+        for (auto& it : items) {
+            const ItbCBlk& cb = P->cblks[it.cblk];
+            const int64_t S = it.long_is_n ? cb.M : cb.N;
+            for (int64_t l = it.row0; l < (int64_t)it.row0 + it.rows; ++l)
+                for (int64_t s2 = 0; s2 < S; ++s2) {
+                    const int64_t m = it.long_is_n ? s2 : l, n = it.long_is_n ? l : s2;
+                    double sum = 0;
+                    for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p)
+                        for (int64_t k = 0; k < P->pairs[p].K; ++k) sum += emu_a(P->pairs[p], A, m, k) * emu_b(P->pairs[p], B, k, n);
+                    C[emu_c(cb, m, n)] = sum;
+                }
+        }
+    };
+    skinny(P->skinny); skinny(P->skinny_q4); skinny(P->skinny_q8);
+    // split-K dots
+    std::vector<double> partial((size_t)P->ndot_slots * 4, 0.0);
+    for (auto& it : P->dots) {
+        const ItbCBlk& cb = P->cblks[it.cblk];
+        const ItbPair& pr = P->pairs[it.pair];
+        for (int64_t k = it.k0; k < (int64_t)it.k0 + it.klen; ++k)
+            for (int64_t n = 0; n < cb.N; ++n)
+                for (int64_t m = 0; m < cb.M; ++m) partial[(size_t)it.slot * 4 + m + cb.M * n] += emu_a(pr, A, m, k) * emu_b(pr, B, k, n);
+    }
+    for (auto& o : P->dot_outs) {
+        const ItbCBlk& cb = P->cblks[o.cblk];
+        for (int64_t i = 0; i < (int64_t)cb.M * cb.N; ++i) {
+            double sum = 0;
+            for (int q = 0; q < o.nslots; ++q) sum += partial[(size_t)(o.slot0 + q) * 4 + i];
+            C[emu_c(cb, i % cb.M, i / cb.M)] = sum;
+        }
+    }
+    return ITB_OK;
+}
+
 extern "C" {
 void itb_contract_plan_release_device(itb_contract_plan*) {}
 void itb_permute_plan_release_device(itb_permute_plan*) {}
@@ -66,6 +192,8 @@ int itb_pool_trim(itb_ctx*) { return ITB_OK; }
 
 int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) {
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK;
+    static const bool walk_tables = [] { const char* e = std::getenv("ITB_MOCK_TABLES"); return e && std::atoi(e) != 0; }();
+    if (walk_tables) { ++c->launches; return emu_contract(P, (const double*)A, (const double*)B, (double*)C); }
     orc_desc a = to_orc(P->A), b = to_orc(P->B), cc = to_orc(P->C);
     ++c->launches;
     // honour the C-block selection (multi-GPU sharding): only pairs of selected C blocks are executed

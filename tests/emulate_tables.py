@@ -1,0 +1,81 @@
+"""Run in a subprocess by tests/test_tables_emulation_cpu.py with ITB200_LIB_PATH=<mock>, ITB_MOCK_TABLES=1: every
+contraction is executed by walking the planner's DEVICE tables on the host (oracle/mock_itb200.cc emu_contract) and
+compared with the CPU oracle (definition-level loops). Prints one summary line; exits non-zero on the first mismatch."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import itensor_b200 as itb
+from itensor_b200 import ITB_C64, ITB_F64, synth
+from itensor_b200._lib import check, lib
+from itensor_b200.tensor import BlockStruct, Index
+from oracle import orc
+
+assert "mock" in os.environ.get("ITB200_LIB_PATH", "") and os.environ.get("ITB_MOCK_TABLES") == "1"
+ctx = C.c_void_p()
+check(lib().itb_ctx_create(0, C.byref(ctx)))
+stats = {"cases": 0, "tiles": 0, "split_pieces": 0, "rowgroups": 0, "skinny": 0, "dots": 0}
+
+
+def classes(P):
+    n = lib().itb_contract_plan_tiles(P._h, None, 0)
+    t = np.zeros((max(n, 1), 8), np.int32)
+    lib().itb_contract_plan_tiles(P._h, t.ctypes.data_as(C.POINTER(C.c_int32)), n)
+    stats["tiles"] += n
+    stats["split_pieces"] += int((t[:n, 7] >= 0).sum())
+    stats["rowgroups"] += lib().itb_contract_plan_rowgroups(P._h, None, 0)
+    stats["skinny"] += P.info.n_skinny
+    stats["dots"] += P.info.n_dot
+
+
+def run(A, Av, B, Bv, what):
+    P = itb.ContractPlan(A, B)
+    Cs, tr, ref = orc.contract(A, Av, B, Bv)
+    assert np.array_equal(Cs.blocks, P.C.blocks) and np.array_equal(Cs.offsets, P.C.offsets)
+    out = np.full(max(P.C.nreal, 1), np.nan)
+    a = np.ascontiguousarray(Av).view(np.float64).reshape(-1)
+    b = np.ascontiguousarray(Bv).view(np.float64).reshape(-1)
+    check(lib().itb_contract_run(ctx, P._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+    got = out[:P.C.nreal]
+    want = np.ascontiguousarray(ref).view(np.float64).reshape(-1)
+    if P.C.nreal:
+        scale = max(np.abs(want).max(), 1e-300)
+        err = np.abs(got - want).max() / scale if not np.isnan(got).any() else np.inf
+        if not err < 1e-12:
+            print(f"MISMATCH in {what}: rel err {err}, nan {int(np.isnan(got).sum())} of {got.size}")
+            sys.exit(1)
+    classes(P)
+    stats["cases"] += 1
+    return P.C, ref
+
+
+rng = np.random.default_rng(11)
+# random block-deficient QN pairs of every real/complex pairing (tiles 32x32, dots, streaming kernels, complex folds)
+for trial in range(160):
+    ra, rb = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+    nc = int(rng.integers(0, min(ra, rb) + 1))
+    A, B = synth.random_qn_pair(rng, ra, rb, nc, dtype_a=int(rng.integers(0, 2)), dtype_b=int(rng.integers(0, 2)))
+    run(A, synth.random_values(A, 2 * trial), B, synth.random_values(B, 2 * trial + 1), f"random pair {trial}")
+# H_eff*phi chains: real (row groups for the MPO steps), complex (C-stationary streaming kernels), and <phi|H phi> dots
+for sizes, dt in (([3, 9, 14, 8, 2], ITB_F64), ([3, 9, 14, 8, 2], ITB_C64), ([20, 70, 45], ITB_F64)):
+    structs = synth.heff_chain(sizes, dtype=dt)
+    vals = [synth.random_values(s, 50 + i) for i, s in enumerate(structs)]
+    cur, cv = structs[0], vals[0]
+    for k in range(1, 5):
+        cur, cv = run(cur, cv, structs[k], vals[k], f"heff {sizes} dtype {dt} step {k}")
+    # scalar product with the (conjugated-structure) bra: rank-0 result through the split-K dot items
+    bra = BlockStruct([i.dag().prime(0) if False else i for i in cur.inds], cur.blocks, cur.dtype)
+    braket_inds = [Index(ix.id, ix.sizes, ix.qns, -ix.dir, ix.mods, ix.plev) for ix in cur.inds]
+    bra = BlockStruct(braket_inds, cur.blocks, cur.dtype)
+    run(bra, synth.random_values(bra, 99), cur, cv, f"heff {sizes} dtype {dt} dot")
+# long K on few tiles: the stream-K partition must cut tiles into pieces (workspace slots + ordered reduction)
+for M, K, N, dt in ((64, 4096, 64, ITB_F64), (150, 3000, 40, ITB_F64), (40, 2500, 33, ITB_C64)):
+    im, ik, inn = Index(1, (M,)), Index(2, (K,)), Index(3, (N,))
+    A, B = BlockStruct.dense([ik, im], dt), BlockStruct.dense([inn, ik], dt)
+    before = stats["split_pieces"]
+    run(A, synth.random_values(A, 7), B, synth.random_values(B, 8), f"dense long-K {M}x{K}x{N}")
+    assert stats["split_pieces"] > before, "expected cut tiles"
+print("tables emulation ok:", stats)
