@@ -226,9 +226,55 @@ static void mock_copy_block(const ItbPermBlk& b, const double* S, double* D, int
         for (int d = 0; d < b.n; ++d) { if (++idx[d] < b.ext[d]) break; idx[d] = 0; }
     }
 }
+// ITB_MOCK_TABLES=1: walk the per-work-item records the permute kernels consume (kernels_permute.cu): 4096-element
+// chunks of the copy-like blocks, PT x PT tiles (64 for 8-byte elements, 32 for complex) of the transposing blocks,
+// zero-fill items
+static void emu_elem(const double* S, double* D, int64_t so, int64_t dof, int scs, int dcs, double ar, double ai, int acc) {
+    const double vr = S[so * scs], vi = scs == 2 ? S[so * scs + 1] : 0.0;
+    const double rr = ar * vr - ai * vi, ri = ar * vi + ai * vr;
+    if (dcs == 2) {
+        if (acc) { D[2 * dof] += rr; D[2 * dof + 1] += ri; } else { D[2 * dof] = rr; D[2 * dof + 1] = ri; }
+    } else {
+        if (acc) D[dof] += rr; else D[dof] = rr;
+    }
+}
+static int emu_permute(itb_permute_plan* P, const double* S, double* D, double ar, double ai, int acc) {
+    const int scs = P->S.dtype == ITB_C64 ? 2 : 1, dcs = P->D.dtype == ITB_C64 ? 2 : 1;
+    if (!acc && P->need_zero) {
+        if (P->zero_ranges.size() <= 2 * 64)
+            for (size_t i = 0; i + 1 < P->zero_ranges.size(); i += 2) std::memset(D + P->zero_ranges[i] * dcs, 0, sizeof(double) * (size_t)P->zero_ranges[i + 1] * dcs);
+        else std::memset(D, 0, sizeof(double) * (size_t)P->D.nelems * dcs);
+    }
+    if ((int64_t)P->chunk_items.size() != P->items_copy || (int64_t)P->tile_items.size() != P->items_tiled) return ITB_ERR_INVALID;
+    for (auto& it : P->chunk_items) {
+        const ItbPermBlk& b = P->blks_copy[it.blk];
+        for (int64_t e = it.e0; e < std::min<int64_t>(it.e0 + itb::kPermCopyChunk, b.nelem); ++e) {
+            int64_t so = b.s_off, dof = b.d_off, rem = e;
+            for (int d = 0; d < b.n; ++d) {
+                if (d == b.n - 1) { so += rem * b.sstr[d]; dof += rem * b.dstr[d]; }
+                else { const int64_t q = rem / b.ext[d], i = rem - q * b.ext[d]; so += i * b.sstr[d]; dof += i * b.dstr[d]; rem = q; }
+            }
+            emu_elem(S, D, so, dof, scs, dcs, ar, ai, acc);
+        }
+    }
+    const int PT = scs == 2 ? 32 : 64;
+    for (auto& it : P->tile_items) {
+        if (it.nT < 0) { // zero-fill item
+            if (!acc) std::memset(D + it.d_base * dcs, 0, sizeof(double) * (size_t)it.n0 * dcs);
+            continue;
+        }
+        if (it.n0 > PT || it.nT > PT) return ITB_ERR_INVALID;
+        for (int iT = 0; iT < it.nT; ++iT)       // src-fastest dim: stride 1 in src, dsT in dst
+            for (int i0 = 0; i0 < it.n0; ++i0)   // dst-fastest dim: stride ss0 in src, 1 in dst
+                emu_elem(S, D, it.s_base + iT + (int64_t)i0 * it.ss0, it.d_base + i0 + (int64_t)iT * it.dsT, scs, dcs, ar, ai, acc);
+    }
+    return ITB_OK;
+}
 int itb_permute_run(itb_ctx* c, itb_permute_plan* P, const void* S, void* D, double ar, double ai, int acc) {
     const int scs = P->S.dtype == ITB_C64 ? 2 : 1, dcs = P->D.dtype == ITB_C64 ? 2 : 1;
     ++c->launches;
+    static const bool walk_tables = [] { const char* e = std::getenv("ITB_MOCK_TABLES"); return e && std::atoi(e) != 0; }();
+    if (walk_tables) return emu_permute(P, (const double*)S, (double*)D, ar, ai, acc);
     if (!acc && (P->need_zero || P->zero_in_items))
         for (size_t i = 0; i + 1 < P->zero_ranges.size(); i += 2)
             std::memset((double*)D + P->zero_ranges[i] * dcs, 0, sizeof(double) * (size_t)P->zero_ranges[i + 1] * dcs);

@@ -78,4 +78,50 @@ for M, K, N, dt in ((64, 4096, 64, ITB_F64), (150, 3000, 40, ITB_F64), (40, 2500
     before = stats["split_pieces"]
     run(A, synth.random_values(A, 7), B, synth.random_values(B, 8), f"dense long-K {M}x{K}x{N}")
     assert stats["split_pieces"] > before, "expected cut tiles"
+# ---- permute / permuting accumulate: per-work-item records (4096-element chunks, PT x PT tiles, zero-fill items) ----
+from itensor_b200.tensor import PermutePlan, permuted_struct
+
+stats.update({"permutes": 0, "zero_filled": 0})
+
+
+def run_permute(S, host, D, perm, alpha=1.0 + 0j, accumulate=False, d_host=None, what=""):
+    want = orc.permute(S, host, D, perm, alpha=alpha, accumulate=accumulate, d_host=d_host)
+    pp = PermutePlan(S, D, perm)
+    nd = D.nreal
+    out = np.full(max(nd, 1), np.nan)
+    if accumulate:
+        out[:nd] = np.ascontiguousarray(d_host).view(np.float64).reshape(-1)
+    src = np.ascontiguousarray(host).view(np.float64).reshape(-1)
+    alpha = complex(alpha)
+    check(lib().itb_permute_run(ctx, pp._h, src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), alpha.real, alpha.imag, 1 if accumulate else 0))
+    got = out[:nd]
+    w = np.ascontiguousarray(want).view(np.float64).reshape(-1)
+    ok = np.array_equal(got, w) if alpha == 1 and not accumulate else np.allclose(got, w, rtol=1e-14, atol=1e-14)
+    if not ok:
+        print(f"PERMUTE MISMATCH in {what}: nan {int(np.isnan(got).sum())} of {got.size}")
+        sys.exit(1)
+    stats["permutes"] += 1
+    stats["zero_filled"] += int(D.nelems > S.nelems and not accumulate)
+
+
+for dtype in (ITB_F64, ITB_C64):
+    prng = np.random.default_rng(3 + dtype)
+    for trial in range(40):  # QN permutes fill in every flux-allowed block (zero-fill items / memset ranges)
+        r = int(prng.integers(1, 6))
+        S, _ = synth.random_qn_pair(prng, r, 1, 0, max_sect=3, max_size=7, dtype_a=dtype, drop=0.2)
+        new_inds = [S.inds[i] for i in prng.permutation(r)]
+        D, perm = permuted_struct(S, new_inds, flux=(0,))
+        host = synth.random_values(S, trial)
+        run_permute(S, host, D, perm, what=f"qn permute {trial}")
+        # accumulate into existing destination data: blocks without a source must stay untouched
+        base = synth.random_values(D, 1000 + trial)
+        run_permute(S, host, D, perm, alpha=0.5 - (0.25j if dtype == ITB_C64 else 0), accumulate=True, d_host=base, what=f"qn accumulate {trial}")
+    for dims in [(7,), (33, 65), (65, 33), (5, 6, 7), (40, 3, 50), (3, 40, 2, 50), (2, 3, 4, 5, 6), (64, 64, 9), (1, 70, 1, 90), (130, 131)]:
+        inds = [Index(10 + j, (d,)) for j, d in enumerate(dims)]
+        S = BlockStruct.dense(inds, dtype)
+        host = synth.random_values(S, 1)
+        for _ in range(3):
+            new_inds = [inds[i] for i in prng.permutation(len(dims))]
+            D, perm = permuted_struct(S, new_inds)
+            run_permute(S, host, D, perm, what=f"dense permute {dims}")
 print("tables emulation ok:", stats)

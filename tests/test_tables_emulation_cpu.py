@@ -1,5 +1,6 @@
 """Every device table the sm_100a kernels consume (block-pair tables, stream-K tile items and their split-K
-reduction, row groups, C-stationary streaming items, split-K dot items) is executed on the host by the table-walking
+reduction, row groups, C-stationary streaming items, split-K dot items; permute chunk / tile / zero-fill items) is
+executed on the host by the table-walking
 executor of the mock ABI (oracle/mock_itb200.cc, test infrastructure) and compared with the CPU oracle."""
 import os
 import subprocess
@@ -21,3 +22,4 @@ def test_device_tables_reproduce_the_oracle():
     # the run really covered every kernel class
     assert stats["cases"] > 170 and stats["tiles"] > 200 and stats["split_pieces"] > 10
     assert stats["rowgroups"] > 10 and stats["skinny"] > 10 and stats["dots"] > 5
+    assert stats["permutes"] > 200 and stats["zero_filled"] > 10
