@@ -232,6 +232,12 @@ class Context:
         self.torch = torch
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(device)
+        # the library's background read of the cuSOLVER/cuBLAS objects (solver warm-up for long DMRG runs, see
+        # itb_solver_ready in include/itb200.h) only competes for I/O in the short test / bench processes this Python
+        # mirror serves: off unless asked for
+        import os
+
+        os.environ.setdefault("ITB_WARM_LIBS", "0")
         self._h = C.c_void_p()
         check(lib().itb_ctx_create(device, C.byref(self._h)))
         self.stream = torch.cuda.current_stream(self.device)

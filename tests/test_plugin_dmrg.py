@@ -52,6 +52,20 @@ def test_plugin_host_logic_on_mock_abi(model, N, qn):
     compare(g, c, 1e-10 if qn == "qn" else 1e-8, per_bond=(qn == "qn"))
 
 
+@pytest.mark.skipif(not os.path.exists(MOCK), reason="build/plugin/dmrg_driver_mock not built (needs /root/reference)")
+def test_plugin_dmrg_through_the_device_tables_on_mock_abi():
+    """Same run with the mock executing every contraction / permute by walking the planner's DEVICE tables
+    (ITB_MOCK_TABLES=1, oracle/mock_itb200.cc) instead of calling the oracle: the tables the GPU kernels consume carry a
+    whole DMRG to the same energy."""
+    env = dict(MOCK_ENV, ITB_MOCK_TABLES="1")
+    sched = ["10,20,40", "1e-10", "2", "1e-7,1e-8,0"]
+    out = subprocess.run([MOCK, "heis_half", "16", "qn", "gpu"] + sched, env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    g = json.loads(out.stdout.strip().split("\n")[-1])
+    c = run(MOCK, "heis_half", 16, "qn", "cpu", sched)
+    compare(g, c, 1e-10)
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(REAL), reason="build/plugin/dmrg_driver not built")
 def test_dmrg_sample_config_energy_parity_on_gpu():
