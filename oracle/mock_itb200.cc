@@ -33,6 +33,20 @@ double orc_nrm2(int64_t n, const double* x);
 
 struct itb_ctx { int64_t launches = 0; };
 
+// ITB_PROFILE: time spent in the mock's arithmetic, so that the plugin's per-entry wall times (gpu_storage.cc scopes)
+// can be split into host bookkeeping and stand-in "device" work
+#include <chrono>
+#include <cstdio>
+struct MockProf {
+    double secs = 0; long calls = 0;
+    ~MockProf() { if (std::getenv("ITB_PROFILE") && calls) std::fprintf(stderr, "[itb200 mock] arithmetic inside contract/permute: %ld calls %.4f s\n", calls, secs); }
+};
+static MockProf g_mock_prof;
+struct MockScope {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~MockScope() { g_mock_prof.secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++g_mock_prof.calls; }
+};
+
 static orc_desc to_orc(const itb::TensorStruct& t) {
     static const int32_t zero32 = 0;
     static const int64_t zero64 = 0;
@@ -192,6 +206,7 @@ int itb_pool_trim(itb_ctx*) { return ITB_OK; }
 
 int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) {
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK;
+    MockScope scope_;
     static const bool walk_tables = [] { const char* e = std::getenv("ITB_MOCK_TABLES"); return e && std::atoi(e) != 0; }();
     if (walk_tables) { ++c->launches; return emu_contract(P, (const double*)A, (const double*)B, (double*)C); }
     orc_desc a = to_orc(P->A), b = to_orc(P->B), cc = to_orc(P->C);
