@@ -669,11 +669,18 @@ int build_contract_tables(itb_contract_plan& P) {
             const ItbCBlk& cb = P.cblks[c];
             const int TM = kTileM[f], TN = kTileN[f];
             const int64_t nch = chunks_of(cb);
+            // a C block has at most four distinct tile shapes (full, m-edge, n-edge, corner): model each once
+            const int64_t rm = cb.M % TM, rn = cb.N % TN;
+            const double w_full = chunk_cycles(f, TM, TN), w_me = rm ? chunk_cycles(f, rm, TN) : w_full, w_ne = rn ? chunk_cycles(f, TM, rn) : w_full,
+                         w_c = (rm && rn) ? chunk_cycles(f, rm, rn) : (rm ? w_me : w_ne);
+            const int np = cb.pair_end - cb.pair_begin;
+            const double ovh = kTileOverhead[f] + kPairOverhead * np;
             for (int32_t n0 = 0; n0 < cb.N; n0 += TN)
                 for (int32_t m0 = 0; m0 < cb.M; m0 += TM) {
-                    const double w = chunk_cycles(f, std::min<int64_t>(TM, cb.M - m0), std::min<int64_t>(TN, cb.N - n0));
-                    protos.push_back({c, m0, n0, f, nch, w, cb.pair_end - cb.pair_begin});
-                    total += w * (double)nch + kTileOverhead[f] + kPairOverhead * (cb.pair_end - cb.pair_begin);
+                    const bool me = m0 + TM > cb.M, ne = n0 + TN > cb.N;
+                    const double w = me ? (ne ? w_c : w_me) : (ne ? w_ne : w_full);
+                    protos.push_back({c, m0, n0, f, nch, w, np});
+                    total += w * (double)nch + ovh;
                 }
         }
         const int G = kNumSMs;
