@@ -159,9 +159,11 @@ OPS_REAL = os.path.join(ROOT, "build", "plugin", "dense_ops_check")
 
 
 @pytest.mark.skipif(not os.path.exists(OPS_MOCK), reason="build/plugin/dense_ops_check_mock not built (needs /root/reference)")
-def test_dense_combiner_delta_diag_overloads_on_mock_abi():
-    """DenseGPU x Combiner / delta / Diag against the reference's host products of the same ITensors"""
-    out = subprocess.run([OPS_MOCK], env=MOCK_ENV, capture_output=True, text=True, timeout=300)
+@pytest.mark.parametrize("walk_tables", ["0", "1"])
+def test_dense_combiner_delta_diag_overloads_on_mock_abi(walk_tables):
+    """DenseGPU x Combiner / delta / Diag and QDiag x QDenseGPU against the reference's host products
+    of the same ITensors; once with oracle arithmetic, once walking the planner's device tables"""
+    out = subprocess.run([OPS_MOCK], env=dict(MOCK_ENV, ITB_MOCK_TABLES=walk_tables), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "all dense-ops cases ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
