@@ -143,7 +143,8 @@ int build_contract_plan(itb_contract_plan& P) {
     std::vector<PackedRec> precs;        // fast path
     std::unordered_map<std::vector<int32_t>, int64_t, VecHash> cpos;
     std::vector<uint64_t> ckeys;         // fast path: sorted unique C keys
-    const bool packed = cbits <= 63 && kbits <= 63;
+    static const bool force_generic = getenv("ITB_PLAN_GENERIC") != nullptr; // tests: exercise the vector-key path
+    const bool packed = cbits <= 63 && kbits <= 63 && !force_generic;
     if (packed) {
         std::vector<std::pair<uint64_t, int64_t>> bkeys(B.nblocks); // (contracted key, B block), sorted: B order kept inside a key
         for (int64_t b = 0; b < B.nblocks; ++b) {

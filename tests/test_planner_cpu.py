@@ -201,3 +201,17 @@ def test_row_groups_read_every_input_once():
             seen += 1
         s = P.C
     assert seen == 2
+
+
+def test_generic_key_path_matches_oracle_too():
+    """Block tuples that do not fit a 64-bit key take the vector-key path of the planner; ITB_PLAN_GENERIC forces it so
+    that the same oracle comparison covers it (subprocess: the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(root, "tests", "test_planner_cpu.py"), "-k",
+                          "structure_matches_oracle_random or heff_census or stream_k"], env=dict(os.environ, ITB_PLAN_GENERIC="1"),
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:]
