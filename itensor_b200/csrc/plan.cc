@@ -337,7 +337,7 @@ static double cblk_cost(int f, int64_t M, int64_t N, double nch, int npairs) {
     // full tiles + the (up to) three distinct edge shapes
     const int64_t fm = M / TM, fn = N / TN, rm = M % TM, rn = N % TN;
     const double ovh = kTileOverhead[f] + kPairOverhead * npairs;
-    cost += (double)fm * fn * (chunk_cycles(f, TM, TN) * nch + ovh);
+    if (fm && fn) cost += (double)fm * fn * (chunk_cycles(f, TM, TN) * nch + ovh);
     if (rm) cost += (double)fn * (chunk_cycles(f, rm, TN) * nch + ovh);
     if (rn) cost += (double)fm * (chunk_cycles(f, TM, rn) * nch + ovh);
     if (rm && rn) cost += chunk_cycles(f, rm, rn) * nch + ovh;
