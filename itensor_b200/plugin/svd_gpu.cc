@@ -392,16 +392,19 @@ svdOrd2(ITensor const& A, Index const& uI, Index const& vI, ITensor & U, ITensor
 // diag_hermitian (hermitian.cc:429-440) likewise: hermitian.cc is compiled with -Ddiag_hermitian=diag_hermitian_host.
 // Block-sparse GPU tensors go through the reference's per-block loop (GetBlocks views; blocks >= 256 are diagonalised
 // by cuSOLVER behind the LAPACK boundary). A dense GPU tensor has no raw host view (ToMatRefc is private to
-// decomp.cc), so it is diagonalised from a host copy and the eigenvectors return to HBM.
+// decomp.cc), so it is diagonalised from a host copy. The eigenvectors return to HBM in both cases.
 Spectrum
 diag_hermitian_host(ITensor H, ITensor & U, ITensor & D, Args const& args);
 
 Spectrum
 diag_hermitian(ITensor H, ITensor & U, ITensor & D, Args const& args)
     {
-    if(H.store() && onGPU(H) && !hasQNs(H))
+    if(H.store() && onGPU(H))
         {
-        auto spec = diag_hermitian_host(toCPU(H),U,D,args);
+        // dense: no raw host view of GPU storage exists, diagonalise a host copy; block-sparse: the reference's loop
+        // reads GetBlocks views of a host snapshot. Either way the eigenvectors go (back) to HBM at once, so that the
+        // products that follow in denmatDecomp (decomp.h:400-418: cmb * dag(U), U * AAc) find both operands there.
+        auto spec = hasQNs(H) ? diag_hermitian_host(H,U,D,args) : diag_hermitian_host(toCPU(H),U,D,args);
         U = toGPU(U);
         return spec;
         }
