@@ -37,6 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "block-sparse contraction FP64 TFLOP/s (H_eff*phi, S=1/2 Heisenberg Sz blocks)"
+WORKLOAD = "H_eff*phi (LocalOp::product: phi*L*W1*W2*R) S=1/2 Heisenberg N=100 centre bond, Sz QDense blocks, maxdim %d"
 
 
 def workload(m: int, nsect: int, dtype: int):
@@ -155,42 +156,64 @@ def measure_dgemm_peak(torch, dev, n=8192, reps=6):
     return 2.0 * n**3 / (best * 1e-3) / 1e12
 
 
+def cpu_modes(structs, hosts, flops, modes=("A", "B", "C"), reps=1):
+    """the reference CPU build on this box's host cores in the three thread modes of SURVEY §8(d), on the given workload"""
+    from oracle import orc
+
+    out = {}
+    for md in modes:
+        if md == "C" and not orc.have_ref_omp():
+            continue
+        _, desc, threads = orc.ref_mode(md)
+        secs, _ = orc.ref_time_heff(structs, hosts, reps, mode=md)
+        out[md] = {"tflops": flops / secs / 1e12, "seconds_per_step": secs, "threads": threads, "mode": desc}
+    return out
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the same step, bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the SAME step (same maxdim, same sectors, same values),
+    every step one full H_eff*phi, on all host cores. Thread counts are set through the libraries' own setters, so the
+    OMP_NUM_THREADS=1 that torchrun exports cannot shrink them."""
     if rank != 0:
         return
-    from itensor_b200 import ITB_F64, synth
+    from itensor_b200 import ITB_C64, ITB_F64, synth
     import itensor_b200 as itb
     from oracle import orc
 
     if not orc.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libitref.so not built (needs /root/reference at build time)"}))
         return
-    m = args.ref_m
-    sizes, structs = workload(m, args.nsect, ITB_F64)
+    dtype = ITB_C64 if args.complex else ITB_F64
+    sizes, structs = workload(args.m, args.nsect, dtype)
     hosts = [synth.random_values(s, 10 + i) for i, s in enumerate(structs)]
     flops, s = 0.0, structs[0]
     for t in structs[1:]:
         p = itb.ContractPlan(s, t)
         flops += p.flops
         s = p.C
-    for _ in range(max(args.warmup, 0) and 1):
-        orc.ref_time_heff(structs, hosts, 1)
+    # pick the faster of the two all-core modes on one untimed step each (B: threaded BLAS; C: the reference's OpenMP loop
+    # over C blocks, its recommended setting for QN tensors, options.mk.sample:114-150), then time that mode
+    probe = cpu_modes(structs, hosts, flops, modes=("B", "C"))
+    best = max(probe, key=lambda k: probe[k]["tflops"])
+    for _ in range(max(args.warmup - 1, 0)):
+        orc.ref_time_heff(structs, hosts, 1, mode=best)
+    steps = max(1, min(args.steps, 40))
     t0 = time.perf_counter()
-    secs = [orc.ref_time_heff(structs, hosts, 1)[0] for _ in range(args.steps)]
+    secs = [orc.ref_time_heff(structs, hosts, 1, mode=best)[0] for _ in range(steps)]
     wall = time.perf_counter() - t0
     per = float(np.mean(secs))
     val = flops / per / 1e12
-    cores = os.cpu_count()
+    cores = orc.host_cores()
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"H_eff*phi (LocalOp::product, 4 contractions) S=1/2 Heisenberg Sz sectors, maxdim {args.m}",
-                   "sample_maxdim": m, "sectors": sizes, "flops_per_step": flops},
+        "dtype": "c128" if args.complex else "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD % args.m, "maxdim": args.m, "sectors": sizes, "d": 2, "mpo_link_sectors": [3, 1, 1],
+                   "flops_per_step": flops},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "reference",
-                         "sample": f"unmodified ITensor (OpenBLAS threads={os.environ.get('OPENBLAS_NUM_THREADS', 'all')}) "
-                                   f"phi*L*W1*W2*R at maxdim {m} (bounded sample of the maxdim-{args.m} workload), wall {wall:.1f}s"},
+                         "sample": f"unmodified ITensor CPU build, full H_eff*phi at maxdim {args.m} per step (the same workload, not a "
+                                   f"reduced sample), mode {best}: {probe[best]['mode']}; {steps} steps, wall {wall:.1f}s",
+                         "modes_probe": probe},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -204,7 +227,6 @@ def main():
     ap.add_argument("--m", type=int, default=2000, help="maxdim (MPS bond dimension)")
     ap.add_argument("--nsect", type=int, default=9, help="Sz sectors on the MPS links")
     ap.add_argument("--complex", action="store_true")
-    ap.add_argument("--ref-m", type=int, default=800, help="maxdim of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -433,25 +455,36 @@ def main():
                      "timing": "mean of 4 back-to-back permutes (alternating destinations, 254 MB each > L2) per CUDA-event pair, best of 3"}
         del dst
 
-    # ---- CPU baseline: the reference itself on this box's host cores, bounded sample ----------------
-    cpu = None
+    # ---- CPU baseline + parity: the reference itself on this box's host cores, on the SAME tensors ---------------------
+    cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import orc
 
         if orc.have_ref():
-            _, cs = workload(args.ref_m, args.nsect, dtype)
-            ch = [synth.random_values(s_, 10 + i) for i, s_ in enumerate(cs)]
-            fl, s_ = 0.0, cs[0]
-            for t_ in cs[1:]:
-                p_ = itb.ContractPlan(s_, t_)
-                fl += p_.flops
-                s_ = p_.C
             t0 = time.perf_counter()
-            secs, _ = orc.ref_time_heff(cs, ch, 2)
-            wall = time.perf_counter() - t0
-            cpu = {"value": fl / secs / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference",
-                   "sample": f"unmodified ITensor CPU build (OpenBLAS, threads={os.environ.get('OPENBLAS_NUM_THREADS', 'all')}), one "
-                             f"H_eff*phi at maxdim {args.ref_m} best of 2 ({fl:.3g} flop, {wall:.1f}s wall)"}
+            modes = cpu_modes(structs, hosts, total_flops)
+            best = max(modes, key=lambda k: modes[k]["tflops"])
+            cpu = {"value": modes[best]["tflops"], "unit": "TFLOP/s", "cores": orc.host_cores(), "kind": "reference",
+                   "modes": modes,
+                   "sample": f"unmodified ITensor CPU build, one full H_eff*phi of this workload (maxdim {args.m}, {total_flops:.3g} flop) per "
+                             f"thread mode A/B/C of SURVEY 8(d); value = fastest mode ({best}); {time.perf_counter() - t0:.1f}s wall"}
+            # element-level parity of THIS workload against the reference (north_star: structure bit-exact, values 1e-12
+            # relative): every one of the four contractions, each fed with the reference's own previous intermediate
+            if world == 1:
+                parity = {"tolerance": 1e-12, "steps": []}
+                cur_s, cur_h = structs[0], hosts[0]
+                for k, p in enumerate(plans):
+                    rr = orc.ref_contract(cur_s, cur_h, structs[k + 1], hosts[k + 1])
+                    d_in = itb.QTensor.from_host(ctx, cur_s, cur_h)
+                    check(lib().itb_contract_run(ctx.handle, p._h, d_in.ptr, dts[k + 1].ptr, outs[k].ptr))
+                    got = outs[k].data.cpu().numpy()
+                    got = got.view(np.complex128) if p.C.is_complex else got
+                    same = bool(np.array_equal(rr.blocks, p.C.blocks) and np.array_equal(rr.offsets, p.C.offsets)
+                                and rr.nelems == p.C.nelems and list(rr.labels) == [int(x) for x in p.C.labels])
+                    err = float(np.abs(got - rr.data).max() / np.abs(rr.data).max())
+                    parity["steps"].append({"step": k + 1, "structure_bit_exact": same, "max_rel_err": err, "elements": int(rr.nelems)})
+                    cur_s, cur_h = p.C, rr.data
+                parity["ok"] = all(st["structure_bit_exact"] and st["max_rel_err"] <= 1e-12 for st in parity["steps"])
         else:
             cpu = {"value": None, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref not built"}
 
@@ -460,14 +493,15 @@ def main():
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128" if args.complex else "f64",
             "data": "synthetic",
-            "config": {"workload": f"H_eff*phi (LocalOp::product: phi*L*W1*W2*R) S=1/2 Heisenberg N=100 centre bond, Sz QDense blocks, maxdim {args.m}",
+            "config": {"workload": WORKLOAD % args.m,
                        "maxdim": args.m, "sectors": sizes, "d": 2, "mpo_link_sectors": [3, 1, 1],
                        "pairs_per_step": [int(p.npairs) for p in plans], "flops_per_step": total_flops,
                        "l2": "flushed between timed iterations (256 MiB memset)",
                        "sharding": ("C blocks by l' sector, max rank share %.3f of flops" % (max_share,)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "permute": perm_info,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity,
+            "permute": perm_info,
         }))
     if world > 1:
         dist.destroy_process_group()

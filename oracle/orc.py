@@ -15,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "liboracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libitref.so")
+REF_OMP_SO = os.path.join(_HERE, "_ref", "libitref_omp.so")  # same sources built with -DITENSOR_USE_OMP -fopenmp
 
 
 class OrcDesc(C.Structure):
@@ -55,6 +56,7 @@ def _p(a, t):
 
 _orc = None
 _ref = None
+_ref_omp = None
 
 
 def build_oracle() -> None:
@@ -78,8 +80,25 @@ def have_ref() -> bool:
     return os.path.exists(REF_SO)
 
 
-def ref():
-    global _ref
+def have_ref_omp() -> bool:
+    return os.path.exists(REF_OMP_SO)
+
+
+def host_cores() -> int:
+    """cores this process may run on (cgroup/affinity aware), the thread count of CPU modes B and C"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def ref(omp: bool = False):
+    global _ref, _ref_omp
+    if omp:
+        if _ref_omp is None:
+            ref()  # preloads the BLAS siblings
+            _ref_omp = _bind(C.CDLL(REF_OMP_SO))
+        return _ref_omp
     if _ref is None:
         # the wheel-bundled OpenBLAS needs its sibling libquadmath/libgfortran: preload them
         import glob
@@ -88,7 +107,12 @@ def ref():
         for pat in ("libquadmath-*.so*", "libgfortran-*.so*"):
             for f in sorted(glob.glob(os.path.join(blas_dir, pat))):
                 C.CDLL(f, mode=C.RTLD_GLOBAL)
-        L = C.CDLL(REF_SO)
+        _ref = _bind(C.CDLL(REF_SO))
+    return _ref
+
+
+def _bind(L):
+    if True:
         for n in ("ref_contract", "ref_permute", "ref_pluseq"):
             getattr(L, n).restype = C.c_void_p
         L.ref_time_contract.restype = C.c_double
@@ -100,8 +124,29 @@ def ref():
                   "ref_result_nflux", "ref_result_labels", "ref_result_blocks", "ref_result_offsets", "ref_result_data",
                   "ref_result_flux", "ref_result_free"):
             getattr(L, n).argtypes = [C.c_void_p] + ([C.c_void_p] if n.split("_")[-1] in ("labels", "blocks", "offsets", "data", "flux") else [])
-        _ref = L
-    return _ref
+        L.ref_time_heff.restype = C.c_double
+    return L
+
+
+# The three CPU modes of SURVEY §8(d): (A) 1 BLAS thread, no OMP; (B) BLAS threads = cores; (C) the reference's own
+# OpenMP loop over C blocks (ITENSOR_USE_OMP build, options.mk.sample:114-150) with cores threads and 1 BLAS thread.
+# Threads are set through the libraries' own setters, so a launcher's OMP_NUM_THREADS=1 (torchrun) cannot change them.
+def ref_mode(mode: str):
+    """(library, description, threads) with the thread counts of CPU mode 'A' | 'B' | 'C' applied"""
+    n = host_cores()
+    if mode == "A":
+        L = ref()
+        L.ref_set_threads(1, 0)
+        return L, "1 BLAS thread, no OpenMP", 1
+    if mode == "B":
+        L = ref()
+        L.ref_set_threads(n, 0)
+        return L, f"OpenBLAS threads={L.ref_get_blas_threads()}, no OpenMP", n
+    if mode == "C":
+        L = ref(omp=True)
+        assert L.ref_set_threads(1, n) == 1
+        return L, f"ITENSOR_USE_OMP=1, OMP threads={L.ref_get_omp_threads()}, OpenBLAS threads=1", n
+    raise ValueError(mode)
 
 
 # ---- oracle wrappers (operate on itensor_b200.tensor.BlockStruct-like objects: duck-typed) ----------
@@ -306,10 +351,10 @@ def ref_dmrg_heisenberg(N, spin2, conserve_qns, maxdim, cutoff, niter, noise):
     return e.value, s.value, ml.value
 
 
-def ref_time_heff(structs, hosts, reps=1, want_result=False):
-    """seconds for one LocalOp::product chain phi*L*W1*W2*R through the reference (best of reps)"""
-    L = ref()
-    L.ref_time_heff.restype = C.c_double
+def ref_time_heff(structs, hosts, reps=1, want_result=False, mode=None):
+    """seconds for one LocalOp::product chain phi*L*W1*W2*R through the reference (best of reps); mode: see ref_mode
+    (None = mode B, all cores in OpenBLAS)"""
+    L = ref_mode(mode or "B")[0]
     keeps = [_Keep(s, h) for s, h in zip(structs, hosts)]
     out = C.c_void_p()
     secs = L.ref_time_heff(*[C.byref(k.t) for k in keeps], C.c_int(reps), C.byref(out) if want_result else None)

@@ -11,8 +11,17 @@
 #include <vector>
 
 #include "itensor/all.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 using namespace itensor;
+
+// OpenBLAS' own thread-count setter (the BLAS this harness links): lets the caller pin the three CPU modes of
+// SURVEY §8(d) explicitly instead of inheriting OMP_NUM_THREADS / OPENBLAS_NUM_THREADS from a launcher (torchrun
+// exports OMP_NUM_THREADS=1 to every rank).
+extern "C" void openblas_set_num_threads(int);
+extern "C" int openblas_get_num_threads(void);
 
 extern "C" {
 
@@ -307,6 +316,32 @@ ref_norm(ref_tensor const* T)
     {
     Registry reg;
     return norm(makeTensor(*T,reg));
+    }
+
+// blas_threads > 0: OpenBLAS threads; omp_threads > 0: threads of the reference's own OpenMP loop over C blocks
+// (itensor/itdata/qutil.h:285-348; only in the -DITENSOR_USE_OMP build, libitref_omp.so). Returns 1 when that loop exists.
+int
+ref_set_threads(int blas_threads, int omp_threads)
+    {
+    if(blas_threads > 0) openblas_set_num_threads(blas_threads);
+#if defined(_OPENMP) && defined(ITENSOR_USE_OMP)
+    if(omp_threads > 0) omp_set_num_threads(omp_threads);
+    return 1;
+#else
+    (void)omp_threads;
+    return 0;
+#endif
+    }
+int
+ref_get_blas_threads(void) { return openblas_get_num_threads(); }
+int
+ref_get_omp_threads(void)
+    {
+#if defined(_OPENMP) && defined(ITENSOR_USE_OMP)
+    return omp_get_max_threads();
+#else
+    return 0;
+#endif
     }
 
 // accessors for ref_result

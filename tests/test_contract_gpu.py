@@ -169,3 +169,41 @@ def test_large_blocks_linearity(ctx):
         want += np.tensordot(ab, bb, axes=([0], [0]))
     got = c1[plan.C.offsets[ic]: plan.C.offsets[ic] + want.size].reshape(want.shape, order="F")
     assert_close(got, want, 1e-12, "block spot check")
+
+
+def test_bench_workload_vs_reference(ctx):
+    """The EXACT bench.py workload (H_eff*phi at maxdim 2000: 148-CTA stream-K cuts, split-K reductions, row groups) against
+    the unmodified reference build (oracle/_ref/libitref.so travels to the GPU box): block list, offsets and index order
+    bit-exact, values <= 1e-12 relative, for each of the four contractions (every step is fed with the reference's own
+    previous intermediate so that errors cannot compound or cancel)."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libitref.so not built")
+    sizes = synth.gaussian_sectors(2000, 9)
+    structs = synth.heff_chain(sizes)
+    hosts = [synth.random_values(s, 10 + i) for i, s in enumerate(structs)]
+    cur_s, cur_h = structs[0], hosts[0]
+    for k in range(4):
+        rr = orc.ref_contract(cur_s, cur_h, structs[k + 1], hosts[k + 1])
+        plan = itb.ContractPlan(cur_s, structs[k + 1])
+        assert np.array_equal(rr.blocks, plan.C.blocks) and np.array_equal(rr.offsets, plan.C.offsets)
+        assert rr.nelems == plan.C.nelems and list(rr.labels) == [int(x) for x in plan.C.labels]
+        got = itb.contract(itb.QTensor.from_host(ctx, cur_s, cur_h), itb.QTensor.from_host(ctx, structs[k + 1], hosts[k + 1]), plan).to_host()
+        assert_close(got, rr.data, 1e-12, f"bench workload step {k + 1}")
+        cur_s, cur_h = plan.C, rr.data
+    assert cur_s.order == 4 and cur_s.nelems == structs[0].nelems
+
+
+def test_bench_workload_complex_vs_reference(ctx):
+    """same chain with complex tensors (folded real-GEMM decomposition) at maxdim 600 against the reference"""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libitref.so not built")
+    structs = synth.heff_chain(synth.gaussian_sectors(600, 7), dtype=Z)
+    hosts = [synth.random_values(s, 20 + i) for i, s in enumerate(structs)]
+    cur_s, cur_h = structs[0], hosts[0]
+    for k in range(4):
+        rr = orc.ref_contract(cur_s, cur_h, structs[k + 1], hosts[k + 1])
+        plan = itb.ContractPlan(cur_s, structs[k + 1])
+        assert np.array_equal(rr.blocks, plan.C.blocks) and np.array_equal(rr.offsets, plan.C.offsets)
+        got = itb.contract(itb.QTensor.from_host(ctx, cur_s, cur_h), itb.QTensor.from_host(ctx, structs[k + 1], hosts[k + 1]), plan).to_host()
+        assert_close(got, rr.data, 1e-12, f"complex chain step {k + 1}")
+        cur_s, cur_h = plan.C, rr.data
