@@ -221,6 +221,9 @@ int itb_svd_batch_values(itb_svd_batch* batch, double* hS);
 int itb_svd_batch_copy_u(itb_svd_batch* batch, int64_t block, int32_t ncols, void* dDst);           /* m x ncols */
 int itb_svd_batch_copy_v(itb_svd_batch* batch, int64_t block, int32_t ncols, void* dDst, int conj); /* n x ncols */
 int itb_svd_batch_destroy(itb_svd_batch* batch);
+/* diagnostics since process start: out = {blocks given to the polar solver, of those redone with Jacobi (failed or perturbed
+ * input, err_sigma > 1e-14 s0), blocks factorised with Jacobi}; returns the largest err_sigma / s0 the polar solver reported */
+double itb_svd_batch_stats(int64_t out[3]);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement

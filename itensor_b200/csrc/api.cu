@@ -70,6 +70,8 @@ struct itb_solver;
 struct itb_svd_batch;
 extern "C" {
 int itb_solver_create(void* stream, itb_solver** out);
+int itb_solver_set_stream(itb_solver* s, void* stream);
+int itb_solver_destroy(itb_solver* s);
 }
 void itb_warm_library_pages(); // solver.cu: background read of the cuSOLVER/cuBLAS shared objects
 extern "C" {
@@ -260,6 +262,10 @@ int itb_ctx_destroy(itb_ctx* c) {
     if (c->aux) cudaStreamDestroy(c->aux);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_staging) cudaEventDestroy(c->ev_staging);
+    for (auto& e : c->pev) if (e) cudaEventDestroy(e);
+    if (c->d_cta_cycles) cudaFree(c->d_cta_cycles);
+    if (c->solver) itb_solver_destroy(c->solver);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return ITB_OK;
@@ -269,9 +275,12 @@ void* itb_ctx_stream(itb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int itb_ctx_set_stream(itb_ctx* c, void* s) {
     if (!c) { set_error("set_stream: null ctx"); return ITB_ERR_INVALID; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // the lazily created solver (its cuSOLVER handle and the batched-SVD lanes' fence target) is bound to the stream
+    if (c->solver) { int rc = itb_solver_set_stream(c->solver, s); if (rc != ITB_OK) return rc; }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
+    c->staging_busy = false; // the old stream was drained above
     return ITB_OK;
 }
 int itb_synchronize(itb_ctx* c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return ITB_OK; }
@@ -434,14 +443,24 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
         }
         return ITB_OK;
     };
-    if (fork) { rc = launch_side(); if (rc != ITB_OK) return rc; CUDA_TRY(cudaEventRecord(c->ev_join, c->aux)); }
+    // from here on every exit path joins the side stream back into the main stream (join_side), so a failed launch or
+    // allocation cannot leave work on aux that the caller's next operation on the main stream would race with
+    auto join_side = [&]() {
+        if (!fork) return;
+        if (cudaEventRecord(c->ev_join, c->aux) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->ev_join, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cudaStreamSynchronize(c->aux);
+        }
+    };
+#define SIDE_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { join_side(); set_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); return ITB_ERR_CUDA; } } while (0)
+    if (fork) { rc = launch_side(); if (rc != ITB_OK) { join_side(); return rc; } SIDE_TRY(cudaEventRecord(c->ev_join, c->aux)); }
     if (has_tiles) {
-        if (P->ws_slots > 0) { rc = ensure_ws(c, (size_t)P->ws_slots * ITB_WS_TILE); if (rc != ITB_OK) return rc; }
+        if (P->ws_slots > 0) { rc = ensure_ws(c, (size_t)P->ws_slots * ITB_WS_TILE); if (rc != ITB_OK) { join_side(); return rc; } }
         PROF_BEGIN(0);
         // the grid is the planner's partition width (one CTA per B200 SM); CTAs whose share is empty exit at once
         const int grid = (int)P->cta_begin.size() - 1;
-        if (c->profile && !c->d_cta_cycles) CUDA_TRY(cudaMalloc(&c->d_cta_cycles, 1024 * sizeof(long long)));
-        CUDA_TRY(launch_gemm(d->tiles, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
+        if (c->profile && !c->d_cta_cycles) SIDE_TRY(cudaMalloc(&c->d_cta_cycles, 1024 * sizeof(long long)));
+        SIDE_TRY(launch_gemm(d->tiles, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
             c->h_cta_cycles.assign(grid, 0);
@@ -454,6 +473,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     else { rc = launch_side(); if (rc != ITB_OK) return rc; }
 #undef PROF_BEGIN
 #undef PROF_END
+#undef SIDE_TRY
     if (c->profile) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         for (int i = 0; i < 5; ++i) {

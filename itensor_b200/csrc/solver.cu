@@ -150,6 +150,12 @@ int itb_solver_create(void* stream, itb_solver** out) {
     return ITB_OK;
 }
 
+int itb_solver_set_stream(itb_solver* s, void* stream) {
+    s->stream = (cudaStream_t)stream;
+    CS_TRY(cusolverDnSetStream(s->h, s->stream));
+    return ITB_OK;
+}
+
 // symmetric / Hermitian eigendecomposition, LAPACK dsyev('V','U') / zheev semantics:
 // A (n x n, column-major, host) is overwritten by the eigenvectors, w gets the eigenvalues ascending
 int itb_solver_syevd(itb_solver* s, int32_t dtype, int32_t n, void* hA, double* hW, int32_t* info) {
@@ -245,8 +251,10 @@ int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* h
         // the polar solver needs a numerically full-rank, not-too-small matrix: small blocks go to Jacobi directly and a
         // failed polar iteration (exactly rank-deficient input) is redone with Jacobi from the untouched host copy
         if (std::min(m, n) < 96) return solver_gesvdj(s, dtype, m, n, hA, hS, hU, hVT, info);
+        // (hA is only read by the polar path, so the Jacobi redo starts from the untouched input.) A nonzero err_sigma means
+        // the solver perturbed the input by that magnitude: accepted only at rounding level relative to the largest value.
         const int rc = solver_gesvdp(s, dtype, m, n, hA, hS, hU, hVT, info);
-        if (rc == ITB_OK && *info == 0) return rc;
+        if (rc == ITB_OK && *info == 0 && s->last_err_sigma <= 1e-14 * hS[0]) return rc;
         return solver_gesvdj(s, dtype, m, n, hA, hS, hU, hVT, info);
     }
     const size_t es = dtype == ITB_C64 ? 16 : 8;
@@ -310,6 +318,8 @@ int itb_solver_gesvd(itb_solver* s, int32_t dtype, int32_t m, int32_t n, void* h
 // values (the truncation decision is host logic), then copies the kept columns straight into the new U and V
 // tensors. Large blocks use the polar-decomposition solver (Xgesvdp), small ones one-sided Jacobi (gesvdj).
 constexpr int SVD_LANES = 4;
+static std::atomic<long> g_polar_blocks{0}, g_polar_redo{0}, g_jacobi_blocks{0}; // ITB_PROFILE: printed by itb_svd_batch_stats
+static std::atomic<double> g_max_sigma_ratio{0.0};
 struct SvdLane {
     cudaStream_t st = nullptr;
     cusolverDnHandle_t h = nullptr;
@@ -352,10 +362,19 @@ static int svd_batch_join(itb_svd_batch* B) {
     for (auto& t : B->threads) t.join();
     B->threads.clear();
     B->joined = true;
+    // everything queued on the context's stream from here on (column copies, the stream-ordered frees of d_uv / d_s) is
+    // ordered after ALL lanes, whether or not one of them failed: a lane that is still running may write U / V
+    int fence_rc = ITB_OK;
+    for (auto& ln : B->lanes->lane) {
+        if (cudaEventRecord(ln.done, ln.st) != cudaSuccess || cudaStreamWaitEvent(B->main, ln.done, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cudaStreamSynchronize(ln.st); // could not fence with an event: wait for the lane on the host instead
+            fence_rc = ITB_ERR_CUDA;
+        }
+    }
     for (int q = 0; q < SVD_LANES; ++q)
         if (B->lane_rc[q]) { itb::set_error(B->lane_err[q]); return B->lane_rc[q]; }
-    // everything queued on the context's stream from here on sees the finished factorisations
-    for (auto& ln : B->lanes->lane) { S_TRY(cudaEventRecord(ln.done, ln.st)); S_TRY(cudaStreamWaitEvent(B->main, ln.done, 0)); }
+    if (fence_rc) { itb::set_error("svd batch: could not order the solver lanes before the context stream"); return fence_rc; }
     return ITB_OK;
 }
 
@@ -403,24 +422,52 @@ static int svd_one(SvdLane& ln, int32_t dtype, int m, int n, const void* dA, dou
         const cusolverStatus_t st = cusolverDnXgesvdp(ln.h, ln.params, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, dt, ln.d_a, m, CUDA_R_64F, dS, dt, dU, m, dt, dV, n, dt,
                                                       ln.d_work, wd, ln.h_work, wh, ln.d_info, &err_sigma);
         int hinfo = 0;
+        double s0 = 0;
         if (st == CUSOLVER_STATUS_SUCCESS) {
             S_TRY(cudaMemcpyAsync(&hinfo, ln.d_info, sizeof(int), cudaMemcpyDeviceToHost, ln.st));
+            S_TRY(cudaMemcpyAsync(&s0, dS, sizeof(double), cudaMemcpyDeviceToHost, ln.st)); // largest singular value
             S_TRY(cudaStreamSynchronize(ln.st));
         }
-        if (st != CUSOLVER_STATUS_SUCCESS || hinfo != 0) {
-            // the polar iteration needs a numerically full-rank matrix: redo exactly rank-deficient blocks with Jacobi
+        // err_sigma != 0: the solver perturbed a (near-)singular input by that magnitude, which bounds the accuracy of the
+        // small singular values and their vectors. Accept it only at the level of LAPACK's own backward error.
+        static double sigma_tol = -1;
+        if (sigma_tol < 0) { const char* e = getenv("ITB_SVD_ERRSIGMA_TOL"); sigma_tol = e ? atof(e) : 1e-14; }
+        const bool perturbed = st == CUSOLVER_STATUS_SUCCESS && hinfo == 0 && !(err_sigma <= sigma_tol * s0);
+        ++g_polar_blocks;
+        if (s0 > 0) { double r = err_sigma / s0, cur = g_max_sigma_ratio.load(); while (r > cur && !g_max_sigma_ratio.compare_exchange_weak(cur, r)) {} }
+        if (st != CUSOLVER_STATUS_SUCCESS || hinfo != 0 || perturbed) {
+            // the polar iteration needs a numerically full-rank matrix: redo rank-deficient / perturbed blocks with Jacobi
             (void)cudaGetLastError();
+            ++g_polar_redo;
             S_TRY(cudaMemcpyAsync(ln.d_a, dA, (size_t)m * n * es, cudaMemcpyDeviceToDevice, ln.st));
             jacobi = true;
         }
     }
     if (jacobi) {
+        ++g_jacobi_blocks;
         int lwork = 0;
         if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)ln.d_a, m, dS, (double*)dU, m, (double*)dV, n, &lwork, ln.jinfo));
         else CS_TRY(cusolverDnZgesvdj_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)ln.d_a, m, dS, (cuDoubleComplex*)dU, m, (cuDoubleComplex*)dV, n, &lwork, ln.jinfo));
         rc = grow(&ln.d_work, &ln.work_bytes, (size_t)lwork * es + 256); if (rc) return rc;
         if (dtype == ITB_F64) CS_TRY(cusolverDnDgesvdj(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (double*)ln.d_a, m, dS, (double*)dU, m, (double*)dV, n, (double*)ln.d_work, lwork, ln.d_info, ln.jinfo));
         else CS_TRY(cusolverDnZgesvdj(ln.h, CUSOLVER_EIG_MODE_VECTOR, 1, m, n, (cuDoubleComplex*)ln.d_a, m, dS, (cuDoubleComplex*)dU, m, (cuDoubleComplex*)dV, n, (cuDoubleComplex*)ln.d_work, lwork, ln.d_info, ln.jinfo));
+        // info < 0: bad argument; info = min(m,n)+1: the sweeps did not reach the 1e-15 tolerance. The latter is accepted only
+        // when the residual (Frobenius norm of what is left off the diagonal) is at rounding level relative to the largest
+        // singular value; anything else is an error the caller sees (these factors go straight into the truncation).
+        int hinfo = 0;
+        double s0 = 0;
+        S_TRY(cudaMemcpyAsync(&hinfo, ln.d_info, sizeof(int), cudaMemcpyDeviceToHost, ln.st));
+        S_TRY(cudaMemcpyAsync(&s0, dS, sizeof(double), cudaMemcpyDeviceToHost, ln.st));
+        S_TRY(cudaStreamSynchronize(ln.st));
+        if (hinfo != 0) {
+            double resid = 0;
+            const bool have = hinfo > 0 && cusolverDnXgesvdjGetResidual(ln.h, ln.jinfo, &resid) == CUSOLVER_STATUS_SUCCESS;
+            if (!have || !(resid <= 1e-12 * s0)) {
+                itb::set_error("svd batch: gesvdj failed on a " + std::to_string(m) + "x" + std::to_string(n) + " block (info " + std::to_string(hinfo) +
+                               ", residual " + std::to_string(resid) + ")");
+                return ITB_ERR_CUDA;
+            }
+        }
     }
     return ITB_OK;
 }
@@ -445,11 +492,22 @@ int itb_solver_svd_batch_run(itb_solver* s, int32_t dtype, int64_t nblocks, cons
     B->ns = ns;
     // stream-ordered allocations on the context's stream: the lanes only start after the `ready` event below
     if (cudaMallocAsync(&B->d_uv, bytes + 256, s->stream) != cudaSuccess || cudaMallocAsync((void**)&B->d_s, (size_t)ns * 8 + 256, s->stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (B->d_uv) cudaFreeAsync(B->d_uv, s->stream);
         itb::set_error("svd batch: out of device memory"); delete B; return ITB_ERR_NOMEM;
     }
     // the tensor was produced on the context's stream
-    S_TRY(cudaEventRecord(s->lanes->ready, s->stream));
-    for (auto& ln : s->lanes->lane) S_TRY(cudaStreamWaitEvent(ln.st, s->lanes->ready, 0));
+    {
+        cudaError_t e = cudaEventRecord(s->lanes->ready, s->stream);
+        for (auto& ln : s->lanes->lane)
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ln.st, s->lanes->ready, 0);
+        if (e != cudaSuccess) {
+            itb::set_error(std::string("svd batch: ") + cudaGetErrorString(e));
+            cudaFreeAsync(B->d_uv, s->stream); cudaFreeAsync(B->d_s, s->stream);
+            delete B;
+            return ITB_ERR_CUDA;
+        }
+    }
     // largest blocks first onto the least loaded lane; one host thread drives each lane (the polar solver
     // synchronises with the host inside the call, so lanes only overlap when they are issued concurrently). The
     // call returns at once: the caller overlaps its own host work and collects with itb_svd_batch_values.
@@ -498,12 +556,45 @@ int itb_svd_batch_copy_v(itb_svd_batch* B, int64_t b, int32_t ncols, void* dDst,
     if (conj && B->dtype == ITB_C64) conj_inplace_kernel<<<148, 256, 0, B->main>>>((double2*)dDst, (size_t)B->n[b] * ncols);
     return ITB_OK;
 }
+// counters since process start: {polar blocks, polar blocks redone with Jacobi, Jacobi blocks}; returns max err_sigma / s0 seen
+double itb_svd_batch_stats(int64_t out[3]) {
+    if (out) { out[0] = g_polar_blocks.load(); out[1] = g_polar_redo.load(); out[2] = g_jacobi_blocks.load(); }
+    return g_max_sigma_ratio.load();
+}
 int itb_svd_batch_destroy(itb_svd_batch* B) {
     if (!B) return ITB_OK;
     svd_batch_join(B);
     cudaFreeAsync(B->d_uv, B->main); // ordered after the column copies queued on the same stream
     cudaFreeAsync(B->d_s, B->main);
     delete B;
+    return ITB_OK;
+}
+
+int itb_solver_destroy(itb_solver* s) {
+    if (!s) return ITB_OK;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->lanes) {
+        for (auto& ln : s->lanes->lane) {
+            if (ln.st) cudaStreamSynchronize(ln.st);
+            if (ln.h) cusolverDnDestroy(ln.h);
+            if (ln.params) cusolverDnDestroyParams(ln.params);
+            if (ln.jinfo) cusolverDnDestroyGesvdjInfo(ln.jinfo);
+            if (ln.d_work) cudaFree(ln.d_work);
+            if (ln.d_a) cudaFree(ln.d_a);
+            free(ln.h_work);
+            if (ln.d_info) cudaFree(ln.d_info);
+            if (ln.done) cudaEventDestroy(ln.done);
+            if (ln.st) cudaStreamDestroy(ln.st);
+        }
+        if (s->lanes->ready) cudaEventDestroy(s->lanes->ready);
+        delete s->lanes;
+    }
+    for (void* p : {s->d_a, s->d_b, s->d_c, s->d_w, s->d_work, (void*)s->d_info}) if (p) cudaFree(p);
+    free(s->h_work);
+    if (s->jinfo) cusolverDnDestroyGesvdjInfo(s->jinfo);
+    if (s->params) cusolverDnDestroyParams(s->params);
+    if (s->h) cusolverDnDestroy(s->h);
+    delete s;
     return ITB_OK;
 }
 

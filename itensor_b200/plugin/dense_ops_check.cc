@@ -29,6 +29,21 @@ main()
         {
         auto T = cplx ? randomITensorC(i,j,k,l) : randomITensor(i,j,k,l);
         auto G = toGPU(T);
+        // element access on GPU storage: set() / apply() (SetElt, ApplyIT) keep the tensor in HBM, also when the storage is
+        // shared with a copy (copy-on-write) and when set() promotes real storage to complex
+        {
+        auto Th = T, Gs = G;
+        auto Gshared = Gs; // second owner: the write below must not change it
+        Th.set(i=2,j=3,k=4,l=1,0.75); Gs.set(i=2,j=3,k=4,l=1,0.75);
+        same("set(real) on GPU storage",Th,Gs);
+        same("  ... shared copy untouched",T,Gshared);
+        if(!cplx) { Th.apply([](Real x) { return 2.*x+1.; }); Gs.apply([](Real x) { return 2.*x+1.; }); same("apply(real f)",Th,Gs); }
+        auto Tc = T, Gc = G;
+        Tc.set(i=1,j=1,k=2,l=2,Cplx(0.5,-1.5)); Gc.set(i=1,j=1,k=2,l=2,Cplx(0.5,-1.5));
+        same("set(complex) (promotes real storage)",Tc,Gc);
+        Tc.apply([](Cplx z) { return z*Cplx(0.,1.); }); Gc.apply([](Cplx z) { return z*Cplx(0.,1.); });
+        same("apply(complex f)",Tc,Gc);
+        }
         // combiner: fused indices adjacent and in order (relabelling), scattered (device permute), and uncombining
         {
         auto [C1,c1] = combiner(j,k);

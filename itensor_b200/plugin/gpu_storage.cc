@@ -265,6 +265,10 @@ struct Desc
         k.append((const char*)nsect.data(),nsect.size()*sizeof(int32_t));
         k.append((const char*)sect.data(),sect.size()*sizeof(int64_t));
         k.append((const char*)blocks.data(),blocks.size()*sizeof(int32_t));
+        // the plans bake the element offsets into every pair / tile record: a tensor with the same block list but another
+        // layout (non-canonical offsets) must not reuse them
+        k.append((const char*)offsets.data(),offsets.size()*sizeof(int64_t));
+        k.append((const char*)&d.nelems,sizeof(int64_t));
         }
     };
 
@@ -342,7 +346,6 @@ getPermutePlan(Desc const& dS, Desc const& dD, std::vector<int32_t> const& perm)
     dS.appendKey(key);
     key.push_back('>');
     dD.appendKey(key);
-    key.append((const char*)dD.offsets.data(),dD.offsets.size()*sizeof(int64_t));
     key.append((const char*)perm.data(),perm.size()*sizeof(int32_t));
     auto& cache = permuteCache();
     if(auto* p = cache.find(key)) return p;

@@ -257,10 +257,44 @@ template<typename T> Cplx doTask(SumEls S, DenseGPU<T> const& d) { return doTask
 template<typename T> void doTask(PrintIT& P, DenseGPU<T> const& d) { doTask(P,d.toHost()); }
 template<typename F, typename T>
 void doTask(VisitIT<F>& V, DenseGPU<T> const& d) { doTask(V,d.toHost()); }
+// element-wise apply / set (dense.h:166-182, dense.cc:48-75) on a host copy; the result is NEW device storage made through
+// the ManageStore. (The reference overloads must not be handed the outer ManageStore: their m.modifyData(d) casts the
+// managed object to ITWrap<Dense<T>>, which a DenseGPU<T> is not.)
 template<typename F, typename T>
-void doTask(ApplyIT<F>& A, DenseGPU<T> const& d, ManageStore& m) { doTask(A,d.toHost(),m); }
+void
+doTask(ApplyIT<F>& A, DenseGPU<T> const& d, ManageStore& m)
+    {
+    using new_type = ApplyIT_result_of<T,F>;
+    auto h = d.toHost();
+    if(switchesType<T>(A))
+        {
+        auto nh = Dense<new_type>(h.size());
+        for(auto i : range(h)) A(h.store[i],nh.store[i]);
+        m.makeNewData<DenseGPU<new_type>>(nh);
+        }
+    else
+        {
+        for(auto& el : h) A(el);
+        m.makeNewData<DenseGPU<T>>(h);
+        }
+    }
 template<typename E, typename T>
-void doTask(SetElt<E> const& S, DenseGPU<T> const& d, ManageStore& m) { doTask(S,d.toHost(),m); }
+void
+doTask(SetElt<E> const& S, DenseGPU<T> const& d, ManageStore& m)
+    {
+    auto h = d.toHost();
+    if constexpr (std::is_same<E,Cplx>::value && std::is_same<T,Real>::value)
+        {
+        auto nh = DenseCplx(h.begin(),h.end());
+        nh[offset(S.is,S.inds)] = S.elt;
+        m.makeNewData<DenseGPUCplx>(nh);
+        }
+    else
+        {
+        h[offset(S.is,S.inds)] = S.elt;
+        m.makeNewData<DenseGPU<T>>(h);
+        }
+    }
 // Dense combiner on the device (combiner.cc:55-178): combining is a relabelling when the fused indices already sit
 // together in combiner order, otherwise one device permute brings them to the front; uncombining is always a
 // relabelling. The result stays in HBM; the decompositions that follow reach it through svdOrd2 / diag_hermitian

@@ -149,7 +149,18 @@ class ContractPlan:
     def __init__(self, A: BlockStruct, B: BlockStruct):
         self.A, self.B = A, B
         self._h = C.c_void_p()
-        la, lb = A.labels, B.labels
+        # labels are assigned per contraction: position of the (id, plev) pair among the distinct indices of A and B
+        # (Index.label = id*8+plev would collide for plev >= 8 and overflow int32 for large ids)
+        key_of = lambda ix: (ix.id, ix.plev)
+        assert len({key_of(i) for i in A.inds}) == A.order, "contract: A carries the same index twice"
+        assert len({key_of(i) for i in B.inds}) == B.order, "contract: B carries the same index twice"
+        pos, by_label = {}, {}
+        for ix in list(A.inds) + list(B.inds):
+            if key_of(ix) not in pos:
+                pos[key_of(ix)] = len(pos)
+                by_label[pos[key_of(ix)]] = ix
+        la = np.array([pos[key_of(i)] for i in A.inds], np.int32)
+        lb = np.array([pos[key_of(i)] for i in B.inds], np.int32)
         da, db = A.desc(), B.desc()
         check(lib().itb_contract_plan_create(C.byref(da), _i32p(la), C.byref(db), _i32p(lb), C.byref(self._h)))
         info = ContractInfo()
@@ -158,7 +169,6 @@ class ContractPlan:
         r = info.c_order
         labels = np.zeros(max(r, 1), np.int32)
         lib().itb_contract_plan_c_labels(self._h, _i32p(labels))
-        by_label = {i.label: i for i in list(A.inds) + list(B.inds)}
         c_inds = [by_label[int(l)] for l in labels[:r]]
         blocks = np.zeros((max(info.c_nblocks, 1), max(r, 1)), np.int32)
         lib().itb_contract_plan_c_blocks(self._h, _i32p(blocks))

@@ -349,6 +349,7 @@ int itb_svd_batch_values(itb_svd_batch*, double*) { return ITB_ERR_UNSUPPORTED; 
 int itb_svd_batch_copy_u(itb_svd_batch*, int64_t, int32_t, void*) { return ITB_ERR_UNSUPPORTED; }
 int itb_svd_batch_copy_v(itb_svd_batch*, int64_t, int32_t, void*, int) { return ITB_ERR_UNSUPPORTED; }
 int itb_svd_batch_destroy(itb_svd_batch*) { return ITB_OK; }
+double itb_svd_batch_stats(int64_t out[3]) { if (out) out[0] = out[1] = out[2] = 0; return 0.0; }
 int itb_peak_fp64(itb_ctx*, int, int, double* t) { *t = 0; return ITB_ERR_UNSUPPORTED; }
 int itb_ctx_set_profile(itb_ctx*, int) { return ITB_OK; }
 int64_t itb_contract_last_cta_cycles(itb_ctx*, int64_t*, int64_t) { return 0; }
