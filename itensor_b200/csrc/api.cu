@@ -13,7 +13,7 @@
 #include "plan.h"
 
 namespace itb {
-cudaError_t launch_gemm(const ItbTile* tiles, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm(const ItbTile* tiles, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles,
                         cudaStream_t st);
@@ -393,6 +393,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     dev->dot_outs = (const ItbDotOut*)(b + o_dout);
     dev->dot_partial = (double*)(b + pk.total);
     dev->counters = (int*)(b + pk.total + partial_bytes);
+    CUDA_TRY(cudaMemsetAsync(dev->counters, 0, 256, c->stream)); // queue head + finished-CTA count of the tile kernel
     P->dev = dev;
     P->dev_ctx = c;
     return ITB_OK;
@@ -457,10 +458,11 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     if (has_tiles) {
         if (P->ws_slots > 0) { rc = ensure_ws(c, (size_t)P->ws_slots * ITB_WS_TILE); if (rc != ITB_OK) { join_side(); return rc; } }
         PROF_BEGIN(0);
-        // the grid is the planner's partition width (one CTA per B200 SM); CTAs whose share is empty exit at once
-        const int grid = (int)P->cta_begin.size() - 1;
+        // persistent grid, one CTA per SM (fewer when the queue is shorter than that); items are pulled from the
+        // in-order queue through the head counter (rearmed by the kernel itself)
+        const int grid = (int)std::min<size_t>((size_t)c->num_sms, P->tiles.size());
         if (c->profile && !c->d_cta_cycles) SIDE_TRY(cudaMalloc(&c->d_cta_cycles, 1024 * sizeof(long long)));
-        SIDE_TRY(launch_gemm(d->tiles, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
+        SIDE_TRY(launch_gemm(d->tiles, (int)P->tiles.size(), d->counters, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
             c->h_cta_cycles.assign(grid, 0);

@@ -73,7 +73,9 @@ constexpr int G_NCONS = 512, G_NPROD = 128, G_NT = G_NCONS + G_NPROD;
 constexpr int G_STAGES = 4, G_BK = ITB_BK, G_PAD = 4, G_MAXT = 128;
 constexpr int G_KT = 1024; // k offsets per shared table fill (per operand)
 constexpr int G_STAGE_ELEMS = G_MAXT * (G_BK + G_PAD); // per operand per stage (covers both layouts)
-constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT) * 8 + (size_t)(2 * G_KT) * 4 + 2 * G_STAGES * 8 + 16;
+constexpr int G_QSLOTS = 4; // look-ahead of the work-queue fetcher (item ring in shared memory)
+constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT) * 8 + (size_t)(2 * G_KT) * 4 + 2 * G_STAGES * 8 +
+                          2 * G_QSLOTS * 8 + G_QSLOTS * 4 + 16;
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -382,7 +384,15 @@ __device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk*
     }
 }
 
-__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, const int32_t* __restrict__ cta_begin,
+// Work distribution: ONE global queue of (tile, K-chunk range) items in C-block order, consumed through an atomic
+// head counter. The planner cuts the tail of the list into pieces of geometrically shrinking modelled cost (guided
+// self-scheduling, plan.cc), so the CTAs finish within one small piece of each other whatever the real per-tile cost is
+// (edge tiles, L2 hits, clocks) — no cycle model has to be right — and at any time the 148 CTAs work on ~148 CONSECUTIVE
+// tiles, i.e. on the few C blocks whose operand panels are then shared through L2 instead of re-read from HBM.
+// Mechanics: producer thread 0 is the fetcher; it publishes item indices G_QSLOTS ahead into a shared ring guarded by
+// full/empty mbarriers, every warp (both roles) reads the same sequence. An index >= n_items is the stop sentinel.
+// The last CTA to stop resets the queue head, so the same tables can be launched again without a memset.
+__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, int n_items, int* __restrict__ queue,
                                                             const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
                                                             double* __restrict__ C, double* __restrict__ ws,
@@ -397,24 +407,50 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
     int* offKb_s = offKa_s + G_KT;
     uint64_t* full = reinterpret_cast<uint64_t*>(offKb_s + G_KT);
     uint64_t* empty = full + G_STAGES;
+    uint64_t* q_full = empty + G_STAGES;
+    uint64_t* q_empty = q_full + G_QSLOTS;
+    volatile int* q_item = reinterpret_cast<volatile int*>(q_empty + G_QSLOTS);
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], G_NPROD);     // one cp.async-completion arrive per producer thread
             mbar_init(&empty[s], G_NCONS / 32); // one arrive per consumer warp
         }
+        for (int s = 0; s < G_QSLOTS; ++s) {
+            mbar_init(&q_full[s], 1);          // the fetcher
+            mbar_init(&q_empty[s], G_NT / 32); // one arrive per warp (both roles) once it has read the slot
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const bool producer = threadIdx.x >= G_NCONS;
+    const bool fetcher = threadIdx.x == G_NCONS;
+    const int lane = threadIdx.x & 31;
     // register re-balancing (warpgroup granular): the kernel launches with 96 regs/thread (640 threads);
     // the producer warpgroup shrinks, the four consumer warpgroups grow (4*112 + 56 per SMSP fits 16K).
     // (setmaxnreg variants measured slower or spilling: see DESIGN.md) if (producer) setmaxnreg.dec 56
     // else setmaxnreg.inc 112
     PipeState ps;
-    // the host planner hands every CTA a contiguous range of (tile, K-chunk range) items of equal modelled cost
-    // (stream-K partition, plan.cc); both roles walk it in the same order
-    const int item_end = cta_begin[blockIdx.x + 1];
-    for (int item = cta_begin[blockIdx.x]; item < item_end; ++item) {
+    int qf = 0;            // fetcher: next sequence number to publish
+    bool exhausted = false;
+    for (int q = 0;; ++q) {
+        if (fetcher) {
+            // keep the ring G_QSLOTS-1 items ahead: the atomic's latency is paid while earlier items are being produced
+            while (!exhausted && qf < q + G_QSLOTS) {
+                const int s = qf % G_QSLOTS;
+                mbar_wait(&q_empty[s], ((qf / G_QSLOTS) & 1) ^ 1);
+                const int idx = atomicAdd(queue, 1);
+                q_item[s] = idx;
+                mbar_arrive(&q_full[s]);
+                exhausted = idx >= n_items;
+                ++qf;
+            }
+        }
+        const int s = q % G_QSLOTS;
+        mbar_wait(&q_full[s], (q / G_QSLOTS) & 1);
+        const int item = q_item[s];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_empty[s]);
+        if (item >= n_items) break;
         const ItbTile tile = tiles[item];
         const ItbCBlk* cb = cblks + tile.cblk;
         if (producer) {
@@ -425,6 +461,14 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
             if (tile.cfg == 0) consume_tile<128, 128>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
             else if (tile.cfg == 1) consume_tile<64, 64>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
             else consume_tile<32, 32>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+        }
+    }
+    if (fetcher) {
+        // this CTA will not touch the queue head again; the last CTA to get here rearms the queue for the next launch
+        __threadfence();
+        if (atomicAdd(queue + 1, 1) == (int)gridDim.x - 1) {
+            atomicExch(queue, 0);
+            atomicExch(queue + 1, 0);
         }
     }
     if (cta_cycles && threadIdx.x == 0) cta_cycles[blockIdx.x] = clock64() - t_begin; // schedule calibration (profile mode)
@@ -878,7 +922,7 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) 
 }
 
 // ---- launchers (called from api.cu) ---------------------------------------------------------------------
-cudaError_t launch_gemm(const ItbTile* tiles, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm(const ItbTile* tiles, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles, cudaStream_t st) {
     static int nocompute = -1; // ITB_DEBUG_NOCOMPUTE=1: consumers skip the DMMA work (measures the producers' gather rate)
@@ -889,7 +933,7 @@ cudaError_t launch_gemm(const ItbTile* tiles, const int32_t* cta_begin, int grid
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, cta_begin, cblks, pairs, A, B, C, ws, cta_cycles, nocompute);
+    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, n_items, queue, cblks, pairs, A, B, C, ws, cta_cycles, nocompute);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {

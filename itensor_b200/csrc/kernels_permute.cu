@@ -10,6 +10,9 @@
 // Block dims arrive fused/canonical from the planner (plan.cc build_permute_plan).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "tables.h"
 
@@ -157,6 +160,75 @@ __global__ void __launch_bounds__(PTN) perm_tile_kernel(const ItbPermTile* __res
     }
 }
 
+// ---- persistent, double-buffered variant of the transposing path -------------------------------------------------
+// Same per-tile records, but a CTA walks a strided sequence of tiles and the global READ side goes through cp.async
+// (LDGSTS: global -> shared without a register round trip, 8-byte units for real data, one 128-bit unit per complex
+// element), so the loads of tile i+1 are in flight while tile i is turned and written. Against the one-tile-per-CTA
+// kernel above this removes the load/store phase alternation inside a CTA (no loads in flight while it stores), the STS
+// half of the shared-memory instruction stream, and the wave-quantisation tail of a ~4000-CTA launch.
+__device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double2* smem_dst, const double2* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+template <bool CS, bool CD, int PT>
+__global__ void __launch_bounds__(PTN) perm_tile_pipe_kernel(const ItbPermTile* __restrict__ items, int nitems, const void* __restrict__ src_,
+                                                             void* __restrict__ dst_, double ar, double ai, int accum) {
+    using Op = ElemOp<CS, CD>;
+    using S = typename Op::S; using D = typename Op::D;
+    constexpr int ROWS = PTN / PT, PER = PT / ROWS;
+    extern __shared__ __align__(16) unsigned char perm_smem[];
+    S (*tile)[PT][PT + 1] = reinterpret_cast<S (*)[PT][PT + 1]>(perm_smem); // [2][PT][PT+1]
+    const int tx = threadIdx.x % PT, ty = threadIdx.x / PT;
+    auto issue = [&](int item, int buf) {
+        const ItbPermTile it = items[item];
+        if (it.nT >= 0 && tx < it.nT) {
+            const S* __restrict__ src = reinterpret_cast<const S*>(src_) + it.s_base + tx;
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const int i0 = ty + r * ROWS;
+                if (i0 < it.n0) cp_async_elem(&tile[buf][i0][tx], src + (int64_t)i0 * it.ss0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int item = blockIdx.x, buf = 0;
+    if (item < nitems) issue(item, 0);
+    for (; item < nitems; item += gridDim.x, buf ^= 1) {
+        const int next = item + gridDim.x;
+        if (next < nitems) { issue(next, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const ItbPermTile it = items[item];
+        D* __restrict__ dst = reinterpret_cast<D*>(dst_) + it.d_base;
+        if (it.nT < 0) { // zero-fill item (permuteQDense fill-in); an accumulating pass leaves such blocks untouched
+            if (!accum)
+                for (int e = threadIdx.x; e < it.n0; e += PTN) dst[e] = D();
+        } else if (accum) {
+            D old[PER];
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const int iT = ty + r * ROWS;
+                old[r] = D();
+                if (iT < it.nT && tx < it.n0) old[r] = dst[(int64_t)tx + (int64_t)iT * it.dsT];
+            }
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const int iT = ty + r * ROWS;
+                if (iT < it.nT && tx < it.n0) dst[(int64_t)tx + (int64_t)iT * it.dsT] = Op::apply(tile[buf][tx][iT], old[r], ar, ai, true);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < PER; ++r) {
+                const int iT = ty + r * ROWS;
+                if (iT < it.nT && tx < it.n0) dst[(int64_t)tx + (int64_t)iT * it.dsT] = Op::apply(tile[buf][tx][iT], D(), ar, ai, false);
+            }
+        }
+        __syncthreads(); // the loads issued in the next iteration overwrite this buffer
+    }
+}
+
 template <bool CS, bool CD>
 static cudaError_t launch_t(const ItbPermBlk* bc, const ItbPermChunk* chunks, int64_t items_c, const ItbPermTile* tiles, int64_t items_t,
                             const void* src, void* dst, double ar, double ai, int accum, cudaStream_t st, int* launches) {
@@ -167,7 +239,28 @@ static cudaError_t launch_t(const ItbPermBlk* bc, const ItbPermChunk* chunks, in
         if (e != cudaSuccess) return e;
     }
     if (items_t > 0) {
-        perm_tile_kernel<CS, CD, CS ? 32 : 64><<<(unsigned)items_t, PTN, 0, st>>>(tiles, src, dst, ar, ai, accum);
+        // ITB_PERM_PIPE=0 selects the one-tile-per-CTA kernel (measurement / fallback switch); ITB_PERM_CTAS: CTAs per SM
+        static int pipe = -1, ctas = 3, sms = 148;
+        if (pipe < 0) {
+            const char* e = getenv("ITB_PERM_PIPE"); pipe = e ? atoi(e) : 1;
+            if (const char* c = getenv("ITB_PERM_CTAS")) ctas = atoi(c) > 0 ? atoi(c) : 3;
+            int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        constexpr int PT = CS ? 32 : 64;
+        using S = typename ElemOp<CS, CD>::S;
+        constexpr size_t smem = 2 * sizeof(S) * PT * (PT + 1);
+        if (pipe) {
+            static bool configured = false;
+            if (!configured) {
+                cudaError_t e = cudaFuncSetAttribute(perm_tile_pipe_kernel<CS, CD, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                configured = true;
+            }
+            const unsigned grid = (unsigned)std::min<int64_t>(items_t, (int64_t)sms * ctas);
+            perm_tile_pipe_kernel<CS, CD, PT><<<grid, PTN, smem, st>>>(tiles, (int)items_t, src, dst, ar, ai, accum);
+        } else {
+            perm_tile_kernel<CS, CD, PT><<<(unsigned)items_t, PTN, 0, st>>>(tiles, src, dst, ar, ai, accum);
+        }
         ++*launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -306,6 +306,7 @@ static const double kDmmaSlack = 1.11;
 static int kForceCfg = -1;
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static const int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this
+static double kGuidedFactor = 1.0;  // piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
 static void read_tile_env() {
     static bool done = false;
     if (done) return;
@@ -314,6 +315,7 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_TILE_OVERHEAD")) sscanf(e, "%lf,%lf,%lf,%lf", &kTileOverhead[0], &kTileOverhead[1], &kTileOverhead[2], &kPairOverhead);
     if (const char* e = getenv("ITB_FORCE_CFG")) kForceCfg = atoi(e);
     if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
+    if (const char* e = getenv("ITB_GUIDED_FACTOR")) kGuidedFactor = std::max(0.25, atof(e));
 }
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
     const int WM = kTileM[f] / 4, WN = kTileN[f] / 4, FM = WM / 8, FN = WN / 8;
@@ -656,11 +658,17 @@ int build_contract_tables(itb_contract_plan& P) {
             }
         }
     }
-    // ---- tile items: stream-K partition of the tile list over the persistent grid -------------------------
-    // Every CTA of the kNumSMs-wide grid gets the same modelled cycle count: the tile list (C-block order, so
-    // neighbouring items share operand panels in L2) is cut at K-chunk boundaries wherever a CTA's share is
-    // full. A tile cut into several pieces writes partial sums to workspace slots which
-    // bsc_splitk_reduce_kernel adds in piece order (deterministic); at most kNumSMs-1 tiles are cut.
+    // ---- tile items: one in-order queue, tail cut into shrinking pieces (guided self-scheduling) ------------------
+    // The kernel's CTAs pull items from the head of this list through an atomic counter (kernels_gemm.cu), so the
+    // assignment of items to CTAs is decided at run time by whoever is free. What the planner fixes is the ORDER
+    // (C-block order, n0 outer / m0 inner: the ~148 items in flight at any time belong to a few neighbouring C blocks
+    // whose operand panels are shared through L2) and the GRANULARITY: an item is a whole tile as long as a tile costs
+    // less than the work still to be handed out divided by the grid width; after that tiles are cut at K-chunk
+    // boundaries into pieces of (remaining work / grid width), never shorter than kMinPiece chunks, so the last CTAs
+    // finish within one small piece of each other. The cycle model only sets piece sizes — an error in it costs
+    // balance in proportion to the smallest pieces, not to the whole share of a CTA as with a static partition.
+    // A cut tile writes partial sums to workspace slots which bsc_splitk_reduce_kernel adds in piece order
+    // (deterministic, independent of which CTA ran which piece).
     {
         struct Proto { int32_t c, m0, n0, f; int64_t nch; double w; int np; };
         std::vector<Proto> protos;
@@ -685,48 +693,38 @@ int build_contract_tables(itb_contract_plan& P) {
                 }
         }
         const int G = kNumSMs;
-        P.cta_begin.assign(G + 1, 0);
-        // pieces cost an extra epilogue/prologue each; spread that too (<= G-1 cuts)
-        double target = total / G, assigned = 0;
-        int b = 0; double load = 0;
-        auto close_cta = [&]() { // re-derive the share from what is left so that rounding never piles up on the last CTA
-            if (b < G - 1) { ++b; P.cta_begin[b] = (int32_t)P.tiles.size(); load = 0; target = std::max(0.0, total - assigned) / (G - b); }
-        };
+        double remaining = total;
+        std::vector<double> item_cost;
         for (auto& t : protos) {
-            // fixed cost of a piece: item prologue/epilogue + one table rebuild per block pair it walks
-            auto piece_ovh = [&](int64_t take) { return kTileOverhead[t.f] + kPairOverhead * std::ceil((double)t.np * (double)take / (double)t.nch); };
-            int64_t c0 = 0;
-            std::vector<std::pair<int64_t, int64_t>> pieces;
-            while (c0 < t.nch) {
-                const int64_t rem = t.nch - c0;
-                const double space = target - load - piece_ovh(t.nch - c0);
-                const int64_t fit = (int64_t)std::floor(space / t.w);
-                int64_t take;
-                if (b == G - 1 || fit >= rem) take = rem;
-                else if (fit >= kMinPiece && rem - fit >= kMinPiece) take = fit; // cut here, a viable piece stays behind
-                else {
-                    // no clean cut: either close this CTA short of its share or overshoot with the smallest viable piece
-                    const int64_t x = (rem - std::max<int64_t>(fit, 0) < kMinPiece || rem < 2 * kMinPiece) ? rem : kMinPiece;
-                    const double over = (double)x * t.w - space, under = target - load;
-                    if (load > 0 && under <= over) { close_cta(); continue; }
-                    take = x;
+            const double ovh = kTileOverhead[t.f] + kPairOverhead * t.np;
+            const double cost = t.w * (double)t.nch + ovh;
+            const double want = std::max(remaining / (kGuidedFactor * G), (double)kMinPiece * t.w);
+            int64_t npieces = 1;
+            if (cost > 1.25 * want) npieces = std::min<int64_t>((int64_t)std::ceil(cost / want), std::max<int64_t>(1, t.nch / kMinPiece));
+            if (npieces <= 1) {
+                P.tiles.push_back({t.c, t.m0, t.n0, t.f, 0, (int32_t)t.nch, -1, 0});
+                item_cost.push_back(cost);
+            } else {
+                P.splits.push_back({t.c, t.m0, t.n0, t.f, (int32_t)P.ws_slots, (int32_t)npieces, {0, 0}});
+                for (int64_t q = 0; q < npieces; ++q) { // chunk ranges as equal as integers allow
+                    const int64_t c0 = t.nch * q / npieces, c1 = t.nch * (q + 1) / npieces;
+                    P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)c1, (int32_t)P.ws_slots++, 0});
+                    item_cost.push_back((double)(c1 - c0) * t.w + ovh);
                 }
-                if (take <= 0) { close_cta(); continue; }
-                if (!pieces.empty()) total += kTileOverhead[t.f] + kPairOverhead; // every extra piece pays its own prologue/epilogue
-                pieces.push_back({c0, c0 + take});
-                // ws slots are fixed up below once the number of pieces is known
-                P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)(c0 + take), -1, 0});
-                load += (double)take * t.w + piece_ovh(take);
-                assigned += (double)take * t.w + piece_ovh(take);
-                c0 += take;
-                if (load >= target - 0.5 * t.w) close_cta();
             }
-            if (pieces.size() > 1) {
-                P.splits.push_back({t.c, t.m0, t.n0, t.f, (int32_t)P.ws_slots, (int32_t)pieces.size(), {0, 0}});
-                for (size_t q = 0; q < pieces.size(); ++q) P.tiles[P.tiles.size() - pieces.size() + q].ws_slot = (int32_t)P.ws_slots++;
-            }
+            remaining -= cost;
         }
-        for (int g = b + 1; g <= G; ++g) P.cta_begin[g] = (int32_t)P.tiles.size();
+        // nominal contiguous partition of the queue by modelled cost: introspection (itb_contract_plan_cta_begin), the
+        // schedule simulator and the table-walking mock use it; the kernel does not
+        P.cta_begin.assign(G + 1, 0);
+        double all = 0, acc = 0;
+        for (double v : item_cost) all += v;
+        int bcta = 0;
+        for (size_t i = 0; i < item_cost.size(); ++i) {
+            while (bcta < G - 1 && acc >= all * (double)(bcta + 1) / G) P.cta_begin[++bcta] = (int32_t)i;
+            acc += item_cost[i];
+        }
+        for (int g = bcta + 1; g <= G; ++g) P.cta_begin[g] = (int32_t)P.tiles.size();
     }
     std::stable_sort(P.skinny.begin(), P.skinny.end(), [&](const ItbSkinny& x, const ItbSkinny& y) {
         return P.cblks[x.cblk].ksum * (P.cblks[x.cblk].M + P.cblks[x.cblk].N) > P.cblks[y.cblk].ksum * (P.cblks[y.cblk].M + P.cblks[y.cblk].N);

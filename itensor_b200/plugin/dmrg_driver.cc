@@ -1,7 +1,13 @@
 //
 // dmrg_driver.cc — the reference's UNMODIFIED dmrg() (itensor/mps/dmrg.h) on host or HBM-resident storage.
 //
-//   dmrg_driver <model> <N> <qn|dense> <cpu|gpu> <maxdims> <cutoffs> <niters> <noises> [json-out]
+//   dmrg_driver <model> <N> <qn|dense> <cpu|gpu> <maxdims> <cutoffs> <niters> <noises> [json-out] [options]
+//     options : --save <prefix>   write the final MPS and its site set (<prefix>.psi / .sites, the reference's binary format,
+//                                 GPU storage goes through write(ostream,QDenseGPU))
+//               --load <prefix>   start from that MPS instead of the product / random state: lets host and HBM storage run
+//                                 the SAME sweep from the SAME state (per-bond parity at large bond dimension without the
+//                                 trajectory sensitivity of a whole unconverged ramp)
+//               --bonds <file>    per-bond record of every half sweep: energy, truncation error, kept spectrum
 //     model   : heis_half | heis_one        (sample/dmrg.cc Hamiltonian, Neel product start)
 //               hubbard                     (sample/hubbard_2d.cc: Nx x Ny cylinder, t=1, U=8 or $HUBBARD_U, Nf and Sz
 //                                            conserved, seeded randomMPS start; <N> is written NxxNy, e.g. 16x4)
@@ -30,6 +36,7 @@ parseList(std::string const& s)
     }
 
 struct SweepRecord { double energy = 0, seconds = 0, maxtrunc = 0; int maxlink = 0; };
+struct BondRecord { int sweep = 0, half = 0, bond = 0; double energy = 0, truncerr = 0; std::vector<double> spectrum; };
 
 class TimingObserver : public DMRGObserver
     {
@@ -42,6 +49,8 @@ class TimingObserver : public DMRGObserver
     std::vector<SweepRecord> sweeps;
     std::vector<double> lastTrunc;   // per bond, last completed half sweep pair
     std::vector<double> centreSpec;  // kept spectrum at the centre bond, last sweep (right-to-left pass)
+    std::vector<BondRecord> bonds;   // --bonds: every bond of every half sweep
+    bool recordBonds = false;
 
     TimingObserver(MPS& psi, Args const& args, bool pin) : DMRGObserver(psi,args), psi_(psi), pin_(pin ? &psi : nullptr), N_(length(psi))
         {
@@ -55,6 +64,14 @@ class TimingObserver : public DMRGObserver
         auto ha = args.getInt("HalfSweep");
         auto terr = args.getReal("Truncerr",0.);
         if(pin_) { pinToGPU(*pin_,b); pinToGPU(*pin_,b+1); }
+        if(recordBonds)
+            {
+            BondRecord r;
+            r.sweep = args.getInt("Sweep",0); r.half = ha; r.bond = b;
+            r.energy = args.getReal("Energy",0.); r.truncerr = terr;
+            for(auto const& e : spectrum().eigsKept()) r.spectrum.push_back(e);
+            bonds.push_back(std::move(r));
+            }
         if(b == 1 && ha == 1) { maxtrunc_ = 0; lastTrunc.assign(2*(N_-1),0.); }
         maxtrunc_ = std::max(maxtrunc_,terr);
         auto slot = (ha == 1) ? (b-1) : (N_-1)+(N_-1-b);
@@ -101,11 +118,28 @@ main(int argc, char* argv[])
     bool qn = std::string(argv[3]) == "qn";
     bool useGPU = std::string(argv[4]) == "gpu";
     auto maxdim = parseList(argv[5]), cutoff = parseList(argv[6]), niter = parseList(argv[7]), noise = parseList(argv[8]);
+    std::string jsonOut, savePrefix, loadPrefix, bondsFile;
+    for(int a = 9; a < argc; ++a)
+        {
+        auto opt = std::string(argv[a]);
+        if(opt == "--save" && a+1 < argc) savePrefix = argv[++a];
+        else if(opt == "--load" && a+1 < argc) loadPrefix = argv[++a];
+        else if(opt == "--bonds" && a+1 < argc) bondsFile = argv[++a];
+        else if(opt.rfind("--",0) != 0 && jsonOut.empty()) jsonOut = opt;
+        else { println("dmrg_driver: unknown option ",opt); return 2; }
+        }
     auto nsweep = int(maxdim.size());
     auto at = [](std::vector<double> const& v, int i) { return v[std::min<size_t>(i,v.size()-1)]; };
 
     SiteSet sites;
-    if(model == "heis_half") sites = SpinHalf(N,{"ConserveQNs=",qn});
+    if(!loadPrefix.empty())
+        {
+        // same site indices as the saved state (index ids are part of the file)
+        if(model == "heis_half") sites = readFromFile<SpinHalf>(loadPrefix+".sites");
+        else if(model == "hubbard") sites = readFromFile<Electron>(loadPrefix+".sites");
+        else sites = readFromFile<SpinOne>(loadPrefix+".sites");
+        }
+    else if(model == "heis_half") sites = SpinHalf(N,{"ConserveQNs=",qn});
     else if(model == "hubbard") sites = Electron(N,{"ConserveQNs=",qn});
     else sites = SpinOne(N,{"ConserveQNs=",qn});
     auto ampo = AutoMPO(sites);
@@ -141,6 +175,7 @@ main(int argc, char* argv[])
         seedRNG(1); // randomMPS is unseeded otherwise (mps.cc:281-287)
         psi = randomMPS(state);
         }
+    if(!loadPrefix.empty()) psi = readFromFile<MPS>(loadPrefix+".psi",sites);
 
     auto sweeps = Sweeps(nsweep);
     for(int s = 1; s <= nsweep; ++s)
@@ -162,9 +197,14 @@ main(int argc, char* argv[])
 #else
     auto args = Args("Silent",true);
 #endif
+    // disk spilling of the environments exactly as the reference does it (dmrg.h:390-401, localmpo.h:620-681): with
+    // GPU storage the environment tensors go through write(ostream,QDenseGPU<T>) and come back as host tensors
+    if(auto* e = std::getenv("DMRG_WRITE_DIM")) args.add("WriteDim",std::atoi(e));
+    if(auto* e = std::getenv("DMRG_WRITE_DIR")) args.add("WriteDir",std::string(e));
     auto t0 = std::chrono::steady_clock::now();
     auto PH = LocalMPO(H,args);
     auto obs = TimingObserver(psi,args,useGPU);
+    obs.recordBonds = !bondsFile.empty();
     auto energy = DMRGWorker(psi,PH,sweeps,obs,args);
     if(useGPU) gpu::synchronize();
     auto total = std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count();
@@ -186,10 +226,32 @@ main(int argc, char* argv[])
     for(size_t i = 0; i < obs.centreSpec.size(); ++i) js << (i ? ", " : "") << obs.centreSpec[i];
     js << "]}";
     println(js.str());
-    if(argc > 9)
+    if(!jsonOut.empty())
         {
-        std::ofstream f(argv[9]);
+        std::ofstream f(jsonOut);
         f << js.str() << "\n";
+        }
+    if(!bondsFile.empty())
+        {
+        std::ofstream f(bondsFile);
+        f.precision(17);
+        f << "[";
+        for(size_t i = 0; i < obs.bonds.size(); ++i)
+            {
+            auto& r = obs.bonds[i];
+            f << (i ? ",\n" : "\n") << "{\"sweep\": " << r.sweep << ", \"half\": " << r.half << ", \"bond\": " << r.bond
+              << ", \"energy\": " << r.energy << ", \"truncerr\": " << r.truncerr << ", \"spectrum\": [";
+            for(size_t k = 0; k < r.spectrum.size(); ++k) f << (k ? "," : "") << r.spectrum[k];
+            f << "]}";
+            }
+        f << "\n]\n";
+        }
+    if(!savePrefix.empty())
+        {
+        // GPU-resident site tensors are written through write(ostream,QDenseGPU<T>) (gpu_storage.h): the file holds the
+        // host wire format and reads back as ordinary host tensors
+        writeToFile(savePrefix+".sites",sites);
+        writeToFile(savePrefix+".psi",psi);
         }
     return 0;
     }

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Schedule analysis of the DMMA tile queue (host only): padded vs algorithmic work, per-CTA load balance of the
-static snake assignment. Usage: python tools/sched_sim.py [--m 2000] [--nsect 9] [--complex]"""
+"""Schedule analysis of the DMMA tile queue (host only): padded vs algorithmic work, and a simulation of the kernel's
+dynamic in-order queue (each free CTA takes the next item) under a deliberately WRONG cost model (per-item multiplicative
+noise), i.e. how much balance depends on the model. Usage: python tools/sched_sim.py [--m 2000] [--nsect 9] [--complex]"""
 import argparse, ctypes as C, sys, os
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -44,11 +45,20 @@ def analyse(plan, G=148, label=""):
     padded = (t[:, 3] * t[:, 4] * ch * 16).sum() * 2
     # cost model: time of an item ~ chunks * tile area / eff + fixed overhead per item (epilogue/prologue ~ 2 chunks)
     cost = np.array([chs * chunk_cycles(tm, a, b) + OVERHEAD[tm] for chs, tm, a, b in zip(ch, t[:, 3], vm, vn)])
-    load = np.array([cost[g[b]:g[b + 1]].sum() for b in range(len(g) - 1)])
     ideal = (vm * vn * ch).sum() * 16 * 2 / 128.0 / G  # cycles at the bare DMMA rate (128 flop/cycle/SM)
-    print(f"{label}: tiles {len(t)} (split items {int((t[:,7]>=0).sum())}), cfg hist {dict(zip(*np.unique(t[:,3]*1000+t[:,4], return_counts=True)))}")
-    print(f"   useful/padded flops {useful/padded:.3f}; max CTA load / mean {load.max()/load.mean():.3f}; "
-          f"modelled fraction of the DMMA peak {ideal/load.max():.3f}")
+    print(f"{label}: items {len(t)} (pieces of cut tiles {int((t[:,7]>=0).sum())}), cfg hist {dict(zip(*np.unique(t[:,3]*1000+t[:,4], return_counts=True)))}")
+    import heapq
+    rng = np.random.default_rng(0)
+    for noise in (0.0, 0.3):
+        real = cost * np.exp(rng.normal(0, noise, len(cost))) if noise else cost
+        free = [(0.0, b) for b in range(G)]
+        heapq.heapify(free)
+        for v in real:  # in-order queue: the CTA that frees up first takes the next item
+            tfree, b = heapq.heappop(free)
+            heapq.heappush(free, (tfree + v, b))
+        ends = np.array([x for x, _ in free])
+        print(f"   dynamic queue, model noise {noise:.1f}: makespan / mean CTA busy time {ends.max() / (real.sum() / G):.3f}; "
+              f"useful/padded flops {useful/padded:.3f}; modelled fraction of the DMMA peak {ideal / ends.max():.3f}")
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
