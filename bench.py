@@ -271,7 +271,7 @@ def main():
     if world > 1:
         from itensor_b200.shard import shard_chain
 
-        shard = shard_chain(plans, world, rank)
+        shard = shard_chain(plans, world, rank).prepare(ctx.empty)
     max_share = 1.0
     if shard is not None:
         t = torch.tensor([shard.my_flops / shard.total_flops], dtype=torch.float64, device=dev)
@@ -288,13 +288,11 @@ def main():
 
     def step():
         cur = dts[0]
-        if shard is not None:
-            shard.zero_unowned(outs[-1].data)  # blocks of H*phi owned by other ranks must read as exact zeros
-        for k, p in enumerate(plans):
+        for k, p in enumerate(plans):  # sharded: every plan is sliced to this rank's rows of l'
             check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
             cur = outs[k]
         if shard is not None:
-            shard.allgather(outs[-1].data)
+            shard.allgather(ctx.handle, outs[-1].data)  # pack own rows -> one NCCL all-gather -> scatter
 
     def barrier():
         if world > 1:

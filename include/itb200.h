@@ -128,6 +128,14 @@ int itb_contract_plan_set_cblock_range(itb_contract_plan* plan, int64_t first, i
 /* general form: mask[c] != 0 selects C block c (c_nblocks entries); NULL selects all. Unselected C blocks
  * are neither computed nor written (their storage is left untouched). */
 int itb_contract_plan_set_cblock_mask(itb_contract_plan* plan, const uint8_t* mask);
+/* finer sharding unit: restrict execution to a row-slice of ONE index of C. C blocks whose coordinate on index c_index
+ * (position in the result's index list) is sector s compute and write only the sub-box lo[s] <= i < hi[s] of that index
+ * (lo/hi: nsect(c_index) entries; hi[s] <= lo[s] skips those blocks; NULL/NULL removes the restriction). Everything outside
+ * the sub-boxes is left untouched. This is the "rows of the primed link inside a QN sector" partition of SURVEY 8(e)
+ * (reference rule: one owner per C block, itensor/itdata/qutil.h:285-348, refined to row ranges for balance). Supported when,
+ * in every executed block, the sliced index is the slowest non-unit uncontracted index of the operand it comes from
+ * (always true for the H_eff*phi chain with QN site indices); otherwise ITB_ERR_UNSUPPORTED and the plan is unchanged. */
+int itb_contract_plan_set_index_slices(itb_contract_plan* plan, int32_t c_index, const int64_t* lo, const int64_t* hi);
 /* introspection of the device work lists (tests, schedule analysis). Tile items of the DMMA kernel in queue
  * order, 8 int32 each: {C block (position in the plan's executed C-block list), m0, n0, tile_m, tile_n,
  * chunk_begin, chunk_end, ws_slot}; executed C blocks, 4 int64 each: {M, N, ksum, npairs} (real-expanded dims).

@@ -85,6 +85,7 @@ SYMBOLS = {
     "itb_contract_plan_pairs": (C.c_int, [_P, _I64P]),
     "itb_contract_plan_set_cblock_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "itb_contract_plan_set_cblock_mask": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    "itb_contract_plan_set_index_slices": (C.c_int, [_P, C.c_int32, _I64P, _I64P]),
     "itb_contract_plan_tiles": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_cta_begin": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_rowgroups": (C.c_int64, [_P, _I64P, C.c_int64]),

@@ -13,7 +13,7 @@
 #include "plan.h"
 
 namespace itb {
-cudaError_t launch_gemm(const ItbTile* tiles, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles,
                         cudaStream_t st);
@@ -42,8 +42,7 @@ struct DeviceTables {
     size_t bytes = 0;
     const ItbPair* pairs = nullptr;
     const ItbCBlk* cblks = nullptr;
-    const ItbTile* tiles = nullptr;
-    const int32_t* cta_begin = nullptr;
+    const ItbQItem* qitems = nullptr;
     const ItbSplitOut* splits = nullptr;
     const ItbRowGroup* rgroups = nullptr;
     const ItbRgIn* rg_in = nullptr;
@@ -356,9 +355,8 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     Packer pk;
     const size_t o_pairs = pk.add(P->pairs.data(), P->pairs.size() * sizeof(ItbPair));
     const size_t o_cblk = pk.add(P->cblks.data(), P->cblks.size() * sizeof(ItbCBlk));
-    const size_t o_tiles = pk.add(P->tiles.data(), P->tiles.size() * sizeof(ItbTile));
+    const size_t o_tiles = pk.add(P->qitems.data(), P->qitems.size() * sizeof(ItbQItem));
     const size_t o_splits = pk.add(P->splits.data(), P->splits.size() * sizeof(ItbSplitOut));
-    const size_t o_cta = pk.add(P->cta_begin.data(), P->cta_begin.size() * sizeof(int32_t));
     const size_t o_rg = pk.add(P->rgroups.data(), P->rgroups.size() * sizeof(ItbRowGroup));
     const size_t o_rgi = pk.add(P->rg_in.data(), P->rg_in.size() * sizeof(ItbRgIn));
     const size_t o_rgo = pk.add(P->rg_out.data(), P->rg_out.size() * sizeof(int64_t));
@@ -376,9 +374,8 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     char* b = (char*)dev->base;
     dev->pairs = (const ItbPair*)(b + o_pairs);
     dev->cblks = (const ItbCBlk*)(b + o_cblk);
-    dev->tiles = (const ItbTile*)(b + o_tiles);
+    dev->qitems = (const ItbQItem*)(b + o_tiles);
     dev->splits = (const ItbSplitOut*)(b + o_splits);
-    dev->cta_begin = (const int32_t*)(b + o_cta);
     dev->rgroups = (const ItbRowGroup*)(b + o_rg);
     dev->rg_in = (const ItbRgIn*)(b + o_rgi);
     dev->rg_out = (const int64_t*)(b + o_rgo);
@@ -462,7 +459,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
         // in-order queue through the head counter (rearmed by the kernel itself)
         const int grid = (int)std::min<size_t>((size_t)c->num_sms, P->tiles.size());
         if (c->profile && !c->d_cta_cycles) SIDE_TRY(cudaMalloc(&c->d_cta_cycles, 1024 * sizeof(long long)));
-        SIDE_TRY(launch_gemm(d->tiles, (int)P->tiles.size(), d->counters, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
+        SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
             c->h_cta_cycles.assign(grid, 0);

@@ -18,6 +18,7 @@
 // Complex arithmetic arrives here already folded into a real problem by the planner (plan.cc).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "tables.h"
@@ -73,9 +74,23 @@ constexpr int G_NCONS = 512, G_NPROD = 128, G_NT = G_NCONS + G_NPROD;
 constexpr int G_STAGES = 4, G_BK = ITB_BK, G_PAD = 4, G_MAXT = 128;
 constexpr int G_KT = 1024; // k offsets per shared table fill (per operand)
 constexpr int G_STAGE_ELEMS = G_MAXT * (G_BK + G_PAD); // per operand per stage (covers both layouts)
-constexpr int G_QSLOTS = 4; // look-ahead of the work-queue fetcher (item ring in shared memory)
+constexpr int G_QSLOTS = 4; // look-ahead of the item fetcher (item ring in shared memory)
+constexpr int G_QPAIRS = ITB_QPAIRS;
+// One slot of the item ring: the host-flattened item record (tile + C block + K/flags of its first pairs), copied from
+// global memory by the first producer warp ahead of time, so that no consumer warp ever waits on global loads between two
+// tiles.
+struct QItem {
+    ItbTile tile;
+    ItbCBlk cb;
+    int32_t pK[G_QPAIRS];
+    int32_t pflags[G_QPAIRS];
+    int32_t pad_[2];
+    int32_t item;     // index in the queue; >= n_items: stop
+    int32_t pad2_[3];
+};
+static_assert(sizeof(ItbQItem) == 160 && offsetof(QItem, item) == 160, "item record layout");
 constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT) * 8 + (size_t)(2 * G_KT) * 4 + 2 * G_STAGES * 8 +
-                          2 * G_QSLOTS * 8 + G_QSLOTS * 4 + 16;
+                          2 * G_QSLOTS * 8 + G_QSLOTS * sizeof(QItem) + 16;
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -153,7 +168,7 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
 }
 
 template <int BM, int BN>
-__device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
+__device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __restrict__ pairs,
                                              double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
                                              uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute) {
     constexpr int BK = G_BK;
@@ -164,8 +179,10 @@ __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk*
     // warp w runs on SMSP w&3: (wm,wn) = ((w ^ (w>>2)) & 3, w>>2) puts one warp of every warp-row and of every
     // warp-column on each SMSP, so fragment skipping on edge tiles unloads all four tensor pipes evenly
     const int wm0 = ((warp ^ (warp >> 2)) & 3) * WM, wn0 = (warp >> 2) * WN;
-    const int M = cb->M, N = cb->N;
-    const int m0 = tile.m0, n0 = tile.n0;
+    const int M = qi.cb.M, N = qi.cb.N;
+    const int m0 = qi.tile.m0, n0 = qi.tile.n0;
+    const int chunk_begin = qi.tile.chunk_begin, chunk_end = qi.tile.chunk_end;
+    const int pair_begin = qi.cb.pair_begin, pair_end = qi.cb.pair_end;
     const int fmv = min(FM, max(0, (M - m0 - wm0 + 7) >> 3)), fnv = min(FN, max(0, (N - n0 - wn0 + 7) >> 3));
     const bool edge = fmv < FM || fnv < FN;
 
@@ -176,13 +193,15 @@ __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk*
         for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     int gchunk = 0;
-    for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
-        const ItbPair* pr = pairs + p;
-        const int nk = (pr->K + BK - 1) / BK;
-        const int c0 = max(tile.chunk_begin - gchunk, 0), c1 = min(tile.chunk_end - gchunk, nk);
+    for (int p = pair_begin; p < pair_end; ++p) {
+        // (K, flags) of the first G_QPAIRS pairs ride in the ring slot; longer pair lists fall back to the global table
+        const int q = p - pair_begin;
+        const int K = q < G_QPAIRS ? qi.pK[q] : pairs[p].K;
+        const int flags = q < G_QPAIRS ? qi.pflags[q] : pairs[p].flags;
+        const int nk = (K + BK - 1) / BK;
+        const int c0 = max(chunk_begin - gchunk, 0), c1 = min(chunk_end - gchunk, nk);
         gchunk += nk;
         if (c0 >= c1) continue;
-        const int flags = pr->flags;
         // sign of the A' = [[Ar,-Ai],[Ai,Ar]] expansion, applied when the fragment is read (row even, col odd)
         const int sgn = ((flags & ITB_PF_CCA) && !(g & 1) && (t4 & 1)) ? (int)0x80000000 : 0;
         if (fmv == 0 || fnv == 0 || dbg_nocompute) { // nothing of this warp's sub-tile is inside the C block: keep the ring moving
@@ -208,30 +227,44 @@ __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk*
 #undef ITB_CONSUME
     }
     // ---- epilogue: each C element is written exactly once (or one partial per split) ----------------------
-    if (tile.ws_slot < 0) {
-        double* __restrict__ Cp = C + cb->c_off;
-        const int64_t cms = cb->c_ms, cns = cb->c_ns;
-        const int nmask = cb->c_nmask, nshift = cb->c_nshift;
+    const int ws_slot = qi.tile.ws_slot;
+    if (ws_slot < 0) {
+        const int64_t cms = qi.cb.c_ms, cns = qi.cb.c_ns;
+        const int nmask = qi.cb.c_nmask, nshift = qi.cb.c_nshift;
+        if (!edge && nmask == 0 && cms == 1) {
+            // interior tile of a plainly laid out block: one base pointer, constant offsets, no bounds checks
+            double* __restrict__ Cp = C + qi.cb.c_off + (m0 + wm0 + g) + (int64_t)(n0 + wn0 + 2 * t4) * cns;
 #pragma unroll
-        for (int i = 0; i < FM; ++i) {
-            const int m = m0 + wm0 + i * 8 + g;
-#pragma unroll
-            for (int j = 0; j < FN; ++j) {
+            for (int j = 0; j < FN; ++j)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int n = n0 + wn0 + j * 8 + 2 * t4 + h;
-                    if (m < M && n < N) Cp[(int64_t)m * cms + (n & nmask) + (int64_t)(n >> nshift) * cns] = acc[i][j][h];
+                    double* __restrict__ col = Cp + (int64_t)(j * 8 + h) * cns;
+#pragma unroll
+                    for (int i = 0; i < FM; ++i) col[i * 8] = acc[i][j][h];
+                }
+        } else {
+            double* __restrict__ Cp = C + qi.cb.c_off;
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int m = m0 + wm0 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < FN; ++j) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int n = n0 + wn0 + j * 8 + 2 * t4 + h;
+                        if (m < M && n < N) Cp[(int64_t)m * cms + (n & nmask) + (int64_t)(n >> nshift) * cns] = acc[i][j][h];
+                    }
                 }
             }
         }
     } else {
-        double* __restrict__ W = ws + (int64_t)tile.ws_slot * ITB_WS_TILE;
+        double* __restrict__ W = ws + (int64_t)ws_slot * ITB_WS_TILE + (wm0 + g) + BM * (wn0 + 2 * t4);
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
             for (int j = 0; j < FN; ++j)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) W[(wm0 + i * 8 + g) + BM * (wn0 + j * 8 + 2 * t4 + h)] = acc[i][j][h];
+                for (int h = 0; h < 2; ++h) W[i * 8 + BM * (j * 8 + h)] = acc[i][j][h];
     }
 }
 
@@ -346,19 +379,22 @@ __device__ __forceinline__ void produce_pair(const ItbPair* __restrict__ pr, int
 }
 
 template <int BM, int BN>
-__device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
+__device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __restrict__ pairs,
                                              const double* __restrict__ A, const double* __restrict__ B, double* As, double* Bs,
                                              int64_t* offM_s, int64_t* offN_s, int* ktabA, int* ktabB, uint64_t* full,
                                              uint64_t* empty, PipeState& ps) {
     constexpr int BK = G_BK, NP = G_NPROD;
     const int pt = threadIdx.x - G_NCONS; // 0..G_NPROD-1
-    const int M = cb->M, N = cb->N;
-    const int m0 = tile.m0, n0 = tile.n0;
+    const int M = qi.cb.M, N = qi.cb.N;
+    const int m0 = qi.tile.m0, n0 = qi.tile.n0;
+    const int chunk_begin = qi.tile.chunk_begin, chunk_end = qi.tile.chunk_end;
+    const int pair_begin = qi.cb.pair_begin, pair_end = qi.cb.pair_end;
     int gchunk = 0;
-    for (int p = cb->pair_begin; p < cb->pair_end; ++p) {
+    for (int p = pair_begin; p < pair_end; ++p) {
         const ItbPair* pr = pairs + p;
-        const int nk = (pr->K + BK - 1) / BK;
-        const int c0 = max(tile.chunk_begin - gchunk, 0), c1 = min(tile.chunk_end - gchunk, nk);
+        const int q = p - pair_begin;
+        const int nk = ((q < G_QPAIRS ? qi.pK[q] : pr->K) + BK - 1) / BK;
+        const int c0 = max(chunk_begin - gchunk, 0), c1 = min(chunk_end - gchunk, nk);
         gchunk += nk;
         if (c0 >= c1) continue;
         const int flags = pr->flags;
@@ -389,11 +425,13 @@ __device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk*
 // self-scheduling, plan.cc), so the CTAs finish within one small piece of each other whatever the real per-tile cost is
 // (edge tiles, L2 hits, clocks) — no cycle model has to be right — and at any time the 148 CTAs work on ~148 CONSECUTIVE
 // tiles, i.e. on the few C blocks whose operand panels are then shared through L2 instead of re-read from HBM.
-// Mechanics: producer thread 0 is the fetcher; it publishes item indices G_QSLOTS ahead into a shared ring guarded by
-// full/empty mbarriers, every warp (both roles) reads the same sequence. An index >= n_items is the stop sentinel.
-// The last CTA to stop resets the queue head, so the same tables can be launched again without a memset.
-__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __restrict__ tiles, int n_items, int* __restrict__ queue,
-                                                            const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
+// Mechanics: the first producer warp is also the FETCHER: before it starts producing item q it makes sure the ring holds
+// items up to q+G_QSLOTS-1: lane 0 pops an index from the global head, the warp copies the host-flattened 160-byte item
+// record into the slot and publishes it through the slot's full barrier (the pop + copy latency, ~1.3k cycles, falls
+// into the producers' slack: they need ~1600 of the ~4500 cycles a chunk takes). All 20 warps read the same sequence of
+// records from shared memory. An index >= n_items is the stop sentinel. The last CTA to stop rearms the queue head.
+__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __restrict__ items, int n_items, int* __restrict__ queue,
+                                                            const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
                                                             double* __restrict__ C, double* __restrict__ ws,
                                                             long long* __restrict__ cta_cycles, int dbg_nocompute) {
@@ -409,7 +447,7 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
     uint64_t* empty = full + G_STAGES;
     uint64_t* q_full = empty + G_STAGES;
     uint64_t* q_empty = q_full + G_QSLOTS;
-    volatile int* q_item = reinterpret_cast<volatile int*>(q_empty + G_QSLOTS);
+    QItem* q_item = reinterpret_cast<QItem*>(q_empty + G_QSLOTS);
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], G_NPROD);     // one cp.async-completion arrive per producer thread
@@ -417,53 +455,56 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbTile* __rest
         }
         for (int s = 0; s < G_QSLOTS; ++s) {
             mbar_init(&q_full[s], 1);          // the fetcher
-            mbar_init(&q_empty[s], G_NT / 32); // one arrive per warp (both roles) once it has read the slot
+            mbar_init(&q_empty[s], G_NT / 32); // one arrive per warp (both roles) once it is done with the slot
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const bool producer = threadIdx.x >= G_NCONS;
-    const bool fetcher = threadIdx.x == G_NCONS;
     const int lane = threadIdx.x & 31;
-    // register re-balancing (warpgroup granular): the kernel launches with 96 regs/thread (640 threads);
-    // the producer warpgroup shrinks, the four consumer warpgroups grow (4*112 + 56 per SMSP fits 16K).
-    // (setmaxnreg variants measured slower or spilling: see DESIGN.md) if (producer) setmaxnreg.dec 56
-    // else setmaxnreg.inc 112
+    const bool producer = threadIdx.x >= G_NCONS;
+    const bool fetch_warp = (threadIdx.x >> 5) == G_NCONS / 32;
     PipeState ps;
     int qf = 0;            // fetcher: next sequence number to publish
     bool exhausted = false;
     for (int q = 0;; ++q) {
-        if (fetcher) {
-            // keep the ring G_QSLOTS-1 items ahead: the atomic's latency is paid while earlier items are being produced
+        if (fetch_warp) {
             while (!exhausted && qf < q + G_QSLOTS) {
                 const int s = qf % G_QSLOTS;
                 mbar_wait(&q_empty[s], ((qf / G_QSLOTS) & 1) ^ 1);
-                const int idx = atomicAdd(queue, 1);
-                q_item[s] = idx;
-                mbar_arrive(&q_full[s]);
+                int idx = 0;
+                if (lane == 0) idx = atomicAdd(queue, 1);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                int* dst = reinterpret_cast<int*>(q_item + s);
+                if (idx < n_items) { // 160 bytes = 40 ints
+                    const int* src = reinterpret_cast<const int*>(items + idx);
+                    dst[lane] = src[lane];
+                    if (lane < 8) dst[32 + lane] = src[32 + lane];
+                }
+                if (lane == 0) q_item[s].item = idx;
+                __syncwarp(); // orders every lane's stores before lane 0's releasing arrive
+                if (lane == 0) mbar_arrive(&q_full[s]);
                 exhausted = idx >= n_items;
                 ++qf;
             }
         }
         const int s = q % G_QSLOTS;
         mbar_wait(&q_full[s], (q / G_QSLOTS) & 1);
-        const int item = q_item[s];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&q_empty[s]);
-        if (item >= n_items) break;
-        const ItbTile tile = tiles[item];
-        const ItbCBlk* cb = cblks + tile.cblk;
+        const QItem& qi = q_item[s];
+        if (qi.item >= n_items) break;
+        const int cfg = qi.tile.cfg;
         if (producer) {
-            if (tile.cfg == 0) produce_tile<128, 128>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
-            else if (tile.cfg == 1) produce_tile<64, 64>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
-            else produce_tile<32, 32>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+            if (cfg == 0) produce_tile<128, 128>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+            else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+            else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
         } else {
-            if (tile.cfg == 0) consume_tile<128, 128>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
-            else if (tile.cfg == 1) consume_tile<64, 64>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
-            else consume_tile<32, 32>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            if (cfg == 0) consume_tile<128, 128>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            else if (cfg == 1) consume_tile<64, 64>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            else consume_tile<32, 32>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_empty[s]); // the slot may be refilled once every warp has finished the item
     }
-    if (fetcher) {
+    if (threadIdx.x == G_NCONS) {
         // this CTA will not touch the queue head again; the last CTA to get here rearms the queue for the next launch
         __threadfence();
         if (atomicAdd(queue + 1, 1) == (int)gridDim.x - 1) {
@@ -922,7 +963,7 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) 
 }
 
 // ---- launchers (called from api.cu) ---------------------------------------------------------------------
-cudaError_t launch_gemm(const ItbTile* tiles, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles, cudaStream_t st) {
     static int nocompute = -1; // ITB_DEBUG_NOCOMPUTE=1: consumers skip the DMMA work (measures the producers' gather rate)
@@ -933,7 +974,7 @@ cudaError_t launch_gemm(const ItbTile* tiles, int n_items, int* queue, int grid,
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(tiles, n_items, queue, cblks, pairs, A, B, C, ws, cta_cycles, nocompute);
+    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, A, B, C, ws, cta_cycles, nocompute);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {

@@ -305,7 +305,7 @@ static double kPairOverhead = 4300.0;
 static const double kDmmaSlack = 1.11;
 static int kForceCfg = -1;
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
-static const int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this
+static int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this (ITB_MIN_PIECE)
 static double kGuidedFactor = 1.0;  // piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
 static void read_tile_env() {
     static bool done = false;
@@ -316,6 +316,7 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_FORCE_CFG")) kForceCfg = atoi(e);
     if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
     if (const char* e = getenv("ITB_GUIDED_FACTOR")) kGuidedFactor = std::max(0.25, atof(e));
+    if (const char* e = getenv("ITB_MIN_PIECE")) kMinPiece = std::max(1, atoi(e));
 }
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
     const int WM = kTileM[f] / 4, WN = kTileN[f] / 4, FM = WM / 8, FN = WN / 8;
@@ -357,7 +358,7 @@ int build_contract_tables(itb_contract_plan& P) {
     const int64_t csA = cA ? 2 : 1, csB = cB ? 2 : 1, csC = (cA || cB) ? 2 : 1;
 
     P.pairs.clear(); P.cblks.clear(); P.skinny.clear(); P.skinny_q4.clear(); P.skinny_q8.clear(); P.dots.clear(); P.dot_outs.clear();
-    P.tiles.clear(); P.splits.clear(); P.ws_slots = 0; P.cta_begin.clear();
+    P.tiles.clear(); P.qitems.clear(); P.splits.clear(); P.ws_slots = 0; P.cta_begin.clear();
     P.rgroups.clear(); P.rg_in.clear(); P.rg_out.clear(); P.rg_w.clear(); P.rg_items.clear();
     P.ndot_slots = 0;
 
@@ -370,13 +371,30 @@ int build_contract_tables(itb_contract_plan& P) {
     const int64_t cb_first = P.cb_first, cb_last = (P.cb_last < 0 ? C.nblocks : P.cb_last);
 
     std::vector<int64_t> strA(rA), strB(rB);
+    std::vector<int> uncA_all, uncB_all; // uncontracted indices of A / B in order == the index list of C
+    for (int i = 0; i < rA; ++i) if (AtoB[i] < 0) uncA_all.push_back(i);
+    for (int j = 0; j < rB; ++j) if (BtoA[j] < 0) uncB_all.push_back(j);
+    if (P.slice_index >= (int)(uncA_all.size() + uncB_all.size())) { set_error("contract: slice index out of range"); return ITB_ERR_INVALID; }
     std::vector<int64_t> pair_ia; // A block of every entry of P.pairs (host only)
+    std::vector<int64_t> cblk_sl;  // per executed C block: extent of the sliced A index (0: not sliced on the A side)
     int64_t pos = 0;
     while (pos < npairs) {
         const int64_t ic = P.triples[3 * order[pos] + 2];
         int64_t end = pos;
         while (end < npairs && P.triples[3 * order[end] + 2] == ic) ++end;
         if (ic < cb_first || ic >= cb_last || (!P.cb_mask.empty() && !P.cb_mask[ic])) { pos = end; continue; }
+        // row-slice of one C index (sharding inside a sector): which operand index it is and the range in this block
+        int sl_a = -1, sl_b = -1; // position of the sliced index in A / in B
+        int64_t sl_lo = 0, sl_hi = 0;
+        if (P.slice_index >= 0) {
+            const int j = P.slice_index;
+            const int32_t sec = C.block(ic)[j];
+            sl_lo = P.slice_lo[sec]; sl_hi = P.slice_hi[sec];
+            if (sl_hi <= sl_lo) { pos = end; continue; }
+            if (sl_lo != 0 || sl_hi != C.ext(j, sec)) {
+                if (j < (int)uncA_all.size()) sl_a = uncA_all[j]; else sl_b = uncB_all[j - (int)uncA_all.size()];
+            }
+        }
 
         ItbCBlk cbk;
         std::memset(&cbk, 0, sizeof(cbk));
@@ -398,10 +416,23 @@ int build_contract_tables(itb_contract_plan& P) {
             for (int j = 0; j < rB && fb < 0; ++j) if (B.ext(j, bb[j]) > 1) fb = j;
             const bool a_kfast = fa >= 0 && AtoB[fa] >= 0;
             const bool b_kfast = fb >= 0 && BtoA[fb] >= 0;
+            int64_t a_shift = 0, b_shift = 0; // element shift of the operand block base when its uncontracted index is sliced
             for (int i = 0; i < rA; ++i)
-                if (AtoB[i] < 0) gm.push_back({A.ext(i, ab[i]), strA[i], 0});
+                if (AtoB[i] < 0) {
+                    if (i == sl_a) { gm.push_back({sl_hi - sl_lo, strA[i], 0}); a_shift = sl_lo * strA[i]; }
+                    else {
+                        if (sl_a >= 0 && i > sl_a && A.ext(i, ab[i]) != 1) { set_error("contract: sliced index is not the slowest non-unit uncontracted index of A"); return ITB_ERR_UNSUPPORTED; }
+                        gm.push_back({A.ext(i, ab[i]), strA[i], 0});
+                    }
+                }
             for (int j = 0; j < rB; ++j)
-                if (BtoA[j] < 0) gn.push_back({B.ext(j, bb[j]), strB[j], 0});
+                if (BtoA[j] < 0) {
+                    if (j == sl_b) { gn.push_back({sl_hi - sl_lo, strB[j], 0}); b_shift = sl_lo * strB[j]; }
+                    else {
+                        if (sl_b >= 0 && j > sl_b && B.ext(j, bb[j]) != 1) { set_error("contract: sliced index is not the slowest non-unit uncontracted index of B"); return ITB_ERR_UNSUPPORTED; }
+                        gn.push_back({B.ext(j, bb[j]), strB[j], 0});
+                    }
+                }
             // K order: follow A unless only B is k-fast (keeps the k-fast operand contiguous in k)
             if (a_kfast || !b_kfast) {
                 for (int i = 0; i < rA; ++i)
@@ -433,8 +464,8 @@ int build_contract_tables(itb_contract_plan& P) {
             }
             ItbPair pr;
             std::memset(&pr, 0, sizeof(pr));
-            pr.a_off = A.offsets[ia] * csA;
-            pr.b_off = B.offsets[ib] * csB;
+            pr.a_off = A.offsets[ia] * csA + a_shift; // (strA/strB are in REAL units already)
+            pr.b_off = B.offsets[ib] * csB + b_shift;
             for (int d = 0; d < ITB_MAXG; ++d) { pr.m_ext[d] = pr.n_ext[d] = pr.k_ext[d] = 1; }
             for (size_t d = 0; d < gm.size(); ++d) { pr.m_ext[d] = (int32_t)gm[d].ext; pr.am_str[d] = gm[d].sa; }
             for (size_t d = 0; d < gn.size(); ++d) { pr.n_ext[d] = (int32_t)gn[d].ext; pr.bn_str[d] = gn[d].sa; }
@@ -457,12 +488,21 @@ int build_contract_tables(itb_contract_plan& P) {
             pair_ia.push_back(ia);
         }
         cbk.pair_end = (int32_t)P.pairs.size();
-        cbk.c_off = C.offsets[ic] * csC;
+        // the C block keeps its full leading dimension; a slice only moves the origin and shrinks M or N
+        int64_t Mfull = 1, c_shift = 0;
+        for (size_t u = 0; u < uncA_all.size(); ++u) Mfull *= C.ext((int)u, C.block(ic)[u]);
+        if (sl_a >= 0 || sl_b >= 0) {
+            int64_t st = 1;
+            for (int j = 0; j < P.slice_index; ++j) st *= C.ext(j, C.block(ic)[j]);
+            c_shift = sl_lo * st;
+        }
+        cbk.c_off = (C.offsets[ic] + c_shift) * csC;
         cbk.M = (int32_t)(M * (cA ? 2 : 1));
         cbk.N = (int32_t)(N * ((!cA && cB) ? 2 : 1));
-        if (!cA && cB) { cbk.c_ms = 2; cbk.c_nmask = 1; cbk.c_nshift = 1; cbk.c_ns = 2 * M; }
-        else { cbk.c_ms = 1; cbk.c_nmask = 0; cbk.c_nshift = 0; cbk.c_ns = cbk.M; }
+        if (!cA && cB) { cbk.c_ms = 2; cbk.c_nmask = 1; cbk.c_nshift = 1; cbk.c_ns = 2 * Mfull; }
+        else { cbk.c_ms = 1; cbk.c_nmask = 0; cbk.c_nshift = 0; cbk.c_ns = Mfull * (cA ? 2 : 1); }
         P.cblks.push_back(cbk);
+        cblk_sl.push_back(sl_a >= 0 ? sl_hi - sl_lo : 0);
         pos = end;
     }
 
@@ -581,9 +621,11 @@ int build_contract_tables(itb_contract_plan& P) {
                     if (std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) == A_blocks.end()) A_blocks.push_back(pair_ia[p]);
             struct LDim { int64_t ext; std::vector<int64_t> str; };
             std::vector<LDim> ld;
+            const int64_t sl_ext = cblk_sl[cs[0]]; // all C blocks of a group share the long-side sectors, hence the slice
             for (size_t u = 0; u < uncA.size(); ++u) {
-                const int64_t e = A.ext(uncA[u], key[u]);
-                if (e == 1) continue;
+                const bool sliced = sl_ext > 0 && P.slice_index == (int)u; // (C's leading indices are A's uncontracted ones)
+                const int64_t e = sliced ? sl_ext : A.ext(uncA[u], key[u]);
+                if (e == 1 && !sliced) continue;
                 LDim d{e, {}};
                 d.str.reserve(A_blocks.size());
                 for (int64_t ia : A_blocks) {
@@ -725,6 +767,18 @@ int build_contract_tables(itb_contract_plan& P) {
             acc += item_cost[i];
         }
         for (int g = bcta + 1; g <= G; ++g) P.cta_begin[g] = (int32_t)P.tiles.size();
+        // flattened device records
+        P.qitems.resize(P.tiles.size());
+        for (size_t i = 0; i < P.tiles.size(); ++i) {
+            ItbQItem& q = P.qitems[i];
+            std::memset(&q, 0, sizeof(q));
+            q.tile = P.tiles[i];
+            q.cb = P.cblks[q.tile.cblk];
+            for (int32_t pp = q.cb.pair_begin; pp < q.cb.pair_end && pp - q.cb.pair_begin < ITB_QPAIRS; ++pp) {
+                q.pK[pp - q.cb.pair_begin] = P.pairs[pp].K;
+                q.pflags[pp - q.cb.pair_begin] = P.pairs[pp].flags;
+            }
+        }
     }
     std::stable_sort(P.skinny.begin(), P.skinny.end(), [&](const ItbSkinny& x, const ItbSkinny& y) {
         return P.cblks[x.cblk].ksum * (P.cblks[x.cblk].M + P.cblks[x.cblk].N) > P.cblks[y.cblk].ksum * (P.cblks[y.cblk].M + P.cblks[y.cblk].N);
@@ -733,7 +787,7 @@ int build_contract_tables(itb_contract_plan& P) {
                               P.rg_w.size() * sizeof(ItbRgW) + P.rg_items.size() * sizeof(ItbRgItem)) +
                     (int64_t)(P.pairs.size() * sizeof(ItbPair) + P.cblks.size() * sizeof(ItbCBlk) +
                               (P.skinny.size() + P.skinny_q4.size() + P.skinny_q8.size()) * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
-                              P.dot_outs.size() * sizeof(ItbDotOut) + P.tiles.size() * sizeof(ItbTile) +
+                              P.dot_outs.size() * sizeof(ItbDotOut) + P.qitems.size() * sizeof(ItbQItem) +
                               P.splits.size() * sizeof(ItbSplitOut) + P.cta_begin.size() * sizeof(int32_t));
     P.tables_built = true;
     return ITB_OK;
@@ -1013,6 +1067,31 @@ int itb_contract_plan_set_cblock_mask(itb_contract_plan* P, const uint8_t* mask)
     else P->cb_mask.clear();
     itb_contract_plan_release_device(P);
     return build_contract_tables(*P);
+}
+
+int itb_contract_plan_set_index_slices(itb_contract_plan* P, int32_t c_index, const int64_t* lo, const int64_t* hi) {
+    if (!P) { set_error("set_index_slices: null"); return ITB_ERR_INVALID; }
+    const int32_t old_index = P->slice_index;
+    const std::vector<int64_t> old_lo = P->slice_lo, old_hi = P->slice_hi;
+    if (!lo || !hi) { P->slice_index = -1; P->slice_lo.clear(); P->slice_hi.clear(); }
+    else {
+        if (c_index < 0 || c_index >= P->C.order) { set_error("set_index_slices: index out of range"); return ITB_ERR_INVALID; }
+        const int32_t ns = P->C.nsect[c_index];
+        for (int32_t q = 0; q < ns; ++q)
+            if (lo[q] < 0 || hi[q] > P->C.ext(c_index, q)) { set_error("set_index_slices: range outside the sector"); return ITB_ERR_INVALID; }
+        P->slice_index = c_index;
+        P->slice_lo.assign(lo, lo + ns);
+        P->slice_hi.assign(hi, hi + ns);
+    }
+    itb_contract_plan_release_device(P);
+    int rc = build_contract_tables(*P);
+    if (rc != ITB_OK) { // leave the plan as it was
+        const std::string msg = last_error_cstr();
+        P->slice_index = old_index; P->slice_lo = old_lo; P->slice_hi = old_hi;
+        build_contract_tables(*P);
+        set_error(msg);
+    }
+    return rc;
 }
 
 int itb_permute_plan_create(const itb_tensor_desc* src, const itb_tensor_desc* dst, const int32_t* perm,

@@ -40,12 +40,17 @@ struct itb_contract_plan {
     double class_flops[5] = {0, 0, 0, 0, 0};
     int64_t cb_first = 0, cb_last = -1; // execution range of C blocks (sharding); -1 => all
     std::vector<uint8_t> cb_mask;       // optional per-C-block selection (empty => all)
+    // optional row-slice of one index of C (multi-GPU sharding inside QN sectors): C blocks whose coordinate on index
+    // slice_index is sector s execute only the rows [slice_lo[s], slice_hi[s]) of that index (empty range: block skipped)
+    int32_t slice_index = -1;
+    std::vector<int64_t> slice_lo, slice_hi;
 
     // device-format tables (built by build_tables(), rebuilt when the range changes)
     bool tables_built = false;
     std::vector<ItbPair> pairs;
     std::vector<ItbCBlk> cblks;
     std::vector<ItbTile> tiles;       // every tile class in one list; CTA b of the persistent grid owns [cta_begin[b], cta_begin[b+1])
+    std::vector<ItbQItem> qitems;     // device form of `tiles` (flattened per-item records, same order)
     std::vector<int32_t> cta_begin;   // kNumSMs+1 entries (stream-K partition: equal modelled cycles per CTA)
     std::vector<ItbSplitOut> splits;  // split-K tiles to be reduced from the workspace
     int64_t ws_slots = 0;

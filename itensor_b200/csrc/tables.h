@@ -52,6 +52,17 @@ struct ItbTile { // work item of the persistent DMMA tile kernel
     int32_t ws_slot;     // -1: write C directly; else partial tile goes to workspace slot ws_slot
     int32_t pad_;
 };
+// Device record of one queue item: the tile plus everything the kernel needs to know about its C block and the first
+// ITB_QPAIRS block pairs (K, flags), flattened by the host so that fetching an item is ONE 160-byte read instead of a
+// chain of dependent loads (tile -> C block -> pairs).
+#define ITB_QPAIRS 8
+struct ItbQItem {
+    ItbTile tile;
+    ItbCBlk cb;
+    int32_t pK[ITB_QPAIRS];
+    int32_t pflags[ITB_QPAIRS];
+    int32_t pad_[2];
+};
 struct ItbSplitOut { // split-K tile: C tile = sum of workspace slots [ws_slot0, ws_slot0+nsplit) in order
     int32_t cblk, m0, n0, cfg, ws_slot0, nsplit, pad_[2];
 };

@@ -167,6 +167,11 @@ main(int argc, char* argv[])
             }
         }
     auto H = toMPO(ampo);
+    // The reference's RNG is seeded from time()+pid (detail/algs.h:87-93) and davidson RANDOMIZES the new basis vector when
+    // Gram-Schmidt leaves less than 1e-10 of it (iterativesolvers.h:325-331), which happens at every bond of a nearly
+    // converged sweep: two runs of the same binary then differ by ~1e-11..1e-9 in the kept spectra. A fixed seed makes runs
+    // (and the host-vs-HBM storage comparison) reproducible; both storages draw the same numbers in the same order.
+    seedRNG(1);
     auto state = InitState(sites);
     for(auto i : range1(N)) state.set(i,i%2==1 ? "Up" : "Dn");
     auto psi = MPS(state);

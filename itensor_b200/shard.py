@@ -1,24 +1,28 @@
-"""Multi-GPU sharding of the H_eff*phi chain by OUTPUT blocks.
+"""Multi-GPU sharding of the H_eff*phi chain by OUTPUT rows.
 
 The primed left link l' is an uncontracted index of every intermediate of LocalOp::product
-(phi*L -> *W1 -> *W2 -> *R, itensor/mps/localop.h:346-362), so assigning the QN sectors of l' to ranks makes
-every intermediate local to its rank: rank g computes exactly the C blocks whose l' coordinate is in its
-sector set (the same "all pairs of one C block go to one worker" rule as the reference's OpenMP path,
-itensor/itdata/qutil.h:285-348). The only communication is re-replicating H*phi once per product.
+(phi*L -> *W1 -> *W2 -> *R, itensor/mps/localop.h:346-362), so partitioning the RANGE of l' makes every
+intermediate local to its rank: rank g computes, in every step, exactly the rows of l' it owns — the same "one
+owner per piece of C" rule as the reference's OpenMP path (itensor/itdata/qutil.h:285-348), refined from whole C
+blocks to row ranges inside a QN sector so that the ranks carry equal flops whatever the sector sizes are (a whole
+sector can hold 46 % of the work). The unit handed to the planner is itb_contract_plan_set_index_slices.
 
-Each element of H*phi is produced by exactly one rank, the others hold zeros there, so the replication is an
-exact (order-independent, bit-reproducible) sum: one NCCL all-reduce over NVLink on the flat buffer. (A packed
-all-gather would move half the bytes)
+The only communication is re-replicating H*phi once per product: every rank packs the rows it owns (strided boxes of
+the blocks of H*phi) into one contiguous segment, ONE all-gather over NVLink moves the segments (each element crosses
+the wire once, half the bytes of an all-reduce of the zero-padded buffer), and the segments of the other ranks are
+scattered back into place. Pack and scatter are launches of the block-copy kernel (itb_blockcopy_plan_create).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Sequence
 
 import numpy as np
 
 
 def sector_assignment(weights: Sequence[float], world: int) -> np.ndarray:
-    """LPT (longest processing time first) assignment of sectors to ranks; returns rank of every sector."""
+    """LPT (longest processing time first) assignment of whole sectors to ranks; returns rank of every sector.
+    (coarse fallback when a plan cannot be row-sliced, see ChainShard)"""
     order = np.argsort(-np.asarray(weights, float), kind="stable")
     load = np.zeros(world)
     owner = np.zeros(len(weights), np.int64)
@@ -29,11 +33,45 @@ def sector_assignment(weights: Sequence[float], world: int) -> np.ndarray:
     return owner
 
 
+def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, align: int = 8):
+    """Cut the concatenated rows of all sectors into `world` contiguous segments of equal weight.
+
+    sizes[s] rows in sector s carrying weights[s] in total (uniform inside a sector). Returns lo, hi of shape
+    (world, nsect): rank g owns rows [lo[g,s], hi[g,s]) of sector s. Cut points inside a sector are rounded to a
+    multiple of `align` rows (DMMA fragments are 8 rows) when that keeps them inside the sector."""
+    sizes = np.asarray(sizes, np.int64)
+    w = np.asarray(weights, float)
+    per_row = np.where(sizes > 0, w / np.maximum(sizes, 1), 0.0)
+    start = np.concatenate([[0], np.cumsum(sizes)])          # first global row of every sector
+    cumw = np.concatenate([[0.0], np.cumsum(w)])
+    total = cumw[-1]
+    cuts = [0]
+    for g in range(1, world):
+        target = total * g / world
+        s = int(np.searchsorted(cumw, target, side="right") - 1)
+        s = min(max(s, 0), len(sizes) - 1)
+        r = int(round((target - cumw[s]) / per_row[s])) if per_row[s] > 0 else 0
+        if align > 1 and 0 < r < sizes[s]:
+            ra = int(round(r / align)) * align
+            if 0 < ra < sizes[s]:
+                r = ra
+        r = min(max(r, 0), int(sizes[s]))
+        cuts.append(max(int(start[s]) + r, cuts[-1]))
+    cuts.append(int(start[-1]))
+    lo = np.zeros((world, len(sizes)), np.int64)
+    hi = np.zeros((world, len(sizes)), np.int64)
+    for g in range(world):
+        a, b = cuts[g], cuts[g + 1]
+        lo[g] = np.clip(a - start[:-1], 0, sizes)
+        hi[g] = np.clip(b - start[:-1], 0, sizes)
+    return lo, hi
+
+
 def pair_flops(plan) -> np.ndarray:
     """flops of every C block of a plan (2*M*N*K summed over its pairs, complex multipliers included)"""
     A, B = plan.A, plan.B
-    lab_b = set(int(x) for x in B.labels)
-    cont = [i for i, l in enumerate(A.labels) if int(l) in lab_b]
+    keyb = {(ix.id, ix.plev) for ix in B.inds}
+    cont = [i for i, ix in enumerate(A.inds) if (ix.id, ix.plev) in keyb]
     out = np.zeros(plan.C.nblocks)
     csize = plan.C.block_sizes().astype(float)
     mult = (2.0 if A.is_complex else 1.0) * (2.0 if B.is_complex else 1.0)
@@ -45,37 +83,142 @@ def pair_flops(plan) -> np.ndarray:
     return out
 
 
+class CopyItem(C.Structure):  # itb_copy_item (include/itb200.h)
+    _fields_ = [("s_off", C.c_int64), ("d_off", C.c_int64), ("n", C.c_int32), ("pad_", C.c_int32),
+                ("ext", C.c_int64 * 12), ("sstr", C.c_int64 * 12), ("dstr", C.c_int64 * 12)]
+
+
+def _owned_boxes(struct, j: int, lo: np.ndarray, hi: np.ndarray):
+    """(block offset shift, box shape, full strides) of the rows [lo[s],hi[s]) of index j in every block, in block order"""
+    out = []
+    for b in range(struct.nblocks):
+        shape = struct.block_shape(b)
+        s = int(struct.blocks[b, j])
+        a, e = int(lo[s]), int(hi[s])
+        if e <= a:
+            continue
+        strides, st = [], 1
+        for d in shape:
+            strides.append(st)
+            st *= d
+        box = list(shape)
+        box[j] = e - a
+        out.append((int(struct.offsets[b]) + a * strides[j], box, strides))
+    return out
+
+
 class ChainShard:
-    def __init__(self, plans: List, world: int, rank: int, shard_index_id: int = 1, shard_index_plev: int = 1):
-        self.world, self.rank = world, rank
-        # position of l' in every step's C and the per-sector work over the whole chain
+    """Row partition of l' over `world` ranks for a chain of plans; slices every plan to this rank's rows."""
+
+    def __init__(self, plans: List, world: int, rank: int, shard_index_id: int = 1, shard_index_plev: int = 1, align: int = 8):
+        self.world, self.rank, self.plans = world, rank, plans
         pos, flops = [], []
-        nsect = None
+        sizes = None
         for p in plans:
             j = [t for t, ix in enumerate(p.C.inds) if ix.id == shard_index_id and ix.plev == shard_index_plev]
             assert len(j) == 1, "the sharding index must be an uncontracted index of every step"
             pos.append(j[0])
-            nsect = p.C.inds[j[0]].nsect
+            sizes = p.C.inds[j[0]].sizes
             flops.append(pair_flops(p))
-        w = np.zeros(nsect)
+        self.pos = pos
+        w = np.zeros(len(sizes))
         for p, j, f in zip(plans, pos, flops):
             np.add.at(w, p.C.blocks[:, j], f)
-        self.owner = sector_assignment(w, world)
         self.sector_work = w
-        self.masks = [(self.owner[p.C.blocks[:, j]] == rank).astype(np.uint8) for p, j in zip(plans, pos)]
-        self.my_flops = float(sum(f[m.astype(bool)].sum() for f, m in zip(flops, self.masks)))
         self.total_flops = float(sum(f.sum() for f in flops))
-        for p, m in zip(plans, self.masks):
-            p.set_cblock_mask(m)
+        self.lo, self.hi = row_partition(sizes, w, world, align)
+        self.mode = "rows"
+        try:
+            for p, j in zip(plans, pos):
+                p.set_index_slices(j, self.lo[rank], self.hi[rank])
+        except Exception:
+            # a step whose sliced index is not the slowest non-unit uncontracted index of its operand (dense site
+            # indices): fall back to whole sectors for the whole chain
+            self.mode = "sectors"
+            owner = sector_assignment(w, world)
+            sz = np.asarray(sizes, np.int64)
+            self.lo = np.zeros((world, len(sz)), np.int64)
+            self.hi = np.stack([np.where(owner == g, sz, 0) for g in range(world)])
+            for p, j in zip(plans, pos):
+                p.set_index_slices(j, self.lo[rank], self.hi[rank])
+        self.my_flops = float(sum(p.executed_flops() for p in plans))
+        # packed segments of H*phi (the last plan's C): rank r's rows, block after block, each box contiguous
+        out = plans[-1].C
+        self.out_struct = out
+        cs = 2 if out.is_complex else 1
+        self.seg_elems = []
+        self._boxes = []
+        for r in range(world):
+            boxes = _owned_boxes(out, pos[-1], self.lo[r], self.hi[r])
+            self._boxes.append(boxes)
+            self.seg_elems.append(int(sum(int(np.prod(b[1])) for b in boxes)))
+        assert sum(self.seg_elems) == out.nelems
+        self.seg_max = max(self.seg_elems)          # elements (of the tensor's dtype) per padded segment
+        self.seg_reals = self.seg_max * cs
+        self._pack = self._unpack = None
+        self.send = self.recv = None
 
-    def zero_unowned(self, out_tensor) -> None:
-        """zero H*phi before the last step so that blocks owned by other ranks contribute exact zeros"""
-        out_tensor.zero_()
+    # ---- device side -----------------------------------------------------------------------------------------
+    def _items(self, ranks, to_packed: bool):
+        items = []
+        for r in ranks:
+            run = r * self.seg_max if not to_packed else 0
+            for off, box, strides in self._boxes[r]:
+                it = CopyItem()
+                it.n = len(box)
+                packed, st = [], 1
+                for d in box:
+                    packed.append(st)
+                    st *= d
+                for d in range(len(box)):
+                    it.ext[d] = box[d]
+                    it.sstr[d] = strides[d] if to_packed else packed[d]
+                    it.dstr[d] = packed[d] if to_packed else strides[d]
+                it.s_off = off if to_packed else run
+                it.d_off = run if to_packed else off
+                run += st
+                items.append(it)
+        return items
 
-    def allgather(self, flat) -> None:
+    def _plan(self, items):
+        from ._lib import check, lib
+
+        arr = (CopyItem * max(len(items), 1))(*items)
+        h = C.c_void_p()
+        dt = self.out_struct.dtype
+        check(lib().itb_blockcopy_plan_create(len(items), C.cast(arr, C.c_void_p), dt, dt, C.byref(h)))
+        return h
+
+    def prepare(self, alloc):
+        """build the pack / scatter plans and the segment buffers; alloc(nreal) returns a flat float64 device tensor"""
+        self._pack = self._plan(self._items([self.rank], True))
+        self._unpack = self._plan(self._items([r for r in range(self.world) if r != self.rank], False))
+        self.recv = alloc(self.seg_reals * self.world)
+        self.send = self.recv[self.rank * self.seg_reals:(self.rank + 1) * self.seg_reals]  # in-place all-gather layout
+        return self
+
+    def allgather(self, ctx_handle, flat) -> None:
+        """re-replicate H*phi: pack own rows -> one all-gather of the segments -> scatter the other ranks' rows into place"""
         import torch.distributed as dist
 
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        from ._lib import check, lib
+
+        p = lambda t: C.c_void_p(t.data_ptr())
+        check(lib().itb_permute_run(ctx_handle, self._pack, p(flat), p(self.send), 1.0, 0.0, 0))
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(self.recv, self.send)
+        else:  # gloo (CPU tests)
+            parts = [self.recv[r * self.seg_reals:(r + 1) * self.seg_reals] for r in range(self.world)]
+            dist.all_gather(parts, self.send.clone())
+        check(lib().itb_permute_run(ctx_handle, self._unpack, p(self.recv), p(flat), 1.0, 0.0, 0))
+
+    def close(self):
+        from ._lib import lib
+
+        for h in (self._pack, self._unpack):
+            if h:
+                lib().itb_permute_plan_destroy(h)
+        self._pack = self._unpack = None
 
 
 def shard_chain(plans, world, rank) -> ChainShard:

@@ -198,6 +198,21 @@ class ContractPlan:
             check(lib().itb_contract_plan_set_cblock_mask(self._h, m.ctypes.data_as(C.POINTER(C.c_uint8))))
         check(lib().itb_contract_plan_info(self._h, C.byref(self.info)))
 
+    def set_index_slices(self, c_index: int, lo, hi) -> None:
+        """restrict execution to rows [lo[s], hi[s]) of C's index c_index in every block whose coordinate there is sector s
+        (None: remove the restriction) — the multi-GPU sharding unit inside QN sectors"""
+        if lo is None:
+            check(lib().itb_contract_plan_set_index_slices(self._h, -1, None, None))
+        else:
+            lo_, hi_ = np.ascontiguousarray(lo, np.int64), np.ascontiguousarray(hi, np.int64)
+            assert lo_.shape == hi_.shape == (self.C.inds[c_index].nsect,)
+            check(lib().itb_contract_plan_set_index_slices(self._h, int(c_index), _i64p(lo_), _i64p(hi_)))
+        check(lib().itb_contract_plan_info(self._h, C.byref(self.info)))
+
+    def executed_flops(self) -> float:
+        """flops of the C blocks / slices this plan executes (== flops when nothing is masked or sliced)"""
+        return float(sum(self.info.class_flops))
+
     def close(self):
         if self._h:
             lib().itb_contract_plan_destroy(self._h)

@@ -208,7 +208,8 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK;
     MockScope scope_;
     static const bool walk_tables = [] { const char* e = std::getenv("ITB_MOCK_TABLES"); return e && std::atoi(e) != 0; }();
-    if (walk_tables) { ++c->launches; return emu_contract(P, (const double*)A, (const double*)B, (double*)C); }
+    // (row-sliced plans only exist as device tables: the oracle works on whole blocks)
+    if (walk_tables || P->slice_index >= 0) { ++c->launches; return emu_contract(P, (const double*)A, (const double*)B, (double*)C); }
     orc_desc a = to_orc(P->A), b = to_orc(P->B), cc = to_orc(P->C);
     ++c->launches;
     // honour the C-block selection (multi-GPU sharding): only pairs of selected C blocks are executed
