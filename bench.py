@@ -356,6 +356,34 @@ def main():
         keep.clear()
 
     keep = []
+    if world > 1:
+        # N > 1: every byte crosses PCIe ONCE per step for the whole job. The five operands live back to back in one arena;
+        # rank g uploads the g-th 1/N of the arena from pinned host memory, one NCCL all-gather over NVLink completes the
+        # arena on every GPU, the sliced chain runs, and every rank reads back only the packed segment of H*phi it owns.
+        offs, tot = [], 0
+        for pth in pinned:
+            offs.append(tot)
+            tot += (pth.numel() + 31) // 32 * 32
+        chunk = (tot + world - 1) // world
+        chunk = (chunk + 31) // 32 * 32
+        h_arena = torch.zeros(chunk * world, dtype=torch.float64).pin_memory()
+        for o, pth in zip(offs, pinned):
+            h_arena[o:o + pth.numel()].copy_(pth)
+        d_arena = ctx.empty(chunk * world)
+        dts_e = [itb.QTensor(ctx, st, d_arena[o:o + st.nreal]) for o, st in zip(offs, structs)]
+        h_seg = torch.empty(shard.seg_reals, dtype=torch.float64).pin_memory()
+        mine = slice(rank * chunk, (rank + 1) * chunk)
+
+        def e2e_step():  # noqa: F811
+            d_arena[mine].copy_(h_arena[mine], non_blocking=True)
+            dist.all_gather_into_tensor(d_arena, d_arena[mine])
+            cur = dts_e[0]
+            for k, p in enumerate(plans):
+                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts_e[k + 1].ptr, outs[k].ptr))
+                cur = outs[k]
+            shard.allgather(ctx.handle, outs[-1].data)
+            h_seg.copy_(shard.send, non_blocking=True)
+            torch.cuda.synchronize()
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -367,8 +395,8 @@ def main():
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    h2d = int(sum(p.numel() * 8 for p in pinned))
-    d2h = int(h_out.numel() * 8)
+    h2d = int(sum(p.numel() * 8 for p in pinned))   # whole job: at N > 1 every rank uploads 1/N of it
+    d2h = int(h_out.numel() * 8)                    # whole job: at N > 1 every rank reads back the rows it owns
 
     # ---- roofline of the dominant kernel (128x128 DMMA tile kernel of step 1), live CUDA events ----
     roof = None
@@ -445,12 +473,26 @@ def main():
             e1.record(); e1.synchronize()
             if it_ > 0:
                 best = min(best, e0.elapsed_time(e1) / reps_in)
+        # the permuting ACCUMULATE (PlusEQ with a permutation: what davidson's q += (-Vq)*V[k] hits): dst += P(src),
+        # algorithmic bytes = read src + read dst + write dst
+        best_acc = 1e9
+        for it_ in range(4):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for q in range(reps_in):
+                check(lib().itb_permute_run(ctx.handle, pp._h, src.ptr, C.c_void_p(dsts[q & 1].data_ptr()), 0.5, 0.0, 1))
+            e1.record(); e1.synchronize()
+            if it_ > 0:
+                best_acc = min(best_acc, e0.elapsed_time(e1) / reps_in)
         dst = dsts[0]
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         gbs = pp.bytes / (best * 1e-3) / 1e9
         perm_info = {"what": "QDense permute, reverse 5 indices of T1=phi*L (fills all flux-allowed blocks)", "elements": int(src.struct.nelems),
                      "bytes": int(pp.bytes), "ms": best, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": gbs / hbm,
-                     "timing": "mean of 4 back-to-back permutes (alternating destinations, 254 MB each > L2) per CUDA-event pair, best of 3"}
+                     "timing": "mean of 4 back-to-back permutes (alternating destinations, 254 MB each > L2) per CUDA-event pair, best of 3",
+                     "accumulate": {"what": "same permutation as PlusEQ: dst += 0.5*P(src)", "bytes": int(pp.bytes * 3 // 2), "ms": best_acc,
+                                    "achieved_gbs": pp.bytes * 1.5 / (best_acc * 1e-3) / 1e9, "frac": pp.bytes * 1.5 / (best_acc * 1e-3) / 1e9 / hbm}}
         del dst
 
     # ---- CPU baseline + parity: the reference itself on this box's host cores, on the SAME tensors ---------------------
@@ -486,6 +528,23 @@ def main():
         else:
             cpu = {"value": None, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref not built"}
 
+    # ---- the same step through the C++ plugin: ITensor::operator* on QDenseGPU storage (separate process, GPU idle here) ----
+    plugin = None
+    hb = os.path.join(ROOT, "build", "plugin", "heff_bench")
+    if rank == 0 and world == 1 and os.path.exists(hb) and not args.complex:
+        import sysconfig
+
+        env = dict(os.environ, ITB_WARM_LIBS="0", LD_LIBRARY_PATH=os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")
+                   + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        try:
+            torch.cuda.synchronize()
+            out = subprocess.run([hb, str(args.m), str(args.nsect), str(max(args.steps, 3)), "3"], env=env, capture_output=True, text=True, timeout=600)
+            plugin = json.loads(out.stdout.strip().split("\n")[-1])
+            plugin["resident_tflops"] = total_flops / (plugin["resident_ms_per_step"] * 1e-3) / 1e12
+            plugin["e2e_tflops"] = total_flops / (plugin["e2e_ms_per_step"] * 1e-3) / 1e12
+        except Exception as e:  # the Python-mirror numbers above stand on their own
+            plugin = {"error": str(e)[:200]}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -495,10 +554,12 @@ def main():
                        "maxdim": args.m, "sectors": sizes, "d": 2, "mpo_link_sectors": [3, 1, 1],
                        "pairs_per_step": [int(p.npairs) for p in plans], "flops_per_step": total_flops,
                        "l2": "flushed between timed iterations (256 MiB memset)",
-                       "sharding": ("C blocks by l' sector, max rank share %.3f of flops" % (max_share,)) if world > 1 else "none"},
+                       "sharding": ("rows of l' (%s), equal-flop contiguous row ranges per rank, max rank share %.3f of flops (ideal %.3f); "
+                                    "H*phi re-replicated by pack -> one NCCL all-gather -> scatter; e2e: 1/N of the operand arena per "
+                                    "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin,
             "permute": perm_info,
         }))
     if world > 1:

@@ -241,6 +241,9 @@ int itb_ctx_set_profile(itb_ctx* ctx, int profile);
 int itb_contract_last_ms(itb_ctx* ctx, float ms[5]);
 /* profile mode: clock64 span of every CTA of the last DMMA tile-kernel launch (schedule calibration); returns the count */
 int64_t itb_contract_last_cta_cycles(itb_ctx* ctx, int64_t* out, int64_t cap);
+/* profile mode: per queue item of the last DMMA tile-kernel launch, 4 int64 each: {CTA that ran it, clock64 at item start, at the
+ * end of its K loop, at the end of its epilogue} (relative to the CTA's start); returns the item count, writes at most cap int64 */
+int64_t itb_contract_last_item_cycles(itb_ctx* ctx, int64_t* out, int64_t cap);
 /* bare DMMA (mma.sync f64) and DFMA issue loops, no memory traffic; returns TFLOP/s */
 int itb_peak_fp64(itb_ctx* ctx, int which /*0=dmma m8n8k4, 1=dfma, 2=dmma m16n8k8*/, int iters, double* tflops);
 /* device-side timing on the context's stream (CUDA events) */

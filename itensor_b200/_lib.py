@@ -121,6 +121,7 @@ SYMBOLS = {
     "itb_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "itb_contract_last_cta_cycles": (C.c_int64, [_P, _I64P, C.c_int64]),
     "itb_contract_last_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "itb_contract_last_item_cycles": (C.c_int64, [_P, _I64P, C.c_int64]),
     "itb_timer_start": (C.c_int, [_P]),
     "itb_timer_stop_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
 }

@@ -108,6 +108,8 @@ struct itb_ctx {
     float last_ms[5] = {0, 0, 0, 0, 0};
     long long* d_cta_cycles = nullptr;   // profile mode: per-CTA clock64 span of the last tile-kernel launch
     std::vector<long long> h_cta_cycles;
+    std::vector<long long> h_item_cycles;
+    size_t cta_cycles_words = 0;
     cudaEvent_t pev[10] = {};
 };
 
@@ -458,12 +460,19 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
         // persistent grid, one CTA per SM (fewer when the queue is shorter than that); items are pulled from the
         // in-order queue through the head counter (rearmed by the kernel itself)
         const int grid = (int)std::min<size_t>((size_t)c->num_sms, P->tiles.size());
-        if (c->profile && !c->d_cta_cycles) SIDE_TRY(cudaMalloc(&c->d_cta_cycles, 1024 * sizeof(long long)));
+        const size_t prof_words = 1024 + 4 * P->tiles.size(); // per-CTA spans, then {cta, start, K-loop end, end} per item
+        if (c->profile && c->cta_cycles_words < prof_words) {
+            if (c->d_cta_cycles) { SIDE_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->d_cta_cycles); c->d_cta_cycles = nullptr; }
+            SIDE_TRY(cudaMalloc(&c->d_cta_cycles, prof_words * sizeof(long long)));
+            c->cta_cycles_words = prof_words;
+        }
         SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
             c->h_cta_cycles.assign(grid, 0);
             CUDA_TRY(cudaMemcpyAsync(c->h_cta_cycles.data(), c->d_cta_cycles, grid * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            c->h_item_cycles.assign(4 * P->tiles.size(), 0);
+            CUDA_TRY(cudaMemcpyAsync(c->h_item_cycles.data(), c->d_cta_cycles + 1024, 4 * P->tiles.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
         }
         PROF_END(0);
         c->launches += P->splits.empty() ? 1 : 2;
@@ -695,6 +704,10 @@ int itb_ctx_set_profile(itb_ctx* c, int profile) { c->profile = profile != 0; re
 int64_t itb_contract_last_cta_cycles(itb_ctx* c, int64_t* out, int64_t cap) {
     for (int64_t i = 0; out && i < (int64_t)c->h_cta_cycles.size() && i < cap; ++i) out[i] = c->h_cta_cycles[i];
     return (int64_t)c->h_cta_cycles.size();
+}
+int64_t itb_contract_last_item_cycles(itb_ctx* c, int64_t* out, int64_t cap) {
+    for (int64_t i = 0; out && i < (int64_t)c->h_item_cycles.size() && i < cap; ++i) out[i] = c->h_item_cycles[i];
+    return (int64_t)c->h_item_cycles.size() / 4;
 }
 int itb_contract_last_ms(itb_ctx* c, float ms[5]) {
     for (int i = 0; i < 5; ++i) ms[i] = c->last_ms[i];

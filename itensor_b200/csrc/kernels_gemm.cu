@@ -167,10 +167,10 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
     }
 }
 
-template <int BM, int BN>
+template <int BM, int BN, bool PROF>
 __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __restrict__ pairs,
                                              double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
-                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute) {
+                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute, long long* rec) {
     constexpr int BK = G_BK;
     constexpr int WM = BM / 4, WN = BN / 4, FM = WM / 8, FN = WN / 8;
     static_assert(FM >= 1 && FN >= 1, "tile too small for a 4x4 warp grid");
@@ -226,12 +226,15 @@ __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __r
         }
 #undef ITB_CONSUME
     }
+    if (PROF && rec && threadIdx.x == 0) rec[2] = clock64(); // end of the K loop of this item (profile build only)
     // ---- epilogue: each C element is written exactly once (or one partial per split) ----------------------
     const int ws_slot = qi.tile.ws_slot;
     if (ws_slot < 0) {
         const int64_t cms = qi.cb.c_ms, cns = qi.cb.c_ns;
         const int nmask = qi.cb.c_nmask, nshift = qi.cb.c_nshift;
-        if (!edge && nmask == 0 && cms == 1) {
+        // (`edge` only says that some 8x8 fragment lies entirely outside; the fast path needs every ROW and COLUMN inside)
+        const bool interior = m0 + wm0 + WM <= M && n0 + wn0 + WN <= N;
+        if (interior && nmask == 0 && cms == 1) {
             // interior tile of a plainly laid out block: one base pointer, constant offsets, no bounds checks
             double* __restrict__ Cp = C + qi.cb.c_off + (m0 + wm0 + g) + (int64_t)(n0 + wn0 + 2 * t4) * cns;
 #pragma unroll
@@ -430,6 +433,7 @@ __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __r
 // record into the slot and publishes it through the slot's full barrier (the pop + copy latency, ~1.3k cycles, falls
 // into the producers' slack: they need ~1600 of the ~4500 cycles a chunk takes). All 20 warps read the same sequence of
 // records from shared memory. An index >= n_items is the stop sentinel. The last CTA to stop rearms the queue head.
+template <bool PROF>
 __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __restrict__ items, int n_items, int* __restrict__ queue,
                                                             const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
@@ -492,14 +496,19 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
         const QItem& qi = q_item[s];
         if (qi.item >= n_items) break;
         const int cfg = qi.tile.cfg;
+        // profile build: consumer thread 0 records {CTA, item start, end of K loop, item end} per item (clock64 relative to
+        // the CTA's start) behind the 1024 per-CTA spans
+        long long* rec = (PROF && cta_cycles && threadIdx.x == 0) ? cta_cycles + 1024 + 4 * (long long)qi.item : nullptr;
+        if (PROF && rec) { rec[0] = blockIdx.x; rec[1] = clock64() - t_begin; }
         if (producer) {
             if (cfg == 0) produce_tile<128, 128>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
             else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
             else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
         } else {
-            if (cfg == 0) consume_tile<128, 128>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
-            else if (cfg == 1) consume_tile<64, 64>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
-            else consume_tile<32, 32>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            if (cfg == 0) consume_tile<128, 128, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
+            else if (cfg == 1) consume_tile<64, 64, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
+            else consume_tile<32, 32, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
+            if (PROF && rec) { rec[2] -= t_begin; rec[3] = clock64() - t_begin; }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&q_empty[s]); // the slot may be refilled once every warp has finished the item
@@ -970,11 +979,13 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid
     if (nocompute < 0) { const char* e = getenv("ITB_DEBUG_NOCOMPUTE"); nocompute = e ? atoi(e) : 0; }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(bsc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(bsc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bsc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    bsc_gemm_kernel<<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, A, B, C, ws, cta_cycles, nocompute);
+    if (cta_cycles) bsc_gemm_kernel<true><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, A, B, C, ws, cta_cycles, nocompute);
+    else bsc_gemm_kernel<false><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, A, B, C, ws, nullptr, nocompute);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {

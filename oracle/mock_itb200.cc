@@ -354,6 +354,7 @@ double itb_svd_batch_stats(int64_t out[3]) { if (out) out[0] = out[1] = out[2] =
 int itb_peak_fp64(itb_ctx*, int, int, double* t) { *t = 0; return ITB_ERR_UNSUPPORTED; }
 int itb_ctx_set_profile(itb_ctx*, int) { return ITB_OK; }
 int64_t itb_contract_last_cta_cycles(itb_ctx*, int64_t*, int64_t) { return 0; }
+int64_t itb_contract_last_item_cycles(itb_ctx*, int64_t*, int64_t) { return 0; }
 int itb_contract_last_ms(itb_ctx*, float ms[5]) { for (int i = 0; i < 5; ++i) ms[i] = 0; return ITB_OK; }
 int itb_timer_start(itb_ctx*) { return ITB_OK; }
 int itb_timer_stop_ms(itb_ctx*, float* ms) { *ms = 0; return ITB_OK; }
