@@ -233,6 +233,19 @@ int itb_svd_batch_destroy(itb_svd_batch* batch);
  * input, err_sigma > 1e-14 s0), blocks factorised with Jacobi}; returns the largest err_sigma / s0 the polar solver reported */
 double itb_svd_batch_stats(int64_t out[3]);
 
+/* Device-resident batched eigh of the (square, Hermitian) blocks of an order-2 block-sparse tensor — the per-block loop of
+ * diagHImpl (itensor/hermitian.cc:231-257) on QDenseGPU storage, i.e. the density-matrix branch of svdBond (noise > 0).
+ * Block b is n[b] x n[b] at ELEMENT offset a_off[b] of dA (not modified). negate != 0 diagonalises -A_b, so that the ascending
+ * order of syevd is the reference's largest-first order (tensor/algs_impl.h:123-137; the caller flips the sign of the values).
+ * Eigenvectors stay on the device; itb_eigh_batch_values reads the eigenvalues back (block order, synchronises), the caller
+ * truncates on the host and copies the kept leading eigenvectors with itb_eigh_batch_copy_vectors (device to device). */
+typedef struct itb_eigh_batch itb_eigh_batch;
+int itb_eigh_batch_run(itb_ctx* ctx, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* n, const void* dA, int negate,
+                       itb_eigh_batch** out);
+int itb_eigh_batch_values(itb_eigh_batch* batch, double* hW);
+int itb_eigh_batch_copy_vectors(itb_eigh_batch* batch, int64_t block, int32_t ncols, void* dDst, int conj); /* n x ncols */
+int itb_eigh_batch_destroy(itb_eigh_batch* batch);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement
  * only). itb_contract_last_ms then returns the device time of the last run by kernel class

@@ -117,6 +117,10 @@ SYMBOLS = {
     "itb_svd_batch_copy_v": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int]),
     "itb_svd_batch_destroy": (C.c_int, [_P]),
     "itb_svd_batch_stats": (C.c_double, [_I64P]),
+    "itb_eigh_batch_run": (C.c_int, [_P, C.c_int32, C.c_int64, _I64P, _I32P, _P, C.c_int, C.POINTER(_P)]),
+    "itb_eigh_batch_values": (C.c_int, [_P, _DP]),
+    "itb_eigh_batch_copy_vectors": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int]),
+    "itb_eigh_batch_destroy": (C.c_int, [_P]),
     "itb_peak_fp64": (C.c_int, [_P, C.c_int, C.c_int, _DP]),
     "itb_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "itb_contract_last_cta_cycles": (C.c_int64, [_P, _I64P, C.c_int64]),

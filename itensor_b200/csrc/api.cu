@@ -67,6 +67,11 @@ using namespace itb;
 
 struct itb_solver;
 struct itb_svd_batch;
+struct itb_eigh_batch;
+extern "C" {
+int itb_solver_eigh_batch_run(itb_solver* s, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* n, const void* dA,
+                              int negate, itb_eigh_batch** out);
+}
 extern "C" {
 int itb_solver_create(void* stream, itb_solver** out);
 int itb_solver_set_stream(itb_solver* s, void* stream);
@@ -698,6 +703,15 @@ int itb_svd_batch_run(itb_ctx* c, int32_t dtype, int64_t nblocks, const int64_t*
     if (rc != ITB_OK) return rc;
     c->launches += nblocks;
     return itb_solver_svd_batch_run(c->solver, dtype, nblocks, a_off, m, n, dA, out);
+}
+
+int itb_eigh_batch_run(itb_ctx* c, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* n, const void* dA, int negate,
+                       itb_eigh_batch** out) {
+    if (!c || !out || nblocks < 0) { set_error("eigh_batch_run: bad arguments"); return ITB_ERR_INVALID; }
+    int rc = ensure_solver(c);
+    if (rc != ITB_OK) return rc;
+    c->launches += 2 * nblocks;
+    return itb_solver_eigh_batch_run(c->solver, dtype, nblocks, a_off, n, dA, negate, out);
 }
 
 int itb_ctx_set_profile(itb_ctx* c, int profile) { c->profile = profile != 0; return ITB_OK; }

@@ -70,6 +70,10 @@ __device__ __forceinline__ int64_t grp_off(int idx, const int32_t* __restrict__ 
 // Producers and consumers walk the same deterministic (tile, pair, chunk) sequence, so there is no
 // CTA-wide barrier anywhere in the main loop: DMMA stretches of the two consumer warps of an SMSP
 // interleave freely and the epilogue of one tile overlaps the loads of the next.
+#ifndef ITB_SETMAXNREG
+#define ITB_SETMAXNREG 0 // ptxas 12.9 / sm_100a does not allocate per region: the smallest setmaxnreg value caps the WHOLE kernel
+                         // (consumer DMMA loop: 90 local loads + 90 stores per K-chunk with dec 64), an inc alone is ignored
+#endif
 constexpr int G_NCONS = 512, G_NPROD = 128, G_NT = G_NCONS + G_NPROD;
 constexpr int G_STAGES = 4, G_BK = ITB_BK, G_PAD = 4, G_MAXT = 128;
 constexpr int G_KT = 1024; // k offsets per shared table fill (per operand)
@@ -116,6 +120,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
         "DONE:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
         "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, int parity) { // non-blocking: has the phase with this parity completed?
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(G_NPROD) : "memory"); }
 
@@ -429,7 +444,7 @@ __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __r
 // (edge tiles, L2 hits, clocks) — no cycle model has to be right — and at any time the 148 CTAs work on ~148 CONSECUTIVE
 // tiles, i.e. on the few C blocks whose operand panels are then shared through L2 instead of re-read from HBM.
 // Mechanics: the first producer warp is also the FETCHER: before it starts producing item q it makes sure the ring holds
-// items up to q+G_QSLOTS-1: lane 0 pops an index from the global head, the warp copies the host-flattened 160-byte item
+// items up to q+G_QSLOTS-1 (as far as slots are free; it never blocks on a look-ahead): lane 0 pops an index from the global head, the warp copies the host-flattened 160-byte item
 // record into the slot and publishes it through the slot's full barrier (the pop + copy latency, ~1.3k cycles, falls
 // into the producers' slack: they need ~1600 of the ~4500 cycles a chunk takes). All 20 warps read the same sequence of
 // records from shared memory. An index >= n_items is the stop sentinel. The last CTA to stop rearms the queue head.
@@ -467,6 +482,12 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
     const int lane = threadIdx.x & 31;
     const bool producer = threadIdx.x >= G_NCONS;
     const bool fetch_warp = (threadIdx.x >> 5) == G_NCONS / 32;
+    // register re-balancing at warpgroup granularity (warps 0-15: four consumer warpgroups, warps 16-19: the producer
+    // warpgroup) would be 4 x 128 x 112 + 128 x 56 = 64512 registers <= 65536; see ITB_SETMAXNREG above for why it is off.
+#if ITB_SETMAXNREG
+    if (producer) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+#endif
     PipeState ps;
     int qf = 0;            // fetcher: next sequence number to publish
     bool exhausted = false;
@@ -474,7 +495,16 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
         if (fetch_warp) {
             while (!exhausted && qf < q + G_QSLOTS) {
                 const int s = qf % G_QSLOTS;
-                mbar_wait(&q_empty[s], ((qf / G_QSLOTS) & 1) ^ 1);
+                // A slot is free once EVERY warp has finished the item that last used it. The consumers lag the producers
+                // by up to G_STAGES chunks, so the slot of item q-1 is normally still busy here: look-ahead fetches only
+                // TEST the barrier (and retry at the next item); blocking there would drain the operand ring at every
+                // item boundary (measured: ~4 chunks = 18k cycles per item). Only the item needed right now waits.
+                const int par = ((qf / G_QSLOTS) & 1) ^ 1;
+                if (qf > q) { // (lane 0 decides for the warp: the phase may complete between two lanes' tests)
+                    const int ok = __shfl_sync(0xffffffffu, (int)mbar_test(&q_empty[s], par), 0);
+                    if (!ok) break;
+                }
+                mbar_wait(&q_empty[s], par);
                 int idx = 0;
                 if (lane == 0) idx = atomicAdd(queue, 1);
                 idx = __shfl_sync(0xffffffffu, idx, 0);

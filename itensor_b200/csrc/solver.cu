@@ -570,6 +570,150 @@ int itb_svd_batch_destroy(itb_svd_batch* B) {
     return ITB_OK;
 }
 
+} // extern "C" (reopened below)
+
+// ---- device-resident batched eigh of the diagonal blocks of an order-2 block-sparse tensor (diagHImpl QN loop,
+// itensor/hermitian.cc:231-257, on QDenseGPU storage: the density-matrix branch of svdBond, noise > 0) ------------------
+// Block b is an n[b] x n[b] Hermitian matrix at element offset a_off[b] of dA (not modified). Each block is copied
+// (optionally NEGATED, so that ascending syevd order is the reference's largest-first order, tensor/algs_impl.h:
+// 123-137) into the batch's own storage and diagonalised in place by cuSOLVER syevd / heevd, blocks spread over the
+// solver lanes' streams; eigenvectors stay on the device, only the eigenvalues come back.
+struct itb_eigh_batch {
+    int32_t dtype = ITB_F64;
+    int64_t nblocks = 0;
+    std::vector<int32_t> n;
+    std::vector<size_t> v_off; // byte offset of block b's n x n eigenvector matrix in d_v
+    std::vector<size_t> w_off; // element offset of block b's eigenvalues in d_w
+    void* d_v = nullptr;
+    double* d_w = nullptr;
+    int* d_info = nullptr;     // one per block
+    int64_t nw = 0;
+    itb_svd_lanes* lanes = nullptr;
+    cudaStream_t main = nullptr;
+    bool joined = false;
+};
+
+template <typename T> struct NegOp;
+template <> struct NegOp<double> { static __device__ double neg(double v) { return -v; } };
+template <> struct NegOp<double2> { static __device__ double2 neg(double2 v) { return make_double2(-v.x, -v.y); } };
+template <typename T>
+__global__ void copy_scale_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n, int negate) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = negate ? NegOp<T>::neg(in[i]) : in[i];
+}
+
+static int eigh_batch_join(itb_eigh_batch* B) {
+    if (B->joined) return ITB_OK;
+    B->joined = true;
+    int rc = ITB_OK;
+    for (auto& ln : B->lanes->lane) {
+        if (cudaEventRecord(ln.done, ln.st) != cudaSuccess || cudaStreamWaitEvent(B->main, ln.done, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cudaStreamSynchronize(ln.st);
+            rc = ITB_ERR_CUDA;
+        }
+    }
+    if (rc) itb::set_error("eigh batch: could not order the solver lanes before the context stream");
+    return rc;
+}
+
+extern "C" {
+
+int itb_solver_eigh_batch_run(itb_solver* s, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* n, const void* dA,
+                              int negate, itb_eigh_batch** out) {
+    if (!s->lanes) s->lanes = new itb_svd_lanes();
+    int rc = lanes_init(s->lanes); if (rc) return rc;
+    const size_t es = dtype == ITB_C64 ? 16 : 8;
+    auto* B = new itb_eigh_batch();
+    B->dtype = dtype; B->nblocks = nblocks; B->lanes = s->lanes; B->main = s->stream;
+    size_t bytes = 0; int64_t nw = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        B->n.push_back(n[b]);
+        B->v_off.push_back(bytes); bytes += ((size_t)n[b] * n[b] * es + 255) & ~(size_t)255;
+        B->w_off.push_back((size_t)nw); nw += n[b];
+    }
+    B->nw = nw;
+    if (cudaMallocAsync(&B->d_v, bytes + 256, s->stream) != cudaSuccess || cudaMallocAsync((void**)&B->d_w, (size_t)nw * 8 + 256, s->stream) != cudaSuccess ||
+        cudaMallocAsync((void**)&B->d_info, (size_t)nblocks * sizeof(int) + 256, s->stream) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (B->d_v) cudaFreeAsync(B->d_v, s->stream);
+        if (B->d_w) cudaFreeAsync(B->d_w, s->stream);
+        itb::set_error("eigh batch: out of device memory"); delete B; return ITB_ERR_NOMEM;
+    }
+    auto fail = [&](const std::string& msg, int code) {
+        itb::set_error(msg);
+        eigh_batch_join(B); // whatever was queued on the lanes finishes before the stream-ordered frees
+        cudaFreeAsync(B->d_v, s->stream); cudaFreeAsync(B->d_w, s->stream); cudaFreeAsync(B->d_info, s->stream);
+        delete B;
+        return code;
+    };
+    cudaError_t e = cudaEventRecord(s->lanes->ready, s->stream);
+    for (auto& ln : s->lanes->lane)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ln.st, s->lanes->ready, 0);
+    if (e != cudaSuccess) return fail(std::string("eigh batch: ") + cudaGetErrorString(e), ITB_ERR_CUDA);
+    // largest blocks first, each onto the least loaded lane (cost ~ n^3)
+    std::vector<int64_t> order(nblocks);
+    for (int64_t b = 0; b < nblocks; ++b) order[b] = b;
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return n[x] > n[y]; });
+    double load[SVD_LANES] = {0, 0, 0, 0};
+    for (int64_t b : order) {
+        int q = 0;
+        for (int t = 1; t < SVD_LANES; ++t) if (load[t] < load[q]) q = t;
+        load[q] += (double)n[b] * n[b] * n[b] + 2e6;
+        SvdLane& ln = s->lanes->lane[q];
+        const int nb = n[b];
+        void* dv = (char*)B->d_v + B->v_off[b];
+        double* dw = B->d_w + B->w_off[b];
+        const size_t ne = (size_t)nb * nb;
+        const int grid = (int)std::min<size_t>(148 * 4, (ne + 255) / 256);
+        if (dtype == ITB_F64) copy_scale_kernel<double><<<grid, 256, 0, ln.st>>>((const double*)dA + a_off[b], (double*)dv, ne, negate);
+        else copy_scale_kernel<double2><<<grid, 256, 0, ln.st>>>((const double2*)dA + a_off[b], (double2*)dv, ne, negate);
+        int lwork = 0;
+        cusolverStatus_t st = dtype == ITB_F64
+            ? cusolverDnDsyevd_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (double*)dv, nb, dw, &lwork)
+            : cusolverDnZheevd_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (cuDoubleComplex*)dv, nb, dw, &lwork);
+        if (st != CUSOLVER_STATUS_SUCCESS) return fail("eigh batch: syevd_bufferSize status " + std::to_string((int)st), ITB_ERR_CUDA);
+        if (ln.work_bytes < (size_t)lwork * es + 256) {
+            // growing a lane's workspace: everything queued on that lane so far must have finished with the old one
+            if (cudaStreamSynchronize(ln.st) != cudaSuccess) return fail("eigh batch: lane synchronise failed", ITB_ERR_CUDA);
+            if (grow(&ln.d_work, &ln.work_bytes, (size_t)lwork * es + 256) != ITB_OK) return fail("eigh batch: out of device memory (workspace)", ITB_ERR_NOMEM);
+        }
+        st = dtype == ITB_F64
+            ? cusolverDnDsyevd(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (double*)dv, nb, dw, (double*)ln.d_work, lwork, B->d_info + b)
+            : cusolverDnZheevd(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (cuDoubleComplex*)dv, nb, dw, (cuDoubleComplex*)ln.d_work, lwork, B->d_info + b);
+        if (st != CUSOLVER_STATUS_SUCCESS) return fail("eigh batch: syevd status " + std::to_string((int)st), ITB_ERR_CUDA);
+    }
+    *out = B;
+    return ITB_OK;
+}
+// eigenvalues of every block (ascending per block, of -A_b when the batch was run with negate), concatenated in block order
+int itb_eigh_batch_values(itb_eigh_batch* B, double* hW) {
+    int rc = eigh_batch_join(B); if (rc) return rc;
+    std::vector<int> infos((size_t)B->nblocks, 0);
+    S_TRY(cudaMemcpyAsync(hW, B->d_w, (size_t)B->nw * 8, cudaMemcpyDeviceToHost, B->main));
+    if (B->nblocks) S_TRY(cudaMemcpyAsync(infos.data(), B->d_info, (size_t)B->nblocks * sizeof(int), cudaMemcpyDeviceToHost, B->main));
+    S_TRY(cudaStreamSynchronize(B->main));
+    for (int64_t b = 0; b < B->nblocks; ++b)
+        if (infos[b] != 0) { itb::set_error("eigh batch: syevd did not converge on block " + std::to_string(b) + " (info " + std::to_string(infos[b]) + ")"); return ITB_ERR_CUDA; }
+    return ITB_OK;
+}
+// first ncols eigenvectors of block b (n x ncols, contiguous; conj != 0: complex conjugate) to dDst, on the context's stream
+int itb_eigh_batch_copy_vectors(itb_eigh_batch* B, int64_t b, int32_t ncols, void* dDst, int conj) {
+    int rc = eigh_batch_join(B); if (rc) return rc;
+    const size_t es = B->dtype == ITB_C64 ? 16 : 8;
+    S_TRY(cudaMemcpyAsync(dDst, (char*)B->d_v + B->v_off[b], (size_t)B->n[b] * ncols * es, cudaMemcpyDeviceToDevice, B->main));
+    if (conj && B->dtype == ITB_C64) conj_inplace_kernel<<<148, 256, 0, B->main>>>((double2*)dDst, (size_t)B->n[b] * ncols);
+    return ITB_OK;
+}
+int itb_eigh_batch_destroy(itb_eigh_batch* B) {
+    if (!B) return ITB_OK;
+    eigh_batch_join(B);
+    cudaFreeAsync(B->d_v, B->main);
+    cudaFreeAsync(B->d_w, B->main);
+    cudaFreeAsync(B->d_info, B->main);
+    delete B;
+    return ITB_OK;
+}
+
 int itb_solver_destroy(itb_solver* s) {
     if (!s) return ITB_OK;
     if (s->stream) cudaStreamSynchronize(s->stream);

@@ -354,6 +354,203 @@ svdDenseGPU(ITensor const& A, DenseGPU<T> const& d, Index const& uI, Index const
     return Spectrum(std::move(DD),{"Truncerr",truncerr});
     }
 
+struct EighGuard
+    {
+    itb_eigh_batch* b = nullptr;
+    ~EighGuard() { if(b) itb_eigh_batch_destroy(b); }
+    };
+
+// ITB_PROFILE: wall time of the phases of the device diag_hermitian, printed at exit
+struct EighProf
+    {
+    double secs[4] = {0,0,0,0}; long calls = 0, dev_blocks = 0, host_blocks = 0;
+    bool on = std::getenv("ITB_PROFILE") != nullptr;
+    ~EighProf()
+        {
+        if(!on || !calls) return;
+        const char* names[4] = {"diagH launch device","diagH host blocks","diagH wait device","diagH truncate+assemble"};
+        for(int i = 0; i < 4; ++i) std::fprintf(stderr,"[itensor_b200 profile] %-28s %10ld %12.4f\n",names[i],calls,secs[i]);
+        std::fprintf(stderr,"[itensor_b200 profile] %-28s %10ld device blocks, %ld host blocks\n","diagH blocks",dev_blocks,host_blocks);
+        }
+    };
+EighProf& eighProf() { static EighProf p; return p; }
+
+// QN branch of diagHImpl (hermitian.cc:180-426) on a QDenseGPU tensor: every diagonal block is diagonalised on the device
+// straight from H's buffer (itb_eigh_batch_run: cuSOLVER syevd / heevd of -block over several streams), only the
+// eigenvalues come back, the reference's truncate() decides what is kept, and the kept eigenvectors are copied device to
+// device into a new QDenseGPU U. The density matrix never leaves HBM (the reference path downloads it through GetBlocks).
+template<typename T>
+Spectrum
+eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args const& args)
+    {
+    auto cutoff = args.getReal("Cutoff",MIN_CUT);
+    auto maxdim = args.getInt("MaxDim",MAX_DIM);
+    auto mindim = args.getInt("MinDim",1);
+    auto do_truncate = args.getBool("Truncate",false);
+    auto doRelCutoff = args.getBool("DoRelCutoff",false);
+    auto absoluteCutoff = args.getBool("AbsoluteCutoff",false);
+    auto itagset = getTagSet(args,"Tags","Link");
+
+    auto i1 = H.inds().front();
+    auto i2 = H.inds().back();
+    auto ai = (primeLevel(i1) < primeLevel(i2)) ? i1 : i2;
+    auto pdiff = std::abs(primeLevel(i1)-primeLevel(i2));
+    // the matrix of a block is M = S (stored, column-major) when ai is the first index and M = S^T = conj(S) otherwise
+    // (GetBlocks::transpose, decomp.h:443-450); eigenvectors of conj(S) are the conjugates of those of S
+    const bool transposed = !(ai == H.inds().front());
+    auto const& is = H.inds();
+    const auto nb = long(d.offsets.size());
+    if(nb == 0) Error("No blocks in IQTensor svd");
+
+    std::vector<int64_t> off(nb);
+    std::vector<int32_t> nn(nb);
+    std::vector<long> sa(nb); // sector of ai
+    for(auto b : range(nb))
+        {
+        auto const& io = d.offsets[b];
+        auto r = is[0].blocksize0(io.block[0]), c = is[1].blocksize0(io.block[1]);
+        if(r != c) Error("diag_hermitian (QDenseGPU): non-square block");
+        off[b] = io.offset;
+        nn[b] = int32_t(r);
+        sa[b] = transposed ? io.block[1] : io.block[0];
+        }
+    // blocks too small to pay a cuSOLVER launch sequence are diagonalised by the reference's own diagHermitian on the host
+    // while the device works on the others
+    static const long dev_min = [] { auto* e = std::getenv("ITB_EIGH_DEVICE_MIN_N"); return e ? std::atol(e) : 96l; }();
+    const bool dev_ready = itb_solver_ready() != 0;
+    std::vector<long> dev_blocks, host_blocks, dev_slot(nb,-1);
+    for(auto b : range(nb))
+        {
+        if(dev_ready && nn[b] >= dev_min) { dev_slot[b] = long(dev_blocks.size()); dev_blocks.push_back(b); }
+        else host_blocks.push_back(b);
+        }
+    Lap lap;
+    auto& prof = eighProf();
+    auto mark = [&](int slot) { auto n = std::chrono::steady_clock::now(); prof.secs[slot] += std::chrono::duration<double>(n-lap.t).count(); lap.t = n; };
+    prof.calls += 1; prof.dev_blocks += long(dev_blocks.size()); prof.host_blocks += long(host_blocks.size());
+    auto hbuf = std::vector<std::vector<T>>(host_blocks.size());
+    for(auto i : range(host_blocks.size()))
+        {
+        auto b = host_blocks[i];
+        hbuf[i].resize(size_t(nn[b])*nn[b]);
+        checkSvd(itb_memcpy_d2h(gpu::context(),hbuf[i].data(),static_cast<const char*>(d.buf.data())+size_t(off[b])*sizeof(T),hbuf[i].size()*sizeof(T)),"eigh block download");
+        }
+    EighGuard batch;
+    if(!dev_blocks.empty())
+        {
+        std::vector<int64_t> o; std::vector<int32_t> n2;
+        for(auto b : dev_blocks) { o.push_back(off[b]); n2.push_back(nn[b]); }
+        checkSvd(itb_eigh_batch_run(gpu::context(),dtypeFor<T>(),int64_t(dev_blocks.size()),o.data(),n2.data(),d.buf.data(),1,&batch.b),"eigh batch");
+        }
+    mark(0);
+    std::vector<long> first(nb+1,0);
+    for(auto b : range(nb)) first[b+1] = first[b] + nn[b];
+    auto eig = std::vector<Real>(size_t(first[nb])); // per block, largest first
+    auto Uh = std::vector<Mat<T>>(nb);
+    for(auto i : range(host_blocks.size()))
+        {
+        auto b = host_blocks[i];
+        auto S = makeMatRef(hbuf[i].data(),hbuf[i].size(),nn[b],nn[b]);
+        Vector dv;
+        // the reference's call is diagHermitian(M,UU,d); conjugate(UU) with M = S or transpose(S): done on S here, the
+        // conjugations are applied when the columns are placed (below), identically for host and device blocks
+        diagHermitian(S,Uh[b],dv);
+        for(auto j : range(dv.size())) eig[first[b]+j] = dv(j);
+        }
+    mark(1);
+    if(batch.b)
+        {
+        long ndev = 0;
+        for(auto b : dev_blocks) ndev += nn[b];
+        auto w = std::vector<Real>(size_t(ndev));
+        checkSvd(itb_eigh_batch_values(batch.b,w.data()),"eigh values");
+        long p = 0;
+        for(auto b : dev_blocks)
+            for(auto i : range(nn[b])) eig[first[b]+i] = -w[p++]; // ascending eigenvalues of -block
+        }
+    mark(2);
+
+    auto alleig = eig;
+    std::sort(alleig.begin(),alleig.end(),std::greater<Real>{});
+    auto probs = Vector(std::move(alleig),VecRange{eig.size()});
+    long m = long(probs.size());
+    Real truncerr = 0, docut_lower = -1, docut_upper = -1;
+    int ndegen = 0;
+    if(do_truncate)
+        {
+        std::tie(truncerr,docut_lower,docut_upper,ndegen) = truncate(probs,maxdim,mindim,cutoff,absoluteCutoff,doRelCutoff,args);
+        m = long(probs.size());
+        }
+    if(m > maxdim) Error("m > maxdim");
+
+    // how many eigenvectors each block keeps (hermitian.cc:325-370)
+    auto kept = std::vector<long>(nb,0);
+    long total_m = 0;
+    for(auto b : range(nb))
+        {
+        auto const* e = eig.data()+first[b];
+        long this_m = 0;
+        if(do_truncate)
+            {
+            while(this_m < nn[b] && total_m < m && e[this_m] > docut_upper) { ++this_m; ++total_m; }
+            while(ndegen > 0 && this_m < nn[b] && total_m < m && e[this_m] > docut_lower) { ++this_m; ++total_m; --ndegen; }
+            }
+        else { this_m = nn[b]; total_m += this_m; }
+        kept[b] = this_m;
+        }
+    Index::qnstorage iq;
+    for(auto b : range(nb)) if(kept[b] > 0) iq.emplace_back(qn(ai,1+sa[b]),kept[b]);
+    bool nothing = iq.empty();
+    if(nothing) { iq.emplace_back(qn(ai,1+sa[0]),1l); }
+    auto dI = Index(std::move(iq),-ai.dir(),itagset);
+    auto Uis = IndexSet(dag(ai),dag(dI));
+    auto Dis = IndexSet(prime(dI,pdiff),dag(dI));
+    BlockOffsets Uoff;
+    long Usize = 0;
+    std::tie(Uoff,Usize) = getBlockOffsets(Uis,QN());
+    auto Ug = QDenseGPU<T>(Uoff,size_t(Usize));
+    Ug.buf.zero();
+    auto Dstore = QDiagReal(Dis);
+    long n = 0;
+    for(auto b : range(nb))
+        {
+        if(kept[b] == 0) continue;
+        auto k = int32_t(kept[b]);
+        auto ublk = Block(2); ublk[0] = sa[b]; ublk[1] = n;
+        auto uo = offsetOf(Ug.offsets,ublk);
+        if(uo < 0) Error("diag_hermitian (QDenseGPU): block of U missing");
+        auto* udst = static_cast<char*>(Ug.buf.data()) + size_t(uo)*sizeof(T);
+        // stored U block = conj(eigenvectors of M): M = S -> conj(W_S); M = S^T = conj(S) -> conj(conj(W_S)) = W_S
+        if(dev_slot[b] >= 0) checkSvd(itb_eigh_batch_copy_vectors(batch.b,dev_slot[b],k,udst,transposed ? 0 : 1),"eigh copy U");
+        else
+            {
+            auto& W = Uh[b];
+            if(isCplx(W) && !transposed) conjugate(W);
+            checkSvd(itb_memcpy_h2d(gpu::context(),udst,W.data(),size_t(nn[b])*k*sizeof(T)),"eigh upload U");
+            }
+        auto dblk = Block(2); dblk[0] = n; dblk[1] = n;
+        auto pD = getBlock(Dstore,Dis,dblk);
+        auto const* e = eig.data()+first[b];
+        for(auto i : range(k)) pD.data()[i] = e[i];
+        ++n;
+        }
+    if(Uh.size()) gpu::synchronize(); // the host eigenvector matrices must outlive their uploads
+    mark(3);
+    U = ITensor(Uis,std::move(Ug));
+    D = ITensor(Dis,std::move(Dstore),H.scale());
+    if(H.scale().isTooBigForReal()) println("scale too big, omitting from reported eigenvalues");
+    else probs *= H.scale().real0();
+    return Spectrum(std::move(probs),{"Truncerr",truncerr});
+    }
+
+struct EighDispatch
+    {
+    ITensor const& H; ITensor& U; ITensor& D; Args const& args; Spectrum& spec; bool& done;
+    void operator()(QDenseGPUReal const& d) { spec = eighBlocksGPU<Real>(H,d,U,D,args); done = true; }
+    void operator()(QDenseGPUCplx const& d) { spec = eighBlocksGPU<Cplx>(H,d,U,D,args); done = true; }
+    template<typename S> void operator()(S const&) { }
+    };
+
 // find out whether A is one of the HBM-resident block-sparse storage types
 struct SvdDispatch
     {
@@ -399,6 +596,16 @@ diag_hermitian_host(ITensor H, ITensor & U, ITensor & D, Args const& args);
 Spectrum
 diag_hermitian(ITensor H, ITensor & U, ITensor & D, Args const& args)
     {
+    static const bool device_eigh = [] { auto* e = std::getenv("ITB_EIGH_DEVICE"); return !(e && std::atoi(e) == 0); }();
+    if(device_eigh && H.store() && onGPU(H) && hasQNs(H) && H.order() == 2 && !args.getBool("ComputeQNs",false) && !args.getBool("ShowEigs",false))
+        {
+        // block-sparse, HBM-resident: batched device eigh, U born in HBM (sign handling as diagHImpl, hermitian.cc:209)
+        if(H.scale().sign() < 0) H.scaleTo(H.scale()*(-1));
+        Spectrum spec;
+        bool done = false;
+        applyFunc(EighDispatch{H,U,D,args,spec,done},H.store());
+        if(done) return spec;
+        }
     if(H.store() && onGPU(H))
         {
         // dense: no raw host view of GPU storage exists, diagonalise a host copy; block-sparse: the reference's loop

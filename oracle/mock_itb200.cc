@@ -350,6 +350,10 @@ int itb_svd_batch_values(itb_svd_batch*, double*) { return ITB_ERR_UNSUPPORTED; 
 int itb_svd_batch_copy_u(itb_svd_batch*, int64_t, int32_t, void*) { return ITB_ERR_UNSUPPORTED; }
 int itb_svd_batch_copy_v(itb_svd_batch*, int64_t, int32_t, void*, int) { return ITB_ERR_UNSUPPORTED; }
 int itb_svd_batch_destroy(itb_svd_batch*) { return ITB_OK; }
+int itb_eigh_batch_run(itb_ctx*, int32_t, int64_t, const int64_t*, const int32_t*, const void*, int, itb_eigh_batch**) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
+int itb_eigh_batch_values(itb_eigh_batch*, double*) { return ITB_ERR_UNSUPPORTED; }
+int itb_eigh_batch_copy_vectors(itb_eigh_batch*, int64_t, int32_t, void*, int) { return ITB_ERR_UNSUPPORTED; }
+int itb_eigh_batch_destroy(itb_eigh_batch*) { return ITB_OK; }
 double itb_svd_batch_stats(int64_t out[3]) { if (out) out[0] = out[1] = out[2] = 0; return 0.0; }
 int itb_peak_fp64(itb_ctx*, int, int, double* t) { *t = 0; return ITB_ERR_UNSUPPORTED; }
 int itb_ctx_set_profile(itb_ctx*, int) { return ITB_OK; }

@@ -112,3 +112,56 @@ def test_svd_batch_device_resident(ctx, cplx):
             torch.cuda.synchronize()
             assert np.array_equal(V1.cpu().numpy().view(dt), V0.cpu().numpy().view(dt).conj())
     check(lib().itb_svd_batch_destroy(h))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_eigh_batch_device_resident(ctx, cplx):
+    """itb_eigh_batch_*: the diagonal blocks of an order-2 block-sparse Hermitian tensor diagonalised from its device
+    buffer (diagHImpl's QN loop, hermitian.cc:231-257, on QDenseGPU — the density-matrix branch of svdBond). With
+    negate=1 the batch diagonalises -A_b, so -w is the reference's largest-first order (tensor/algs_impl.h:123-137)."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    dt = np.complex128 if cplx else np.float64
+    sizes = [130, 1, 7, 96, 257, 40]
+    blocks = []
+    for i, n in enumerate(sizes):
+        a = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0)
+        a = a @ a.conj().T / n                      # positive semi-definite like a density matrix
+        if i == 5:
+            a = a[:, :10] @ a[:, :10].conj().T      # rank 10: degenerate zero eigenvalues
+        blocks.append(np.asfortranarray(((a + a.conj().T) / 2).astype(dt)))
+    flat = np.concatenate([b.reshape(-1, order="F") for b in blocks])
+    d = torch.from_numpy(flat.view(np.float64)).to(ctx.device)
+    before = d.clone()
+    off = np.cumsum([0] + [n * n for n in sizes[:-1]]).astype(np.int64)
+    nn = np.array(sizes, np.int32)
+    h = C.c_void_p()
+    check(lib().itb_eigh_batch_run(ctx.handle, 1 if cplx else 0, len(sizes), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   nn.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(d.data_ptr()), 1, C.byref(h)))
+    w = np.zeros(sum(sizes))
+    check(lib().itb_eigh_batch_values(h, w.ctypes.data_as(C.POINTER(C.c_double))))
+    assert torch.equal(d, before)  # the input tensor is not modified
+    cs = 2 if cplx else 1
+    p = 0
+    for b, n in enumerate(sizes):
+        ev = -w[p:p + n]            # largest first
+        p += n
+        ref = np.linalg.eigvalsh(blocks[b])[::-1]
+        assert np.all(np.diff(ev) <= 1e-13 * max(ref[0], 1e-300))
+        assert np.allclose(ev, ref, rtol=0, atol=1e-13 * max(ref[0], 1.0)), n
+        for k in (n, max(1, n // 3)):
+            U = torch.zeros(n * k * cs, dtype=torch.float64, device=ctx.device)
+            check(lib().itb_eigh_batch_copy_vectors(h, b, k, C.c_void_p(U.data_ptr()), 0))
+            torch.cuda.synchronize()
+            Uh = U.cpu().numpy().view(dt).reshape(n, k, order="F")
+            assert np.allclose(Uh.conj().T @ Uh, np.eye(k), atol=1e-11)
+            assert np.abs(blocks[b] @ Uh - Uh * ev[:k]).max() <= 1e-11 * max(ref[0], 1.0)   # A u = lambda u
+        if cplx:
+            U1 = torch.zeros(n * n * cs, dtype=torch.float64, device=ctx.device)
+            U0 = torch.zeros(n * n * cs, dtype=torch.float64, device=ctx.device)
+            check(lib().itb_eigh_batch_copy_vectors(h, b, n, C.c_void_p(U0.data_ptr()), 0))
+            check(lib().itb_eigh_batch_copy_vectors(h, b, n, C.c_void_p(U1.data_ptr()), 1))
+            torch.cuda.synchronize()
+            assert np.array_equal(U1.cpu().numpy().view(dt), U0.cpu().numpy().view(dt).conj())
+    check(lib().itb_eigh_batch_destroy(h))
