@@ -375,7 +375,8 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     const size_t o_dot = pk.add(P->dots.data(), P->dots.size() * sizeof(ItbDot));
     const size_t o_dout = pk.add(P->dot_outs.data(), P->dot_outs.size() * sizeof(ItbDotOut));
     const size_t partial_bytes = ((size_t)P->ndot_slots * 4 * sizeof(double) + 255) & ~(size_t)255;
-    const size_t extra = partial_bytes + 256;
+    const size_t counter_bytes = ((16 + P->splits.size()) * sizeof(int) + 255) & ~(size_t)255; // queue head, finished CTAs, per-cut-tile arrivals
+    const size_t extra = partial_bytes + counter_bytes;
     int rc = upload(c, pk, extra, dev);
     if (rc != ITB_OK) { delete dev; return rc; }
     char* b = (char*)dev->base;
@@ -397,7 +398,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     dev->dot_outs = (const ItbDotOut*)(b + o_dout);
     dev->dot_partial = (double*)(b + pk.total);
     dev->counters = (int*)(b + pk.total + partial_bytes);
-    CUDA_TRY(cudaMemsetAsync(dev->counters, 0, 256, c->stream)); // queue head + finished-CTA count of the tile kernel
+    CUDA_TRY(cudaMemsetAsync(dev->counters, 0, counter_bytes, c->stream)); // all rearmed by the kernel itself after every launch
     P->dev = dev;
     P->dev_ctx = c;
     return ITB_OK;
@@ -480,7 +481,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
             CUDA_TRY(cudaMemcpyAsync(c->h_item_cycles.data(), c->d_cta_cycles + 1024, 4 * P->tiles.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
         }
         PROF_END(0);
-        c->launches += P->splits.empty() ? 1 : 2;
+        c->launches += 1;
     }
     if (fork) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     else { rc = launch_side(); if (rc != ITB_OK) return rc; }

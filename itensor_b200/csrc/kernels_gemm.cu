@@ -94,7 +94,7 @@ struct QItem {
 };
 static_assert(sizeof(ItbQItem) == 160 && offsetof(QItem, item) == 160, "item record layout");
 constexpr size_t G_SMEM = (size_t)(2 * G_STAGES * G_STAGE_ELEMS) * 8 + (size_t)(2 * G_MAXT) * 8 + (size_t)(2 * G_KT) * 4 + 2 * G_STAGES * 8 +
-                          2 * G_QSLOTS * 8 + G_QSLOTS * sizeof(QItem) + 16;
+                          2 * G_QSLOTS * 8 + G_QSLOTS * sizeof(QItem) + 32;
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -185,7 +185,8 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
 template <int BM, int BN, bool PROF>
 __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __restrict__ pairs,
                                              double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
-                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute, long long* rec) {
+                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute, long long* rec,
+                                             const ItbSplitOut* __restrict__ splits, int* __restrict__ split_cnt, volatile int* last_flag) {
     constexpr int BK = G_BK;
     constexpr int WM = BM / 4, WN = BN / 4, FM = WM / 8, FN = WN / 8;
     static_assert(FM >= 1 && FN >= 1, "tile too small for a 4x4 warp grid");
@@ -219,7 +220,7 @@ __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __r
         if (c0 >= c1) continue;
         // sign of the A' = [[Ar,-Ai],[Ai,Ar]] expansion, applied when the fragment is read (row even, col odd)
         const int sgn = ((flags & ITB_PF_CCA) && !(g & 1) && (t4 & 1)) ? (int)0x80000000 : 0;
-        if (fmv == 0 || fnv == 0 || dbg_nocompute) { // nothing of this warp's sub-tile is inside the C block: keep the ring moving
+        if (fmv == 0 || fnv == 0 || (dbg_nocompute & 1)) { // nothing of this warp's sub-tile is inside the C block: keep the ring moving
             // (dbg_nocompute: producer-rate measurement, tools/tile_calib.py --nocompute; results are garbage)
             for (int kc = c0; kc < c1; ++kc) {
                 mbar_wait(&full[ps.stage], ps.phase);
@@ -276,13 +277,61 @@ __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __r
             }
         }
     } else {
-        double* __restrict__ W = ws + (int64_t)ws_slot * ITB_WS_TILE + (wm0 + g) + BM * (wn0 + 2 * t4);
+        // piece of a cut tile: park the partial sums in this piece's workspace slot, then count arrivals; whoever arrives
+        // LAST adds all slots of the tile in piece order (fixed order -> bitwise reproducible whatever the arrival order
+        // was) and writes C. No second kernel, and the partials are still in L2 when they are read back.
+        const int64_t woff = (wm0 + g) + BM * (wn0 + 2 * t4);
+        double* __restrict__ W = ws + (int64_t)ws_slot * ITB_WS_TILE + woff;
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
             for (int j = 0; j < FN; ++j)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) W[i * 8 + BM * (j * 8 + h)] = acc[i][j][h];
+        __threadfence();                                                  // this thread's partials are visible device-wide ...
+        asm volatile("bar.sync 2, %0;" ::"n"(G_NCONS) : "memory");       // ... and so are those of all consumer threads
+        const ItbSplitOut so = splits[qi.tile.split];
+        if (threadIdx.x == 0) {
+            const int old = atomicAdd(split_cnt + qi.tile.split, 1);
+            const int last = old == so.nsplit - 1;
+            if (last) split_cnt[qi.tile.split] = 0;                        // rearm for the next launch (everyone has arrived)
+            *last_flag = last;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(G_NCONS) : "memory");
+        if (*last_flag) {
+            __threadfence();
+            const double* __restrict__ W0 = ws + (int64_t)so.ws_slot0 * ITB_WS_TILE + woff;
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) acc[i][j][h] = 0.0;
+            for (int q = 0; q < so.nsplit; ++q) {
+                const double* __restrict__ Wq = W0 + (int64_t)q * ITB_WS_TILE;
+#pragma unroll
+                for (int i = 0; i < FM; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) acc[i][j][h] += __ldcg(Wq + i * 8 + BM * (j * 8 + h)); // L2 (never a stale L1 line)
+            }
+            const int64_t cms = qi.cb.c_ms, cns = qi.cb.c_ns;
+            const int nmask = qi.cb.c_nmask, nshift = qi.cb.c_nshift;
+            double* __restrict__ Cp = C + qi.cb.c_off;
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int m = m0 + wm0 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < FN; ++j) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int n = n0 + wn0 + j * 8 + 2 * t4 + h;
+                        if (m < M && n < N) Cp[(int64_t)m * cms + (n & nmask) + (int64_t)(n >> nshift) * cns] = acc[i][j][h];
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -362,7 +411,7 @@ template <int BM, int BN, bool AKF, bool BKF>
 __device__ __forceinline__ void produce_pair(const ItbPair* __restrict__ pr, int c0, int c1, const double* __restrict__ Ap,
                                              const double* __restrict__ Bp, double* As, double* Bs, const int64_t* offM_s,
                                              const int64_t* offN_s, int* ktabA, int* ktabB, uint64_t* full, uint64_t* empty,
-                                             PipeState& ps) {
+                                             PipeState& ps, int dbg) {
     constexpr int BK = G_BK, NP = G_NPROD;
     const int pt = threadIdx.x - G_NCONS;
     const int K = pr->K;
@@ -387,9 +436,11 @@ __device__ __forceinline__ void produce_pair(const ItbPair* __restrict__ pr, int
             const int* ta = ktabA + (kc - kb) * BK;
             const int* tb = ktabB + (kc - kb) * BK;
             const int kleft = K - kc * BK;
-            if (cca) ga.template issue<true>(as, ta, kleft);
-            else ga.template issue<false>(as, ta, kleft);
-            gb.template issue<false>(bs, tb, kleft);
+            if (!(dbg & 2)) { // (ITB_DEBUG_NOCOMPUTE=2: no operand loads at all — the consumers' own rate; results are garbage)
+                if (cca) ga.template issue<true>(as, ta, kleft);
+                else ga.template issue<false>(as, ta, kleft);
+                gb.template issue<false>(bs, tb, kleft);
+            }
             mbar_arrive_cp_async(&full[ps.stage]);
             ps.advance();
         }
@@ -400,7 +451,7 @@ template <int BM, int BN>
 __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __restrict__ pairs,
                                              const double* __restrict__ A, const double* __restrict__ B, double* As, double* Bs,
                                              int64_t* offM_s, int64_t* offN_s, int* ktabA, int* ktabB, uint64_t* full,
-                                             uint64_t* empty, PipeState& ps) {
+                                             uint64_t* empty, PipeState& ps, int dbg) {
     constexpr int BK = G_BK, NP = G_NPROD;
     const int pt = threadIdx.x - G_NCONS; // 0..G_NPROD-1
     const int M = qi.cb.M, N = qi.cb.N;
@@ -430,10 +481,10 @@ __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __r
         const double* __restrict__ Ap = A + pr->a_off;
         const double* __restrict__ Bp = B + pr->b_off;
         switch (flags & (ITB_PF_A_KFAST | ITB_PF_B_KFAST)) {
-            case 0: produce_pair<BM, BN, false, false>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
-            case ITB_PF_A_KFAST: produce_pair<BM, BN, true, false>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
-            case ITB_PF_B_KFAST: produce_pair<BM, BN, false, true>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
-            default: produce_pair<BM, BN, true, true>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps); break;
+            case 0: produce_pair<BM, BN, false, false>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps, dbg); break;
+            case ITB_PF_A_KFAST: produce_pair<BM, BN, true, false>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps, dbg); break;
+            case ITB_PF_B_KFAST: produce_pair<BM, BN, false, true>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps, dbg); break;
+            default: produce_pair<BM, BN, true, true>(pr, c0, c1, Ap, Bp, As, Bs, offM_s, offN_s, ktabA, ktabB, full, empty, ps, dbg); break;
         }
     }
 }
@@ -450,7 +501,8 @@ __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __r
 // records from shared memory. An index >= n_items is the stop sentinel. The last CTA to stop rearms the queue head.
 template <bool PROF>
 __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __restrict__ items, int n_items, int* __restrict__ queue,
-                                                            const ItbPair* __restrict__ pairs,
+                                                            const ItbPair* __restrict__ pairs, const ItbSplitOut* __restrict__ splits,
+                                                            int* __restrict__ split_cnt,
                                                             const double* __restrict__ A, const double* __restrict__ B,
                                                             double* __restrict__ C, double* __restrict__ ws,
                                                             long long* __restrict__ cta_cycles, int dbg_nocompute) {
@@ -467,6 +519,7 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
     uint64_t* q_full = empty + G_STAGES;
     uint64_t* q_empty = q_full + G_QSLOTS;
     QItem* q_item = reinterpret_cast<QItem*>(q_empty + G_QSLOTS);
+    volatile int* last_flag = reinterpret_cast<volatile int*>(q_item + G_QSLOTS); // split-K: "this CTA arrived last" broadcast
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], G_NPROD);     // one cp.async-completion arrive per producer thread
@@ -531,13 +584,13 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
         long long* rec = (PROF && cta_cycles && threadIdx.x == 0) ? cta_cycles + 1024 + 4 * (long long)qi.item : nullptr;
         if (PROF && rec) { rec[0] = blockIdx.x; rec[1] = clock64() - t_begin; }
         if (producer) {
-            if (cfg == 0) produce_tile<128, 128>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
-            else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
-            else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
+            if (cfg == 0) produce_tile<128, 128>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
+            else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
+            else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
         } else {
-            if (cfg == 0) consume_tile<128, 128, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
-            else if (cfg == 1) consume_tile<64, 64, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
-            else consume_tile<32, 32, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
+            if (cfg == 0) consume_tile<128, 128, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec, splits, split_cnt, last_flag);
+            else if (cfg == 1) consume_tile<64, 64, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec, splits, split_cnt, last_flag);
+            else consume_tile<32, 32, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec, splits, split_cnt, last_flag);
             if (PROF && rec) { rec[2] -= t_begin; rec[3] = clock64() - t_begin; }
         }
         __syncwarp();
@@ -1014,15 +1067,11 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (cta_cycles) bsc_gemm_kernel<true><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, A, B, C, ws, cta_cycles, nocompute);
-    else bsc_gemm_kernel<false><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, A, B, C, ws, nullptr, nocompute);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (nsouts > 0) {
-        bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C);
-        e = cudaGetLastError();
-    }
-    return e;
+    // (queue[0]: head, queue[1]: finished CTAs, queue + 16: one arrival counter per cut tile)
+    if (cta_cycles) bsc_gemm_kernel<true><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, souts, queue + 16, A, B, C, ws, cta_cycles, nocompute);
+    else bsc_gemm_kernel<false><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, souts, queue + 16, A, B, C, ws, nullptr, nocompute);
+    (void)nsouts; (void)cblks;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,

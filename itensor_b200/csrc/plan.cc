@@ -709,8 +709,9 @@ int build_contract_tables(itb_contract_plan& P) {
     // boundaries into pieces of (remaining work / grid width), never shorter than kMinPiece chunks, so the last CTAs
     // finish within one small piece of each other. The cycle model only sets piece sizes — an error in it costs
     // balance in proportion to the smallest pieces, not to the whole share of a CTA as with a static partition.
-    // A cut tile writes partial sums to workspace slots which bsc_splitk_reduce_kernel adds in piece order
-    // (deterministic, independent of which CTA ran which piece).
+    // A cut tile writes partial sums to workspace slots; the piece that ARRIVES LAST (a per-tile counter) adds the slots in
+    // piece order and writes C (kernels_gemm.cu): deterministic, independent of which CTA ran which piece and of the
+    // arrival order, and the partials are read back from L2 while they are still there.
     {
         struct Proto { int32_t c, m0, n0, f; int64_t nch; double w; int np; };
         std::vector<Proto> protos;
@@ -744,13 +745,13 @@ int build_contract_tables(itb_contract_plan& P) {
             int64_t npieces = 1;
             if (cost > 1.25 * want) npieces = std::min<int64_t>((int64_t)std::ceil(cost / want), std::max<int64_t>(1, t.nch / kMinPiece));
             if (npieces <= 1) {
-                P.tiles.push_back({t.c, t.m0, t.n0, t.f, 0, (int32_t)t.nch, -1, 0});
+                P.tiles.push_back({t.c, t.m0, t.n0, t.f, 0, (int32_t)t.nch, -1, -1});
                 item_cost.push_back(cost);
             } else {
                 P.splits.push_back({t.c, t.m0, t.n0, t.f, (int32_t)P.ws_slots, (int32_t)npieces, {0, 0}});
                 for (int64_t q = 0; q < npieces; ++q) { // chunk ranges as equal as integers allow
                     const int64_t c0 = t.nch * q / npieces, c1 = t.nch * (q + 1) / npieces;
-                    P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)c1, (int32_t)P.ws_slots++, 0});
+                    P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)c1, (int32_t)P.ws_slots++, (int32_t)P.splits.size() - 1});
                     item_cost.push_back((double)(c1 - c0) * t.w + ovh);
                 }
             }

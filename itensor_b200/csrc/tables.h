@@ -50,7 +50,7 @@ struct ItbTile { // work item of the persistent DMMA tile kernel
     int32_t chunk_begin; // range of BK-chunks of the C block's concatenated K loop (split-K)
     int32_t chunk_end;
     int32_t ws_slot;     // -1: write C directly; else partial tile goes to workspace slot ws_slot
-    int32_t pad_;
+    int32_t split;       // index of this tile's ItbSplitOut record (arrival counter, first slot, piece count); -1 if uncut
 };
 // Device record of one queue item: the tile plus everything the kernel needs to know about its C block and the first
 // ITB_QPAIRS block pairs (K, flags), flattened by the host so that fetching an item is ONE 160-byte read instead of a

@@ -383,13 +383,17 @@ template<typename T>
 Spectrum
 eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args const& args)
     {
-    auto cutoff = args.getReal("Cutoff",MIN_CUT);
-    auto maxdim = args.getInt("MaxDim",MAX_DIM);
-    auto mindim = args.getInt("MinDim",1);
-    auto do_truncate = args.getBool("Truncate",false);
-    auto doRelCutoff = args.getBool("DoRelCutoff",false);
+    // argument defaults exactly as diagHImpl (hermitian.cc:60-92)
+    auto origdim = dim(H.inds().front());
+    auto cutoff = args.getReal("Cutoff",0.);
+    auto maxdim = args.getInt("MaxDim",args.getInt("Maxm",origdim));
+    auto mindim = args.getInt("MinDim",args.getInt("Minm",1));
+    auto def_do_trunc = args.defined("Cutoff") || args.defined("MaxDim") || args.defined("Maxm");
+    auto do_truncate = args.getBool("Truncate",def_do_trunc);
+    auto doRelCutoff = args.getBool("DoRelCutoff",true);
     auto absoluteCutoff = args.getBool("AbsoluteCutoff",false);
     auto itagset = getTagSet(args,"Tags","Link");
+    if(!do_truncate) maxdim = origdim;
 
     auto i1 = H.inds().front();
     auto i2 = H.inds().back();
@@ -565,8 +569,33 @@ struct SvdDispatch
 
 } // namespace
 
+// ITB_SPECTRUM_LOG=<file>: every svdOrd2 (host or device route) appends one JSON line with its truncation error and kept
+// spectrum: the per-scale / per-bond comparison points of the parity runs (TRG: two factorisations per scale)
+static void
+logSpectrum(Spectrum const& spec)
+    {
+    static FILE* f = [] { auto* e = std::getenv("ITB_SPECTRUM_LOG"); return e ? std::fopen(e,"w") : nullptr; }();
+    if(!f) return;
+    std::fprintf(f,"{\"truncerr\": %.17g, \"eigs\": [",spec.truncerr());
+    bool first = true;
+    for(auto const& e : spec.eigsKept()) { std::fprintf(f,"%s%.17g",first ? "" : ",",e); first = false; }
+    std::fprintf(f,"]}\n");
+    std::fflush(f);
+    }
+
+static Spectrum
+svdOrd2Dispatch(ITensor const& A, Index const& uI, Index const& vI, ITensor & U, ITensor & D, ITensor & V, Args args);
+
 Spectrum
 svdOrd2(ITensor const& A, Index const& uI, Index const& vI, ITensor & U, ITensor & D, ITensor & V, Args args)
+    {
+    auto spec = svdOrd2Dispatch(A,uI,vI,U,D,V,args);
+    logSpectrum(spec);
+    return spec;
+    }
+
+static Spectrum
+svdOrd2Dispatch(ITensor const& A, Index const& uI, Index const& vI, ITensor & U, ITensor & D, ITensor & V, Args args)
     {
     static const bool device_svd = [] { auto* e = std::getenv("ITB_SVD_DEVICE"); return !(e && std::atoi(e) == 0); }();
     const bool plain = !args.getBool("ComputeQNs",false) && !args.getBool("ShowEigs",false);
