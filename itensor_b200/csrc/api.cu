@@ -13,7 +13,8 @@
 #include "plan.h"
 
 namespace itb {
-cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const int32_t* cta_begin, int n_static_ctas, int grid,
+                        const ItbSplitOut* souts, int nsouts,
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles,
                         cudaStream_t st);
@@ -43,6 +44,7 @@ struct DeviceTables {
     const ItbPair* pairs = nullptr;
     const ItbCBlk* cblks = nullptr;
     const ItbQItem* qitems = nullptr;
+    const int32_t* cta_begin = nullptr;
     const ItbSplitOut* splits = nullptr;
     const ItbRowGroup* rgroups = nullptr;
     const ItbRgIn* rg_in = nullptr;
@@ -364,6 +366,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     const size_t o_cblk = pk.add(P->cblks.data(), P->cblks.size() * sizeof(ItbCBlk));
     const size_t o_tiles = pk.add(P->qitems.data(), P->qitems.size() * sizeof(ItbQItem));
     const size_t o_splits = pk.add(P->splits.data(), P->splits.size() * sizeof(ItbSplitOut));
+    const size_t o_cta = pk.add(P->cta_begin.data(), P->cta_begin.size() * sizeof(int32_t));
     const size_t o_rg = pk.add(P->rgroups.data(), P->rgroups.size() * sizeof(ItbRowGroup));
     const size_t o_rgi = pk.add(P->rg_in.data(), P->rg_in.size() * sizeof(ItbRgIn));
     const size_t o_rgo = pk.add(P->rg_out.data(), P->rg_out.size() * sizeof(int64_t));
@@ -383,6 +386,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     dev->pairs = (const ItbPair*)(b + o_pairs);
     dev->cblks = (const ItbCBlk*)(b + o_cblk);
     dev->qitems = (const ItbQItem*)(b + o_tiles);
+    dev->cta_begin = (const int32_t*)(b + o_cta);
     dev->splits = (const ItbSplitOut*)(b + o_splits);
     dev->rgroups = (const ItbRowGroup*)(b + o_rg);
     dev->rg_in = (const ItbRgIn*)(b + o_rgi);
@@ -465,14 +469,17 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
         PROF_BEGIN(0);
         // persistent grid, one CTA per SM (fewer when the queue is shorter than that); items are pulled from the
         // in-order queue through the head counter (rearmed by the kernel itself)
-        const int grid = (int)std::min<size_t>((size_t)c->num_sms, P->tiles.size());
+        // hybrid plans carry one static range per CTA of the planner's grid width: launch exactly that many CTAs
+        const int n_static = (int)P->cta_begin.size() - 2;
+        const bool has_static = n_static > 0 && P->cta_begin[n_static] > 0;
+        const int grid = has_static ? n_static : (int)std::min<size_t>((size_t)c->num_sms, P->tiles.size());
         const size_t prof_words = 1024 + 4 * P->tiles.size(); // per-CTA spans, then {cta, start, K-loop end, end} per item
         if (c->profile && c->cta_cycles_words < prof_words) {
             if (c->d_cta_cycles) { SIDE_TRY(cudaStreamSynchronize(c->stream)); cudaFree(c->d_cta_cycles); c->d_cta_cycles = nullptr; }
             SIDE_TRY(cudaMalloc(&c->d_cta_cycles, prof_words * sizeof(long long)));
             c->cta_cycles_words = prof_words;
         }
-        SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
+        SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, d->cta_begin, n_static, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
             c->h_cta_cycles.assign(grid, 0);
@@ -481,7 +488,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
             CUDA_TRY(cudaMemcpyAsync(c->h_item_cycles.data(), c->d_cta_cycles + 1024, 4 * P->tiles.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
         }
         PROF_END(0);
-        c->launches += 1;
+        c->launches += P->splits.empty() ? 1 : 2;
     }
     if (fork) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     else { rc = launch_side(); if (rc != ITB_OK) return rc; }

@@ -185,8 +185,7 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
 template <int BM, int BN, bool PROF>
 __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __restrict__ pairs,
                                              double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
-                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute, long long* rec,
-                                             const ItbSplitOut* __restrict__ splits, int* __restrict__ split_cnt, volatile int* last_flag) {
+                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute, long long* rec) {
     constexpr int BK = G_BK;
     constexpr int WM = BM / 4, WN = BN / 4, FM = WM / 8, FN = WN / 8;
     static_assert(FM >= 1 && FN >= 1, "tile too small for a 4x4 warp grid");
@@ -277,61 +276,17 @@ __device__ __forceinline__ void consume_tile(const QItem& qi, const ItbPair* __r
             }
         }
     } else {
-        // piece of a cut tile: park the partial sums in this piece's workspace slot, then count arrivals; whoever arrives
-        // LAST adds all slots of the tile in piece order (fixed order -> bitwise reproducible whatever the arrival order
-        // was) and writes C. No second kernel, and the partials are still in L2 when they are read back.
-        const int64_t woff = (wm0 + g) + BM * (wn0 + 2 * t4);
-        double* __restrict__ W = ws + (int64_t)ws_slot * ITB_WS_TILE + woff;
+        // piece of a cut tile: park the partial sums in this piece's workspace slot; bsc_splitk_reduce_kernel adds the slots of
+        // a tile in piece order afterwards. (Letting the LAST-ARRIVING piece do that sum inside this kernel was measured and
+        // dropped: the fences + two consumer-wide barriers cost ~4000 cycles per piece and the sums of the final tiles land
+        // on whichever CTA finishes last — 1.52 ms instead of 1.38 ms per H_eff*phi.)
+        double* __restrict__ W = ws + (int64_t)ws_slot * ITB_WS_TILE + (wm0 + g) + BM * (wn0 + 2 * t4);
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
             for (int j = 0; j < FN; ++j)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) W[i * 8 + BM * (j * 8 + h)] = acc[i][j][h];
-        __threadfence();                                                  // this thread's partials are visible device-wide ...
-        asm volatile("bar.sync 2, %0;" ::"n"(G_NCONS) : "memory");       // ... and so are those of all consumer threads
-        const ItbSplitOut so = splits[qi.tile.split];
-        if (threadIdx.x == 0) {
-            const int old = atomicAdd(split_cnt + qi.tile.split, 1);
-            const int last = old == so.nsplit - 1;
-            if (last) split_cnt[qi.tile.split] = 0;                        // rearm for the next launch (everyone has arrived)
-            *last_flag = last;
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(G_NCONS) : "memory");
-        if (*last_flag) {
-            __threadfence();
-            const double* __restrict__ W0 = ws + (int64_t)so.ws_slot0 * ITB_WS_TILE + woff;
-#pragma unroll
-            for (int i = 0; i < FM; ++i)
-#pragma unroll
-                for (int j = 0; j < FN; ++j)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) acc[i][j][h] = 0.0;
-            for (int q = 0; q < so.nsplit; ++q) {
-                const double* __restrict__ Wq = W0 + (int64_t)q * ITB_WS_TILE;
-#pragma unroll
-                for (int i = 0; i < FM; ++i)
-#pragma unroll
-                    for (int j = 0; j < FN; ++j)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) acc[i][j][h] += __ldcg(Wq + i * 8 + BM * (j * 8 + h)); // L2 (never a stale L1 line)
-            }
-            const int64_t cms = qi.cb.c_ms, cns = qi.cb.c_ns;
-            const int nmask = qi.cb.c_nmask, nshift = qi.cb.c_nshift;
-            double* __restrict__ Cp = C + qi.cb.c_off;
-#pragma unroll
-            for (int i = 0; i < FM; ++i) {
-                const int m = m0 + wm0 + i * 8 + g;
-#pragma unroll
-                for (int j = 0; j < FN; ++j) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int n = n0 + wn0 + j * 8 + 2 * t4 + h;
-                        if (m < M && n < N) Cp[(int64_t)m * cms + (n & nmask) + (int64_t)(n >> nshift) * cns] = acc[i][j][h];
-                    }
-                }
-            }
-        }
     }
 }
 
@@ -494,6 +449,8 @@ __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __r
 // self-scheduling, plan.cc), so the CTAs finish within one small piece of each other whatever the real per-tile cost is
 // (edge tiles, L2 hits, clocks) — no cycle model has to be right — and at any time the 148 CTAs work on ~148 CONSECUTIVE
 // tiles, i.e. on the few C blocks whose operand panels are then shared through L2 instead of re-read from HBM.
+// (Hybrid: every CTA first walks its own static range of the list, cta_begin[b]..cta_begin[b+1], and only then pulls from the
+// shared queue that starts at cta_begin[n_static_ctas] — see plan.cc.)
 // Mechanics: the first producer warp is also the FETCHER: before it starts producing item q it makes sure the ring holds
 // items up to q+G_QSLOTS-1 (as far as slots are free; it never blocks on a look-ahead): lane 0 pops an index from the global head, the warp copies the host-flattened 160-byte item
 // record into the slot and publishes it through the slot's full barrier (the pop + copy latency, ~1.3k cycles, falls
@@ -501,8 +458,8 @@ __device__ __forceinline__ void produce_tile(const QItem& qi, const ItbPair* __r
 // records from shared memory. An index >= n_items is the stop sentinel. The last CTA to stop rearms the queue head.
 template <bool PROF>
 __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __restrict__ items, int n_items, int* __restrict__ queue,
-                                                            const ItbPair* __restrict__ pairs, const ItbSplitOut* __restrict__ splits,
-                                                            int* __restrict__ split_cnt,
+                                                            const int32_t* __restrict__ cta_begin, int n_static_ctas,
+                                                            const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
                                                             double* __restrict__ C, double* __restrict__ ws,
                                                             long long* __restrict__ cta_cycles, int dbg_nocompute) {
@@ -519,7 +476,6 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
     uint64_t* q_full = empty + G_STAGES;
     uint64_t* q_empty = q_full + G_QSLOTS;
     QItem* q_item = reinterpret_cast<QItem*>(q_empty + G_QSLOTS);
-    volatile int* last_flag = reinterpret_cast<volatile int*>(q_item + G_QSLOTS); // split-K: "this CTA arrived last" broadcast
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], G_NPROD);     // one cp.async-completion arrive per producer thread
@@ -544,6 +500,10 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
     PipeState ps;
     int qf = 0;            // fetcher: next sequence number to publish
     bool exhausted = false;
+    // hybrid schedule (plan.cc): this CTA's static range of the item list first, then the shared queue behind it
+    int st_next = 0, st_end = 0;
+    const int tail_begin = cta_begin[n_static_ctas];
+    if ((int)blockIdx.x < n_static_ctas) { st_next = cta_begin[blockIdx.x]; st_end = cta_begin[blockIdx.x + 1]; }
     for (int q = 0;; ++q) {
         if (fetch_warp) {
             while (!exhausted && qf < q + G_QSLOTS) {
@@ -559,8 +519,11 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
                 }
                 mbar_wait(&q_empty[s], par);
                 int idx = 0;
-                if (lane == 0) idx = atomicAdd(queue, 1);
-                idx = __shfl_sync(0xffffffffu, idx, 0);
+                if (st_next < st_end) idx = st_next++;
+                else {
+                    if (lane == 0) idx = tail_begin + atomicAdd(queue, 1);
+                    idx = __shfl_sync(0xffffffffu, idx, 0);
+                }
                 int* dst = reinterpret_cast<int*>(q_item + s);
                 if (idx < n_items) { // 160 bytes = 40 ints
                     const int* src = reinterpret_cast<const int*>(items + idx);
@@ -588,9 +551,9 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
             else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
             else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
         } else {
-            if (cfg == 0) consume_tile<128, 128, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec, splits, split_cnt, last_flag);
-            else if (cfg == 1) consume_tile<64, 64, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec, splits, split_cnt, last_flag);
-            else consume_tile<32, 32, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec, splits, split_cnt, last_flag);
+            if (cfg == 0) consume_tile<128, 128, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
+            else if (cfg == 1) consume_tile<64, 64, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
+            else consume_tile<32, 32, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
             if (PROF && rec) { rec[2] -= t_begin; rec[3] = clock64() - t_begin; }
         }
         __syncwarp();
@@ -1055,7 +1018,8 @@ __global__ void __launch_bounds__(256) peak_dfma_kernel(double* out, int iters) 
 }
 
 // ---- launchers (called from api.cu) ---------------------------------------------------------------------
-cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const int32_t* cta_begin, int n_static_ctas, int grid,
+                        const ItbSplitOut* souts, int nsouts,
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles, cudaStream_t st) {
     static int nocompute = -1; // ITB_DEBUG_NOCOMPUTE=1: consumers skip the DMMA work (measures the producers' gather rate)
@@ -1067,11 +1031,15 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, int grid
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    // (queue[0]: head, queue[1]: finished CTAs, queue + 16: one arrival counter per cut tile)
-    if (cta_cycles) bsc_gemm_kernel<true><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, souts, queue + 16, A, B, C, ws, cta_cycles, nocompute);
-    else bsc_gemm_kernel<false><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, pairs, souts, queue + 16, A, B, C, ws, nullptr, nocompute);
-    (void)nsouts; (void)cblks;
-    return cudaGetLastError();
+    if (cta_cycles) bsc_gemm_kernel<true><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, cta_begin, n_static_ctas, pairs, A, B, C, ws, cta_cycles, nocompute);
+    else bsc_gemm_kernel<false><<<grid, G_NT, G_SMEM, st>>>(items, n_items, queue, cta_begin, n_static_ctas, pairs, A, B, C, ws, nullptr, nocompute);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (nsouts > 0) {
+        bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C);
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,

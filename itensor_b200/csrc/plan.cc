@@ -300,13 +300,14 @@ static void canon(DimList& g, bool two) {
 // Least-squares fit of measured per-CTA cycles on the maxdim-2000 H_eff workload (tools/sched_fit.py): a 128x128
 // chunk costs 2466 + 0.54 x (DMMA cycles of the busiest SMSP), i.e. 4680 full and ~3150 for a 34-wide edge.
 static double g_tile_floor[ITB_NCFG] = {2950.0, 1700.0, 1050.0};
-static double kTileOverhead[ITB_NCFG] = {1200.0, 8000.0, 5300.0};
-static double kPairOverhead = 4300.0;
+static double kTileOverhead[ITB_NCFG] = {3800.0, 8000.0, 5300.0}; // 128x128: epilogue ~3000 + ~800 to the next item (tools/tile_probe.py)
+static double kPairOverhead = 1000.0; // per block pair an item walks (K loop of the 3-pair *R tiles: +85 cycles per chunk)
 static const double kDmmaSlack = 1.11;
 static int kForceCfg = -1;
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this (ITB_MIN_PIECE)
-static double kGuidedFactor = 1.0;  // piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
+static double kGuidedFactor = 2.0;  // shared queue: piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
+static double kStaticFrac = 0.85;   // fraction of the modelled work handed out as static per-CTA ranges; ITB_STATIC_FRAC (0: all dynamic)
 static void read_tile_env() {
     static bool done = false;
     if (done) return;
@@ -317,6 +318,7 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
     if (const char* e = getenv("ITB_GUIDED_FACTOR")) kGuidedFactor = std::max(0.25, atof(e));
     if (const char* e = getenv("ITB_MIN_PIECE")) kMinPiece = std::max(1, atoi(e));
+    if (const char* e = getenv("ITB_STATIC_FRAC")) kStaticFrac = std::min(0.98, std::max(0.0, atof(e)));
 }
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
     const int WM = kTileM[f] / 4, WN = kTileN[f] / 4, FM = WM / 8, FN = WN / 8;
@@ -709,9 +711,8 @@ int build_contract_tables(itb_contract_plan& P) {
     // boundaries into pieces of (remaining work / grid width), never shorter than kMinPiece chunks, so the last CTAs
     // finish within one small piece of each other. The cycle model only sets piece sizes — an error in it costs
     // balance in proportion to the smallest pieces, not to the whole share of a CTA as with a static partition.
-    // A cut tile writes partial sums to workspace slots; the piece that ARRIVES LAST (a per-tile counter) adds the slots in
-    // piece order and writes C (kernels_gemm.cu): deterministic, independent of which CTA ran which piece and of the
-    // arrival order, and the partials are read back from L2 while they are still there.
+    // A cut tile writes partial sums to workspace slots which bsc_splitk_reduce_kernel adds in piece order
+    // (deterministic, independent of which CTA ran which piece).
     {
         struct Proto { int32_t c, m0, n0, f; int64_t nch; double w; int np; };
         std::vector<Proto> protos;
@@ -736,38 +737,87 @@ int build_contract_tables(itb_contract_plan& P) {
                 }
         }
         const int G = kNumSMs;
-        double remaining = total;
+        // Hybrid schedule. STATIC part: the first kStaticFrac of the modelled work is cut stream-K fashion into G
+        // contiguous ranges of (tile, K-chunk) space, one per CTA — at most G-1 tiles are cut there, which keeps the
+        // split-K workspace traffic (one 128 KB partial per piece, written and read back by the reduce kernel) at its
+        // minimum where tiles are few and K loops long (the *R step: 230 tiles of ~150 chunks for 148 CTAs). DYNAMIC part:
+        // the rest of the list is a shared queue of pieces of geometrically shrinking cost (guided self-scheduling) that
+        // the CTAs pull through an atomic head once their static range is done; it absorbs whatever the cycle model got
+        // wrong in the static part and lets the CTAs finish within one small piece of each other.
+        // cta_begin: G+2 entries — static range of CTA b = [cta_begin[b], cta_begin[b+1]), shared queue =
+        // [cta_begin[G], cta_begin[G+1]).
         std::vector<double> item_cost;
-        for (auto& t : protos) {
-            const double ovh = kTileOverhead[t.f] + kPairOverhead * t.np;
-            const double cost = t.w * (double)t.nch + ovh;
-            const double want = std::max(remaining / (kGuidedFactor * G), (double)kMinPiece * t.w);
-            int64_t npieces = 1;
-            if (cost > 1.25 * want) npieces = std::min<int64_t>((int64_t)std::ceil(cost / want), std::max<int64_t>(1, t.nch / kMinPiece));
-            if (npieces <= 1) {
-                P.tiles.push_back({t.c, t.m0, t.n0, t.f, 0, (int32_t)t.nch, -1, -1});
-                item_cost.push_back(cost);
-            } else {
-                P.splits.push_back({t.c, t.m0, t.n0, t.f, (int32_t)P.ws_slots, (int32_t)npieces, {0, 0}});
-                for (int64_t q = 0; q < npieces; ++q) { // chunk ranges as equal as integers allow
-                    const int64_t c0 = t.nch * q / npieces, c1 = t.nch * (q + 1) / npieces;
-                    P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)c1, (int32_t)P.ws_slots++, (int32_t)P.splits.size() - 1});
-                    item_cost.push_back((double)(c1 - c0) * t.w + ovh);
+        struct Piece { int64_t c0, c1; };
+        size_t first_item_of_tile = 0;
+        std::vector<Piece> cur_pieces; // pieces of the tile being emitted (consecutive items)
+        auto flush_tile = [&](const Proto& t) { // assign workspace slots once the number of pieces of a tile is known
+            if (cur_pieces.size() > 1) {
+                P.splits.push_back({t.c, t.m0, t.n0, t.f, (int32_t)P.ws_slots, (int32_t)cur_pieces.size(), {0, 0}});
+                for (size_t q = 0; q < cur_pieces.size(); ++q) {
+                    P.tiles[first_item_of_tile + q].ws_slot = (int32_t)P.ws_slots++;
+                    P.tiles[first_item_of_tile + q].split = (int32_t)P.splits.size() - 1;
                 }
             }
+            cur_pieces.clear();
+        };
+        auto emit = [&](const Proto& t, int64_t c0, int64_t c1) {
+            if (cur_pieces.empty()) first_item_of_tile = P.tiles.size();
+            cur_pieces.push_back({c0, c1});
+            P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)c1, -1, -1});
+            item_cost.push_back((double)(c1 - c0) * t.w + kTileOverhead[t.f] + kPairOverhead * t.np);
+        };
+        P.cta_begin.assign(G + 2, 0);
+        size_t ti = 0;      // current tile
+        int64_t coff = 0;   // chunks of it already emitted
+        const bool hybrid = kStaticFrac > 0 && total / G >= 40.0 * 4700.0 && protos.size() >= (size_t)G / 2;
+        double remaining = total;
+        if (hybrid) {
+            const double share = kStaticFrac * total / G;
+            for (int b = 0; b < G; ++b) {
+                P.cta_begin[b] = (int32_t)P.tiles.size();
+                double load = 0;
+                while (ti < protos.size() && load < share) {
+                    const Proto& t = protos[ti];
+                    const double ovh = kTileOverhead[t.f] + kPairOverhead * t.np;
+                    const int64_t rem = t.nch - coff;
+                    const double cost_rem = (double)rem * t.w + ovh, space = share - load;
+                    if (cost_rem <= space * 1.05) { // the rest of the tile fits
+                        emit(t, coff, t.nch);
+                        flush_tile(t);
+                        load += cost_rem; remaining -= cost_rem;
+                        ++ti; coff = 0;
+                        continue;
+                    }
+                    const int64_t fit = (int64_t)std::floor((space - ovh) / t.w);
+                    if (fit >= kMinPiece && rem - fit >= kMinPiece) { // cut here: a viable piece stays behind
+                        emit(t, coff, coff + fit);
+                        remaining -= (double)fit * t.w + ovh;
+                        coff += fit;
+                    } else if (load == 0) { // nothing fits an empty range: take the rest of the tile anyway
+                        emit(t, coff, t.nch);
+                        flush_tile(t);
+                        remaining -= cost_rem;
+                        ++ti; coff = 0;
+                    }
+                    break; // range closed
+                }
+            }
+        }
+        P.cta_begin[G] = (int32_t)P.tiles.size();
+        // shared queue: what is left, cut by the guided rule
+        for (; ti < protos.size(); ++ti, coff = 0) {
+            const Proto& t = protos[ti];
+            const double ovh = kTileOverhead[t.f] + kPairOverhead * t.np;
+            const int64_t rem = t.nch - coff;
+            const double cost = t.w * (double)rem + ovh;
+            const double want = std::max(remaining / (kGuidedFactor * G), (double)kMinPiece * t.w);
+            int64_t npieces = 1;
+            if (cost > 1.25 * want) npieces = std::min<int64_t>((int64_t)std::ceil(cost / want), std::max<int64_t>(1, rem / kMinPiece));
+            for (int64_t q = 0; q < npieces; ++q) emit(t, coff + rem * q / npieces, coff + rem * (q + 1) / npieces); // as equal as integers allow
+            flush_tile(t);
             remaining -= cost;
         }
-        // nominal contiguous partition of the queue by modelled cost: introspection (itb_contract_plan_cta_begin), the
-        // schedule simulator and the table-walking mock use it; the kernel does not
-        P.cta_begin.assign(G + 1, 0);
-        double all = 0, acc = 0;
-        for (double v : item_cost) all += v;
-        int bcta = 0;
-        for (size_t i = 0; i < item_cost.size(); ++i) {
-            while (bcta < G - 1 && acc >= all * (double)(bcta + 1) / G) P.cta_begin[++bcta] = (int32_t)i;
-            acc += item_cost[i];
-        }
-        for (int g = bcta + 1; g <= G; ++g) P.cta_begin[g] = (int32_t)P.tiles.size();
+        P.cta_begin[G + 1] = (int32_t)P.tiles.size();
         // flattened device records
         P.qitems.resize(P.tiles.size());
         for (size_t i = 0; i < P.tiles.size(); ++i) {

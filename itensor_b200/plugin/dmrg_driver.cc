@@ -181,6 +181,21 @@ main(int argc, char* argv[])
         psi = randomMPS(state);
         }
     if(!loadPrefix.empty()) psi = readFromFile<MPS>(loadPrefix+".psi",sites);
+    // DMRG_PERTURB=eps: multiply every element of the starting MPS by (1 + eps*u), u uniform in (-1,1) from a fixed-seed
+    // generator of our own. Measures how far a rounding-sized change of the INPUT moves the per-bond record of a sweep,
+    // i.e. the amplification any two arithmetically different implementations (summation order, FMA use) are subject to.
+    if(auto* e = std::getenv("DMRG_PERTURB"))
+        {
+        Real eps = std::atof(e);
+        unsigned long long st = 0x9E3779B97F4A7C15ull;
+        auto next = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (st >> 11) * (1.0/9007199254740992.0); };
+        for(auto j : range1(N))
+            {
+            auto l = psi.leftLim(), r = psi.rightLim();
+            psi.ref(j).apply([&](Real x) { return x*(1.+eps*(2.*next()-1.)); });
+            psi.leftLim(l); psi.rightLim(r);
+            }
+        }
 
     auto sweeps = Sweeps(nsweep);
     for(int s = 1; s <= nsweep; ++s)
