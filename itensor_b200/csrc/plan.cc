@@ -307,7 +307,8 @@ static int kForceCfg = -1;
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this (ITB_MIN_PIECE)
 static double kGuidedFactor = 2.0;  // shared queue: piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
-static double kStaticFrac = 0.85;   // fraction of the modelled work handed out as static per-CTA ranges; ITB_STATIC_FRAC (0: all dynamic)
+static double kStaticFrac = 0.0;    // fraction of the modelled work handed out as static per-CTA ranges; ITB_STATIC_FRAC (0: all dynamic).
+                                    // Measured (profiles/r03_tile_schedule_variants.txt): 0 -> 1378 us per H_eff*phi, 0.85 -> 1391-1419, 0.92 -> 1412
 static void read_tile_env() {
     static bool done = false;
     if (done) return;

@@ -182,10 +182,11 @@ def test_stream_k_partition_covers_every_tile_once(sizes, dtype):
         if P.flops > 1e9:  # enough work to balance: static ranges carry ~85 % of the work, none more than 1.5x their mean
             w = np.array([(c1 - c0) * tm * tn for _, _, _, tm, tn, c0, c1, _ in t.tolist()], float)
             load = np.array([w[g[b]:g[b + 1]].sum() for b in range(148)])
-            assert load.max() <= 1.5 * load.mean()
             tail = w[g[148]:g[149]]
-            assert 0.05 <= tail.sum() / w.sum() <= 0.30
-            assert tail[-148:].max() <= 0.35 * load.mean()  # the queue ends in small pieces: that is what balances the CTAs
+            if g[148] > 0:  # hybrid schedule (ITB_STATIC_FRAC > 0): the static ranges carry most of the work
+                assert load.max() <= 1.5 * load.mean() and 0.05 <= tail.sum() / w.sum() <= 0.30
+            # the queue ends in small pieces: that is what lets the CTAs finish together
+            assert tail[-148:].max() <= 0.35 * w.sum() / 148
 
 
 def test_row_groups_read_every_input_once():
