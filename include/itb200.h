@@ -246,6 +246,24 @@ int itb_eigh_batch_values(itb_eigh_batch* batch, double* hW);
 int itb_eigh_batch_copy_vectors(itb_eigh_batch* batch, int64_t block, int32_t ncols, void* dDst, int conj); /* n x ncols */
 int itb_eigh_batch_destroy(itb_eigh_batch* batch);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ---------------------------------------------
+ * The path shards by ROWS of one uncontracted index (itb_contract_plan_set_index_slices); the only exchange is re-replicating
+ * a row-sharded tensor: pack own rows (itb_blockcopy_plan_create) -> itb_comm_allgather -> scatter the other ranks' rows.
+ * NCCL (libnccl.so.2) is loaded on first use. Rank 0 obtains an id with itb_comm_unique_id and hands it to the other processes
+ * (the plugin does that through a file, plugin/gpu_storage.cc); every process then calls itb_comm_create (collective). */
+#define ITB_COMM_ID_BYTES 128
+typedef struct itb_comm itb_comm;
+int itb_comm_unique_id(uint8_t out[ITB_COMM_ID_BYTES]);
+int itb_comm_create(itb_ctx* ctx, int32_t world, int32_t rank, const uint8_t id[ITB_COMM_ID_BYTES], itb_comm** out);
+int32_t itb_comm_world(const itb_comm* comm);
+int32_t itb_comm_rank(const itb_comm* comm);
+/* every rank contributes count doubles at dSend; dRecv receives world*count doubles in rank order (in place when
+ * dSend == (double*)dRecv + rank*count); ordered on the context's stream */
+int itb_comm_allgather(itb_comm* comm, itb_ctx* ctx, const void* dSend, void* dRecv, int64_t count);
+int itb_comm_destroy(itb_comm* comm);
+/* flops of every C block of a plan (2*M*N*K summed over its pairs, complex multipliers included): the weights of a row partition */
+int itb_contract_plan_cblock_flops(const itb_contract_plan* plan, double* out /*[c_nblocks]*/);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement
  * only). itb_contract_last_ms then returns the device time of the last run by kernel class

@@ -86,6 +86,13 @@ SYMBOLS = {
     "itb_contract_plan_set_cblock_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "itb_contract_plan_set_cblock_mask": (C.c_int, [_P, C.POINTER(C.c_uint8)]),
     "itb_contract_plan_set_index_slices": (C.c_int, [_P, C.c_int32, _I64P, _I64P]),
+    "itb_contract_plan_cblock_flops": (C.c_int, [_P, _DP]),
+    "itb_comm_unique_id": (C.c_int, [_P]),
+    "itb_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
+    "itb_comm_world": (C.c_int32, [_P]),
+    "itb_comm_rank": (C.c_int32, [_P]),
+    "itb_comm_allgather": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    "itb_comm_destroy": (C.c_int, [_P]),
     "itb_contract_plan_tiles": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_cta_begin": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_rowgroups": (C.c_int64, [_P, _I64P, C.c_int64]),

@@ -1,0 +1,96 @@
+// comm.cu — one-process-per-GPU communicator behind the C ABI (include/itb200.h, itb_comm_*): the all-gather that
+// re-replicates row-sharded tensors (H*phi after LocalOp::product) over NVLink / NVSwitch.
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2) and only when a communicator is created: a single-GPU process,
+// the Python mirror (which brings torch's own NCCL) and the CPU-only build check never load it. The transport is plain
+// ncclAllGather on the context's stream; what is B200-specific is how little is sent: the caller packs exactly the rows
+// a rank owns, so every element of the result crosses the switch once.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <string>
+
+#include "../../include/itb200.h"
+
+namespace itb { void set_error(const std::string& msg); }
+
+struct itb_comm {
+    void* lib = nullptr;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static void* nccl_lib() {
+    static void* h = nullptr;
+    if (!h) {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+    }
+    return h;
+}
+template <typename F> static bool sym(void* lib, const char* name, F& f) {
+    f = reinterpret_cast<F>(dlsym(lib, name));
+    return f != nullptr;
+}
+
+extern "C" {
+
+int itb_comm_unique_id(uint8_t out[ITB_COMM_ID_BYTES]) {
+    static_assert(ITB_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "unique id size");
+    void* lib = nccl_lib();
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    if (!lib || !sym(lib, "ncclGetUniqueId", GetUniqueId)) { itb::set_error("itb_comm: libnccl.so.2 not found"); return ITB_ERR_UNSUPPORTED; }
+    ncclUniqueId id;
+    if (GetUniqueId(&id) != ncclSuccess) { itb::set_error("itb_comm: ncclGetUniqueId failed"); return ITB_ERR_CUDA; }
+    std::memcpy(out, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return ITB_OK;
+}
+
+int itb_comm_create(itb_ctx* ctx, int32_t world, int32_t rank, const uint8_t id_bytes[ITB_COMM_ID_BYTES], itb_comm** out) {
+    if (!ctx || !out || world < 1 || rank < 0 || rank >= world) { itb::set_error("itb_comm_create: bad arguments"); return ITB_ERR_INVALID; }
+    void* lib = nccl_lib();
+    ncclResult_t (*InitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    auto* c = new itb_comm();
+    c->lib = lib; c->world = world; c->rank = rank;
+    if (!lib || !sym(lib, "ncclCommInitRank", InitRank) || !sym(lib, "ncclAllGather", c->AllGather) ||
+        !sym(lib, "ncclCommDestroy", c->CommDestroy) || !sym(lib, "ncclGetErrorString", c->GetErrorString)) {
+        delete c;
+        itb::set_error("itb_comm: libnccl.so.2 not found or incomplete");
+        return ITB_ERR_UNSUPPORTED;
+    }
+    ncclUniqueId id;
+    std::memcpy(id.internal, id_bytes, NCCL_UNIQUE_ID_BYTES);
+    const ncclResult_t r = InitRank(&c->comm, world, id, rank); // (the caller has made the context's device current)
+    if (r != ncclSuccess) { itb::set_error(std::string("ncclCommInitRank: ") + c->GetErrorString(r)); delete c; return ITB_ERR_CUDA; }
+    *out = c;
+    return ITB_OK;
+}
+
+int32_t itb_comm_world(const itb_comm* c) { return c ? c->world : 1; }
+int32_t itb_comm_rank(const itb_comm* c) { return c ? c->rank : 0; }
+
+// every rank contributes count doubles at dSend; dRecv receives world*count doubles in rank order (in place when
+// dSend == dRecv + rank*count). Ordered on the context's stream like every other launch.
+int itb_comm_allgather(itb_comm* c, itb_ctx* ctx, const void* dSend, void* dRecv, int64_t count) {
+    if (!c || !ctx || count < 0) { itb::set_error("itb_comm_allgather: bad arguments"); return ITB_ERR_INVALID; }
+    if (count == 0) return ITB_OK;
+    const ncclResult_t r = c->AllGather(dSend, dRecv, (size_t)count, ncclDouble, c->comm, (cudaStream_t)itb_ctx_stream(ctx));
+    if (r != ncclSuccess) { itb::set_error(std::string("ncclAllGather: ") + c->GetErrorString(r)); return ITB_ERR_CUDA; }
+    return ITB_OK;
+}
+
+int itb_comm_destroy(itb_comm* c) {
+    if (!c) return ITB_OK;
+    if (c->comm) c->CommDestroy(c->comm);
+    delete c;
+    return ITB_OK;
+}
+
+} // extern "C"

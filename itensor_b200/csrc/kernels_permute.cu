@@ -240,10 +240,10 @@ static cudaError_t launch_t(const ItbPermBlk* bc, const ItbPermChunk* chunks, in
     }
     if (items_t > 0) {
         // ITB_PERM_PIPE=0 selects the one-tile-per-CTA kernel (measurement / fallback switch); ITB_PERM_CTAS: CTAs per SM
-        static int pipe = -1, ctas = 3, sms = 148;
+        static int pipe = -1, ctas = 2, sms = 148; // 2 CTAs/SM measured best (0.758 of the copy peak; 3: 0.68, 4: 0.75, 6: 0.757)
         if (pipe < 0) {
             const char* e = getenv("ITB_PERM_PIPE"); pipe = e ? atoi(e) : 1;
-            if (const char* c = getenv("ITB_PERM_CTAS")) ctas = atoi(c) > 0 ? atoi(c) : 3;
+            if (const char* c = getenv("ITB_PERM_CTAS")) ctas = atoi(c) > 0 ? atoi(c) : 2;
             int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
         constexpr int PT = CS ? 32 : 64;

@@ -307,6 +307,7 @@ static int kForceCfg = -1;
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this (ITB_MIN_PIECE)
 static double kGuidedFactor = 2.0;  // shared queue: piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
+static bool kSchedStreamK = false;  // ITB_SCHED=streamk: pure static stream-K partition instead of the guided queue
 static double kStaticFrac = 0.0;    // fraction of the modelled work handed out as static per-CTA ranges; ITB_STATIC_FRAC (0: all dynamic).
                                     // Measured (profiles/r03_tile_schedule_variants.txt): 0 -> 1378 us per H_eff*phi, 0.85 -> 1391-1419, 0.92 -> 1412
 static void read_tile_env() {
@@ -319,6 +320,7 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
     if (const char* e = getenv("ITB_GUIDED_FACTOR")) kGuidedFactor = std::max(0.25, atof(e));
     if (const char* e = getenv("ITB_MIN_PIECE")) kMinPiece = std::max(1, atoi(e));
+    if (const char* e = getenv("ITB_SCHED")) kSchedStreamK = std::string(e) == "streamk";
     if (const char* e = getenv("ITB_STATIC_FRAC")) kStaticFrac = std::min(0.98, std::max(0.0, atof(e)));
 }
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
@@ -770,7 +772,48 @@ int build_contract_tables(itb_contract_plan& P) {
         P.cta_begin.assign(G + 2, 0);
         size_t ti = 0;      // current tile
         int64_t coff = 0;   // chunks of it already emitted
-        const bool hybrid = kStaticFrac > 0 && total / G >= 40.0 * 4700.0 && protos.size() >= (size_t)G / 2;
+        if (kSchedStreamK) {
+            // Pure static stream-K partition (the round-1 schedule, kept selectable: ITB_SCHED=streamk): every CTA gets the
+            // same modelled cycles, the tile list is cut at K-chunk boundaries where a share is full (<= G-1 cut tiles), no
+            // shared queue. Its constants were fitted to per-CTA clock64 spans of this kernel on the bench workload.
+            const double ovh0 = 1200.0, pair0 = 4300.0; // fitted with the partition below (tools/sched_fit.py)
+            double tot = 0;
+            for (auto& t : protos) tot += t.w * (double)t.nch + ovh0 + pair0 * t.np;
+            double target = tot / G, assigned = 0;
+            int b = 0; double load = 0;
+            auto close_cta = [&]() {
+                if (b < G - 1) { ++b; P.cta_begin[b] = (int32_t)P.tiles.size(); load = 0; target = std::max(0.0, tot - assigned) / (G - b); }
+            };
+            for (auto& t : protos) {
+                auto piece_ovh = [&](int64_t take) { return ovh0 + pair0 * std::ceil((double)t.np * (double)take / (double)t.nch); };
+                int64_t c0 = 0;
+                while (c0 < t.nch) {
+                    const int64_t rem = t.nch - c0;
+                    const double space = target - load - piece_ovh(t.nch - c0);
+                    const int64_t fit = (int64_t)std::floor(space / t.w);
+                    int64_t take;
+                    if (b == G - 1 || fit >= rem) take = rem;
+                    else if (fit >= kMinPiece && rem - fit >= kMinPiece) take = fit;
+                    else {
+                        const int64_t x = (rem - std::max<int64_t>(fit, 0) < kMinPiece || rem < 2 * kMinPiece) ? rem : kMinPiece;
+                        const double over = (double)x * t.w - space, under = target - load;
+                        if (load > 0 && under <= over) { close_cta(); continue; }
+                        take = x;
+                    }
+                    if (take <= 0) { close_cta(); continue; }
+                    if (!cur_pieces.empty()) tot += ovh0 + pair0;
+                    emit(t, c0, c0 + take);
+                    load += (double)take * t.w + piece_ovh(take);
+                    assigned += (double)take * t.w + piece_ovh(take);
+                    c0 += take;
+                    if (load >= target - 0.5 * t.w) close_cta();
+                }
+                flush_tile(t);
+            }
+            for (int g = b + 1; g <= G; ++g) P.cta_begin[g] = (int32_t)P.tiles.size();
+            ti = protos.size();
+        }
+        const bool hybrid = !kSchedStreamK && kStaticFrac > 0 && total / G >= 40.0 * 4700.0 && protos.size() >= (size_t)G / 2;
         double remaining = total;
         if (hybrid) {
             const double share = kStaticFrac * total / G;
@@ -804,7 +847,7 @@ int build_contract_tables(itb_contract_plan& P) {
                 }
             }
         }
-        P.cta_begin[G] = (int32_t)P.tiles.size();
+        if (!kSchedStreamK) P.cta_begin[G] = (int32_t)P.tiles.size();
         // shared queue: what is left, cut by the guided rule
         for (; ti < protos.size(); ++ti, coff = 0) {
             const Proto& t = protos[ti];
@@ -1119,6 +1162,25 @@ int itb_contract_plan_set_cblock_mask(itb_contract_plan* P, const uint8_t* mask)
     else P->cb_mask.clear();
     itb_contract_plan_release_device(P);
     return build_contract_tables(*P);
+}
+
+int itb_contract_plan_cblock_flops(const itb_contract_plan* P, double* out) {
+    if (!P || !out) { set_error("cblock_flops: null"); return ITB_ERR_INVALID; }
+    const TensorStruct &A = P->A, &B = P->B;
+    for (int64_t c = 0; c < P->C.nblocks; ++c) out[c] = 0;
+    std::vector<char> contA(A.order, 0), contB(B.order, 0);
+    for (int i = 0; i < A.order; ++i)
+        for (int j = 0; j < B.order; ++j)
+            if (P->labA[i] == P->labB[j] && !contB[j]) { contA[i] = 1; contB[j] = 1; break; }
+    const double cmul = (A.dtype == ITB_C64 ? 2.0 : 1.0) * (B.dtype == ITB_C64 ? 2.0 : 1.0);
+    for (size_t p = 0; p + 2 < P->triples.size() + 0; p += 3) {
+        const int64_t ia = P->triples[p], ib = P->triples[p + 1], ic = P->triples[p + 2];
+        double m = 1, n = 1, k = 1;
+        for (int i = 0; i < A.order; ++i) { const double e = (double)A.ext(i, A.block(ia)[i]); if (contA[i]) k *= e; else m *= e; }
+        for (int j = 0; j < B.order; ++j) if (!contB[j]) n *= (double)B.ext(j, B.block(ib)[j]);
+        out[ic] += 2.0 * m * n * k * cmul;
+    }
+    return ITB_OK;
 }
 
 int itb_contract_plan_set_index_slices(itb_contract_plan* P, int32_t c_index, const int64_t* lo, const int64_t* hi) {

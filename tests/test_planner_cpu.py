@@ -185,8 +185,10 @@ def test_stream_k_partition_covers_every_tile_once(sizes, dtype):
             tail = w[g[148]:g[149]]
             if g[148] > 0:  # hybrid schedule (ITB_STATIC_FRAC > 0): the static ranges carry most of the work
                 assert load.max() <= 1.5 * load.mean() and 0.05 <= tail.sum() / w.sum() <= 0.30
-            # the queue ends in small pieces: that is what lets the CTAs finish together
-            assert tail[-148:].max() <= 0.35 * w.sum() / 148
+            if len(tail):  # the queue ends in small pieces: that is what lets the CTAs finish together
+                assert tail[-148:].max() <= 0.35 * w.sum() / 148
+            else:          # ITB_SCHED=streamk: pure static partition, balanced by the cycle model
+                assert load.max() <= 1.5 * load.mean()
 
 
 def test_row_groups_read_every_input_once():

@@ -252,10 +252,16 @@ def test_config2_sweep_parity_at_maxdim_800(tmp_path):
     assert len(gb) == len(cb) == 198
     worst = {"energy": 0.0, "truncerr": 0.0, "spectrum": 0.0}
     for a, b in zip(gb, cb):
-        assert (a["half"], a["bond"]) == (b["half"], b["bond"]) and len(a["spectrum"]) == len(b["spectrum"])
+        assert (a["half"], a["bond"]) == (b["half"], b["bond"])
         worst["energy"] = max(worst["energy"], abs(a["energy"] - b["energy"]))
         worst["truncerr"] = max(worst["truncerr"], abs(a["truncerr"] - b["truncerr"]))
-        worst["spectrum"] = max(worst["spectrum"], float(np.abs(np.array(a["spectrum"]) - np.array(b["spectrum"])).max()))
+        # cutoff 0 keeps every eigenvalue that is > 0: near the chain ends the blocks are rank deficient and whether a
+        # rounding-level eigenvalue (1e-30) comes out positive differs between SVD implementations, so the two spectra are
+        # compared over their common leading part and whatever one side keeps beyond it must be numerically zero
+        sa, sb = np.array(a["spectrum"]), np.array(b["spectrum"])
+        k = min(len(sa), len(sb))
+        assert k > 0 and np.all(sa[k:] <= 1e-20) and np.all(sb[k:] <= 1e-20)
+        worst["spectrum"] = max(worst["spectrum"], float(np.abs(sa[:k] - sb[:k]).max()))
     print("config 2 @ maxdim 800, one sweep from the same state: max per-bond |dE| %.2e, |dtruncerr| %.2e, |dspectrum| %.2e; "
           "sweep seconds gpu %.1f cpu %.1f (%s threads)" % (worst["energy"], worst["truncerr"], worst["spectrum"],
                                                              g["sweeps"][-1]["seconds"], c["sweeps"][-1]["seconds"], ncpu))
