@@ -21,7 +21,9 @@
 #include "itb200.h"
 
 #include <chrono>
+#include <fstream>
 #include <map>
+#include <thread>
 
 namespace itensor {
 
@@ -92,6 +94,73 @@ synchronize() { check(itb_synchronize(context()),"synchronize"); }
 long
 launchCount() { return g_ctx ? long(itb_launch_count(g_ctx)) : 0; }
 
+//
+// ---- multi-GPU: one process per GPU ---------------------------------------------------------------------------------
+//
+static int
+envInt(const char* name, int dflt) { auto* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
+int
+world() { static int w = std::max(1,envInt("ITB_WORLD",1)); return w; }
+int
+rank() { static int r = envInt("ITB_RANK",0); return r; }
+
+// communicator: rank 0 creates the NCCL id and publishes it in the file $ITB_COMM_FILE (atomically, by rename), the
+// other ranks poll for it; itb_comm_create is collective
+static itb_comm*
+comm()
+    {
+    static itb_comm* c = nullptr;
+    if(c) return c;
+    auto* path = std::getenv("ITB_COMM_FILE");
+    if(!path) Error("itensor_b200: ITB_WORLD > 1 needs ITB_COMM_FILE (a path all ranks can see) for the communicator id");
+    uint8_t id[ITB_COMM_ID_BYTES];
+    auto file = std::string(path);
+    if(rank() == 0)
+        {
+        check(itb_comm_unique_id(id),"comm id");
+        auto tmp = file+".tmp";
+        { std::ofstream f(tmp,std::ios::binary); f.write((const char*)id,sizeof(id)); }
+        std::rename(tmp.c_str(),file.c_str());
+        }
+    else
+        {
+        for(int tries = 0;; ++tries)
+            {
+            std::ifstream f(file,std::ios::binary);
+            if(f && f.read((char*)id,sizeof(id))) break;
+            if(tries > 60000) Error("itensor_b200: timed out waiting for the communicator id file");
+            std::this_thread::sleep_for(std::chrono::milliseconds(5));
+            }
+        }
+    check(itb_comm_create(context(),world(),rank(),id,&c),"comm create");
+    return c;
+    }
+
+struct Pending
+    {
+    itb_permute_plan* pack = nullptr;   // own rows of the tensor -> this rank's segment (cached plans, not owned)
+    itb_permute_plan* unpack = nullptr; // the other ranks' segments -> their places in the tensor
+    long segDoubles = 0;                // padded segment length in doubles
+    // what a follow-up contraction needs to keep working on the same rows
+    Index shardIndex;
+    int nsect = 0;
+    std::vector<int64_t> lo, hi;        // [world*nsect]: rows of sector s owned by rank r = [lo[r*nsect+s], hi[r*nsect+s])
+    };
+
+static void
+runPending(Pending const& P, void* p)
+    {
+    ITB_SCOPE("all-gather rows");
+    auto* ctx = context();
+    void* seg = nullptr;
+    check(itb_malloc(ctx,size_t(P.segDoubles)*world()*sizeof(double),&seg),"malloc (gather segments)");
+    auto* mine = static_cast<double*>(seg)+size_t(P.segDoubles)*rank();
+    check(itb_permute_run(ctx,P.pack,p,mine,1.,0.,0),"pack rows");
+    check(itb_comm_allgather(comm(),ctx,mine,seg,P.segDoubles),"all-gather");
+    check(itb_permute_run(ctx,P.unpack,seg,p,1.,0.,0),"scatter rows");
+    check(itb_free(ctx,seg),"free (gather segments)"); // stream-ordered pool: reused only behind the scatter
+    }
+
 Buffer::
 Buffer(size_t bytes) : bytes_(bytes)
     {
@@ -103,7 +172,19 @@ Buffer(Buffer const& o) : bytes_(o.bytes_)
     {
     if(!o.p_) return;
     check(itb_malloc(context(),bytes_ ? bytes_ : 1,&p_),"malloc");
-    check(itb_memcpy_d2d(context(),p_,o.p_,bytes_),"d2d");
+    check(itb_memcpy_d2d(context(),p_,o.data(),bytes_),"d2d"); // (o.data(): a row-sharded source is completed first)
+    }
+
+void* Buffer::
+data() const
+    {
+    if(pending_)
+        {
+        auto p = std::move(pending_);
+        pending_.reset();
+        runPending(*p,p_);
+        }
+    return p_;
     }
 
 Buffer& Buffer::
@@ -120,7 +201,7 @@ operator=(Buffer&& o) noexcept
     {
     if(this == &o) return *this;
     if(p_ && g_ctx) itb_free(g_ctx,p_);
-    p_ = o.p_; bytes_ = o.bytes_;
+    p_ = o.p_; bytes_ = o.bytes_; pending_ = std::move(o.pending_);
     o.p_ = nullptr; o.bytes_ = 0;
     return *this;
     }
@@ -132,13 +213,13 @@ Buffer::
     }
 
 void Buffer::
-upload(void const* host, size_t bytes) { check(itb_memcpy_h2d(context(),p_,host,bytes),"h2d"); }
+upload(void const* host, size_t bytes) { if(bytes == bytes_) pending_.reset(); check(itb_memcpy_h2d(context(),data(),host,bytes),"h2d"); }
 
 void Buffer::
-download(void* host, size_t bytes) const { check(itb_memcpy_d2h(context(),host,p_,bytes),"d2h"); }
+download(void* host, size_t bytes) const { check(itb_memcpy_d2h(context(),host,data(),bytes),"d2h"); }
 
 void Buffer::
-zero() { check(itb_memset0(context(),p_,bytes_),"memset"); }
+zero() { pending_.reset(); check(itb_memset0(context(),p_,bytes_),"memset"); }
 
 } //namespace gpu
 
@@ -320,8 +401,11 @@ contractCache() { static PlanCache<itb_contract_plan,itb_contract_plan_destroy> 
 static PlanCache<itb_permute_plan,itb_permute_plan_destroy>&
 permuteCache() { static PlanCache<itb_permute_plan,itb_permute_plan_destroy> c(planCacheCap(32)); return c; }
 
+// sliceIndex >= 0: the plan executes only rows [lo[s],hi[s]) of C's index sliceIndex (multi-GPU row sharding); returns
+// nullptr when the planner cannot slice that index (ITB_ERR_UNSUPPORTED: the caller runs the contraction unsharded)
 static itb_contract_plan*
-getContractPlan(Desc const& dA, std::vector<int32_t> const& la, Desc const& dB, std::vector<int32_t> const& lb)
+getContractPlan(Desc const& dA, std::vector<int32_t> const& la, Desc const& dB, std::vector<int32_t> const& lb,
+                int sliceIndex = -1, int64_t const* lo = nullptr, int64_t const* hi = nullptr, int nsect = 0)
     {
     std::string key;
     key.reserve(256);
@@ -330,10 +414,23 @@ getContractPlan(Desc const& dA, std::vector<int32_t> const& la, Desc const& dB, 
     key.push_back('|');
     dB.appendKey(key);
     key.append((const char*)lb.data(),lb.size()*sizeof(int32_t));
+    if(sliceIndex >= 0)
+        {
+        key.push_back('/');
+        key.append((const char*)&sliceIndex,sizeof(int));
+        key.append((const char*)lo,size_t(nsect)*sizeof(int64_t));
+        key.append((const char*)hi,size_t(nsect)*sizeof(int64_t));
+        }
     auto& cache = contractCache();
     if(auto* p = cache.find(key)) return p;
     itb_contract_plan* p = nullptr;
     check(itb_contract_plan_create(&dA.d,la.data(),&dB.d,lb.data(),&p),"contract plan");
+    if(sliceIndex >= 0)
+        {
+        auto rc = itb_contract_plan_set_index_slices(p,sliceIndex,lo,hi);
+        if(rc == ITB_ERR_UNSUPPORTED) { itb_contract_plan_destroy(p); return nullptr; }
+        check(rc,"contract plan slices");
+        }
     cache.insert(key,p);
     return p;
     }
@@ -572,12 +669,136 @@ doTask(Order const& O, QDenseGPU<T>& dB)
 template void doTask(Order const&,QDenseGPU<Real>&);
 template void doTask(Order const&,QDenseGPU<Cplx>&);
 
+//
+// ---- multi-GPU row sharding of contractions -----------------------------------------------------------------
+//
+// cut the concatenated rows of all sectors into world() contiguous segments of equal weight (same rule as
+// itensor_b200/shard.py row_partition): lo/hi[r*nsect+s] = rows of sector s owned by rank r
+static void
+rowPartition(std::vector<int64_t> const& sizes, std::vector<double> const& w, std::vector<int64_t>& lo, std::vector<int64_t>& hi)
+    {
+    const int W = gpu::world(), ns = int(sizes.size());
+    std::vector<int64_t> start(ns+1,0);
+    std::vector<double> cumw(ns+1,0.);
+    for(int s = 0; s < ns; ++s) { start[s+1] = start[s]+sizes[s]; cumw[s+1] = cumw[s]+w[s]; }
+    std::vector<int64_t> cuts(W+1,0);
+    for(int g = 1; g < W; ++g)
+        {
+        double target = cumw[ns]*g/W;
+        int s = 0;
+        while(s+1 < ns && cumw[s+1] <= target) ++s;
+        double per_row = sizes[s] > 0 ? w[s]/double(sizes[s]) : 0.;
+        int64_t r = per_row > 0 ? int64_t(std::llround((target-cumw[s])/per_row)) : 0;
+        if(r > 0 && r < sizes[s]) { int64_t ra = (r+4)/8*8; if(ra > 0 && ra < sizes[s]) r = ra; } // cuts on 8-row (DMMA fragment) boundaries
+        r = std::min<int64_t>(std::max<int64_t>(r,0),sizes[s]);
+        cuts[g] = std::max(start[s]+r,cuts[g-1]);
+        }
+    cuts[W] = start[ns];
+    lo.assign(size_t(W)*ns,0); hi.assign(size_t(W)*ns,0);
+    for(int g = 0; g < W; ++g)
+        for(int s = 0; s < ns; ++s)
+            {
+            lo[size_t(g)*ns+s] = std::min(std::max(cuts[g]-start[s],int64_t(0)),sizes[s]);
+            hi[size_t(g)*ns+s] = std::min(std::max(cuts[g+1]-start[s],int64_t(0)),sizes[s]);
+            }
+    }
+
+// pack / scatter plans for the rows [lo,hi) of index j of a tensor with structure (is, off): rank r's rows go, block
+// after block and each box contiguous, into segment r of a (world x segment) buffer
+static std::shared_ptr<gpu::Pending>
+makePending(IndexSet const& is, BlockOffsets const& off, int dtype, int j, Index const& shardIndex,
+            std::vector<int64_t> const& lo, std::vector<int64_t> const& hi)
+    {
+    const int W = gpu::world(), r = order(is), ns = int(is[j].nblock());
+    auto P = std::make_shared<gpu::Pending>();
+    P->shardIndex = shardIndex; P->nsect = ns; P->lo = lo; P->hi = hi;
+    std::string key;
+    key.append((const char*)&dtype,sizeof(int)); key.append((const char*)&j,sizeof(int));
+    for(auto i : range(r)) for(auto b : range(is[i].nblock())) { long e = is[i].blocksize0(b); key.append((const char*)&e,sizeof(long)); key.push_back(';'); }
+    for(auto const& bo : off) { for(auto i : range(r)) { int32_t c = int32_t(bo.block[i]); key.append((const char*)&c,4); } key.append((const char*)&bo.offset,sizeof(bo.offset)); }
+    key.append((const char*)lo.data(),lo.size()*sizeof(int64_t)); key.append((const char*)hi.data(),hi.size()*sizeof(int64_t));
+    // segment length: the largest rank share, in elements
+    std::vector<int64_t> seg(W,0);
+    for(int g = 0; g < W; ++g)
+        for(auto const& bo : off)
+            {
+            auto sct = bo.block[j];
+            auto rows = hi[size_t(g)*ns+sct]-lo[size_t(g)*ns+sct];
+            if(rows <= 0) continue;
+            int64_t rest = 1;
+            for(auto i : range(r)) if(int(i) != j) rest *= is[i].blocksize0(bo.block[i]);
+            seg[g] += rows*rest;
+            }
+    int64_t segMax = 1;
+    for(auto v : seg) segMax = std::max(segMax,v);
+    P->segDoubles = segMax*(dtype == ITB_C64 ? 2 : 1);
+    auto build = [&](bool pack) -> itb_permute_plan*
+        {
+        auto k = key; k.push_back(pack ? 'P' : 'U');
+        auto& cache = permuteCache();
+        if(auto* p = cache.find(k)) return p;
+        std::vector<itb_copy_item> items;
+        for(int g = 0; g < W; ++g)
+            {
+            if(pack ? g != gpu::rank() : g == gpu::rank()) continue;
+            int64_t run = pack ? 0 : int64_t(g)*segMax;
+            for(auto const& bo : off)
+                {
+                auto sct = bo.block[j];
+                auto a = lo[size_t(g)*ns+sct], e = hi[size_t(g)*ns+sct];
+                if(e <= a) continue;
+                itb_copy_item it;
+                std::memset(&it,0,sizeof(it));
+                it.n = r;
+                int64_t full = 1, packed = 1;
+                int64_t shift = 0;
+                for(auto i : range(r))
+                    {
+                    int64_t ext = is[i].blocksize0(bo.block[i]);
+                    int64_t box = int(i) == j ? e-a : ext;
+                    it.ext[i] = box;
+                    (pack ? it.sstr[i] : it.dstr[i]) = full;
+                    (pack ? it.dstr[i] : it.sstr[i]) = packed;
+                    if(int(i) == j) shift = a*full;
+                    full *= ext; packed *= box;
+                    }
+                (pack ? it.s_off : it.d_off) = bo.offset+shift;
+                (pack ? it.d_off : it.s_off) = run;
+                run += packed;
+                items.push_back(it);
+                }
+            }
+        itb_permute_plan* p = nullptr;
+        check(itb_blockcopy_plan_create(int64_t(items.size()),items.data(),dtype,dtype,&p),"row pack/scatter plan");
+        cache.insert(k,p);
+        return p;
+        };
+    P->pack = build(true);
+    P->unpack = build(false);
+    return P;
+    }
+
+// position of index I in an IndexSet, -1 if absent
+static int
+findIndexPos(IndexSet const& is, Index const& I)
+    {
+    for(auto i : range(order(is))) if(is[i] == I) return int(i);
+    return -1;
+    }
+
 // doTask(Contract,QDense,QDense) qdense.cc:671-747 (+ getContractedOffsets, loopContractedBlocks, contract, gemm)
+//
+// With ITB_WORLD > 1 (one process per GPU, every process running the same program on the same data) large contractions
+// are ROW-SHARDED: each rank computes the rows of one uncontracted index it owns and the result stays "pending" — it is
+// only all-gathered when something needs the whole tensor (gpu::Buffer::data()). A contraction that finds a pending
+// operand whose sharded index stays uncontracted simply continues on the same rows: phi*L -> *W1 -> *W2 -> *R
+// (LocalOp::product, localop.h:346-362) therefore runs without communication and H*phi is re-replicated by ONE
+// all-gather when davidson first touches it; environment tensors stay row-sharded from one bond to the next.
 template<typename VA, typename VB>
 static void
 contractQ(Contract& Con,
-          BlockOffsets const& Aoff, void const* Adata, size_t An,
-          BlockOffsets const& Boff, void const* Bdata, size_t Bn,
+          BlockOffsets const& Aoff, gpu::Buffer const& Abuf, size_t An,
+          BlockOffsets const& Boff, gpu::Buffer const& Bbuf, size_t Bn,
           ManageStore& m)
     {
     using VC = common_type<VA,VB>;
@@ -589,7 +810,8 @@ contractQ(Contract& Con,
 
     auto dA = Desc(Con.Lis,Aoff,An,dtypeOf<VA>());
     auto dB = Desc(Con.Ris,Boff,Bn,dtypeOf<VB>());
-    auto* plan = getContractPlan(dA,toLabels(Lind),dB,toLabels(Rind));
+    auto la = toLabels(Lind), lb = toLabels(Rind);
+    auto* plan = getContractPlan(dA,la,dB,lb);
     itb_contract_info info;
     check(itb_contract_plan_info(plan,&info),"plan info");
     auto rC = long(info.c_order);
@@ -605,29 +827,87 @@ contractQ(Contract& Con,
         for(auto j : range(rC)) b[j] = cb[c*rC+j];
         Coffsets.push_back(make_blof(b,co[c]));
         }
+
+    // ---- row sharding -------------------------------------------------------------------------------------------
+    std::shared_ptr<gpu::Pending> next;
+    itb_contract_plan* sliced = nullptr;
+    if(gpu::world() > 1 && info.c_nblocks > 0 && rC > 0)
+        {
+        static const double min_flops = [] { auto* e = std::getenv("ITB_SHARD_MIN_FLOPS"); return e ? std::atof(e) : 2e8; }();
+        auto pa = Abuf.pending(), pb = Bbuf.pending();
+        if(pa && pb) { Bbuf.data(); pb.reset(); }       // two sharded operands: complete one of them
+        auto& pend = pa ? pa : pb;
+        int cpos = -1;
+        std::vector<int64_t> lo, hi;
+        Index shardIndex;
+        if(pend)
+            {
+            // continue on the same rows if the sharded index survives this contraction, else complete the operand now
+            cpos = findIndexPos(Con.Nis,pend->shardIndex);
+            if(cpos >= 0) { lo = pend->lo; hi = pend->hi; shardIndex = pend->shardIndex; }
+            else { (pa ? Abuf : Bbuf).data(); pend.reset(); }
+            }
+        if(cpos < 0 && !pend && info.flops >= min_flops)
+            {
+            // start sharding here: the primed index of largest dimension (the bra-side link of an effective-Hamiltonian
+            // product survives the whole chain), else the largest index; weights = flops per row of every sector
+            long best = -1;
+            for(auto j : range(rC))
+                {
+                auto const& I = Con.Nis[j];
+                if(dim(I) < 8*gpu::world()) continue;
+                long score = dim(I)+(primeLevel(I) > 0 ? (1l << 40) : 0);
+                if(score > best) { best = score; cpos = int(j); }
+                }
+            if(cpos >= 0)
+                {
+                shardIndex = Con.Nis[cpos];
+                auto ns = shardIndex.nblock();
+                std::vector<double> bf(size_t(info.c_nblocks),0.), w(size_t(ns),0.);
+                check(itb_contract_plan_cblock_flops(plan,bf.data()),"cblock flops");
+                for(auto c : range(info.c_nblocks)) w[size_t(cb[c*rC+cpos])] += bf[size_t(c)];
+                std::vector<int64_t> sizes(size_t(ns),0);
+                for(auto q : range(ns)) sizes[size_t(q)] = shardIndex.blocksize0(q);
+                rowPartition(sizes,w,lo,hi);
+                }
+            }
+        if(cpos >= 0)
+            {
+            auto ns = int(shardIndex.nblock());
+            sliced = getContractPlan(dA,la,dB,lb,cpos,lo.data()+size_t(gpu::rank())*ns,hi.data()+size_t(gpu::rank())*ns,ns);
+            if(sliced) next = makePending(Con.Nis,Coffsets,dtypeOf<VC>(),cpos,shardIndex,lo,hi);
+            else if(pend) { (pa ? Abuf : Bbuf).data(); } // this step cannot be sliced on that index: complete the operand, run unsharded
+            }
+        }
     auto* nd = m.makeNewData<QDenseGPU<VC>>(Coffsets,size_t(info.c_nelems));
-    check(itb_contract_run(context(),plan,Adata,Bdata,nd->buf.data()),"contract");
+    if(sliced)
+        {
+        // operands as they are: a pending operand contributes exactly the rows this rank owns
+        check(itb_contract_run(context(),sliced,Abuf.rawData(),Bbuf.rawData(),nd->buf.rawData()),"contract (row-sharded)");
+        nd->buf.setPending(next);
+        }
+    else check(itb_contract_run(context(),plan,Abuf.data(),Bbuf.data(),nd->buf.rawData()),"contract");
     }
 
 template<typename VA, typename VB>
 void
 doTask(Contract& Con, QDenseGPU<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m)
     {
-    contractQ<VA,VB>(Con,A.offsets,A.buf.data(),A.n,B.offsets,B.buf.data(),B.n,m);
+    contractQ<VA,VB>(Con,A.offsets,A.buf,A.n,B.offsets,B.buf,B.n,m);
     }
 template<typename VA, typename VB>
 void
 doTask(Contract& Con, QDenseGPU<VA> const& A, QDense<VB> const& B, ManageStore& m)
     {
     auto gB = QDenseGPU<VB>(B); // upload the host operand
-    contractQ<VA,VB>(Con,A.offsets,A.buf.data(),A.n,gB.offsets,gB.buf.data(),gB.n,m);
+    contractQ<VA,VB>(Con,A.offsets,A.buf,A.n,gB.offsets,gB.buf,gB.n,m);
     }
 template<typename VA, typename VB>
 void
 doTask(Contract& Con, QDense<VA> const& A, QDenseGPU<VB> const& B, ManageStore& m)
     {
     auto gA = QDenseGPU<VA>(A);
-    contractQ<VA,VB>(Con,gA.offsets,gA.buf.data(),gA.n,B.offsets,B.buf.data(),B.n,m);
+    contractQ<VA,VB>(Con,gA.offsets,gA.buf,gA.n,B.offsets,B.buf,B.n,m);
     }
 #define ITB_INST_CONTRACT(TA,TB) \
 template void doTask(Contract&,QDenseGPU<TA> const&,QDenseGPU<TB> const&,ManageStore&); \
@@ -690,7 +970,7 @@ doTask(Contract& C, QDenseGPU<TA> const& d, QDiag<TB> const& t, ManageStore& m)
     if(order(C.Ris) == 2 && (Rind[0] < 0 || Rind[1] < 0))
         {
         auto g = qdiagAsMatrix(t,C.Ris);
-        contractQ<TA,TB>(C,d.offsets,d.buf.data(),d.n,g.offsets,g.buf.data(),g.n,m);
+        contractQ<TA,TB>(C,d.offsets,d.buf,d.n,g.offsets,g.buf,g.n,m);
         return;
         }
     doTask(C,d.toHost(),t,m);
@@ -704,7 +984,7 @@ doTask(Contract& C, QDiag<TA> const& t, QDenseGPU<TB> const& d, ManageStore& m)
     if(order(C.Lis) == 2 && (Lind[0] < 0 || Lind[1] < 0))
         {
         auto g = qdiagAsMatrix(t,C.Lis);
-        contractQ<TA,TB>(C,g.offsets,g.buf.data(),g.n,d.offsets,d.buf.data(),d.n,m);
+        contractQ<TA,TB>(C,g.offsets,g.buf,g.n,d.offsets,d.buf,d.n,m);
         return;
         }
     doTask(C,t,d.toHost(),m);

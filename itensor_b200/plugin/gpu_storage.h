@@ -42,20 +42,35 @@ itb_ctx* context();
 void synchronize();
 long launchCount();
 
+// Multi-GPU (one process per GPU, ITB_WORLD / ITB_RANK in the environment): world size and rank of this process
+int world();
+int rank();
+
+// A row-sharded tensor that has not been re-replicated yet: this rank's buffer holds only the rows of one index it
+// computed itself (one owner per piece of C, itensor/itdata/qutil.h:285-348, refined to row ranges). The
+// all-gather that completes it runs the first time anybody needs the whole buffer (Buffer::data()); a contraction that
+// leaves the sharded index uncontracted keeps working on the rows it owns instead (gpu_storage.cc, contractQ), which is
+// how the four steps of LocalOp::product (localop.h:346-362) run without communication until H*phi is complete.
+struct Pending;
+
 // RAII device buffer from the context's caching pool; copies are deep (device-to-device)
 class Buffer
     {
     void* p_ = nullptr;
     size_t bytes_ = 0;
+    mutable std::shared_ptr<Pending> pending_; // set: only this rank's rows are valid until data() completes the buffer
     public:
     Buffer() { }
     explicit Buffer(size_t bytes);
     Buffer(Buffer const& o);
-    Buffer(Buffer&& o) noexcept : p_(o.p_), bytes_(o.bytes_) { o.p_ = nullptr; o.bytes_ = 0; }
+    Buffer(Buffer&& o) noexcept : p_(o.p_), bytes_(o.bytes_), pending_(std::move(o.pending_)) { o.p_ = nullptr; o.bytes_ = 0; }
     Buffer& operator=(Buffer const& o);
     Buffer& operator=(Buffer&& o) noexcept;
     ~Buffer();
-    void* data() const { return p_; }
+    void* data() const;                       // the complete buffer (runs a pending all-gather first)
+    void* rawData() const { return p_; }      // the buffer as it is (only own rows valid while pending() is set)
+    std::shared_ptr<Pending> const& pending() const { return pending_; }
+    void setPending(std::shared_ptr<Pending> p) const { pending_ = std::move(p); }
     size_t bytes() const { return bytes_; }
     void upload(void const* host, size_t bytes);
     void download(void* host, size_t bytes) const;

@@ -350,6 +350,53 @@ int itb_svd_batch_values(itb_svd_batch*, double*) { return ITB_ERR_UNSUPPORTED; 
 int itb_svd_batch_copy_u(itb_svd_batch*, int64_t, int32_t, void*) { return ITB_ERR_UNSUPPORTED; }
 int itb_svd_batch_copy_v(itb_svd_batch*, int64_t, int32_t, void*, int) { return ITB_ERR_UNSUPPORTED; }
 int itb_svd_batch_destroy(itb_svd_batch*) { return ITB_OK; }
+// ---- communicator: file-based all-gather between the processes of a CPU test (world_size 2-3, small tensors) ----------
+} // extern "C"
+#include <chrono>
+#include <fstream>
+#include <thread>
+#include <sys/stat.h>
+#include <unistd.h>
+struct itb_comm { int world = 1, rank = 0; std::string dir; long seq = 0; };
+extern "C" {
+int itb_comm_unique_id(uint8_t out[ITB_COMM_ID_BYTES]) {
+    std::memset(out, 0, ITB_COMM_ID_BYTES);
+    const unsigned long long v = (unsigned long long)getpid() * 1000003ull ^ (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count();
+    std::snprintf((char*)out, ITB_COMM_ID_BYTES, "/tmp/itbmock_comm_%llx", v);
+    return ITB_OK;
+}
+int itb_comm_create(itb_ctx*, int32_t world, int32_t rank, const uint8_t id[ITB_COMM_ID_BYTES], itb_comm** out) {
+    auto* c = new itb_comm();
+    c->world = world; c->rank = rank; c->dir = std::string((const char*)id);
+    mkdir(c->dir.c_str(), 0700);
+    *out = c;
+    return ITB_OK;
+}
+int32_t itb_comm_world(const itb_comm* c) { return c ? c->world : 1; }
+int32_t itb_comm_rank(const itb_comm* c) { return c ? c->rank : 0; }
+int itb_comm_allgather(itb_comm* c, itb_ctx*, const void* send, void* recv, int64_t count) {
+    auto name = [&](int r) { return c->dir + "/" + std::to_string(c->seq) + "_" + std::to_string(r); };
+    {
+        std::ofstream f(name(c->rank) + ".tmp", std::ios::binary);
+        f.write((const char*)send, (std::streamsize)count * 8);
+    }
+    std::rename((name(c->rank) + ".tmp").c_str(), name(c->rank).c_str());
+    for (int r = 0; r < c->world; ++r) {
+        double* dst = (double*)recv + (int64_t)r * count;
+        if (r == c->rank) { if ((const void*)dst != send) std::memmove(dst, send, (size_t)count * 8); continue; }
+        for (int tries = 0;; ++tries) {
+            std::ifstream f(name(r), std::ios::binary);
+            if (f && f.read((char*)dst, (std::streamsize)count * 8)) break;
+            if (tries > 200000) { itb::set_error("mock all-gather: timed out"); return ITB_ERR_CUDA; }
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
+    if (c->seq >= 2) std::remove((c->dir + "/" + std::to_string(c->seq - 2) + "_" + std::to_string(c->rank)).c_str()); // everyone is past it
+    ++c->seq;
+    return ITB_OK;
+}
+int itb_comm_destroy(itb_comm* c) { delete c; return ITB_OK; }
+
 int itb_eigh_batch_run(itb_ctx*, int32_t, int64_t, const int64_t*, const int32_t*, const void*, int, itb_eigh_batch**) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
 int itb_eigh_batch_values(itb_eigh_batch*, double*) { return ITB_ERR_UNSUPPORTED; }
 int itb_eigh_batch_copy_vectors(itb_eigh_batch*, int64_t, int32_t, void*, int) { return ITB_ERR_UNSUPPORTED; }
