@@ -136,10 +136,21 @@ comm()
     return c;
     }
 
+// pack / scatter plans are shared between the structure cache and every pending tensor that still needs them (an
+// environment tensor can stay row-sharded across many bonds, long after the cache has recycled its entry)
+struct CopyPlan
+    {
+    itb_permute_plan* p = nullptr;
+    explicit CopyPlan(itb_permute_plan* p_) : p(p_) { }
+    CopyPlan(CopyPlan const&) = delete;
+    CopyPlan& operator=(CopyPlan const&) = delete;
+    ~CopyPlan() { if(p) itb_permute_plan_destroy(p); }
+    };
+
 struct Pending
     {
-    itb_permute_plan* pack = nullptr;   // own rows of the tensor -> this rank's segment (cached plans, not owned)
-    itb_permute_plan* unpack = nullptr; // the other ranks' segments -> their places in the tensor
+    std::shared_ptr<CopyPlan> pack;     // own rows of the tensor -> this rank's segment
+    std::shared_ptr<CopyPlan> unpack;   // the other ranks' segments -> their places in the tensor
     long segDoubles = 0;                // padded segment length in doubles
     // what a follow-up contraction needs to keep working on the same rows
     Index shardIndex;
@@ -155,9 +166,9 @@ runPending(Pending const& P, void* p)
     void* seg = nullptr;
     check(itb_malloc(ctx,size_t(P.segDoubles)*world()*sizeof(double),&seg),"malloc (gather segments)");
     auto* mine = static_cast<double*>(seg)+size_t(P.segDoubles)*rank();
-    check(itb_permute_run(ctx,P.pack,p,mine,1.,0.,0),"pack rows");
+    check(itb_permute_run(ctx,P.pack->p,p,mine,1.,0.,0),"pack rows");
     check(itb_comm_allgather(comm(),ctx,mine,seg,P.segDoubles),"all-gather");
-    check(itb_permute_run(ctx,P.unpack,seg,p,1.,0.,0),"scatter rows");
+    check(itb_permute_run(ctx,P.unpack->p,seg,p,1.,0.,0),"scatter rows");
     check(itb_free(ctx,seg),"free (gather segments)"); // stream-ordered pool: reused only behind the scatter
     }
 
@@ -732,11 +743,14 @@ makePending(IndexSet const& is, BlockOffsets const& off, int dtype, int j, Index
     int64_t segMax = 1;
     for(auto v : seg) segMax = std::max(segMax,v);
     P->segDoubles = segMax*(dtype == ITB_C64 ? 2 : 1);
-    auto build = [&](bool pack) -> itb_permute_plan*
+    // small LRU of shared plans keyed on structure + partition (davidson gathers the same H*phi structure every iteration)
+    static std::unordered_map<std::string,std::shared_ptr<gpu::CopyPlan>> cache;
+    static std::deque<std::string> lru;
+    auto build = [&](bool pack) -> std::shared_ptr<gpu::CopyPlan>
         {
         auto k = key; k.push_back(pack ? 'P' : 'U');
-        auto& cache = permuteCache();
-        if(auto* p = cache.find(k)) return p;
+        auto hit = cache.find(k);
+        if(hit != cache.end()) return hit->second;
         std::vector<itb_copy_item> items;
         for(int g = 0; g < W; ++g)
             {
@@ -770,8 +784,11 @@ makePending(IndexSet const& is, BlockOffsets const& off, int dtype, int j, Index
             }
         itb_permute_plan* p = nullptr;
         check(itb_blockcopy_plan_create(int64_t(items.size()),items.data(),dtype,dtype,&p),"row pack/scatter plan");
-        cache.insert(k,p);
-        return p;
+        auto sp = std::make_shared<gpu::CopyPlan>(p);
+        if(lru.size() >= 64) { cache.erase(lru.front()); lru.pop_front(); }
+        cache[k] = sp;
+        lru.push_back(k);
+        return sp;
         };
     P->pack = build(true);
     P->unpack = build(false);
