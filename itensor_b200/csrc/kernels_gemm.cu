@@ -40,6 +40,20 @@ __device__ __forceinline__ void dmma884_if(double& d0, double& d1, double a, dou
         : "d"(a), "d"(b), "r"(on));
 }
 
+// four DMMAs of one accumulator row under ONE predicate. A predicated mma must leave its accumulator untouched when the
+// predicate is false, so ptxas has to keep D == C (in place); the unpredicated form lets it pick D != C and it then
+// restores the loop-carried registers with ~2 moves per DMMA (120 IMAD.MOV per K-chunk in the hot loop).
+__device__ __forceinline__ void dmma884_row4(double (&c)[4][2], double a, const double (&b)[4], int on) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %13, 0;\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%8}, {%9}, {%0,%1};\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%8}, {%10}, {%2,%3};\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%4,%5}, {%8}, {%11}, {%4,%5};\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%6,%7}, {%8}, {%12}, {%6,%7};\n\t}"
+        : "+d"(c[0][0]), "+d"(c[0][1]), "+d"(c[1][0]), "+d"(c[1][1]), "+d"(c[2][0]), "+d"(c[2][1]), "+d"(c[3][0]), "+d"(c[3][1])
+        : "d"(a), "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]), "r"(on));
+}
+
 // offset of linear index idx within an index group (extents fastest-first)
 __device__ __forceinline__ int64_t grp_off(int idx, const int32_t* __restrict__ ext, const int64_t* __restrict__ str, int n) {
     int64_t o = 0;
@@ -168,13 +182,18 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
             }
 #pragma unroll
             for (int j = 0; j < FN; ++j) fb[j] = bs[j * 8 * sBn + ks * 4 * sBk];
+            if constexpr (!EDGE && FN == 4) {
 #pragma unroll
-            for (int i = 0; i < FM; ++i)
+                for (int i = 0; i < FM; ++i) dmma884_row4(acc[i], fa[i], fb, nchunks);
+            } else {
 #pragma unroll
-                for (int j = 0; j < FN; ++j) {
-                    if (EDGE) dmma884_if(acc[i][j][0], acc[i][j][1], fa[i], fb[j], (i < fmv) & (j < fnv));
-                    else dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-                }
+                for (int i = 0; i < FM; ++i)
+#pragma unroll
+                    for (int j = 0; j < FN; ++j) {
+                        if (EDGE) dmma884_if(acc[i][j][0], acc[i][j][1], fa[i], fb[j], (i < fmv) & (j < fnv));
+                        else dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                    }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[ps.stage]);
