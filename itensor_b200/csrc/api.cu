@@ -18,6 +18,8 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const in
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles,
                         cudaStream_t st);
+cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbCBlk* cblks, const ItbPair* pairs,
+                               const double* A, const double* B, double* C, double* ws, long long* cta_cycles, cudaStream_t st);
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st);
 cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
@@ -479,6 +481,12 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
             SIDE_TRY(cudaMalloc(&c->d_cta_cycles, prof_words * sizeof(long long)));
             c->cta_cycles_words = prof_words;
         }
+        static const bool static_kernel = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "static"; }();
+        if (static_kernel && has_static && P->cta_begin[n_static] == (int32_t)P->tiles.size()) {
+            // A/B measurement: the round-1 kernel on a purely static schedule (ITB_SCHED=streamk)
+            SIDE_TRY(launch_gemm_static(d->qitems, d->cta_begin, grid, d->cblks, d->pairs, A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
+            if (!P->splits.empty()) SIDE_TRY(launch_gemm(d->qitems, 0, d->counters, d->cta_begin, 0, 1, d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws, nullptr, c->stream));
+        } else
         SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, d->cta_begin, n_static, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
