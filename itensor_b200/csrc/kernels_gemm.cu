@@ -517,66 +517,81 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 #endif
     PipeState ps;
-    int qf = 0;            // fetcher: next sequence number to publish
-    bool exhausted = false;
-    // hybrid schedule (plan.cc): this CTA's static range of the item list first, then the shared queue behind it
-    int st_next = 0, st_end = 0;
-    const int tail_begin = cta_begin[n_static_ctas];
-    if ((int)blockIdx.x < n_static_ctas) { st_next = cta_begin[blockIdx.x]; st_end = cta_begin[blockIdx.x + 1]; }
-    for (int q = 0;; ++q) {
-        if (fetch_warp) {
-            while (!exhausted && qf < q + G_QSLOTS) {
-                const int s = qf % G_QSLOTS;
-                // A slot is free once EVERY warp has finished the item that last used it. The consumers lag the producers
-                // by up to G_STAGES chunks, so the slot of item q-1 is normally still busy here: look-ahead fetches only
-                // TEST the barrier (and retry at the next item); blocking there would drain the operand ring at every
-                // item boundary (measured: ~4 chunks = 18k cycles per item). Only the item needed right now waits.
-                const int par = ((qf / G_QSLOTS) & 1) ^ 1;
-                if (qf > q) { // (lane 0 decides for the warp: the phase may complete between two lanes' tests)
-                    const int ok = __shfl_sync(0xffffffffu, (int)mbar_test(&q_empty[s], par), 0);
-                    if (!ok) break;
-                }
-                mbar_wait(&q_empty[s], par);
-                int idx = 0;
-                if (st_next < st_end) idx = st_next++;
-                else {
-                    if (lane == 0) idx = tail_begin + atomicAdd(queue, 1);
-                    idx = __shfl_sync(0xffffffffu, idx, 0);
-                }
-                int* dst = reinterpret_cast<int*>(q_item + s);
-                if (idx < n_items) { // 160 bytes = 40 ints
-                    const int* src = reinterpret_cast<const int*>(items + idx);
-                    dst[lane] = src[lane];
-                    if (lane < 8) dst[32 + lane] = src[32 + lane];
-                }
-                if (lane == 0) q_item[s].item = idx;
-                __syncwarp(); // orders every lane's stores before lane 0's releasing arrive
-                if (lane == 0) mbar_arrive(&q_full[s]);
-                exhausted = idx >= n_items;
-                ++qf;
-            }
-        }
-        const int s = q % G_QSLOTS;
-        mbar_wait(&q_full[s], (q / G_QSLOTS) & 1);
-        const QItem& qi = q_item[s];
-        if (qi.item >= n_items) break;
-        const int cfg = qi.tile.cfg;
-        // profile build: consumer thread 0 records {CTA, item start, end of K loop, item end} per item (clock64 relative to
-        // the CTA's start) behind the 1024 per-CTA spans
-        long long* rec = (PROF && cta_cycles && threadIdx.x == 0) ? cta_cycles + 1024 + 4 * (long long)qi.item : nullptr;
-        if (PROF && rec) { rec[0] = blockIdx.x; rec[1] = clock64() - t_begin; }
-        if (producer) {
-            if (cfg == 0) produce_tile<128, 128>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
-            else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
-            else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
-        } else {
+    // Three separate loops, one per role, so that the fetcher's bookkeeping (queue positions, look-ahead state) is not
+    // live in the consumers' register allocation: with one shared loop ptxas carried it through the DMMA loop (318
+    // instead of 261 instructions per K-chunk, more accumulator spills) and every K-chunk cost ~250 cycles more.
+    if (!producer) {
+        // ---- consumers ---------------------------------------------------------------------------------------------
+        for (int q = 0;; ++q) {
+            const int s = q % G_QSLOTS;
+            mbar_wait(&q_full[s], (q / G_QSLOTS) & 1);
+            const QItem& qi = q_item[s];
+            if (qi.item >= n_items) break;
+            const int cfg = qi.tile.cfg;
+            // profile build: consumer thread 0 records {CTA, item start, end of K loop, item end} per item (clock64 relative
+            // to the CTA's start) behind the 1024 per-CTA spans
+            long long* rec = (PROF && cta_cycles && threadIdx.x == 0) ? cta_cycles + 1024 + 4 * (long long)qi.item : nullptr;
+            if (PROF && rec) { rec[0] = blockIdx.x; rec[1] = clock64() - t_begin; }
             if (cfg == 0) consume_tile<128, 128, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
             else if (cfg == 1) consume_tile<64, 64, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
             else consume_tile<32, 32, PROF>(qi, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, rec);
             if (PROF && rec) { rec[2] -= t_begin; rec[3] = clock64() - t_begin; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[s]); // the slot may be refilled once every warp has finished the item
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&q_empty[s]); // the slot may be refilled once every warp has finished the item
+    } else {
+        // ---- producers (the first producer warp also fetches) ------------------------------------------------------------
+        const bool fetch_warp = (threadIdx.x >> 5) == G_NCONS / 32;
+        int qf = 0;            // fetcher: next sequence number to publish
+        bool exhausted = false;
+        // hybrid schedule (plan.cc): this CTA's static range of the item list first, then the shared queue behind it
+        int st_next = 0, st_end = 0;
+        const int tail_begin = cta_begin[n_static_ctas];
+        if ((int)blockIdx.x < n_static_ctas) { st_next = cta_begin[blockIdx.x]; st_end = cta_begin[blockIdx.x + 1]; }
+        for (int q = 0;; ++q) {
+            if (fetch_warp) {
+                while (!exhausted && qf < q + G_QSLOTS) {
+                    const int s = qf % G_QSLOTS;
+                    // A slot is free once EVERY warp has finished the item that last used it. The consumers lag the producers
+                    // by up to G_STAGES chunks, so the slot of item q-1 is normally still busy here: look-ahead fetches only
+                    // TEST the barrier (and retry at the next item); blocking there would drain the operand ring at every
+                    // item boundary (measured: ~4 chunks = 18k cycles per item). Only the item needed right now waits.
+                    const int par = ((qf / G_QSLOTS) & 1) ^ 1;
+                    if (qf > q) { // (lane 0 decides for the warp: the phase may complete between two lanes' tests)
+                        const int ok = __shfl_sync(0xffffffffu, (int)mbar_test(&q_empty[s], par), 0);
+                        if (!ok) break;
+                    }
+                    mbar_wait(&q_empty[s], par);
+                    int idx = 0;
+                    if (st_next < st_end) idx = st_next++;
+                    else {
+                        if (lane == 0) idx = tail_begin + atomicAdd(queue, 1);
+                        idx = __shfl_sync(0xffffffffu, idx, 0);
+                    }
+                    int* dst = reinterpret_cast<int*>(q_item + s);
+                    if (idx < n_items) { // 160 bytes = 40 ints
+                        const int* src = reinterpret_cast<const int*>(items + idx);
+                        dst[lane] = src[lane];
+                        if (lane < 8) dst[32 + lane] = src[32 + lane];
+                    }
+                    if (lane == 0) q_item[s].item = idx;
+                    __syncwarp(); // orders every lane's stores before lane 0's releasing arrive
+                    if (lane == 0) mbar_arrive(&q_full[s]);
+                    exhausted = idx >= n_items;
+                    ++qf;
+                }
+            }
+            const int s = q % G_QSLOTS;
+            mbar_wait(&q_full[s], (q / G_QSLOTS) & 1);
+            const QItem& qi = q_item[s];
+            if (qi.item >= n_items) break;
+            const int cfg = qi.tile.cfg;
+            if (cfg == 0) produce_tile<128, 128>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
+            else if (cfg == 1) produce_tile<64, 64>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
+            else produce_tile<32, 32>(qi, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps, dbg_nocompute);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[s]);
+        }
     }
     if (threadIdx.x == G_NCONS) {
         // this CTA will not touch the queue head again; the last CTA to get here rearms the queue for the next launch
