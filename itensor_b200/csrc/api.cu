@@ -18,8 +18,9 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const in
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles,
                         cudaStream_t st);
-cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbCBlk* cblks, const ItbPair* pairs,
-                               const double* A, const double* B, double* C, double* ws, long long* cta_cycles, cudaStream_t st);
+cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+                               const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
+                               long long* cta_cycles, cudaStream_t st);
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st);
 cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
@@ -481,19 +482,23 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
             SIDE_TRY(cudaMalloc(&c->d_cta_cycles, prof_words * sizeof(long long)));
             c->cta_cycles_words = prof_words;
         }
-        static const bool static_kernel = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "static"; }();
-        if (static_kernel && has_static && P->cta_begin[n_static] == (int32_t)P->tiles.size()) {
-            // A/B measurement: the round-1 kernel on a purely static schedule (ITB_SCHED=streamk)
-            SIDE_TRY(launch_gemm_static(d->qitems, d->cta_begin, grid, d->cblks, d->pairs, A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
-            if (!P->splits.empty()) SIDE_TRY(launch_gemm(d->qitems, 0, d->counters, d->cta_begin, 0, 1, d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws, nullptr, c->stream));
+        // two kernels with the same producer / consumer loops: a purely static schedule (every item in some CTA's range,
+        // nothing in the shared queue) runs on the kernel without the item ring (kernels_gemm_static.cu; ITB_TILE_KERNEL=ring
+        // forces the other one), anything with a dynamic part on the ring kernel (kernels_gemm.cu)
+        static const bool force_ring = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "ring"; }();
+        if (!force_ring && has_static && P->cta_begin[n_static] == (int32_t)P->tiles.size()) {
+            SIDE_TRY(launch_gemm_static(d->qitems, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
+                                        c->profile ? c->d_cta_cycles : nullptr, c->stream));
+            c->h_item_cycles.clear();
         } else
         SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, d->cta_begin, n_static, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));
         if (c->profile) {
             c->h_cta_cycles.assign(grid, 0);
             CUDA_TRY(cudaMemcpyAsync(c->h_cta_cycles.data(), c->d_cta_cycles, grid * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-            c->h_item_cycles.assign(4 * P->tiles.size(), 0);
-            CUDA_TRY(cudaMemcpyAsync(c->h_item_cycles.data(), c->d_cta_cycles + 1024, 4 * P->tiles.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+            const bool ring_ran = force_ring || !(has_static && P->cta_begin[n_static] == (int32_t)P->tiles.size());
+            c->h_item_cycles.assign(ring_ran ? 4 * P->tiles.size() : 0, 0);
+            if (ring_ran) CUDA_TRY(cudaMemcpyAsync(c->h_item_cycles.data(), c->d_cta_cycles + 1024, 4 * P->tiles.size() * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
         }
         PROF_END(0);
         c->launches += P->splits.empty() ? 1 : 2;

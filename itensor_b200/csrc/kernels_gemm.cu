@@ -1076,6 +1076,11 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const in
     return e;
 }
 
+cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks, const double* ws, double* C, cudaStream_t st) {
+    bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st) {
     static int variant = -1; // tuning hook: ITB_SKINNY_VARIANT=0 (KU=1, 4 CTAs/SM) | 1 (KU=4, 3 CTAs/SM) | 2 (KU=2, 4 CTAs/SM)

@@ -1,6 +1,8 @@
-// kernels_gemm_static.cu — the round-1 tile kernel (static per-CTA item ranges, no item ring), kept side by side with
-// kernels_gemm.cu for A/B measurements on the same plans: ITB_TILE_KERNEL=static selects it for plans scheduled with
-// ITB_SCHED=streamk. Same producer / consumer loops; the roles read the tile records straight from global memory.
+// kernels_gemm_static.cu — the tile kernel for purely STATIC schedules (stream-K partition, plan.cc): every CTA walks its
+// own contiguous range of the item list, cta_begin[b]..cta_begin[b+1]; no work queue, no item ring. Same warp-specialised
+// producer / consumer loops as kernels_gemm.cu (which adds the dynamic queue); both roles read the tile records straight
+// from global memory. On the bench workload this kernel + the fitted static partition is the fastest combination
+// measured (same-box A/B, profiles/r03_tile_schedule_ab.txt), so it is the default; ITB_SCHED=guided selects the queue.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -415,8 +417,11 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbQItem
 
 } // namespace r1
 
-cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbCBlk* cblks, const ItbPair* pairs,
-                               const double* A, const double* B, double* C, double* ws, long long* cta_cycles, cudaStream_t st) {
+cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks, const double* ws, double* C, cudaStream_t st); // kernels_gemm.cu
+
+cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+                               const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
+                               long long* cta_cycles, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(r1::bsc_gemm_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r1::G_SMEM);
@@ -424,7 +429,9 @@ cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, 
         configured = true;
     }
     r1::bsc_gemm_static_kernel<<<grid, r1::G_NT, r1::G_SMEM, st>>>(items, cta_begin, cblks, pairs, A, B, C, ws, cta_cycles, 0);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || nsouts == 0) return e;
+    return launch_splitk_reduce(souts, nsouts, cblks, ws, C, st);
 }
 
 } // namespace itb

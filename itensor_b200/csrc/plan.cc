@@ -307,7 +307,11 @@ static int kForceCfg = -1;
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this (ITB_MIN_PIECE)
 static double kGuidedFactor = 2.0;  // shared queue: piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
-static bool kSchedStreamK = false;  // ITB_SCHED=streamk: pure static stream-K partition instead of the guided queue
+static bool kSchedStreamK = true;   // ITB_SCHED=streamk (default) | guided: static stream-K partition or the guided dynamic queue.
+                                    // Same-box A/B on the bench workload (profiles/r03_tile_schedule_ab.txt): static partition +
+                                    // static kernel 22.9 TFLOP/s; guided queue + ring kernel 22.1-22.2 (better balance, 1.03 vs
+                                    // 1.10 max/mean, and 40 % less DRAM traffic, but +4.5 % CTA cycles for the same items and a
+                                    // three times larger split-K reduction)
 static double kStaticFrac = 0.0;    // fraction of the modelled work handed out as static per-CTA ranges; ITB_STATIC_FRAC (0: all dynamic).
                                     // Measured (profiles/r03_tile_schedule_variants.txt): 0 -> 1378 us per H_eff*phi, 0.85 -> 1391-1419, 0.92 -> 1412
 static void read_tile_env() {
@@ -320,7 +324,12 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
     if (const char* e = getenv("ITB_GUIDED_FACTOR")) kGuidedFactor = std::max(0.25, atof(e));
     if (const char* e = getenv("ITB_MIN_PIECE")) kMinPiece = std::max(1, atoi(e));
-    if (const char* e = getenv("ITB_SCHED")) kSchedStreamK = std::string(e) == "streamk";
+    if (const char* e = getenv("ITB_SCHED")) kSchedStreamK = std::string(e) != "guided";
+    if (kSchedStreamK && !getenv("ITB_TILE_OVERHEAD")) {
+        // the static partition is only as good as its cycle model: these are the constants fitted WITH this partition to
+        // per-CTA clock64 spans of the static kernel (tools/sched_fit.py); the guided queue uses per-item measurements
+        kTileOverhead[0] = 1200.0; kPairOverhead = 4300.0;
+    }
     if (const char* e = getenv("ITB_STATIC_FRAC")) kStaticFrac = std::min(0.98, std::max(0.0, atof(e)));
 }
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
@@ -776,16 +785,16 @@ int build_contract_tables(itb_contract_plan& P) {
             // Pure static stream-K partition (the round-1 schedule, kept selectable: ITB_SCHED=streamk): every CTA gets the
             // same modelled cycles, the tile list is cut at K-chunk boundaries where a share is full (<= G-1 cut tiles), no
             // shared queue. Its constants were fitted to per-CTA clock64 spans of this kernel on the bench workload.
-            const double ovh0 = 1200.0, pair0 = 4300.0; // fitted with the partition below (tools/sched_fit.py)
+            const double pair0 = kPairOverhead;
             double tot = 0;
-            for (auto& t : protos) tot += t.w * (double)t.nch + ovh0 + pair0 * t.np;
+            for (auto& t : protos) tot += t.w * (double)t.nch + kTileOverhead[t.f] + pair0 * t.np;
             double target = tot / G, assigned = 0;
             int b = 0; double load = 0;
             auto close_cta = [&]() {
                 if (b < G - 1) { ++b; P.cta_begin[b] = (int32_t)P.tiles.size(); load = 0; target = std::max(0.0, tot - assigned) / (G - b); }
             };
             for (auto& t : protos) {
-                auto piece_ovh = [&](int64_t take) { return ovh0 + pair0 * std::ceil((double)t.np * (double)take / (double)t.nch); };
+                auto piece_ovh = [&](int64_t take) { return kTileOverhead[t.f] + pair0 * std::ceil((double)t.np * (double)take / (double)t.nch); };
                 int64_t c0 = 0;
                 while (c0 < t.nch) {
                     const int64_t rem = t.nch - c0;
@@ -801,7 +810,7 @@ int build_contract_tables(itb_contract_plan& P) {
                         take = x;
                     }
                     if (take <= 0) { close_cta(); continue; }
-                    if (!cur_pieces.empty()) tot += ovh0 + pair0;
+                    if (!cur_pieces.empty()) tot += kTileOverhead[t.f] + pair0;
                     emit(t, c0, c0 + take);
                     load += (double)take * t.w + piece_ovh(take);
                     assigned += (double)take * t.w + piece_ovh(take);

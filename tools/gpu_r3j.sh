@@ -4,6 +4,16 @@ N=${1:-2}
 OUT=gpurun_out; mkdir -p $OUT
 export LD_LIBRARY_PATH=/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+if [ "$N" = "2" ]; then
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/j_bench_n1.json 2> $OUT/j_bench_n1.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/j_bench_n1.json").read().strip().split("\n")[-1]); r=d["roofline"]; p=d["permute"]
+print("N=1 default: value %.2f ms %.3f frac %.3f tile_ms %.3f e2e %.2f perm %.3f acc %.3f"%(d["value"],d["ms_per_step"],r["frac"],r["ms_per_step"]["tile_kernel"],d["e2e"]["value"],p["frac"],p["accumulate"]["frac"]))
+PY
+ITB_SCHED=guided timeout 600 python -m pytest tests/test_contract_gpu.py -m gpu -x -q 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_contract_gpu.py tests/test_golden.py -m gpu -x -q 2>&1 | tail -1
+fi
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $OUT/j_bench_n$N.json 2> $OUT/j_bench_n$N.err; echo "bench N=$N rc=$?"
 tail -3 $OUT/j_bench_n$N.err
 python - <<PY
