@@ -324,6 +324,26 @@ def main():
         ms = float(t.item())
     value = total_flops / (ms * 1e-3) / 1e12
 
+    # ---- N > 1: where one step goes (chain of sliced contractions / pack / all-gather / scatter), rank 0's view -------------
+    phases = None
+    if world > 1:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        acc = np.zeros(4)
+        for _ in range(5):
+            flush.zero_()
+            dist.barrier()
+            evs[4].record()
+            cur = dts[0]
+            for k, p in enumerate(plans):
+                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
+                cur = outs[k]
+            shard.allgather(ctx.handle, outs[-1].data, evs[:4])
+            torch.cuda.synchronize()
+            acc += np.array([evs[4].elapsed_time(evs[0]), evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])])
+        acc /= 5
+        phases = {"contractions_ms": float(acc[0]), "pack_ms": float(acc[1]), "allgather_ms": float(acc[2]), "scatter_ms": float(acc[3]),
+                  "allgather_bytes_per_rank": int(shard.seg_reals * 8), "note": "rank 0, CUDA events, mean of 5 steps (the all-gather includes waiting for the slowest rank)"}
+
     # ---- e2e: host buffers in, host buffer out, every step ---------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
     ev_r = torch.cuda.Event()
@@ -559,7 +579,7 @@ def main():
                                     "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin, "multi_gpu_phases": phases,
             "permute": perm_info,
         }))
     if world > 1:

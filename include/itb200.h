@@ -115,6 +115,9 @@ int itb_contract_plan_create(const itb_tensor_desc* A, const int32_t* labA,
                              itb_contract_plan** out);
 int itb_contract_plan_destroy(itb_contract_plan* plan);
 int itb_contract_plan_info(const itb_contract_plan* plan, itb_contract_info* out);
+/* result structure and flop count only (never builds the device tables; any out pointer may be NULL) */
+int itb_contract_plan_shape(const itb_contract_plan* plan, int32_t* c_order, int32_t* c_dtype, int64_t* c_nblocks, int64_t* c_nelems,
+                            int64_t* npairs, double* flops);
 /* result structure, in the reference's order (contractIS with sortResult=false) */
 int itb_contract_plan_c_labels(const itb_contract_plan* plan, int32_t* labels /*[c_order]*/);
 int itb_contract_plan_c_nsect(const itb_contract_plan* plan, int32_t* nsect /*[c_order]*/);

@@ -77,6 +77,7 @@ SYMBOLS = {
     "itb_contract_plan_create": (C.c_int, [_DESCP, _I32P, _DESCP, _I32P, C.POINTER(_P)]),
     "itb_contract_plan_destroy": (C.c_int, [_P]),
     "itb_contract_plan_info": (C.c_int, [_P, C.POINTER(ContractInfo)]),
+    "itb_contract_plan_shape": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _I64P, _I64P, _I64P, _DP]),
     "itb_contract_plan_c_labels": (C.c_int, [_P, _I32P]),
     "itb_contract_plan_c_nsect": (C.c_int, [_P, _I32P]),
     "itb_contract_plan_c_sect": (C.c_int, [_P, _I64P]),

@@ -605,29 +605,33 @@ int build_contract_tables(itb_contract_plan& P) {
             return o;
         };
         // candidates sorted by their long-side coordinates (first appearance order of the groups is kept)
-        std::vector<std::vector<int32_t>> cand_key(rg_cands.size());
+        // (keys are flat: uncA.size() coordinates per candidate, compared lexicographically)
+        const size_t nu = uncA.size();
+        std::vector<int32_t> cand_key(rg_cands.size() * std::max<size_t>(nu, 1));
         for (size_t i = 0; i < rg_cands.size(); ++i) {
             const int32_t* ab = A.block(pair_ia[P.cblks[rg_cands[i]].pair_begin]);
-            cand_key[i].reserve(uncA.size());
-            for (int u : uncA) cand_key[i].push_back(ab[u]);
+            for (size_t u = 0; u < nu; ++u) cand_key[i * nu + u] = ab[uncA[u]];
         }
+        auto key_less = [&](size_t x, size_t y) { return std::lexicographical_compare(&cand_key[x * nu], &cand_key[x * nu] + nu, &cand_key[y * nu], &cand_key[y * nu] + nu); };
+        auto key_eq = [&](size_t x, size_t y) { return std::equal(&cand_key[x * nu], &cand_key[x * nu] + nu, &cand_key[y * nu]); };
         std::vector<size_t> ord(rg_cands.size());
         std::iota(ord.begin(), ord.end(), (size_t)0);
-        std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return cand_key[x] < cand_key[y]; });
-        std::vector<std::pair<size_t, std::vector<int32_t>>> groups; // (first candidate position, members)
+        std::stable_sort(ord.begin(), ord.end(), key_less);
+        struct Grp { size_t first, begin, end; }; // first candidate position; members = ord[begin..end)
+        std::vector<Grp> groups;
         for (size_t q = 0; q < ord.size();) {
-            size_t e = q;
-            std::vector<int32_t> members;
-            size_t first = ord[q];
-            while (e < ord.size() && cand_key[ord[e]] == cand_key[ord[q]]) { members.push_back(rg_cands[ord[e]]); first = std::min(first, ord[e]); ++e; }
-            groups.push_back({first, std::move(members)});
+            size_t e = q, first = ord[q];
+            while (e < ord.size() && key_eq(ord[e], ord[q])) { first = std::min(first, ord[e]); ++e; }
+            groups.push_back({first, q, e});
             q = e;
         }
-        std::sort(groups.begin(), groups.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+        std::sort(groups.begin(), groups.end(), [](const Grp& x, const Grp& y) { return x.first < y.first; });
         std::vector<int64_t> A_blocks;
+        std::vector<int32_t> cs;
         for (auto& grp : groups) {
-            const std::vector<int32_t>& cs = grp.second;
-            const std::vector<int32_t>& key = cand_key[grp.first];
+            cs.clear();
+            for (size_t q = grp.begin; q < grp.end; ++q) cs.push_back(rg_cands[ord[q]]);
+            const int32_t* key = &cand_key[grp.first * nu];
             // long-side dims (unit extents dropped), strides per A block of the group
             A_blocks.clear();
             for (int32_t c : cs)
@@ -670,18 +674,19 @@ int build_contract_tables(itb_contract_plan& P) {
                 for (int d = 0; d < ITB_RG_MAXL; ++d) g.ext[d] = d < g.nL ? (int32_t)ld[d].ext : 1;
                 g.L = L;
                 g.in_begin = (int32_t)P.rg_in.size(); g.out_begin = (int32_t)P.rg_out.size(); g.w_begin = (int32_t)P.rg_w.size();
-                std::vector<std::pair<int64_t, int32_t>> slot_of; // A element offset of (block, k) -> input slot (<= ITB_RG_MAXIN entries)
-                auto find_slot = [&](int64_t ae) { for (auto& kv : slot_of) if (kv.first == ae) return kv.second; return (int32_t)-1; };
+                int64_t slot_key[ITB_RG_MAXIN]; // A element offset of (block, k) of every input slot taken so far (slot = position)
+                auto find_slot = [&](int64_t ae) { for (int32_t q = 0; q < g.nin; ++q) if (slot_key[q] == ae) return q; return (int32_t)-1; };
                 while (ci < cs.size()) {
                     const ItbCBlk& cb = P.cblks[cs[ci]];
                     // input slots this C block would add
-                    std::vector<int64_t> fresh;
+                    int64_t fresh[ITB_RG_MAXIN + 1]; // (a C block has ksum <= ITB_RG_MAXIN, checked by `eligible`)
+                    int nfresh = 0;
                     for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p)
                         for (int32_t k = 0; k < P.pairs[p].K; ++k) {
                             const int64_t ae = P.pairs[p].a_off + host_off(k, P.pairs[p].k_ext, P.pairs[p].ak_str, P.pairs[p].k_n);
-                            if (find_slot(ae) < 0 && std::find(fresh.begin(), fresh.end(), ae) == fresh.end()) fresh.push_back(ae);
+                            if (find_slot(ae) < 0 && std::find(fresh, fresh + nfresh, ae) == fresh + nfresh && nfresh <= ITB_RG_MAXIN) fresh[nfresh++] = ae;
                         }
-                    if (g.nout > 0 && (g.nout + cb.N > ITB_RG_MAXOUT || g.nin + (int)fresh.size() > ITB_RG_MAXIN)) break;
+                    if (g.nout > 0 && (g.nout + cb.N > ITB_RG_MAXOUT || g.nin + nfresh > ITB_RG_MAXIN)) break;
                     for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
                         const ItbPair& pr = P.pairs[p];
                         const size_t qa = std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) - A_blocks.begin();
@@ -694,7 +699,7 @@ int build_contract_tables(itb_contract_plan& P) {
                                 in.base = ae;
                                 for (int d = 0; d < g.nL; ++d) in.str[d] = ld[d].str[qa];
                                 slot = g.nin++;
-                                slot_of.push_back({ae, slot});
+                                slot_key[slot] = ae;
                                 P.rg_in.push_back(in);
                             }
                             const int64_t bk = pr.b_off + host_off(k, pr.k_ext, pr.bk_str, pr.k_n);
@@ -1085,9 +1090,27 @@ int itb_contract_plan_create(const itb_tensor_desc* A, const int32_t* labA, cons
         P->labB.assign(labB, labB + B->order);
         rc = build_contract_plan(*P);
     }
-    if (rc == ITB_OK) rc = build_contract_tables(*P);
+    // the device tables are built on first need (run, info, introspection, slicing): a caller that first looks at the
+    // result structure and then restricts the plan to a row slice pays for ONE table build, not two
     if (rc != ITB_OK) { delete P; return rc; }
     *out = P;
+    return ITB_OK;
+}
+
+static int ensure_tables(const itb_contract_plan* P) {
+    if (P->tables_built) return ITB_OK;
+    return build_contract_tables(*const_cast<itb_contract_plan*>(P));
+}
+
+int itb_contract_plan_shape(const itb_contract_plan* P, int32_t* c_order, int32_t* c_dtype, int64_t* c_nblocks, int64_t* c_nelems,
+                            int64_t* npairs, double* flops) {
+    if (!P) { set_error("plan_shape: null"); return ITB_ERR_INVALID; }
+    if (c_order) *c_order = P->C.order;
+    if (c_dtype) *c_dtype = P->C.dtype;
+    if (c_nblocks) *c_nblocks = P->C.nblocks;
+    if (c_nelems) *c_nelems = P->C.nelems;
+    if (npairs) *npairs = (int64_t)P->triples.size() / 3;
+    if (flops) *flops = P->flops;
     return ITB_OK;
 }
 
@@ -1103,6 +1126,7 @@ int itb_contract_plan_destroy(itb_contract_plan* plan) {
 
 int itb_contract_plan_info(const itb_contract_plan* P, itb_contract_info* o) {
     if (!P || !o) { set_error("plan_info: null"); return ITB_ERR_INVALID; }
+    { int rc = ensure_tables(P); if (rc != ITB_OK) return rc; }
     o->c_order = P->C.order;
     o->c_dtype = P->C.dtype;
     o->c_nblocks = P->C.nblocks;
@@ -1125,6 +1149,7 @@ int itb_contract_plan_pairs(const itb_contract_plan* P, int64_t* v) { std::copy(
 
 int64_t itb_contract_plan_tiles(const itb_contract_plan* P, int32_t* out, int64_t cap) {
     if (!P) return ITB_ERR_INVALID;
+    if (ensure_tables(P) != ITB_OK) return ITB_ERR_INVALID;
     for (int64_t i = 0; out && i < (int64_t)P->tiles.size() && i < cap; ++i) {
         const ItbTile& t = P->tiles[i];
         const int32_t v[8] = {t.cblk, t.m0, t.n0, kTileM[t.cfg], kTileN[t.cfg], t.chunk_begin, t.chunk_end, t.ws_slot};
@@ -1134,11 +1159,13 @@ int64_t itb_contract_plan_tiles(const itb_contract_plan* P, int32_t* out, int64_
 }
 int64_t itb_contract_plan_cta_begin(const itb_contract_plan* P, int32_t* out, int64_t cap) {
     if (!P) return ITB_ERR_INVALID;
+    if (ensure_tables(P) != ITB_OK) return ITB_ERR_INVALID;
     for (int64_t i = 0; out && i < (int64_t)P->cta_begin.size() && i < cap; ++i) out[i] = P->cta_begin[i];
     return (int64_t)P->cta_begin.size();
 }
 int64_t itb_contract_plan_rowgroups(const itb_contract_plan* P, int64_t* out, int64_t cap) {
     if (!P) return ITB_ERR_INVALID;
+    if (ensure_tables(P) != ITB_OK) return ITB_ERR_INVALID;
     for (int64_t i = 0; out && i < (int64_t)P->rgroups.size() && i < cap; ++i) {
         const ItbRowGroup& g = P->rgroups[i];
         const int64_t v[4] = {g.nin, g.nout, g.nL, g.L};
@@ -1148,6 +1175,7 @@ int64_t itb_contract_plan_rowgroups(const itb_contract_plan* P, int64_t* out, in
 }
 int64_t itb_contract_plan_cblks(const itb_contract_plan* P, int64_t* out, int64_t cap) {
     if (!P) return ITB_ERR_INVALID;
+    if (ensure_tables(P) != ITB_OK) return ITB_ERR_INVALID;
     for (int64_t i = 0; out && i < (int64_t)P->cblks.size() && i < cap; ++i) {
         const ItbCBlk& c = P->cblks[i];
         const int64_t v[4] = {c.M, c.N, c.ksum, c.pair_end - c.pair_begin};

@@ -119,6 +119,9 @@ main(int argc, char* argv[])
     bool useGPU = std::string(argv[4]) == "gpu";
     auto maxdim = parseList(argv[5]), cutoff = parseList(argv[6]), niter = parseList(argv[7]), noise = parseList(argv[8]);
     std::string jsonOut, savePrefix, loadPrefix, bondsFile;
+    // one process per GPU (tools/run_ranks.sh): every rank runs the same program; ranks > 0 write their files with a suffix
+    auto rankSuffix = std::string();
+    if(auto* e = std::getenv("ITB_RANK")) if(std::atoi(e) > 0) rankSuffix = std::string(".rank")+e;
     for(int a = 9; a < argc; ++a)
         {
         auto opt = std::string(argv[a]);
@@ -248,12 +251,12 @@ main(int argc, char* argv[])
     println(js.str());
     if(!jsonOut.empty())
         {
-        std::ofstream f(jsonOut);
+        std::ofstream f(jsonOut+rankSuffix);
         f << js.str() << "\n";
         }
     if(!bondsFile.empty())
         {
-        std::ofstream f(bondsFile);
+        std::ofstream f(bondsFile+rankSuffix);
         f.precision(17);
         f << "[";
         for(size_t i = 0; i < obs.bonds.size(); ++i)
@@ -266,7 +269,7 @@ main(int argc, char* argv[])
             }
         f << "\n]\n";
         }
-    if(!savePrefix.empty())
+    if(!savePrefix.empty() && rankSuffix.empty())
         {
         // GPU-resident site tensors are written through write(ostream,QDenseGPU<T>) (gpu_storage.h): the file holds the
         // host wire format and reads back as ordinary host tensors

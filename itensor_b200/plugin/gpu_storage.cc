@@ -828,9 +828,9 @@ contractQ(Contract& Con,
     auto dA = Desc(Con.Lis,Aoff,An,dtypeOf<VA>());
     auto dB = Desc(Con.Ris,Boff,Bn,dtypeOf<VB>());
     auto la = toLabels(Lind), lb = toLabels(Rind);
-    auto* plan = getContractPlan(dA,la,dB,lb);
-    itb_contract_info info;
-    check(itb_contract_plan_info(plan,&info),"plan info");
+    auto* plan = getContractPlan(dA,la,dB,lb); // (pair enumeration + C structure; device tables are built on first run)
+    struct { int32_t c_order = 0, c_dtype = 0; int64_t c_nblocks = 0, c_nelems = 0, npairs = 0; double flops = 0; } info;
+    check(itb_contract_plan_shape(plan,&info.c_order,&info.c_dtype,&info.c_nblocks,&info.c_nelems,&info.npairs,&info.flops),"plan shape");
     auto rC = long(info.c_order);
     auto cb = std::vector<int32_t>(size_t(info.c_nblocks*rC)+1);
     auto co = std::vector<int64_t>(size_t(info.c_nblocks)+1);

@@ -197,20 +197,29 @@ class ChainShard:
         self.send = self.recv[self.rank * self.seg_reals:(self.rank + 1) * self.seg_reals]  # in-place all-gather layout
         return self
 
-    def allgather(self, ctx_handle, flat) -> None:
-        """re-replicate H*phi: pack own rows -> one all-gather of the segments -> scatter the other ranks' rows into place"""
+    def allgather(self, ctx_handle, flat, events=None) -> None:
+        """re-replicate H*phi: pack own rows -> one all-gather of the segments -> scatter the other ranks' rows into place
+        (events: optional list of 4 CUDA events recorded around the three phases, for the bench's phase breakdown)"""
         import torch.distributed as dist
 
         from ._lib import check, lib
 
         p = lambda t: C.c_void_p(t.data_ptr())
+        if events:
+            events[0].record()
         check(lib().itb_permute_run(ctx_handle, self._pack, p(flat), p(self.send), 1.0, 0.0, 0))
+        if events:
+            events[1].record()
         if dist.get_backend() == "nccl":
             dist.all_gather_into_tensor(self.recv, self.send)
         else:  # gloo (CPU tests)
             parts = [self.recv[r * self.seg_reals:(r + 1) * self.seg_reals] for r in range(self.world)]
             dist.all_gather(parts, self.send.clone())
+        if events:
+            events[2].record()
         check(lib().itb_permute_run(ctx_handle, self._unpack, p(self.recv), p(flat), 1.0, 0.0, 0))
+        if events:
+            events[3].record()
 
     def close(self):
         from ._lib import lib
