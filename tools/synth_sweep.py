@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""BASELINE configs[3]: synthetic block-sparse contraction sweep — equal-size Sz sectors S in {4,8,16}, bond
-dimension m in {512..8192}, real and complex: TFLOP/s of phi*L (the tensor-pipe step) and of the whole
-H_eff*phi chain, device-resident, CUDA events, best of 3. Writes one JSON line per case."""
+"""BASELINE configs[3]: synthetic block-sparse contraction sweep — Sz sectors S in {4,8,16}, equal-size and
+binomial-weighted (--dist binomial), bond dimension m in {512..8192}, real and complex: TFLOP/s of phi*L (the
+tensor-pipe step) and of the whole H_eff*phi chain, device-resident, CUDA events, best of 3. One JSON line per case."""
 import argparse, ctypes as C, json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,15 +14,26 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ms", default="512,1024,2048,4096,8192")
 ap.add_argument("--sectors", default="4,8,16")
 ap.add_argument("--out", default="gpurun_out/synth_sweep.jsonl")
+ap.add_argument("--dist", default="equal,binomial")
+ap.add_argument("--dtypes", default="real,complex")
 args = ap.parse_args()
 ctx = itb.Context(0)
 dev = ctx.device
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 out = open(args.out, "w")
-for dtype, dname in ((ITB_F64, "real"), (ITB_C64, "complex")):
+def binomial_sectors(m, S):
+    """sector sizes proportional to binomial(S-1, q), at least 1, summing to ~m"""
+    from math import comb
+    w = np.array([comb(S - 1, q) for q in range(S)], float)
+    return [int(v) for v in np.maximum(1, np.rint(m * w / w.sum()))]
+
+for dtype, dname in [(ITB_F64, "real"), (ITB_C64, "complex")]:
+  if dname not in args.dtypes.split(","):
+    continue
+  for dist in args.dist.split(","):
     for S in [int(x) for x in args.sectors.split(",")]:
         for m in [int(x) for x in args.ms.split(",")]:
-            sizes = synth.equal_sectors(m, S)
+            sizes = synth.equal_sectors(m, S) if dist == "equal" else binomial_sectors(m, S)
             structs = synth.heff_chain(sizes, dtype=dtype)
             plans, s = [], structs[0]
             for t in structs[1:]:
@@ -49,7 +60,7 @@ for dtype, dname in ((ITB_F64, "real"), (ITB_C64, "complex")):
             t_all = timed(0, 4)
             t_1 = timed(0, 1)
             fl_all = sum(p.flops for p in plans)
-            rec = {"dtype": dname, "sectors": S, "m": m, "pairs": [int(p.npairs) for p in plans], "flops_heff": fl_all,
+            rec = {"dtype": dname, "dist": dist, "sectors": S, "m": m, "sector_sizes": sizes, "pairs": [int(p.npairs) for p in plans], "flops_heff": fl_all,
                    "heff_ms": t_all, "heff_tflops": fl_all / t_all / 1e9, "phiL_ms": t_1, "phiL_tflops": plans[0].flops / t_1 / 1e9}
             print(json.dumps(rec), flush=True)
             out.write(json.dumps(rec) + "\n"); out.flush()
