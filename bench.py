@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--complex", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-refine", action="store_true", help="keep the modelled tile partition (no measured re-partitioning of the plans)")
+    ap.add_argument("--refine-rounds", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -300,6 +302,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Plans that are executed many times refine their static tile partition from measured per-CTA cycles (plan set-up, like
+    # the planning itself: itb_contract_plan_refine runs each contraction rounds+1 times on the real operands, in chain order
+    # so that every input is valid). --no-refine keeps the modelled partition.
+    refine_gain = None
+    if not args.no_refine:
+        refine_gain, cur = [], dts[0]
+        for k, p in enumerate(plans):
+            refine_gain.append(round(p.refine(ctx, cur.ptr, dts[k + 1].ptr, outs[k].ptr, rounds=args.refine_rounds), 4))
+            cur = outs[k]
     for _ in range(args.warmup):
         step()
     barrier()
@@ -488,7 +499,7 @@ def main():
             traffic = float(np.mean(tj["per_launch_bytes"]))  # DRAM bytes per launch (mean of the step-1 and step-4 launches)
             traffic_src = "profiles/r02_traffic.json (ncu --set full of this command; algorithmic bytes per launch %.3g)" % float(np.mean(tj["algorithmic_bytes_per_launch"]))
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "bsc_gemm_kernel (persistent warp-specialised DMMA tiles 128/64/32, stream-K partition)",
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "bsc_gemm_static_kernel (persistent warp-specialised DMMA tiles 128/64/32, stream-K partition)",
                 "peak_source": "measured in this run: torch.matmul fp64 8192^3 best of 6 (MEASURED_PEAKS.json has no FP64 entry)",
                 "launches_per_step": n_launch, "ms_per_step": {"tile_kernel": float(cls_ms[0]), "streaming_kernel": float(cls_ms[3]), "dot_kernel": float(cls_ms[4])},
                 "flops_per_step_by_class": {"tile128": float(cls_fl[0]), "tile64": float(cls_fl[1]), "tile32": float(cls_fl[2]),
@@ -608,6 +619,7 @@ def main():
                        "maxdim": args.m, "sectors": sizes, "d": 2, "mpo_link_sectors": [3, 1, 1],
                        "pairs_per_step": [int(p.npairs) for p in plans], "flops_per_step": total_flops,
                        "l2": "flushed between timed iterations (256 MiB memset)", "launch": launch_mode,
+                       "tile_partition": ("modelled" if refine_gain is None else "refined from measured per-CTA cycles at plan set-up (itb_contract_plan_refine, %d rounds; longest-CTA gain per plan %s)" % (args.refine_rounds, refine_gain)),
                        "sharding": ("rows of l' (%s), equal-flop contiguous row ranges per rank, max rank share %.3f of flops (ideal %.3f); "
                                     "H*phi re-replicated by pack -> one NCCL all-gather -> scatter; e2e: 1/N of the operand arena per "
                                     "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world)) if world > 1 else "none"},

@@ -267,6 +267,14 @@ int itb_comm_destroy(itb_comm* comm);
 /* flops of every C block of a plan (2*M*N*K summed over its pairs, complex multipliers included): the weights of a row partition */
 int itb_contract_plan_cblock_flops(const itb_contract_plan* plan, double* out /*[c_nblocks]*/);
 
+/* Measured refinement of a plan's static tile partition (no counterpart in the reference: its OpenMP loop over C blocks,
+ * itensor/itdata/qutil.h:285-348, is scheduled dynamically by the runtime). Executes the plan rounds+1 times on the given
+ * operands (dC holds the correct result afterwards), reads the per-CTA clock64 spans of the tile kernel after each run,
+ * rescales the modelled cost of every tile by measured/modelled and re-partitions; keeps the partition with the shortest
+ * longest span. *gain (optional) = longest span before / after. Synchronises the stream; meant for plans that are executed
+ * many times (Davidson repeats the same structures). Plans without tile items are left as they are. */
+int itb_contract_plan_refine(itb_ctx* ctx, itb_contract_plan* plan, const void* dA, const void* dB, void* dC, int rounds, double* gain);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* profile!=0: itb_contract_run brackets every kernel launch with CUDA events (adds syncs; measurement
  * only). itb_contract_last_ms then returns the device time of the last run by kernel class

@@ -518,6 +518,69 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     return ITB_OK;
 }
 
+// Measured refinement of the static stream-K partition. The planner's cycle model decides how much of the (tile, K-chunk)
+// list every CTA of the persistent grid gets; what it gets wrong shows up as spread between the per-CTA clock64 spans
+// (max/mean 1.09-1.12 on the maxdim-2000 H_eff step, i.e. ~10 % of the tile kernel's time). A plan that is executed many
+// times (Davidson repeats the same four structures) can close that loop: run, read the spans, scale the modelled cost of
+// every tile by measured/modelled of the CTAs that ran it, re-partition, and keep the partition with the smallest
+// longest span. The result of every run is the correct C, so this can replace the first executions of the plan.
+int itb_contract_plan_refine(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC, int rounds, double* gain) {
+    if (!c || !P) { set_error("plan_refine: null"); return ITB_ERR_INVALID; }
+    if (gain) *gain = 1.0;
+    const bool was_profile = c->profile;
+    c->profile = true;
+    struct Restore { itb_ctx* c; bool v; ~Restore() { c->profile = v; } } restore{c, was_profile};
+    std::vector<double> best_scale;
+    double best_max = 0, first_max = 0;
+    bool have_best = false;
+    for (int r = 0; r <= rounds; ++r) {
+        int rc = itb_contract_run(c, P, dA, dB, dC); // profile mode: synchronises, h_cta_cycles valid afterwards
+        if (rc != ITB_OK) return rc;
+        const int n_static = (int)P->cta_begin.size() - 2;
+        const bool purely_static = n_static > 0 && !P->tiles.empty() && P->cta_begin[n_static] == (int32_t)P->tiles.size();
+        if (!purely_static || (int)c->h_cta_cycles.size() < n_static || P->item_tile.size() != P->tiles.size()) return ITB_OK; // nothing to refine
+        int32_t ntile = 0;
+        for (int32_t t : P->item_tile) ntile = std::max(ntile, t + 1);
+        if (P->tile_scale.size() != (size_t)ntile) P->tile_scale.assign(ntile, 1.0);
+        double mx = 0;
+        for (int b = 0; b < n_static; ++b) mx = std::max(mx, (double)c->h_cta_cycles[b]);
+        if (r == 0) first_max = mx;
+        if (!have_best || mx < best_max) { best_max = mx; best_scale = P->tile_scale; have_best = true; }
+        if (r == rounds) break;
+        // per-CTA measured / modelled, normalised to mean 1 so that the scales do not drift
+        std::vector<double> ratio(n_static, 1.0);
+        double sum_meas = 0, sum_model = 0;
+        for (int b = 0; b < n_static; ++b) {
+            double model = 0;
+            for (int32_t i = P->cta_begin[b]; i < P->cta_begin[b + 1]; ++i) model += P->item_cost[i];
+            ratio[b] = model > 0 ? (double)c->h_cta_cycles[b] / model : 1.0;
+            if (model > 0) { sum_meas += (double)c->h_cta_cycles[b]; sum_model += model; }
+        }
+        const double norm = sum_model > 0 ? sum_meas / sum_model : 1.0;
+        // tile factor = cost-weighted mean of the ratios of the CTAs that ran its pieces (damped)
+        std::vector<double> num(ntile, 0.0), den(ntile, 0.0);
+        for (int b = 0; b < n_static; ++b)
+            for (int32_t i = P->cta_begin[b]; i < P->cta_begin[b + 1]; ++i) {
+                num[P->item_tile[i]] += P->item_cost[i] * ratio[b] / norm;
+                den[P->item_tile[i]] += P->item_cost[i];
+            }
+        for (int32_t t = 0; t < ntile; ++t)
+            if (den[t] > 0) {
+                const double f = std::min(1.5, std::max(0.67, num[t] / den[t]));
+                P->tile_scale[t] *= std::pow(f, 0.8);
+            }
+        P->tables_built = false;
+        if (P->dev) { CUDA_TRY(cudaStreamSynchronize(c->stream)); release_tables(P->dev, P->dev_ctx); P->dev = nullptr; }
+    }
+    if (have_best && best_scale != P->tile_scale) {
+        P->tile_scale = best_scale;
+        P->tables_built = false;
+        if (P->dev) { CUDA_TRY(cudaStreamSynchronize(c->stream)); release_tables(P->dev, P->dev_ctx); P->dev = nullptr; }
+    }
+    if (gain && best_max > 0) *gain = first_max / best_max;
+    return ITB_OK;
+}
+
 int itb_contract_host(itb_ctx* c, itb_contract_plan* P, const void* hA, const void* hB, void* hC) {
     if (!c || !P) { set_error("contract_host: null"); return ITB_ERR_INVALID; }
     const size_t ba = (size_t)P->A.nelems * (P->A.dtype == ITB_C64 ? 16 : 8);

@@ -753,6 +753,16 @@ int build_contract_tables(itb_contract_plan& P) {
                     total += w * (double)nch + ovh;
                 }
         }
+        // measured correction of the cycle model (itb_contract_plan_refine): one factor per tile on its per-chunk cost
+        if (P.tile_scale.size() == protos.size()) {
+            total = 0;
+            for (size_t i = 0; i < protos.size(); ++i) {
+                protos[i].w *= P.tile_scale[i];
+                total += protos[i].w * (double)protos[i].nch + kTileOverhead[protos[i].f] + kPairOverhead * protos[i].np;
+            }
+        } else
+            P.tile_scale.clear();
+        P.item_tile.clear();
         const int G = kNumSMs;
         // Hybrid schedule. STATIC part: the first kStaticFrac of the modelled work is cut stream-K fashion into G
         // contiguous ranges of (tile, K-chunk) space, one per CTA — at most G-1 tiles are cut there, which keeps the
@@ -763,7 +773,8 @@ int build_contract_tables(itb_contract_plan& P) {
         // wrong in the static part and lets the CTAs finish within one small piece of each other.
         // cta_begin: G+2 entries — static range of CTA b = [cta_begin[b], cta_begin[b+1]), shared queue =
         // [cta_begin[G], cta_begin[G+1]).
-        std::vector<double> item_cost;
+        std::vector<double>& item_cost = P.item_cost;
+        item_cost.clear();
         struct Piece { int64_t c0, c1; };
         size_t first_item_of_tile = 0;
         std::vector<Piece> cur_pieces; // pieces of the tile being emitted (consecutive items)
@@ -781,7 +792,8 @@ int build_contract_tables(itb_contract_plan& P) {
             if (cur_pieces.empty()) first_item_of_tile = P.tiles.size();
             cur_pieces.push_back({c0, c1});
             P.tiles.push_back({t.c, t.m0, t.n0, t.f, (int32_t)c0, (int32_t)c1, -1, -1});
-            item_cost.push_back((double)(c1 - c0) * t.w + kTileOverhead[t.f] + kPairOverhead * t.np);
+            P.item_tile.push_back((int32_t)(&t - protos.data()));
+            item_cost.push_back((double)(c1 - c0) * t.w + kTileOverhead[t.f] + kPairOverhead * std::ceil((double)t.np * (double)(c1 - c0) / (double)t.nch));
         };
         P.cta_begin.assign(G + 2, 0);
         size_t ti = 0;      // current tile
@@ -1235,6 +1247,7 @@ int itb_contract_plan_set_index_slices(itb_contract_plan* P, int32_t c_index, co
         P->slice_hi.assign(hi, hi + ns);
     }
     itb_contract_plan_release_device(P);
+    P->tile_scale.clear(); // measured corrections belong to the tiles of the previous extent
     int rc = build_contract_tables(*P);
     if (rc != ITB_OK) { // leave the plan as it was
         const std::string msg = last_error_cstr();

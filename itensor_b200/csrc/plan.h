@@ -54,6 +54,11 @@ struct itb_contract_plan {
     std::vector<int32_t> cta_begin;   // kNumSMs+1 entries (stream-K partition: equal modelled cycles per CTA)
     std::vector<ItbSplitOut> splits;  // split-K tiles to be reduced from the workspace
     int64_t ws_slots = 0;
+    // measured refinement of the static partition (itb_contract_plan_refine): tile_scale[t] multiplies the modelled
+    // cost of tile t (planner order); item_tile / item_cost describe the items of the current partition
+    std::vector<double> tile_scale;
+    std::vector<int32_t> item_tile;
+    std::vector<double> item_cost;
     std::vector<ItbSkinny> skinny;    // generic streaming items
     std::vector<ItbSkinny> skinny_q4; // small-K fast path, short side <= 4
     std::vector<ItbSkinny> skinny_q8; // small-K fast path, short side <= 8

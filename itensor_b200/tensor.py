@@ -213,6 +213,13 @@ class ContractPlan:
         """flops of the C blocks / slices this plan executes (== flops when nothing is masked or sliced)"""
         return float(sum(self.info.class_flops))
 
+    def refine(self, ctx, a_ptr, b_ptr, c_ptr, rounds: int = 3) -> float:
+        """itb_contract_plan_refine: re-partition the tile work from measured per-CTA cycles; returns longest CTA span
+        before / after"""
+        gain = C.c_double(1.0)
+        check(lib().itb_contract_plan_refine(ctx.handle, self._h, a_ptr, b_ptr, c_ptr, rounds, C.byref(gain)))
+        return gain.value
+
     def close(self):
         if self._h:
             lib().itb_contract_plan_destroy(self._h)

@@ -49,6 +49,16 @@ def run(A, Av, B, Bv, what):
             sys.exit(1)
     classes(P)
     stats["cases"] += 1
+    if P.info.n_gemm_tiles > 0:
+        # re-cut the tile partition with perturbed per-tile costs (what itb_contract_plan_refine does from measured cycles;
+        # the mock perturbs pseudo-randomly) and walk the re-cut tables: same result
+        out2 = np.full(max(P.C.nreal, 1), np.nan)
+        check(lib().itb_contract_plan_refine(ctx, P._h, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out2.ctypes.data_as(C.c_void_p), 1, None))
+        err2 = np.abs(out2[:P.C.nreal] - want).max() / scale if not np.isnan(out2[:P.C.nreal]).any() else np.inf
+        if not err2 < 1e-12:
+            print(f"MISMATCH after re-partition in {what}: rel err {err2}")
+            sys.exit(1)
+        stats["refined"] = stats.get("refined", 0) + 1
     return P.C, ref
 
 

@@ -193,6 +193,31 @@ def test_bench_workload_vs_reference(ctx):
     assert cur_s.order == 4 and cur_s.nelems == structs[0].nelems
 
 
+def test_refined_partition_vs_reference(ctx):
+    """itb_contract_plan_refine re-cuts the stream-K partition from measured per-CTA cycles: the refined plans of the bench
+    workload (steps 1 and 4, the two tile-kernel launches) must still reproduce the reference to 1e-12, the refinement run
+    itself must leave the correct result in C, and re-running a refined plan must be bitwise reproducible."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libitref.so not built")
+    sizes = synth.gaussian_sectors(2000, 9)
+    structs = synth.heff_chain(sizes)
+    hosts = [synth.random_values(s, 10 + i) for i, s in enumerate(structs)]
+    cur_s, cur_h = structs[0], hosts[0]
+    for k in range(4):
+        rr = orc.ref_contract(cur_s, cur_h, structs[k + 1], hosts[k + 1])
+        plan = itb.ContractPlan(cur_s, structs[k + 1])
+        ta, tb = itb.QTensor.from_host(ctx, cur_s, cur_h), itb.QTensor.from_host(ctx, structs[k + 1], hosts[k + 1])
+        tc = itb.QTensor(ctx, plan.C, ctx.empty(plan.C.nreal))
+        gain = plan.refine(ctx, ta.ptr, tb.ptr, tc.ptr, rounds=3)
+        assert gain >= 1.0 - 1e-12  # the best measured partition is kept, the first one included
+        assert_close(tc.to_host(), rr.data, 1e-12, f"result left by the refinement, step {k + 1}")
+        got1 = itb.contract(ta, tb, plan).to_host()
+        got2 = itb.contract(ta, tb, plan).to_host()
+        assert_close(got1, rr.data, 1e-12, f"refined plan, step {k + 1}")
+        assert np.array_equal(got1, got2)
+        cur_s, cur_h = plan.C, rr.data
+
+
 def test_bench_workload_complex_vs_reference(ctx):
     """same chain with complex tensors (folded real-GEMM decomposition) at maxdim 600 against the reference"""
     if not orc.have_ref():

@@ -338,11 +338,11 @@ def test_row_sharded_dmrg_on_two_gpus(tmp_path):
 
 
 # ---- BASELINE configs[4]: TRG at maxdim 64 (all 20 scales) and maxdim 128, kept spectrum per scale --------------------
-def _trg_with_spectra(maxdim, topscale, tmp_path):
+def _trg_with_spectra(maxdim, topscale, tmp_path, ok_codes=(0,)):
     log = str(tmp_path / f"trg_{maxdim}.jsonl")
     env = dict(GPU_ENV, ITB_SPECTRUM_LOG=log)
     out = subprocess.run([TRG, str(maxdim), str(topscale), "gpu"], env=env, capture_output=True, text=True, timeout=3000)
-    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.returncode in ok_codes, out.stderr[-2000:]
     return json.loads(out.stdout.strip().split("\n")[-1]), [json.loads(l) for l in open(log)]
 
 
@@ -353,7 +353,9 @@ def test_trg_per_scale_spectra_vs_reference(tmp_path):
     trg_cpu_spectra.json: two factorisations per scale). maxdim 64, all 20 scales: while nothing is truncated (scales 1-5,
     truncation error < 1e-25) the spectra agree to 1e-12; afterwards the cut goes through exactly degenerate multiplets, so
     which vectors survive depends on the SVD library and the later spectra / kappa agree to the size of the truncation
-    error (1e-6) only. maxdim 128: the first four scales (16384^2 SVDs from scale 3 on) against the host spectra."""
+    error (1e-6) only. maxdim 128: the factorisations of the first four scales (the fourth is two 16384^2 SVDs) against the
+    host spectra. The sample's pairwise contraction of the four factors then needs a chi^5 intermediate = 275 GB at chi = 128:
+    the reference's host run dies there with bad_alloc, the device run reports the failed allocation (exit code 3)."""
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "trg_cpu_spectra.json")))
     res, spec = _trg_with_spectra(64, 20, tmp_path)
     ref = gold["maxdim64_topscale20"]["spectra"]
@@ -364,13 +366,13 @@ def test_trg_per_scale_spectra_vs_reference(tmp_path):
         tol = 1e-12 if b["truncerr"] < 1e-25 else 5e-6
         assert np.abs(sa - sb).max() <= tol * sb[0], (k, float(np.abs(sa - sb).max()), b["truncerr"])
     assert abs(res["kappa"] - gold["maxdim64_topscale20"]["kappa"]) < 2e-6
-    res, spec = _trg_with_spectra(128, 4, tmp_path)
+    res, spec = _trg_with_spectra(128, 4, tmp_path, ok_codes=(0, 3))
     ref = gold["maxdim128_first4scales"]["spectra"]
-    assert len(spec) == len(ref) == 8
+    assert len(spec) == len(ref) == 8 and ("aborted" not in res or "out of memory" in res["aborted"])
     worst = 0.0
     for a, b in zip(spec, ref):
         sa, sb = np.array(a["eigs"]), np.array(b["eigs"])
         assert len(sa) == len(sb)
         worst = max(worst, float(np.abs(sa - sb).max() / sb[0]))
-    print("TRG maxdim 128, 4 scales on GPU: %.1f s, max relative spectrum difference vs the host run %.2e" % (res["seconds"], worst))
+    print("TRG maxdim 128, factorisations of 4 scales on GPU: max relative spectrum difference vs the host run %.2e" % worst)
     assert worst <= 1e-10

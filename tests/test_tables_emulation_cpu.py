@@ -23,3 +23,4 @@ def test_device_tables_reproduce_the_oracle():
     assert stats["cases"] > 170 and stats["tiles"] > 200 and stats["split_pieces"] > 10
     assert stats["rowgroups"] > 10 and stats["skinny"] > 10 and stats["dots"] > 5
     assert stats["permutes"] > 200 and stats["zero_filled"] > 10
+    assert stats["refined"] > 25  # re-cut partitions (itb_contract_plan_refine) walked as well
