@@ -391,30 +391,31 @@ def main():
 
     # ---- e2e: host buffers in, host buffer out, every step ---------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
-    ev_r = torch.cuda.Event()
+    ev_in = [torch.cuda.Event() for _ in range(5)]
 
     def e2e_step():
         # what a caller of the reference-facing API pays per product: upload the operands, plan every
         # contraction afresh (host integer work + table upload, as operator* does on every call), run,
-        # read H phi back. R is only needed by the last contraction, so its upload rides a second stream.
+        # read H phi back. The operands go up on ONE copy stream in the order the chain consumes them (phi, L, W1, W2, R:
+        # one direction of PCIe is a serial resource, so concurrent uploads would only delay the first operands) with an
+        # event after each; contraction k waits for operand k+1 only, so steps 1-3 run under the upload of R.
         main = torch.cuda.current_stream(dev)
         copy_stream.wait_stream(main)
         with torch.cuda.stream(copy_stream):
-            dts[4].data.copy_(pinned[4], non_blocking=True)
-            ev_r.record(copy_stream)
-        for d, p in zip(dts[:4], pinned[:4]):
-            d.data.copy_(p, non_blocking=True)
+            for d, p, ev in zip(dts, pinned, ev_in):
+                d.data.copy_(p, non_blocking=True)
+                ev.record(copy_stream)
         if world == 1:
             cur = dts[0]
+            main.wait_event(ev_in[0])
             for k in range(4):
                 p = itb.ContractPlan(cur.struct, structs[k + 1])
-                if k == 3:
-                    main.wait_event(ev_r)
+                main.wait_event(ev_in[k + 1])
                 check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
                 cur = itb.QTensor(ctx, p.C, outs[k].data)
                 keep.append(p)
         else:
-            main.wait_event(ev_r)
+            main.wait_event(ev_in[4])
             step()
         h_out.copy_(outs[-1].data, non_blocking=True)
         torch.cuda.synchronize()
@@ -629,7 +630,26 @@ def main():
             "permute": perm_info,
         }))
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down must never outlive the measurement: a captured graph that holds NCCL kernels keeps the communicator
+        # busy inside destroy_process_group (seen on 2 GPUs: the JSON line was out, the processes sat in ncclCommDestroy until
+        # the launcher's timeout). Release the graph first, and leave through os._exit if the orderly shutdown stalls.
+        import threading
+
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        run_step = None
+        if "g" in locals():
+            try:
+                g.reset()
+            except Exception:  # noqa: BLE001
+                pass
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":

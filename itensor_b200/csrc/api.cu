@@ -415,6 +415,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     if (!c || !P) { set_error("contract_run: null"); return ITB_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(c->device));
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK; // no output blocks: nothing to do
+    if (plan_note_run(*P) && P->dev) release_tables(P->dev, P->dev_ctx); // (stream-ordered pool: launches already queued keep their tables)
     int rc = ensure_contract_tables(c, P);
     if (rc != ITB_OK) return rc;
     DeviceTables* d = P->dev;

@@ -14,6 +14,9 @@
 //   * all pairs of one C block form one K-loop owned by one CTA tile (no beta, no atomics);
 //   * complex operands are folded into a REAL problem (see fold_complex) so one FP64 kernel
 //     serves the four real/complex pairings (reference: 4 DGEMMs, tensor/gemm.cc:165-230).
+#ifdef ITB_PLAN_PROFILE
+#include <chrono>
+#endif
 #include "plan.h"
 
 #include <algorithm>
@@ -304,6 +307,8 @@ static double kTileOverhead[ITB_NCFG] = {3800.0, 8000.0, 5300.0}; // 128x128: ep
 static double kPairOverhead = 1000.0; // per block pair an item walks (K loop of the 3-pair *R tiles: +85 cycles per chunk)
 static const double kDmmaSlack = 1.11;
 static int kForceCfg = -1;
+static int64_t kRowGroupMinBytes = 32ll << 20; // streaming class smaller than this (bytes of C): row groups only once the plan proves hot
+static int64_t kRowGroupAfterRuns = 3;          // ... i.e. from this execution of the plan on (ITB_ROWGROUP_TIER="bytes,runs")
 static bool kUseRowGroups = true; // ITB_ROWGROUPS=0 routes every streaming C block to the C-stationary kernels
 static int64_t kMinPiece = 8; // K-chunks: never cut a tile into pieces shorter than this (ITB_MIN_PIECE)
 static double kGuidedFactor = 2.0;  // shared queue: piece cost = remaining work / (kGuidedFactor x grid width); ITB_GUIDED_FACTOR
@@ -322,6 +327,7 @@ static void read_tile_env() {
     if (const char* e = getenv("ITB_TILE_OVERHEAD")) sscanf(e, "%lf,%lf,%lf,%lf", &kTileOverhead[0], &kTileOverhead[1], &kTileOverhead[2], &kPairOverhead);
     if (const char* e = getenv("ITB_FORCE_CFG")) kForceCfg = atoi(e);
     if (const char* e = getenv("ITB_ROWGROUPS")) kUseRowGroups = atoi(e) != 0;
+    if (const char* e = getenv("ITB_ROWGROUP_TIER")) { long long b = 0, r = 0; if (sscanf(e, "%lld,%lld", &b, &r) == 2) { kRowGroupMinBytes = b; kRowGroupAfterRuns = r; } }
     if (const char* e = getenv("ITB_GUIDED_FACTOR")) kGuidedFactor = std::max(0.25, atof(e));
     if (const char* e = getenv("ITB_MIN_PIECE")) kMinPiece = std::max(1, atoi(e));
     if (const char* e = getenv("ITB_SCHED")) kSchedStreamK = std::string(e) != "guided";
@@ -332,7 +338,21 @@ static void read_tile_env() {
     }
     if (const char* e = getenv("ITB_STATIC_FRAC")) kStaticFrac = std::min(0.98, std::max(0.0, atof(e)));
 }
+static double chunk_cycles_compute(int f, int64_t vm, int64_t vn);
+// the model only depends on the number of 8-row / 8-column fragments that hold valid data: one table per configuration
 static double chunk_cycles(int f, int64_t vm, int64_t vn) {
+    static double tab[ITB_NCFG][17][17];
+    static bool built = false;
+    if (!built) {
+        for (int g = 0; g < ITB_NCFG; ++g)
+            for (int a = 0; a <= kTileM[g] / 8; ++a)
+                for (int b = 0; b <= kTileN[g] / 8; ++b) tab[g][a][b] = chunk_cycles_compute(g, 8 * a, 8 * b);
+        built = true;
+    }
+    const int64_t a = std::min<int64_t>((std::max<int64_t>(vm, 0) + 7) / 8, kTileM[f] / 8), b = std::min<int64_t>((std::max<int64_t>(vn, 0) + 7) / 8, kTileN[f] / 8);
+    return tab[f][a][b];
+}
+static double chunk_cycles_compute(int f, int64_t vm, int64_t vn) {
     const int WM = kTileM[f] / 4, WN = kTileN[f] / 4, FM = WM / 8, FN = WN / 8;
     int fm[4], fn[4];
     for (int i = 0; i < 4; ++i) {
@@ -361,7 +381,23 @@ static double cblk_cost(int f, int64_t M, int64_t N, double nch, int npairs) {
     return cost;
 }
 
+#ifdef ITB_PLAN_PROFILE
+double g_plan_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // harness builds only (build/planprof)
+#define PLAN_T0() auto plan_t_ = std::chrono::steady_clock::now()
+#define PLAN_PHASE(i) do { auto n_ = std::chrono::steady_clock::now(); g_plan_phase[i] += std::chrono::duration<double>(n_ - plan_t_).count(); plan_t_ = n_; } while (0)
+#else
+#define PLAN_T0() do {} while (0)
+#define PLAN_PHASE(i) do {} while (0)
+#endif
+bool plan_note_run(itb_contract_plan& P) {
+    read_tile_env();
+    ++P.runs;
+    if (P.tables_built && P.rg_deferred && P.runs >= kRowGroupAfterRuns) { P.tables_built = false; return true; }
+    return false;
+}
+
 int build_contract_tables(itb_contract_plan& P) {
+    PLAN_T0();
     const TensorStruct &A = P.A, &B = P.B, &C = P.C;
     const int rA = A.order, rB = B.order;
     std::vector<int> AtoB(rA, -1), BtoA(rB, -1);
@@ -378,19 +414,45 @@ int build_contract_tables(itb_contract_plan& P) {
 
     const int64_t npairs = (int64_t)P.triples.size() / 3;
     // group pairs by C block, keeping the reference enumeration order inside a block
+    // (counting sort on the C block number: stable and linear)
     std::vector<int64_t> order(npairs);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int64_t x, int64_t y) { return P.triples[3 * x + 2] < P.triples[3 * y + 2]; });
+    {
+        std::vector<int64_t> start((size_t)C.nblocks + 1, 0);
+        for (int64_t p = 0; p < npairs; ++p) ++start[(size_t)P.triples[3 * p + 2] + 1];
+        for (int64_t c = 0; c < C.nblocks; ++c) start[c + 1] += start[c];
+        for (int64_t p = 0; p < npairs; ++p) order[(size_t)start[(size_t)P.triples[3 * p + 2]]++] = p;
+    }
     const int64_t cb_first = P.cb_first, cb_last = (P.cb_last < 0 ? C.nblocks : P.cb_last);
 
-    std::vector<int64_t> strA(rA), strB(rB);
+    PLAN_PHASE(0);
     std::vector<int> uncA_all, uncB_all; // uncontracted indices of A / B in order == the index list of C
     for (int i = 0; i < rA; ++i) if (AtoB[i] < 0) uncA_all.push_back(i);
     for (int j = 0; j < rB; ++j) if (BtoA[j] < 0) uncB_all.push_back(j);
     if (P.slice_index >= (int)(uncA_all.size() + uncB_all.size())) { set_error("contract: slice index out of range"); return ITB_ERR_INVALID; }
     std::vector<int64_t> pair_ia; // A block of every entry of P.pairs (host only)
     std::vector<int64_t> cblk_sl;  // per executed C block: extent of the sliced A index (0: not sliced on the A side)
+    P.pairs.reserve((size_t)npairs); pair_ia.reserve((size_t)npairs);
+    P.cblks.reserve((size_t)C.nblocks); cblk_sl.reserve((size_t)C.nblocks);
+    // per-block extents / strides / sizes / fastest non-unit index, computed once per block instead of once per pair
+    // (a block takes part in several pairs: 2.3 per A block and 30 per B block in the MPO steps at Hubbard scale)
+    std::vector<int64_t> extA_all((size_t)A.nblocks * rA), strA_all((size_t)A.nblocks * rA), sizeA((size_t)A.nblocks);
+    std::vector<int64_t> extB_all((size_t)B.nblocks * rB), strB_all((size_t)B.nblocks * rB), sizeB((size_t)B.nblocks);
+    std::vector<int8_t> fastA((size_t)A.nblocks, -1), fastB((size_t)B.nblocks, -1);
+    auto fill_block_tables = [](const TensorStruct& T, int r, int64_t cs, std::vector<int64_t>& ext, std::vector<int64_t>& str,
+                                std::vector<int64_t>& size, std::vector<int8_t>& fast) {
+        for (int64_t b = 0; b < T.nblocks; ++b) {
+            const int32_t* blk = T.block(b);
+            int64_t st = cs;
+            for (int i = 0; i < r; ++i) {
+                const int64_t e = T.ext(i, blk[i]);
+                ext[(size_t)b * r + i] = e; str[(size_t)b * r + i] = st; st *= e;
+                if (e > 1 && fast[b] < 0) fast[b] = (int8_t)i;
+            }
+            size[b] = st;
+        }
+    };
+    fill_block_tables(A, rA, csA, extA_all, strA_all, sizeA, fastA);
+    fill_block_tables(B, rB, csB, extB_all, strB_all, sizeB, fastB);
     int64_t pos = 0;
     while (pos < npairs) {
         const int64_t ic = P.triples[3 * order[pos] + 2];
@@ -417,17 +479,13 @@ int build_contract_tables(itb_contract_plan& P) {
         for (int64_t q = pos; q < end; ++q) {
             const int64_t p = order[q];
             const int64_t ia = P.triples[3 * p], ib = P.triples[3 * p + 1];
-            const int32_t* ab = A.block(ia);
-            const int32_t* bb = B.block(ib);
-            int64_t s = csA;
-            for (int i = 0; i < rA; ++i) { strA[i] = s; s *= A.ext(i, ab[i]); }
-            s = csB;
-            for (int j = 0; j < rB; ++j) { strB[j] = s; s *= B.ext(j, bb[j]); }
+            const int64_t* extA = extA_all.data() + (size_t)ia * rA;
+            const int64_t* extB = extB_all.data() + (size_t)ib * rB;
+            const int64_t* strA = strA_all.data() + (size_t)ia * rA;
+            const int64_t* strB = strB_all.data() + (size_t)ib * rB;
             DimList gm, gk, gn;
             // which operand-fastest (non-unit) index is contracted?
-            int fa = -1, fb = -1;
-            for (int i = 0; i < rA && fa < 0; ++i) if (A.ext(i, ab[i]) > 1) fa = i;
-            for (int j = 0; j < rB && fb < 0; ++j) if (B.ext(j, bb[j]) > 1) fb = j;
+            const int fa = fastA[ia], fb = fastB[ib];
             const bool a_kfast = fa >= 0 && AtoB[fa] >= 0;
             const bool b_kfast = fb >= 0 && BtoA[fb] >= 0;
             int64_t a_shift = 0, b_shift = 0; // element shift of the operand block base when its uncontracted index is sliced
@@ -435,25 +493,25 @@ int build_contract_tables(itb_contract_plan& P) {
                 if (AtoB[i] < 0) {
                     if (i == sl_a) { gm.push_back({sl_hi - sl_lo, strA[i], 0}); a_shift = sl_lo * strA[i]; }
                     else {
-                        if (sl_a >= 0 && i > sl_a && A.ext(i, ab[i]) != 1) { set_error("contract: sliced index is not the slowest non-unit uncontracted index of A"); return ITB_ERR_UNSUPPORTED; }
-                        gm.push_back({A.ext(i, ab[i]), strA[i], 0});
+                        if (sl_a >= 0 && i > sl_a && extA[i] != 1) { set_error("contract: sliced index is not the slowest non-unit uncontracted index of A"); return ITB_ERR_UNSUPPORTED; }
+                        gm.push_back({extA[i], strA[i], 0});
                     }
                 }
             for (int j = 0; j < rB; ++j)
                 if (BtoA[j] < 0) {
                     if (j == sl_b) { gn.push_back({sl_hi - sl_lo, strB[j], 0}); b_shift = sl_lo * strB[j]; }
                     else {
-                        if (sl_b >= 0 && j > sl_b && B.ext(j, bb[j]) != 1) { set_error("contract: sliced index is not the slowest non-unit uncontracted index of B"); return ITB_ERR_UNSUPPORTED; }
-                        gn.push_back({B.ext(j, bb[j]), strB[j], 0});
+                        if (sl_b >= 0 && j > sl_b && extB[j] != 1) { set_error("contract: sliced index is not the slowest non-unit uncontracted index of B"); return ITB_ERR_UNSUPPORTED; }
+                        gn.push_back({extB[j], strB[j], 0});
                     }
                 }
             // K order: follow A unless only B is k-fast (keeps the k-fast operand contiguous in k)
             if (a_kfast || !b_kfast) {
                 for (int i = 0; i < rA; ++i)
-                    if (AtoB[i] >= 0) gk.push_back({A.ext(i, ab[i]), strA[i], strB[AtoB[i]]});
+                    if (AtoB[i] >= 0) gk.push_back({extA[i], strA[i], strB[AtoB[i]]});
             } else {
                 for (int j = 0; j < rB; ++j)
-                    if (BtoA[j] >= 0) gk.push_back({B.ext(j, bb[j]), strA[BtoA[j]], strB[j]});
+                    if (BtoA[j] >= 0) gk.push_back({extB[j], strA[BtoA[j]], strB[j]});
             }
             int64_t m = 1, n = 1, k = 1;
             for (auto& d : gm) m *= d.ext;
@@ -486,9 +544,7 @@ int build_contract_tables(itb_contract_plan& P) {
             for (size_t d = 0; d < gk.size(); ++d) { pr.k_ext[d] = (int32_t)gk[d].ext; pr.ak_str[d] = gk[d].sa; pr.bk_str[d] = gk[d].sb; }
             pr.m_n = (int32_t)gm.size(); pr.n_n = (int32_t)gn.size(); pr.k_n = (int32_t)gk.size();
             const int64_t Kr = k * ((cA && cB) ? 2 : 1);
-            int64_t abl = csA, bbl = csB; // real elements of the two blocks: device row offsets are 32-bit
-            for (int i = 0; i < rA; ++i) abl *= A.ext(i, ab[i]);
-            for (int j = 0; j < rB; ++j) bbl *= B.ext(j, bb[j]);
+            const int64_t abl = sizeA[ia], bbl = sizeB[ib]; // real elements of the two blocks: device row offsets are 32-bit
             if (Kr >= (1ll << 31) || m * 2 >= (1ll << 31) || n * 2 >= (1ll << 31) || abl >= (1ll << 31) || bbl >= (1ll << 31)) {
                 set_error("contract: block dimension exceeds 2^31");
                 return ITB_ERR_UNSUPPORTED;
@@ -520,6 +576,7 @@ int build_contract_tables(itb_contract_plan& P) {
         pos = end;
     }
 
+    PLAN_PHASE(1);
     // ---- classify C blocks into kernel work lists --------------------------------------------------
     read_tile_env();
     auto chunks_of = [&](const ItbCBlk& cb) {
@@ -583,14 +640,24 @@ int build_contract_tables(itb_contract_plan& P) {
         int64_t stream_elems = 0;
         for (int32_t c : stream_cands) stream_elems += (int64_t)P.cblks[c].M * P.cblks[c].N;
         const bool ride = !tile_cblks.empty() && stream_elems < kStreamMinTotal;
+        // Tiered planning of the streaming class. The row-group tables below cost about as much host time as all the rest
+        // of the plan (0.7-1.0 ms for the MPO steps at Hubbard scale) and buy ~2x on an HBM-bound kernel: worth it for a
+        // step that streams tens of MB or that keeps coming back (Davidson), not for the many contractions of a DMRG bond
+        // that run once on a few MB. Small streaming classes therefore start on the C-stationary kernels (their item lists
+        // are trivial to build); itb_contract_run re-plans with row groups when the plan reaches its kRowGroupAfterRuns-th
+        // execution.
+        const bool want_rg = kUseRowGroups && (stream_elems * 8 >= kRowGroupMinBytes || P.runs >= kRowGroupAfterRuns);
+        P.rg_deferred = false;
         for (int32_t c : stream_cands) {
             if (ride) { to_tiles(c); continue; }
             const ItbCBlk& cb = P.cblks[c];
             P.class_flops[3] += 2.0 * (double)cb.M * (double)cb.N * (double)cb.ksum;
-            if (!cA && !cB && cb.M >= cb.N && kUseRowGroups) rg_cands.push_back(c); // row-group kernel (below); else C-stationary kernels
-            else push_skinny(c);
+            const bool eligible = !cA && !cB && cb.M >= cb.N && kUseRowGroups;
+            if (eligible && want_rg) rg_cands.push_back(c); // row-group kernel (below); else C-stationary kernels
+            else { push_skinny(c); P.rg_deferred |= eligible; }
         }
     }
+    PLAN_PHASE(2);
     // ---- row groups: streaming C blocks that share their long-side (A-uncontracted) block coordinates ----------
     if (!rg_cands.empty()) {
         std::vector<int> uncA; // A's uncontracted indices, in order (they lead the C index list)
@@ -719,6 +786,7 @@ int build_contract_tables(itb_contract_plan& P) {
             }
         }
     }
+    PLAN_PHASE(3);
     // ---- tile items: one in-order queue, tail cut into shrinking pieces (guided self-scheduling) ------------------
     // The kernel's CTAs pull items from the head of this list through an atomic counter (kernels_gemm.cu), so the
     // assignment of items to CTAs is decided at run time by whoever is free. What the planner fixes is the ORDER
@@ -888,6 +956,7 @@ int build_contract_tables(itb_contract_plan& P) {
             remaining -= cost;
         }
         P.cta_begin[G + 1] = (int32_t)P.tiles.size();
+        PLAN_PHASE(4);
         // flattened device records
         P.qitems.resize(P.tiles.size());
         for (size_t i = 0; i < P.tiles.size(); ++i) {
@@ -910,6 +979,7 @@ int build_contract_tables(itb_contract_plan& P) {
                               (P.skinny.size() + P.skinny_q4.size() + P.skinny_q8.size()) * sizeof(ItbSkinny) + P.dots.size() * sizeof(ItbDot) +
                               P.dot_outs.size() * sizeof(ItbDotOut) + P.qitems.size() * sizeof(ItbQItem) +
                               P.splits.size() * sizeof(ItbSplitOut) + P.cta_begin.size() * sizeof(int32_t));
+    PLAN_PHASE(5);
     P.tables_built = true;
     return ITB_OK;
 }

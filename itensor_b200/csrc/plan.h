@@ -47,6 +47,8 @@ struct itb_contract_plan {
 
     // device-format tables (built by build_tables(), rebuilt when the range changes)
     bool tables_built = false;
+    int64_t runs = 0;        // executions so far (itb_contract_run): drives the tiered planning of the streaming class
+    bool rg_deferred = false; // the current tables route row-group-eligible C blocks to the C-stationary kernels
     std::vector<ItbPair> pairs;
     std::vector<ItbCBlk> cblks;
     std::vector<ItbTile> tiles;       // every tile class in one list; CTA b of the persistent grid owns [cta_begin[b], cta_begin[b+1])
@@ -98,6 +100,9 @@ void set_error(const std::string& msg);
 int parse_desc(const itb_tensor_desc* d, TensorStruct& out, const char* what);
 int build_contract_plan(itb_contract_plan& P);
 int build_contract_tables(itb_contract_plan& P);
+// counts one execution; true when the tables must be rebuilt first (tiered planning: a plan that keeps coming back gets
+// its row-group tables now)
+bool plan_note_run(itb_contract_plan& P);
 int build_permute_plan(itb_permute_plan& P);
 
 constexpr int kPermCopyChunk = 4096; // elements per work item, copy-like path

@@ -23,6 +23,7 @@
 #include <chrono>
 #include <fstream>
 #include <map>
+#include <optional>
 #include <thread>
 
 namespace itensor {
@@ -435,6 +436,7 @@ getContractPlan(Desc const& dA, std::vector<int32_t> const& la, Desc const& dB, 
     auto& cache = contractCache();
     if(auto* p = cache.find(key)) return p;
     itb_contract_plan* p = nullptr;
+    gpu::Scope missScope("Contract: b' plan create (cache miss)");
     check(itb_contract_plan_create(&dA.d,la.data(),&dB.d,lb.data(),&p),"contract plan");
     if(sliceIndex >= 0)
         {
@@ -821,6 +823,8 @@ contractQ(Contract& Con,
     using VC = common_type<VA,VB>;
     Labels Lind, Rind, Cind;
     ITB_SCOPE("Contract QDenseGPU");
+    std::optional<gpu::Scope> sub; // finer host-side breakdown under ITB_PROFILE
+    sub.emplace("Contract: a labels+desc");
     computeLabels(Con.Lis,order(Con.Lis),Con.Ris,order(Con.Ris),Lind,Rind);
     const bool sortResult = false;
     contractIS(Con.Lis,Lind,Con.Ris,Rind,Con.Nis,Cind,sortResult);
@@ -828,7 +832,9 @@ contractQ(Contract& Con,
     auto dA = Desc(Con.Lis,Aoff,An,dtypeOf<VA>());
     auto dB = Desc(Con.Ris,Boff,Bn,dtypeOf<VB>());
     auto la = toLabels(Lind), lb = toLabels(Rind);
+    sub.emplace("Contract: b plan lookup/create");
     auto* plan = getContractPlan(dA,la,dB,lb); // (pair enumeration + C structure; device tables are built on first run)
+    sub.emplace("Contract: c result structure");
     struct { int32_t c_order = 0, c_dtype = 0; int64_t c_nblocks = 0, c_nelems = 0, npairs = 0; double flops = 0; } info;
     check(itb_contract_plan_shape(plan,&info.c_order,&info.c_dtype,&info.c_nblocks,&info.c_nelems,&info.npairs,&info.flops),"plan shape");
     auto rC = long(info.c_order);
@@ -896,7 +902,9 @@ contractQ(Contract& Con,
             else if(pend) { (pa ? Abuf : Bbuf).data(); } // this step cannot be sliced on that index: complete the operand, run unsharded
             }
         }
+    sub.emplace("Contract: d alloc result");
     auto* nd = m.makeNewData<QDenseGPU<VC>>(Coffsets,size_t(info.c_nelems));
+    sub.emplace("Contract: e tables+launch");
     if(sliced)
         {
         // operands as they are: a pending operand contributes exactly the rows this rank owns

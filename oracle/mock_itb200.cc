@@ -207,6 +207,7 @@ int itb_pool_trim(itb_ctx*) { return ITB_OK; }
 int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C) {
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK;
     MockScope scope_;
+    itb::plan_note_run(*P);
     static const bool walk_tables = [] { const char* e = std::getenv("ITB_MOCK_TABLES"); return e && std::atoi(e) != 0; }();
     // (row-sliced plans only exist as device tables: the oracle works on whole blocks)
     if (walk_tables || P->slice_index >= 0) { ++c->launches; return emu_contract(P, (const double*)A, (const double*)B, (double*)C); }
