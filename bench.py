@@ -231,6 +231,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-refine", action="store_true", help="keep the modelled tile partition (no measured re-partitioning of the plans)")
     ap.add_argument("--refine-rounds", type=int, default=4)
+    ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep equal flops per rank (no measured re-balancing of the row partition)")
+    ap.add_argument("--rebalance-rounds", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -306,11 +308,71 @@ def main():
     # the planning itself: itb_contract_plan_refine runs each contraction rounds+1 times on the real operands, in chain order
     # so that every input is valid). --no-refine keeps the modelled partition.
     refine_gain = None
-    if not args.no_refine:
-        refine_gain, cur = [], dts[0]
+
+    def refine_plans():
+        gains, cur = [], dts[0]
         for k, p in enumerate(plans):
-            refine_gain.append(round(p.refine(ctx, cur.ptr, dts[k + 1].ptr, outs[k].ptr, rounds=args.refine_rounds), 4))
+            gains.append(round(p.refine(ctx, cur.ptr, dts[k + 1].ptr, outs[k].ptr, rounds=args.refine_rounds), 4))
             cur = outs[k]
+        return gains
+
+    def chain_ms(reps=5):
+        # device time of this rank's four contractions (CUDA events, L2 flushed), mean of reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0.record()
+            cur = dts[0]
+            for k, p in enumerate(plans):
+                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
+                cur = outs[k]
+            e1.record()
+            e1.synchronize()
+            acc += e0.elapsed_time(e1)
+        return acc / reps
+
+    if not args.no_refine:
+        refine_gain = refine_plans()
+    # N > 1: equal flops per rank is not equal time per rank (another mix of tile shapes and cut tiles on every rank), and the
+    # all-gather waits for the slowest. Same idea as the per-CTA refinement one level up: measure every rank's chain, hand a
+    # slower rank a smaller share of the rows, re-slice, re-refine; keep the partition with the shortest slowest rank.
+    rank_balance = None
+    if shard is not None and not args.no_rebalance and shard.mode == "rows":
+        try:
+            def all_times():
+                t = torch.tensor([chain_ms()], dtype=torch.float64, device=dev)
+                out_t = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(out_t, t)
+                return np.array([float(x.item()) for x in out_t])
+
+            shares = np.full(world, 1.0 / world)
+            times = all_times()
+            history = [(shares.copy(), times.copy())]
+            for _ in range(args.rebalance_rounds):
+                speed = shares / times                      # rows-share per ms of every rank
+                new = speed / speed.sum()
+                shares = 0.5 * shares + 0.5 * new           # damped
+                shard.close()
+                shard = shard_chain(plans, world, rank, shares=shares).prepare(ctx.empty)
+                if not args.no_refine:
+                    refine_gain = refine_plans()
+                times = all_times()
+                history.append((shares.copy(), times.copy()))
+            best = min(range(len(history)), key=lambda i: history[i][1].max())
+            if best != len(history) - 1:
+                shard.close()
+                shard = shard_chain(plans, world, rank, shares=history[best][0]).prepare(ctx.empty)
+                if not args.no_refine:
+                    refine_gain = refine_plans()
+            rank_balance = {"chain_ms_per_rank_equal_flops": [round(x, 4) for x in history[0][1]],
+                            "chain_ms_per_rank_rebalanced": [round(x, 4) for x in history[best][1]],
+                            "row_shares": [round(float(x), 4) for x in history[best][0]], "rounds": args.rebalance_rounds}
+            t = torch.tensor([shard.my_flops / shard.total_flops], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            max_share = float(t.item())
+        except Exception as e:  # noqa: BLE001  (keeps the equal-flop partition)
+            rank_balance = {"error": str(e)[:200]}
     for _ in range(args.warmup):
         step()
     barrier()
@@ -626,7 +688,7 @@ def main():
                                     "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin, "multi_gpu_phases": phases,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin, "multi_gpu_phases": phases, "multi_gpu_rank_balance": rank_balance,
             "permute": perm_info,
         }))
     if world > 1:

@@ -102,8 +102,13 @@ struct itb_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live;
     size_t pooled_bytes = 0;
-    void* staging = nullptr; // pinned host staging for small uploads (tables)
-    size_t staging_bytes = 0;
+    // pinned host staging for table uploads: a ring of buffers, so that the host can plan and queue up to kStagingSlots
+    // new structures ahead of the GPU (with ONE buffer every upload waited for the previous one, which sits in stream order
+    // behind the previous contraction: host planning and device execution took turns instead of overlapping)
+    static constexpr int kStagingSlots = 8;
+    void* staging[kStagingSlots] = {};
+    size_t staging_bytes[kStagingSlots] = {};
+    int staging_next = 0;
     double* scratch = nullptr; // device scratch for reductions
     double* ws = nullptr;      // split-K workspace (grow-only, stream-ordered reuse)
     size_t ws_doubles = 0;
@@ -113,8 +118,8 @@ struct itb_ctx {
     bool profile = false;
     cudaStream_t aux = nullptr;          // side stream: small streaming / split-K-dot launches overlap the tile kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaEvent_t ev_staging = nullptr;    // completion of the last table upload out of the pinned staging buffer
-    bool staging_busy = false;
+    cudaEvent_t ev_staging[kStagingSlots] = {}; // completion of the last table upload out of each staging buffer
+    bool staging_busy[kStagingSlots] = {};
     float last_ms[5] = {0, 0, 0, 0, 0};
     long long* d_cta_cycles = nullptr;   // profile mode: per-CTA clock64 span of the last tile-kernel launch
     std::vector<long long> h_cta_cycles;
@@ -148,15 +153,19 @@ static int pool_alloc(itb_ctx* c, size_t bytes, void** out) {
         c->free_blocks.erase(it);
         return ITB_OK;
     }
+    // A miss goes to the driver's stream-ordered allocator (release threshold raised at context creation, so its memory
+    // stays mapped): unlike cudaMalloc it neither synchronises the device nor costs 0.1-0.3 ms — in a DMRG ramp the block
+    // sizes change at every bond and a third of all result allocations miss (75 us per Contract on average before).
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, r);
+    cudaError_t e = cudaMallocAsync(&p, r, c->stream);
     if (e != cudaSuccess) {
         // trim the cache and retry once
         for (auto& kv : c->free_blocks) cudaFree(kv.second);
         c->free_blocks.clear();
         c->pooled_bytes = 0;
         (void)cudaGetLastError();
-        e = cudaMalloc(&p, r);
+        cudaStreamSynchronize(c->stream);
+        e = cudaMallocAsync(&p, r, c->stream);
         if (e != cudaSuccess) {
             set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
             return e == cudaErrorMemoryAllocation ? ITB_ERR_NOMEM : ITB_ERR_CUDA;
@@ -190,12 +199,12 @@ static int ensure_ws(itb_ctx* c, size_t doubles) {
     c->ws_doubles = doubles;
     return ITB_OK;
 }
-static int ensure_staging(itb_ctx* c, size_t bytes) {
-    if (c->staging_bytes >= bytes) return ITB_OK;
-    if (c->staging) { CUDA_TRY(cudaStreamSynchronize(c->stream)); c->staging_busy = false; cudaFreeHost(c->staging); c->staging = nullptr; }
-    size_t nb = std::max<size_t>(bytes, 1u << 20);
-    CUDA_TRY(cudaMallocHost(&c->staging, nb));
-    c->staging_bytes = nb;
+static int ensure_staging(itb_ctx* c, int slot, size_t bytes) { // (the slot is idle: its last copy has completed)
+    if (c->staging_bytes[slot] >= bytes) return ITB_OK;
+    if (c->staging[slot]) { cudaFreeHost(c->staging[slot]); c->staging[slot] = nullptr; c->staging_bytes[slot] = 0; }
+    size_t nb = std::max<size_t>(bytes, 256u << 10);
+    CUDA_TRY(cudaMallocHost(&c->staging[slot], nb));
+    c->staging_bytes[slot] = nb;
     return ITB_OK;
 }
 
@@ -246,13 +255,21 @@ int itb_ctx_create(int device, itb_ctx** out) {
         return ITB_ERR_CUDA;
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // keep the stream-ordered allocator's memory mapped between uses (the context's own pool sits on top of it)
+        cudaMemPool_t mp = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     CUDA_TRY(cudaMallocHost(&c->h_result, 8 * sizeof(double)));
     CUDA_TRY(cudaEventCreate(&c->ev0));
     CUDA_TRY(cudaEventCreate(&c->ev1));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_staging, cudaEventDisableTiming));
+    for (auto& e : c->ev_staging) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     itb_warm_library_pages();
     *out = c;
     return ITB_OK;
@@ -266,14 +283,14 @@ int itb_ctx_destroy(itb_ctx* c) {
     for (auto& kv : c->live) cudaFree(kv.first);
     if (c->scratch) cudaFree(c->scratch);
     if (c->ws) cudaFree(c->ws);
-    if (c->staging) cudaFreeHost(c->staging);
+    for (void* p : c->staging) if (p) cudaFreeHost(p);
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->aux) cudaStreamDestroy(c->aux);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->ev_staging) cudaEventDestroy(c->ev_staging);
+    for (auto e : c->ev_staging) if (e) cudaEventDestroy(e);
     for (auto& e : c->pev) if (e) cudaEventDestroy(e);
     if (c->d_cta_cycles) cudaFree(c->d_cta_cycles);
     if (c->solver) itb_solver_destroy(c->solver);
@@ -291,7 +308,7 @@ int itb_ctx_set_stream(itb_ctx* c, void* s) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
-    c->staging_busy = false; // the old stream was drained above
+    for (bool& b : c->staging_busy) b = false; // the old stream was drained above
     return ITB_OK;
 }
 int itb_synchronize(itb_ctx* c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return ITB_OK; }
@@ -346,15 +363,18 @@ static int upload(itb_ctx* c, Packer& pk, size_t extra_dev_bytes, DeviceTables* 
     if (rc != ITB_OK) return rc;
     dev->bytes = total;
     if (pk.total) {
-        rc = ensure_staging(c, pk.total);
+        const int slot = c->staging_next;
+        c->staging_next = (slot + 1) % itb_ctx::kStagingSlots;
+        // this buffer's previous upload (kStagingSlots uploads ago) may still be in flight: wait for THAT copy only
+        if (c->staging_busy[slot]) { CUDA_TRY(cudaEventSynchronize(c->ev_staging[slot])); c->staging_busy[slot] = false; }
+        rc = ensure_staging(c, slot, pk.total);
         if (rc != ITB_OK) return rc;
-        // the staging buffer may still be in flight from the previous upload: wait for THAT copy only
-        if (c->staging_busy) { CUDA_TRY(cudaEventSynchronize(c->ev_staging)); c->staging_busy = false; }
+        char* stg = (char*)c->staging[slot];
         for (size_t i = 0; i < pk.parts.size(); ++i)
-            if (pk.parts[i].second) std::memcpy((char*)c->staging + pk.offs[i], pk.parts[i].first, pk.parts[i].second);
-        CUDA_TRY(cudaMemcpyAsync(dev->base, c->staging, pk.total, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaEventRecord(c->ev_staging, c->stream));
-        c->staging_busy = true;
+            if (pk.parts[i].second) std::memcpy(stg + pk.offs[i], pk.parts[i].first, pk.parts[i].second);
+        CUDA_TRY(cudaMemcpyAsync(dev->base, stg, pk.total, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_staging[slot], c->stream));
+        c->staging_busy[slot] = true;
     }
     return ITB_OK;
 }
@@ -793,6 +813,7 @@ int itb_svd_batch_run(itb_ctx* c, int32_t dtype, int64_t nblocks, const int64_t*
 int itb_eigh_batch_run(itb_ctx* c, int32_t dtype, int64_t nblocks, const int64_t* a_off, const int32_t* n, const void* dA, int negate,
                        itb_eigh_batch** out) {
     if (!c || !out || nblocks < 0) { set_error("eigh_batch_run: bad arguments"); return ITB_ERR_INVALID; }
+    CUDA_TRY(cudaSetDevice(c->device)); // (the plugin drives this call from a helper thread)
     int rc = ensure_solver(c);
     if (rc != ITB_OK) return rc;
     c->launches += 2 * nblocks;

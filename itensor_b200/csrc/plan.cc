@@ -91,7 +91,16 @@ struct VecHash {
     }
 };
 
+#ifdef ITB_PLAN_PROFILE
+double g_plan_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // harness builds only (build/planprof)
+#define PLAN_T0() auto plan_t_ = std::chrono::steady_clock::now()
+#define PLAN_PHASE(i) do { auto n_ = std::chrono::steady_clock::now(); g_plan_phase[i] += std::chrono::duration<double>(n_ - plan_t_).count(); plan_t_ = n_; } while (0)
+#else
+#define PLAN_T0() do {} while (0)
+#define PLAN_PHASE(i) do {} while (0)
+#endif
 int build_contract_plan(itb_contract_plan& P) {
+    PLAN_T0();
     const TensorStruct &A = P.A, &B = P.B;
     TensorStruct& C = P.C;
     const int rA = A.order, rB = B.order;
@@ -127,6 +136,7 @@ int build_contract_plan(itb_contract_plan& P) {
     if (rC > ITB_MAX_ORDER) { set_error("contract: result order too large"); return ITB_ERR_UNSUPPORTED; }
     C.order = rC;
 
+    PLAN_PHASE(6);
     // ---- pair enumeration + C block list ----------------------------------------------------------
     std::vector<int> contA, contB;
     for (int i = 0; i < rA; ++i)
@@ -234,6 +244,7 @@ int build_contract_plan(itb_contract_plan& P) {
         }
         C.nelems = off;
     }
+    PLAN_PHASE(7);
     const size_t nrec = packed ? precs.size() : recs.size();
     // ---- triples + flops -----------------------------------------------------------------------
     P.triples.resize(nrec * 3);
@@ -253,6 +264,7 @@ int build_contract_plan(itb_contract_plan& P) {
             if (BtoA[j] < 0) n *= (double)B.ext(j, B.block(rb)[j]);
         P.flops += 2.0 * m * n * k * cmul;
     }
+    PLAN_PHASE(6);
     P.tables_built = false;
     return ITB_OK;
 }
@@ -381,14 +393,6 @@ static double cblk_cost(int f, int64_t M, int64_t N, double nch, int npairs) {
     return cost;
 }
 
-#ifdef ITB_PLAN_PROFILE
-double g_plan_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // harness builds only (build/planprof)
-#define PLAN_T0() auto plan_t_ = std::chrono::steady_clock::now()
-#define PLAN_PHASE(i) do { auto n_ = std::chrono::steady_clock::now(); g_plan_phase[i] += std::chrono::duration<double>(n_ - plan_t_).count(); plan_t_ = n_; } while (0)
-#else
-#define PLAN_T0() do {} while (0)
-#define PLAN_PHASE(i) do {} while (0)
-#endif
 bool plan_note_run(itb_contract_plan& P) {
     read_tile_env();
     ++P.runs;

@@ -15,7 +15,7 @@ scattered back into place. Pack and scatter are launches of the block-copy kerne
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -33,8 +33,9 @@ def sector_assignment(weights: Sequence[float], world: int) -> np.ndarray:
     return owner
 
 
-def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, align: int = 8):
-    """Cut the concatenated rows of all sectors into `world` contiguous segments of equal weight.
+def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, align: int = 8, shares: Optional[Sequence[float]] = None):
+    """Cut the concatenated rows of all sectors into `world` contiguous segments of equal weight (or of the given
+    `shares` of the total weight, one per rank: the measured re-balancing of bench.py hands a slower rank less).
 
     sizes[s] rows in sector s carrying weights[s] in total (uniform inside a sector). Returns lo, hi of shape
     (world, nsect): rank g owns rows [lo[g,s], hi[g,s]) of sector s. Cut points inside a sector are rounded to a
@@ -46,8 +47,9 @@ def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, al
     cumw = np.concatenate([[0.0], np.cumsum(w)])
     total = cumw[-1]
     cuts = [0]
+    cum_share = np.arange(world + 1) / world if shares is None else np.concatenate([[0.0], np.cumsum(np.asarray(shares, float) / np.sum(shares))])
     for g in range(1, world):
-        target = total * g / world
+        target = total * cum_share[g]
         s = int(np.searchsorted(cumw, target, side="right") - 1)
         s = min(max(s, 0), len(sizes) - 1)
         r = int(round((target - cumw[s]) / per_row[s])) if per_row[s] > 0 else 0
@@ -110,7 +112,8 @@ def _owned_boxes(struct, j: int, lo: np.ndarray, hi: np.ndarray):
 class ChainShard:
     """Row partition of l' over `world` ranks for a chain of plans; slices every plan to this rank's rows."""
 
-    def __init__(self, plans: List, world: int, rank: int, shard_index_id: int = 1, shard_index_plev: int = 1, align: int = 8):
+    def __init__(self, plans: List, world: int, rank: int, shard_index_id: int = 1, shard_index_plev: int = 1, align: int = 8,
+                 shares: Optional[Sequence[float]] = None):
         self.world, self.rank, self.plans = world, rank, plans
         pos, flops = [], []
         sizes = None
@@ -126,7 +129,8 @@ class ChainShard:
             np.add.at(w, p.C.blocks[:, j], f)
         self.sector_work = w
         self.total_flops = float(sum(f.sum() for f in flops))
-        self.lo, self.hi = row_partition(sizes, w, world, align)
+        self.shares = None if shares is None else [float(x) for x in shares]
+        self.lo, self.hi = row_partition(sizes, w, world, align, shares)
         self.mode = "rows"
         try:
             for p, j in zip(plans, pos):
@@ -230,5 +234,5 @@ class ChainShard:
         self._pack = self._unpack = None
 
 
-def shard_chain(plans, world, rank) -> ChainShard:
-    return ChainShard(plans, world, rank)
+def shard_chain(plans, world, rank, shares=None) -> ChainShard:
+    return ChainShard(plans, world, rank, shares=shares)

@@ -2,7 +2,7 @@
 # bench.py under torchrun on N GPUs (the driver's launch line)
 N=${1:-2}
 OUT=gpurun_out; mkdir -p $OUT
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $OUT/q_bench_n$N.json 2> $OUT/q_bench_n$N.err; echo "bench N=$N rc=$?"
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > $OUT/q_bench_n$N.json 2> $OUT/q_bench_n$N.err; echo "bench N=$N rc=$?"
 tail -2 $OUT/q_bench_n$N.err
 python - <<PY
 import json
