@@ -231,6 +231,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-refine", action="store_true", help="keep the modelled tile partition (no measured re-partitioning of the plans)")
     ap.add_argument("--refine-rounds", type=int, default=4)
+    ap.add_argument("--no-p2p", action="store_true", help="N > 1: re-replicate H*phi with pack / NCCL all-gather / scatter instead of direct peer-memory stores")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep equal flops per rank (no measured re-balancing of the row partition)")
     ap.add_argument("--rebalance-rounds", type=int, default=2)
     args = ap.parse_args()
@@ -291,13 +292,23 @@ def main():
     h_out = torch.empty(plans[-1].C.nreal, dtype=torch.float64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step():
+    p2p_out = None  # N > 1: H*phi in peer-mapped buffers, rows exchanged by direct NVLink stores (set up below)
+    step_no = [0]
+
+    def step(b=None):
+        if b is None:  # alternate between the two H*phi buffers (see ChainShard.prepare_p2p)
+            b = step_no[0] & 1
+            step_no[0] += 1
         cur = dts[0]
         for k, p in enumerate(plans):  # sharded: every plan is sliced to this rank's rows of l'
-            check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
-            cur = outs[k]
+            dst = p2p_out[b] if (p2p_out is not None and k == len(plans) - 1) else outs[k]
+            check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, dst.ptr))
+            cur = dst
         if shard is not None:
-            shard.allgather(ctx.handle, outs[-1].data)  # pack own rows -> one NCCL all-gather -> scatter
+            if p2p_out is not None:
+                shard.push(ctx.handle, b)   # own rows -> every peer's buffer b over NVLink, then the arrival barrier
+            else:
+                shard.allgather(ctx.handle, outs[-1].data)  # pack own rows -> one NCCL all-gather -> scatter
 
     def barrier():
         if world > 1:
@@ -373,6 +384,36 @@ def main():
             max_share = float(t.item())
         except Exception as e:  # noqa: BLE001  (keeps the equal-flop partition)
             rank_balance = {"error": str(e)[:200]}
+    exchange = "none"
+    p2p_check = None
+    if shard is not None:
+        exchange = "pack -> one NCCL all-gather -> scatter"
+        if not args.no_p2p:
+            bufs = shard.prepare_p2p(ctx)
+            if bufs is not None:
+                p2p_out = [itb.QTensor(ctx, plans[-1].C, t) for t in bufs]
+                exchange = "direct NVLink stores of the owned rows into every peer's H*phi buffer (CUDA IPC peer memory, block-copy kernel) + one-element all-reduce as arrival barrier; two buffers used alternately"
+                # every rank's assembled H*phi against its own UNSHARDED recomputation of the chain
+                for b in (0, 1):
+                    p2p_out[b].data.fill_(float("nan"))
+                barrier()
+                step(0); step(1)
+                barrier()
+                full, cur_t = [itb.ContractPlan(structs[0], structs[1])], None
+                for t in structs[2:]:
+                    full.append(itb.ContractPlan(full[-1].C, t))
+                tmp = [itb.QTensor(ctx, q.C, ctx.empty(q.C.nreal)) for q in full]
+                cur_t = dts[0]
+                for k, q in enumerate(full):
+                    check(lib().itb_contract_run(ctx.handle, q._h, cur_t.ptr, dts[k + 1].ptr, tmp[k].ptr))
+                    cur_t = tmp[k]
+                ref_t = tmp[-1].data
+                errs = [float(((p2p_out[b].data - ref_t).abs().max() / ref_t.abs().max()).item()) for b in (0, 1)]
+                errs = [e if e == e else float("inf") for e in errs]
+                t = torch.tensor([max(errs)], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                p2p_check = {"max_rel_err_vs_unsharded_chain_over_ranks": float(t.item()), "bar": 1e-12, "ok": bool(float(t.item()) <= 1e-12)}
+                del tmp, full
     for _ in range(args.warmup):
         step()
     barrier()
@@ -384,20 +425,30 @@ def main():
     run_step = step
     if not args.no_graph:
         try:
-            g = torch.cuda.CUDAGraph()
+            nbuf = 2 if p2p_out is not None else 1
+            graphs = [torch.cuda.CUDAGraph() for _ in range(nbuf)]
+            g = graphs[0]
             cap_stream = torch.cuda.Stream(device=dev)
             cap_stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(cap_stream):
                 check(lib().itb_ctx_set_stream(ctx.handle, C.c_void_p(cap_stream.cuda_stream)))
-                step()  # (warm the capture stream)
+                for b in range(nbuf):
+                    step(b)  # (warm the capture stream)
                 torch.cuda.synchronize()
-                with torch.cuda.graph(g, stream=cap_stream):
-                    step()
+                for b in range(nbuf):
+                    with torch.cuda.graph(graphs[b], stream=cap_stream):
+                        step(b)
             check(lib().itb_ctx_set_stream(ctx.handle, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
             torch.cuda.synchronize()
-            g.replay()
+            for gg in graphs:
+                gg.replay()
             torch.cuda.synchronize()
-            run_step = g.replay
+            replay_no = [0]
+
+            def run_step():
+                graphs[replay_no[0] % nbuf].replay()
+                replay_no[0] += 1
+
             launch_mode = "cuda-graph replay of the captured step"
         except Exception as e:  # noqa: BLE001
             check(lib().itb_ctx_set_stream(ctx.handle, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
@@ -444,12 +495,23 @@ def main():
             for k, p in enumerate(plans):
                 check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
                 cur = outs[k]
-            shard.allgather(ctx.handle, outs[-1].data, evs[:4])
-            torch.cuda.synchronize()
-            acc += np.array([evs[4].elapsed_time(evs[0]), evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])])
+            if p2p_out is not None:
+                evs[3].record()  # (unused slot)
+                shard.push(ctx.handle, 0, evs[:3])
+                torch.cuda.synchronize()
+                acc += np.array([evs[4].elapsed_time(evs[0]), evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), 0.0])
+            else:
+                shard.allgather(ctx.handle, outs[-1].data, evs[:4])
+                torch.cuda.synchronize()
+                acc += np.array([evs[4].elapsed_time(evs[0]), evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])])
         acc /= 5
-        phases = {"contractions_ms": float(acc[0]), "pack_ms": float(acc[1]), "allgather_ms": float(acc[2]), "scatter_ms": float(acc[3]),
-                  "allgather_bytes_per_rank": int(shard.seg_reals * 8), "note": "rank 0, CUDA events, mean of 5 steps (the all-gather includes waiting for the slowest rank)"}
+        if p2p_out is not None:
+            phases = {"contractions_ms": float(acc[0]), "push_ms": float(acc[1]), "arrival_barrier_ms": float(acc[2]),
+                      "pushed_bytes_per_rank": int(shard.seg_elems[rank] * (16 if plans[-1].C.is_complex else 8) * (world - 1)),
+                      "note": "rank 0, CUDA events, mean of 5 steps (the contractions here write the ordinary output buffer; the barrier includes waiting for the slowest rank)"}
+        else:
+            phases = {"contractions_ms": float(acc[0]), "pack_ms": float(acc[1]), "allgather_ms": float(acc[2]), "scatter_ms": float(acc[3]),
+                      "allgather_bytes_per_rank": int(shard.seg_reals * 8), "note": "rank 0, CUDA events, mean of 5 steps (the all-gather includes waiting for the slowest rank)"}
 
     # ---- e2e: host buffers in, host buffer out, every step ---------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -501,15 +563,23 @@ def main():
         dts_e = [itb.QTensor(ctx, st, d_arena[o:o + st.nreal]) for o, st in zip(offs, structs)]
         h_seg = torch.empty(shard.seg_reals, dtype=torch.float64).pin_memory()
         mine = slice(rank * chunk, (rank + 1) * chunk)
+        e2e_no = [0]
 
         def e2e_step():  # noqa: F811
             d_arena[mine].copy_(h_arena[mine], non_blocking=True)
             dist.all_gather_into_tensor(d_arena, d_arena[mine])
             cur = dts_e[0]
+            b = e2e_no[0] & 1
+            e2e_no[0] += 1
             for k, p in enumerate(plans):
-                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts_e[k + 1].ptr, outs[k].ptr))
-                cur = outs[k]
-            shard.allgather(ctx.handle, outs[-1].data)
+                dst = p2p_out[b] if (p2p_out is not None and k == len(plans) - 1) else outs[k]
+                check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts_e[k + 1].ptr, dst.ptr))
+                cur = dst
+            if p2p_out is not None:
+                shard.push(ctx.handle, b)
+                shard.pack_own(ctx.handle, p2p_out[b].data)
+            else:
+                shard.allgather(ctx.handle, outs[-1].data)
             h_seg.copy_(shard.send, non_blocking=True)
             torch.cuda.synchronize()
     e2e_step()
@@ -556,11 +626,11 @@ def main():
         dfma = C.c_double()
         lib().itb_peak_fp64(ctx.handle, 1, 4096, C.byref(dfma))
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r03_traffic.json")
         if os.path.exists(tp) and args.m == 2000 and args.nsect == 9 and not args.complex and world == 1:
-            tj = json.load(open(tp))["bsc_gemm_kernel"]
+            tj = json.load(open(tp))["bsc_gemm_static_kernel"]
             traffic = float(np.mean(tj["per_launch_bytes"]))  # DRAM bytes per launch (mean of the step-1 and step-4 launches)
-            traffic_src = "profiles/r02_traffic.json (ncu --set full of this command; algorithmic bytes per launch %.3g)" % float(np.mean(tj["algorithmic_bytes_per_launch"]))
+            traffic_src = "profiles/r03_traffic.json (ncu --set full of this command; algorithmic bytes per launch %.3g)" % float(np.mean(tj["algorithmic_bytes_per_launch"]))
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": "bsc_gemm_static_kernel (persistent warp-specialised DMMA tiles 128/64/32, stream-K partition)",
                 "peak_source": "measured in this run: torch.matmul fp64 8192^3 best of 6 (MEASURED_PEAKS.json has no FP64 entry)",
@@ -684,11 +754,11 @@ def main():
                        "l2": "flushed between timed iterations (256 MiB memset)", "launch": launch_mode,
                        "tile_partition": ("modelled" if refine_gain is None else "refined from measured per-CTA cycles at plan set-up (itb_contract_plan_refine, %d rounds; longest-CTA gain per plan %s)" % (args.refine_rounds, refine_gain)),
                        "sharding": ("rows of l' (%s), equal-flop contiguous row ranges per rank, max rank share %.3f of flops (ideal %.3f); "
-                                    "H*phi re-replicated by pack -> one NCCL all-gather -> scatter; e2e: 1/N of the operand arena per "
-                                    "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world)) if world > 1 else "none"},
+                                    "H*phi re-replicated by %s; e2e: 1/N of the operand arena per "
+                                    "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world, exchange)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin, "multi_gpu_phases": phases, "multi_gpu_rank_balance": rank_balance,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin, "multi_gpu_phases": phases, "multi_gpu_rank_balance": rank_balance, "multi_gpu_exchange_check": p2p_check,
             "permute": perm_info,
         }))
     if world > 1:
@@ -700,9 +770,9 @@ def main():
         sys.stdout.flush()
         threading.Timer(20.0, lambda: os._exit(0)).start()
         run_step = None
-        if "g" in locals():
+        for gg in locals().get("graphs", []):
             try:
-                g.reset()
+                gg.reset()
             except Exception:  # noqa: BLE001
                 pass
         torch.cuda.synchronize()

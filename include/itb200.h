@@ -95,6 +95,7 @@ int itb_device_count(void);
 int itb_ctx_create(int device, itb_ctx** out);
 int itb_ctx_destroy(itb_ctx* ctx);
 void* itb_ctx_stream(itb_ctx* ctx);                 /* the cudaStream_t every launch goes to */
+int itb_ctx_device(itb_ctx* ctx);                   /* CUDA device ordinal of the context */
 int itb_ctx_set_stream(itb_ctx* ctx, void* stream); /* adopt a caller-owned stream */
 int itb_synchronize(itb_ctx* ctx);
 int64_t itb_launch_count(itb_ctx* ctx);             /* kernels launched through this context */
@@ -264,6 +265,17 @@ int32_t itb_comm_rank(const itb_comm* comm);
  * dSend == (double*)dRecv + rank*count); ordered on the context's stream */
 int itb_comm_allgather(itb_comm* comm, itb_ctx* ctx, const void* dSend, void* dRecv, int64_t count);
 int itb_comm_destroy(itb_comm* comm);
+/* Peer memory for the direct row exchange (no counterpart in the reference: its OpenMP workers share one address space,
+ * itensor/itdata/qutil.h:285-348). itb_p2p_alloc: a device buffer other ranks may map + its 64-byte export handle (publish it
+ * through any host channel); itb_p2p_open: map a peer's buffer into this process (enables peer access over NVLink from the
+ * context's device); the mapped pointer is a plain device pointer for every itb_* call, e.g. as the destination of a
+ * block-copy plan whose items carry the rows this rank owns. ITB_ERR_UNSUPPORTED where CUDA IPC / peer access is missing
+ * (callers fall back to itb_comm_allgather). */
+#define ITB_P2P_HANDLE_BYTES 64
+int itb_p2p_alloc(itb_ctx* ctx, int64_t bytes, void** dptr, uint8_t handle[ITB_P2P_HANDLE_BYTES]);
+int itb_p2p_open(itb_ctx* ctx, const uint8_t handle[ITB_P2P_HANDLE_BYTES], void** peer_ptr);
+int itb_p2p_close(itb_ctx* ctx, void* peer_ptr);
+int itb_p2p_free(itb_ctx* ctx, void* dptr);
 /* flops of every C block of a plan (2*M*N*K summed over its pairs, complex multipliers included): the weights of a row partition */
 int itb_contract_plan_cblock_flops(const itb_contract_plan* plan, double* out /*[c_nblocks]*/);
 

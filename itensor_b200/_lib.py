@@ -94,6 +94,11 @@ SYMBOLS = {
     "itb_comm_rank": (C.c_int32, [_P]),
     "itb_comm_allgather": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "itb_comm_destroy": (C.c_int, [_P]),
+    "itb_ctx_device": (C.c_int, [_P]),
+    "itb_p2p_alloc": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "itb_p2p_open": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "itb_p2p_close": (C.c_int, [_P, _P]),
+    "itb_p2p_free": (C.c_int, [_P, _P]),
     "itb_contract_plan_tiles": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_cta_begin": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_rowgroups": (C.c_int64, [_P, _I64P, C.c_int64]),

@@ -300,6 +300,7 @@ int itb_ctx_destroy(itb_ctx* c) {
 }
 
 void* itb_ctx_stream(itb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int itb_ctx_device(itb_ctx* c) { return c ? c->device : -1; }
 int itb_ctx_set_stream(itb_ctx* c, void* s) {
     if (!c) { set_error("set_stream: null ctx"); return ITB_ERR_INVALID; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));

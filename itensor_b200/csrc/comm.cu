@@ -86,6 +86,51 @@ int itb_comm_allgather(itb_comm* c, itb_ctx* ctx, const void* dSend, void* dRecv
     return ITB_OK;
 }
 
+// ---- peer memory (one process per GPU on one NVSwitch domain) ---------------------------------------------------
+// A buffer that the other ranks' kernels store into directly over NVLink: the owner allocates it (plain cudaMalloc, the
+// pointer is the base of its allocation, which is what CUDA IPC exports) and publishes the 64-byte handle through
+// whatever channel the host has; every peer maps it with itb_p2p_open, which also turns on peer access from the
+// calling context's device. No NCCL involved: the rows of H*phi a rank owns are written into every peer's copy by a
+// launch of the block-copy kernel whose destination offsets point into the mapped buffers.
+int itb_p2p_alloc(itb_ctx* ctx, int64_t bytes, void** dptr, uint8_t handle[ITB_P2P_HANDLE_BYTES]) {
+    if (!ctx || !dptr || !handle || bytes <= 0) { itb::set_error("itb_p2p_alloc: bad arguments"); return ITB_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= ITB_P2P_HANDLE_BYTES, "handle size");
+    if (cudaSetDevice(itb_ctx_device(ctx)) != cudaSuccess) { itb::set_error("itb_p2p_alloc: cudaSetDevice failed"); return ITB_ERR_CUDA; }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) { itb::set_error(std::string("itb_p2p_alloc: ") + cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? ITB_ERR_NOMEM : ITB_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); itb::set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); return ITB_ERR_UNSUPPORTED; }
+    std::memset(handle, 0, ITB_P2P_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof(h));
+    *dptr = p;
+    return ITB_OK;
+}
+int itb_p2p_open(itb_ctx* ctx, const uint8_t handle[ITB_P2P_HANDLE_BYTES], void** peer_ptr) {
+    if (!ctx || !handle || !peer_ptr) { itb::set_error("itb_p2p_open: bad arguments"); return ITB_ERR_INVALID; }
+    if (cudaSetDevice(itb_ctx_device(ctx)) != cudaSuccess) { itb::set_error("itb_p2p_open: cudaSetDevice failed"); return ITB_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); itb::set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return ITB_ERR_UNSUPPORTED; }
+    *peer_ptr = p;
+    return ITB_OK;
+}
+int itb_p2p_close(itb_ctx* ctx, void* peer_ptr) {
+    if (!peer_ptr) return ITB_OK;
+    if (ctx) cudaSetDevice(itb_ctx_device(ctx));
+    if (cudaIpcCloseMemHandle(peer_ptr) != cudaSuccess) { (void)cudaGetLastError(); itb::set_error("cudaIpcCloseMemHandle failed"); return ITB_ERR_CUDA; }
+    return ITB_OK;
+}
+int itb_p2p_free(itb_ctx* ctx, void* dptr) {
+    if (!dptr) return ITB_OK;
+    if (ctx) cudaSetDevice(itb_ctx_device(ctx));
+    if (cudaFree(dptr) != cudaSuccess) { (void)cudaGetLastError(); itb::set_error("itb_p2p_free: cudaFree failed"); return ITB_ERR_CUDA; }
+    return ITB_OK;
+}
+
 int itb_comm_destroy(itb_comm* c) {
     if (!c) return ITB_OK;
     if (c->comm) c->CommDestroy(c->comm);

@@ -225,6 +225,124 @@ class ChainShard:
         if events:
             events[3].record()
 
+    # ---- direct exchange over peer memory (NVLink stores, no NCCL on the data path) -----------------------------------
+    def prepare_p2p(self, ctx, nbuf: int = 2):
+        """H*phi lives in `nbuf` peer-mapped buffers per rank (itb_p2p_alloc / itb_p2p_open); returns the list of local
+        output tensors (flat float64, one per buffer) or None when peer memory is unavailable (caller keeps the all-gather).
+
+        push(k) then stores the rows this rank owns straight into buffer k of EVERY peer — one launch of the block-copy
+        kernel whose items carry, per peer, the owned boxes with the destination offset shifted into that peer's mapping —
+        followed by a one-element all-reduce that tells every rank all pushes into its buffer have landed. Two buffers
+        used alternately make a single barrier per product sufficient: a rank can run at most one barrier ahead, so it
+        writes buffer k+1 while a slower peer may still be reading buffer k, never the buffer being read."""
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+
+        nreal = self.out_struct.nreal
+        self._p2p_ctx = ctx
+        self._p2p_local, self._p2p_peers, self._p2p_push, self._p2p_tensors = [], [], [], []
+        try:
+            handles = []
+            for _ in range(nbuf):
+                ptr = C.c_void_p()
+                h = C.create_string_buffer(64)
+                check(lib().itb_p2p_alloc(ctx.handle, max(nreal, 1) * 8, C.byref(ptr), h))
+                self._p2p_local.append(ptr.value)
+                handles.append(h.raw)
+            ok = 1
+        except Exception:  # noqa: BLE001
+            handles, ok = [], 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=ctx.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        allh = [None] * self.world
+        dist.all_gather_object(allh, handles)
+        if int(flag.item()) == 0:
+            self.close_p2p()
+            return None
+        try:
+            for b in range(nbuf):
+                peers = {}
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    pp = C.c_void_p()
+                    check(lib().itb_p2p_open(ctx.handle, allh[r][b], C.byref(pp)))
+                    peers[r] = pp.value
+                self._p2p_peers.append(peers)
+            ok = 1
+        except Exception:  # noqa: BLE001
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=ctx.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self.close_p2p()
+            return None
+        cs = 2 if self.out_struct.is_complex else 1
+        for b in range(nbuf):
+            items = []
+            for r, pptr in self._p2p_peers[b].items():
+                delta = pptr - self._p2p_local[b]
+                assert delta % (8 * cs) == 0
+                for off, box, strides in self._boxes[self.rank]:
+                    it = CopyItem()
+                    it.n = len(box)
+                    for d in range(len(box)):
+                        it.ext[d] = box[d]
+                        it.sstr[d] = strides[d]
+                        it.dstr[d] = strides[d]
+                    it.s_off = off
+                    it.d_off = off + delta // (8 * cs)   # (offsets are in elements of the tensor's dtype)
+                    items.append(it)
+            self._p2p_push.append(self._plan(items))
+
+            class _Raw:  # zero-copy torch view of the peer-mappable buffer
+                pass
+
+            raw = _Raw()
+            raw.__cuda_array_interface__ = {"shape": (max(nreal, 1),), "typestr": "<f8", "data": (self._p2p_local[b], False), "version": 3, "strides": None}
+            self._p2p_tensors.append(torch.as_tensor(raw, device=ctx.device)[:nreal])
+        self._p2p_token = torch.zeros(1, dtype=torch.float32, device=ctx.device)
+        return self._p2p_tensors
+
+    def push(self, ctx_handle, b: int, events=None) -> None:
+        """store this rank's rows of H*phi (local buffer b) into buffer b of every peer, then the arrival barrier"""
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+
+        base = C.c_void_p(self._p2p_local[b])
+        if events:
+            events[0].record()
+        check(lib().itb_permute_run(ctx_handle, self._p2p_push[b], base, base, 1.0, 0.0, 0))
+        if events:
+            events[1].record()
+        dist.all_reduce(self._p2p_token)
+        if events:
+            events[2].record()
+
+    def pack_own(self, ctx_handle, flat) -> None:
+        """this rank's rows of `flat` -> its packed segment (self.send): what an end-to-end caller reads back"""
+        from ._lib import check, lib
+
+        p = lambda t: C.c_void_p(t.data_ptr())
+        check(lib().itb_permute_run(ctx_handle, self._pack, p(flat), p(self.send), 1.0, 0.0, 0))
+
+    def close_p2p(self):
+        from ._lib import lib
+
+        ctx = getattr(self, "_p2p_ctx", None)
+        for h in getattr(self, "_p2p_push", []):
+            lib().itb_permute_plan_destroy(h)
+        for peers in getattr(self, "_p2p_peers", []):
+            for pp in peers.values():
+                lib().itb_p2p_close(ctx.handle if ctx else None, C.c_void_p(pp))
+        self._p2p_tensors = []
+        for p in getattr(self, "_p2p_local", []):
+            lib().itb_p2p_free(ctx.handle if ctx else None, C.c_void_p(p))
+        self._p2p_push, self._p2p_peers, self._p2p_local = [], [], []
+
     def close(self):
         from ._lib import lib
 

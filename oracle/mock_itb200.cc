@@ -193,6 +193,7 @@ int itb_device_count(void) { return 0; }
 int itb_ctx_create(int, itb_ctx** out) { *out = new itb_ctx(); return ITB_OK; }
 int itb_ctx_destroy(itb_ctx* c) { delete c; return ITB_OK; }
 void* itb_ctx_stream(itb_ctx*) { return nullptr; }
+int itb_ctx_device(itb_ctx*) { return -1; }
 int itb_ctx_set_stream(itb_ctx*, void*) { return ITB_OK; }
 int itb_synchronize(itb_ctx*) { return ITB_OK; }
 int64_t itb_launch_count(itb_ctx* c) { return c->launches; }
@@ -397,6 +398,11 @@ int itb_comm_allgather(itb_comm* c, itb_ctx*, const void* send, void* recv, int6
     return ITB_OK;
 }
 int itb_comm_destroy(itb_comm* c) { delete c; return ITB_OK; }
+// no peer memory between host processes: callers fall back to the all-gather
+int itb_p2p_alloc(itb_ctx*, int64_t, void**, uint8_t*) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
+int itb_p2p_open(itb_ctx*, const uint8_t*, void**) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
+int itb_p2p_close(itb_ctx*, void*) { return ITB_OK; }
+int itb_p2p_free(itb_ctx*, void*) { return ITB_OK; }
 
 int itb_eigh_batch_run(itb_ctx*, int32_t, int64_t, const int64_t*, const int32_t*, const void*, int, itb_eigh_batch**) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
 int itb_eigh_batch_values(itb_eigh_batch*, double*) { return ITB_ERR_UNSUPPORTED; }
