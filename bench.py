@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--refine-rounds", type=int, default=4)
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: re-replicate H*phi with pack / NCCL all-gather / scatter instead of direct peer-memory stores")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep equal flops per rank (no measured re-balancing of the row partition)")
-    ap.add_argument("--rebalance-rounds", type=int, default=2)
+    ap.add_argument("--rebalance-rounds", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -363,7 +363,7 @@ def main():
             for _ in range(args.rebalance_rounds):
                 speed = shares / times                      # rows-share per ms of every rank
                 new = speed / speed.sum()
-                shares = 0.5 * shares + 0.5 * new           # damped
+                shares = 0.3 * shares + 0.7 * new           # damped
                 shard.close()
                 shard = shard_chain(plans, world, rank, shares=shares).prepare(ctx.empty)
                 if not args.no_refine:
@@ -392,7 +392,7 @@ def main():
             bufs = shard.prepare_p2p(ctx)
             if bufs is not None:
                 p2p_out = [itb.QTensor(ctx, plans[-1].C, t) for t in bufs]
-                exchange = "direct NVLink stores of the owned rows into every peer's H*phi buffer (CUDA IPC peer memory, block-copy kernel) + one-element all-reduce as arrival barrier; two buffers used alternately"
+                exchange = "direct NVLink stores of the owned rows into every peer's H*phi buffer (CUDA IPC peer memory, block-copy kernel) + flag barrier over peer memory (itb_p2p_barrier); two buffers used alternately"
                 # every rank's assembled H*phi against its own UNSHARDED recomputation of the chain
                 for b in (0, 1):
                     p2p_out[b].data.fill_(float("nan"))
@@ -761,6 +761,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity_vs_reference": parity, "e2e_plugin": plugin, "multi_gpu_phases": phases, "multi_gpu_rank_balance": rank_balance, "multi_gpu_exchange_check": p2p_check,
             "permute": perm_info,
         }))
+    if world > 1 and p2p_out is not None:
+        ep, berr = shard.barrier_status()
+        if berr:
+            print(json.dumps({"error": "rank %d: peer-memory barrier wait expired at epoch %d" % (rank, berr)}), file=sys.stderr, flush=True)
     if world > 1:
         # Tear-down must never outlive the measurement: a captured graph that holds NCCL kernels keeps the communicator
         # busy inside destroy_process_group (seen on 2 GPUs: the JSON line was out, the processes sat in ncclCommDestroy until

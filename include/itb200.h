@@ -276,6 +276,16 @@ int itb_p2p_alloc(itb_ctx* ctx, int64_t bytes, void** dptr, uint8_t handle[ITB_P
 int itb_p2p_open(itb_ctx* ctx, const uint8_t handle[ITB_P2P_HANDLE_BYTES], void** peer_ptr);
 int itb_p2p_close(itb_ctx* ctx, void* peer_ptr);
 int itb_p2p_free(itb_ctx* ctx, void* dptr);
+/* arrival barrier over peer memory: a flag block of ITB_P2P_FLAG_BYTES per rank (itb_p2p_alloc + itb_p2p_barrier_init),
+ * mapped by every peer; one tiny launch per barrier on the context's stream (CUDA-graph friendly: the epoch lives in the
+ * block). Everything this rank stored into peer buffers before the call is visible to a peer once its barrier returns.
+ * peer_flags[r] = rank r's block as mapped here (entry `rank` ignored). The wait is bounded; itb_p2p_barrier_status
+ * reports an expired wait. */
+#define ITB_P2P_MAX_WORLD 8
+#define ITB_P2P_FLAG_BYTES 256
+int itb_p2p_barrier_init(itb_ctx* ctx, void* local_flags);
+int itb_p2p_barrier(itb_ctx* ctx, void* local_flags, void* const* peer_flags, int32_t world, int32_t rank);
+int itb_p2p_barrier_status(itb_ctx* ctx, const void* local_flags, int64_t* epoch, int64_t* error);
 /* flops of every C block of a plan (2*M*N*K summed over its pairs, complex multipliers included): the weights of a row partition */
 int itb_contract_plan_cblock_flops(const itb_contract_plan* plan, double* out /*[c_nblocks]*/);
 

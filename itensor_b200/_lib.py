@@ -99,6 +99,9 @@ SYMBOLS = {
     "itb_p2p_open": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_void_p)]),
     "itb_p2p_close": (C.c_int, [_P, _P]),
     "itb_p2p_free": (C.c_int, [_P, _P]),
+    "itb_p2p_barrier_init": (C.c_int, [_P, _P]),
+    "itb_p2p_barrier": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "itb_p2p_barrier_status": (C.c_int, [_P, _P, _I64P, _I64P]),
     "itb_contract_plan_tiles": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_cta_begin": (C.c_int64, [_P, _I32P, C.c_int64]),
     "itb_contract_plan_rowgroups": (C.c_int64, [_P, _I64P, C.c_int64]),

@@ -131,6 +131,61 @@ int itb_p2p_free(itb_ctx* ctx, void* dptr) {
     return ITB_OK;
 }
 
+// Arrival barrier over peer memory. Every rank owns a small flag block (itb_p2p_alloc'ed, zeroed by itb_p2p_barrier_init)
+// that its peers have mapped: word r is written by rank r only. One launch per barrier: the kernel takes the next epoch from
+// the block's own counter (so a CUDA-graph replay needs no changing argument), publishes it into word `rank` of every peer's
+// block with a system-scope release (the stores of the kernels launched before it on this stream — the pushed rows — are
+// ordered before it), then waits until every peer's word in the local block has reached the epoch. The wait is bounded
+// (~2 s of clock): on expiry the error word is set instead of hanging the device.
+struct P2PFlags { unsigned long long arrive[ITB_P2P_MAX_WORLD]; unsigned long long epoch; unsigned long long error; };
+struct P2PPeers { P2PFlags* p[ITB_P2P_MAX_WORLD]; };
+
+__global__ void p2p_barrier_kernel(P2PFlags* local, P2PPeers peers, int world, int rank) {
+    const int t = threadIdx.x;
+    unsigned long long e = 0;
+    if (t == 0) { e = local->epoch + 1; local->epoch = e; }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    __threadfence_system();
+    if (t < world && t != rank) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peers.p[t]->arrive[rank]), "l"(e) : "memory");
+        const long long t0 = clock64();
+        unsigned long long seen = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(&local->arrive[t]) : "memory");
+            if (seen >= e) break;
+            if (clock64() - t0 > 4000000000ll) { local->error = e; break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
+int itb_p2p_barrier_init(itb_ctx* ctx, void* local_flags) {
+    if (!ctx || !local_flags) { itb::set_error("itb_p2p_barrier_init: bad arguments"); return ITB_ERR_INVALID; }
+    if (cudaMemsetAsync(local_flags, 0, sizeof(P2PFlags), (cudaStream_t)itb_ctx_stream(ctx)) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)itb_ctx_stream(ctx)) != cudaSuccess) { itb::set_error("itb_p2p_barrier_init: memset failed"); return ITB_ERR_CUDA; }
+    return ITB_OK;
+}
+int itb_p2p_barrier(itb_ctx* ctx, void* local_flags, void* const* peer_flags, int32_t world, int32_t rank) {
+    if (!ctx || !local_flags || !peer_flags || world < 1 || world > ITB_P2P_MAX_WORLD || rank < 0 || rank >= world) { itb::set_error("itb_p2p_barrier: bad arguments"); return ITB_ERR_INVALID; }
+    P2PPeers pp;
+    for (int r = 0; r < ITB_P2P_MAX_WORLD; ++r) pp.p[r] = (r < world && r != rank) ? (P2PFlags*)peer_flags[r] : nullptr;
+    p2p_barrier_kernel<<<1, 32, 0, (cudaStream_t)itb_ctx_stream(ctx)>>>((P2PFlags*)local_flags, pp, world, rank);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { itb::set_error(std::string("itb_p2p_barrier: ") + cudaGetErrorString(e)); return ITB_ERR_CUDA; }
+    return ITB_OK;
+}
+// epochs completed and the epoch at which a wait expired (0: never); synchronises the stream
+int itb_p2p_barrier_status(itb_ctx* ctx, const void* local_flags, int64_t* epoch, int64_t* error) {
+    if (!ctx || !local_flags) { itb::set_error("itb_p2p_barrier_status: bad arguments"); return ITB_ERR_INVALID; }
+    P2PFlags h;
+    if (cudaMemcpyAsync(&h, local_flags, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)itb_ctx_stream(ctx)) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)itb_ctx_stream(ctx)) != cudaSuccess) { itb::set_error("itb_p2p_barrier_status: copy failed"); return ITB_ERR_CUDA; }
+    if (epoch) *epoch = (int64_t)h.epoch;
+    if (error) *error = (int64_t)h.error;
+    return ITB_OK;
+}
+
 int itb_comm_destroy(itb_comm* c) {
     if (!c) return ITB_OK;
     if (c->comm) c->CommDestroy(c->comm);

@@ -243,6 +243,7 @@ class ChainShard:
         nreal = self.out_struct.nreal
         self._p2p_ctx = ctx
         self._p2p_local, self._p2p_peers, self._p2p_push, self._p2p_tensors = [], [], [], []
+        self._p2p_flags = None
         try:
             handles = []
             for _ in range(nbuf):
@@ -251,6 +252,13 @@ class ChainShard:
                 check(lib().itb_p2p_alloc(ctx.handle, max(nreal, 1) * 8, C.byref(ptr), h))
                 self._p2p_local.append(ptr.value)
                 handles.append(h.raw)
+            # flag block of the arrival barrier (itb_p2p_barrier)
+            ptr = C.c_void_p()
+            h = C.create_string_buffer(64)
+            check(lib().itb_p2p_alloc(ctx.handle, 256, C.byref(ptr), h))
+            check(lib().itb_p2p_barrier_init(ctx.handle, ptr))
+            self._p2p_flags = ptr.value
+            handles.append(h.raw)
             ok = 1
         except Exception:  # noqa: BLE001
             handles, ok = [], 0
@@ -271,6 +279,13 @@ class ChainShard:
                     check(lib().itb_p2p_open(ctx.handle, allh[r][b], C.byref(pp)))
                     peers[r] = pp.value
                 self._p2p_peers.append(peers)
+            self._p2p_flag_peers = (C.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                pp = C.c_void_p()
+                check(lib().itb_p2p_open(ctx.handle, allh[r][nbuf], C.byref(pp)))
+                self._p2p_flag_peers[r] = pp.value
             ok = 1
         except Exception:  # noqa: BLE001
             ok = 0
@@ -304,7 +319,17 @@ class ChainShard:
             raw.__cuda_array_interface__ = {"shape": (max(nreal, 1),), "typestr": "<f8", "data": (self._p2p_local[b], False), "version": 3, "strides": None}
             self._p2p_tensors.append(torch.as_tensor(raw, device=ctx.device)[:nreal])
         self._p2p_token = torch.zeros(1, dtype=torch.float32, device=ctx.device)
+        self.flag_barrier = True   # False: one-element NCCL all-reduce instead of the flag kernel
+        dist.barrier()             # every rank has zeroed its flag block and mapped its peers' before the first push
         return self._p2p_tensors
+
+    def barrier_status(self):
+        """(epochs completed, epoch at which a bounded wait expired or 0) of this rank's flag block"""
+        from ._lib import check, lib
+
+        e, err = C.c_int64(), C.c_int64()
+        check(lib().itb_p2p_barrier_status(self._p2p_ctx.handle, C.c_void_p(self._p2p_flags), C.byref(e), C.byref(err)))
+        return int(e.value), int(err.value)
 
     def push(self, ctx_handle, b: int, events=None) -> None:
         """store this rank's rows of H*phi (local buffer b) into buffer b of every peer, then the arrival barrier"""
@@ -318,7 +343,10 @@ class ChainShard:
         check(lib().itb_permute_run(ctx_handle, self._p2p_push[b], base, base, 1.0, 0.0, 0))
         if events:
             events[1].record()
-        dist.all_reduce(self._p2p_token)
+        if self.flag_barrier:
+            check(lib().itb_p2p_barrier(ctx_handle, C.c_void_p(self._p2p_flags), self._p2p_flag_peers, self.world, self.rank))
+        else:
+            dist.all_reduce(self._p2p_token)
         if events:
             events[2].record()
 
@@ -339,6 +367,15 @@ class ChainShard:
             for pp in peers.values():
                 lib().itb_p2p_close(ctx.handle if ctx else None, C.c_void_p(pp))
         self._p2p_tensors = []
+        fp = getattr(self, "_p2p_flag_peers", None)
+        if fp is not None:
+            for r in range(self.world):
+                if fp[r]:
+                    lib().itb_p2p_close(ctx.handle if ctx else None, C.c_void_p(fp[r]))
+            self._p2p_flag_peers = None
+        if getattr(self, "_p2p_flags", None):
+            lib().itb_p2p_free(ctx.handle if ctx else None, C.c_void_p(self._p2p_flags))
+            self._p2p_flags = None
         for p in getattr(self, "_p2p_local", []):
             lib().itb_p2p_free(ctx.handle if ctx else None, C.c_void_p(p))
         self._p2p_push, self._p2p_peers, self._p2p_local = [], [], []

@@ -403,6 +403,9 @@ int itb_p2p_alloc(itb_ctx*, int64_t, void**, uint8_t*) { itb::set_error("mock: n
 int itb_p2p_open(itb_ctx*, const uint8_t*, void**) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
 int itb_p2p_close(itb_ctx*, void*) { return ITB_OK; }
 int itb_p2p_free(itb_ctx*, void*) { return ITB_OK; }
+int itb_p2p_barrier_init(itb_ctx*, void*) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
+int itb_p2p_barrier(itb_ctx*, void*, void* const*, int32_t, int32_t) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
+int itb_p2p_barrier_status(itb_ctx*, const void*, int64_t*, int64_t*) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
 
 int itb_eigh_batch_run(itb_ctx*, int32_t, int64_t, const int64_t*, const int32_t*, const void*, int, itb_eigh_batch**) { itb::set_error("mock: no device solver"); return ITB_ERR_UNSUPPORTED; }
 int itb_eigh_batch_values(itb_eigh_batch*, double*) { return ITB_ERR_UNSUPPORTED; }

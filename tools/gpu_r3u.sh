@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT
 if [ "$N" = "2" ]; then
 timeout 300 python -m pytest tests/test_p2p_gpu.py -m gpu -x -q > $OUT/u_pytest_p2p.log 2>&1; echo "p2p test rc=$?"; tail -15 $OUT/u_pytest_p2p.log
 fi
-for MODE in p2p nccl; do
+for MODE in ${MODES:-p2p nccl}; do
   FLAG=""; [ "$MODE" = "nccl" ] && FLAG="--no-p2p"
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 $FLAG > $OUT/u_bench_n${N}_$MODE.json 2> $OUT/u_bench_n${N}_$MODE.err; echo "bench N=$N $MODE rc=$?"
   tail -2 $OUT/u_bench_n${N}_$MODE.err | cut -c1-300
