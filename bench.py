@@ -345,9 +345,11 @@ def main():
 
     if not args.no_refine:
         refine_gain = refine_plans()
-    # N > 1: equal flops per rank is not equal time per rank (another mix of tile shapes and cut tiles on every rank), and the
-    # all-gather waits for the slowest. Same idea as the per-CTA refinement one level up: measure every rank's chain, hand a
-    # slower rank a smaller share of the rows, re-slice, re-refine; keep the partition with the shortest slowest rank.
+    # N > 1: equal flops per rank is not equal time per rank. A cut inside a sector leaves both sides a remainder tile row
+    # that costs almost a full tile per K-chunk, and the all-gather / barrier waits for the slowest rank. The row partition is
+    # therefore optimised against the planner's cycle model (ChainShard optimise=True: cuts snap to multiples of the tile
+    # height where that pays) and then corrected with measured per-rank factors, one level above the per-CTA refinement;
+    # the partition with the shortest slowest rank (measured) is kept.
     rank_balance = None
     if shard is not None and not args.no_rebalance and shard.mode == "rows":
         try:
@@ -357,32 +359,32 @@ def main():
                 dist.all_gather(out_t, t)
                 return np.array([float(x.item()) for x in out_t])
 
-            shares = np.full(world, 1.0 / world)
-            times = all_times()
-            history = [(shares.copy(), times.copy())]
+            def reshard(**kw):
+                nonlocal shard, refine_gain
+                shard.close()
+                shard = shard_chain(plans, world, rank, **kw).prepare(ctx.empty)
+                if not args.no_refine:
+                    refine_gain = refine_plans()
+
+            history = [(list(shard.cuts), all_times(), None)]          # equal flops
+            factors = None
             for _ in range(args.rebalance_rounds):
-                speed = shares / times                      # rows-share per ms of every rank
-                new = speed / speed.sum()
-                shares = 0.3 * shares + 0.7 * new           # damped
-                shard.close()
-                shard = shard_chain(plans, world, rank, shares=shares).prepare(ctx.empty)
-                if not args.no_refine:
-                    refine_gain = refine_plans()
+                reshard(optimise=True, factors=factors)
                 times = all_times()
-                history.append((shares.copy(), times.copy()))
+                history.append((list(shard.cuts), times, list(shard.model_ms)))
+                f = times / np.asarray(shard.model_ms)
+                factors = f / f.mean()
             best = min(range(len(history)), key=lambda i: history[i][1].max())
-            if best != len(history) - 1:
-                shard.close()
-                shard = shard_chain(plans, world, rank, shares=history[best][0]).prepare(ctx.empty)
-                if not args.no_refine:
-                    refine_gain = refine_plans()
-            rank_balance = {"chain_ms_per_rank_equal_flops": [round(x, 4) for x in history[0][1]],
-                            "chain_ms_per_rank_rebalanced": [round(x, 4) for x in history[best][1]],
-                            "row_shares": [round(float(x), 4) for x in history[best][0]], "rounds": args.rebalance_rounds}
+            if history[best][0] != list(shard.cuts):
+                reshard(cuts=history[best][0])
+            rank_balance = {"chain_ms_per_rank_equal_flops": [round(x, 4) for x in history[0][1]], "cuts_equal_flops": history[0][0],
+                            "chain_ms_per_rank_optimised": [round(x, 4) for x in history[best][1]], "cuts_optimised": history[best][0],
+                            "modelled_ms_per_rank": None if history[best][2] is None else [round(x, 4) for x in history[best][2]],
+                            "rounds": args.rebalance_rounds, "kept_round": best}
             t = torch.tensor([shard.my_flops / shard.total_flops], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             max_share = float(t.item())
-        except Exception as e:  # noqa: BLE001  (keeps the equal-flop partition)
+        except Exception as e:  # noqa: BLE001  (keeps the partition it has)
             rank_balance = {"error": str(e)[:200]}
     exchange = "none"
     p2p_check = None
@@ -753,7 +755,7 @@ def main():
                        "pairs_per_step": [int(p.npairs) for p in plans], "flops_per_step": total_flops,
                        "l2": "flushed between timed iterations (256 MiB memset)", "launch": launch_mode,
                        "tile_partition": ("modelled" if refine_gain is None else "refined from measured per-CTA cycles at plan set-up (itb_contract_plan_refine, %d rounds; longest-CTA gain per plan %s)" % (args.refine_rounds, refine_gain)),
-                       "sharding": ("rows of l' (%s), equal-flop contiguous row ranges per rank, max rank share %.3f of flops (ideal %.3f); "
+                       "sharding": ("rows of l' (%s), contiguous row ranges per rank (equal flops, cuts then moved by the cycle model + measured rank times), max rank share %.3f of flops (ideal %.3f); "
                                     "H*phi re-replicated by %s; e2e: 1/N of the operand arena per "
                                     "rank over PCIe + NCCL all-gather" % (shard.mode, max_share, 1.0 / world, exchange)) if world > 1 else "none"},
             "e2e": {"value": total_flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -286,6 +286,10 @@ int itb_p2p_free(itb_ctx* ctx, void* dptr);
 int itb_p2p_barrier_init(itb_ctx* ctx, void* local_flags);
 int itb_p2p_barrier(itb_ctx* ctx, void* local_flags, void* const* peer_flags, int32_t world, int32_t rank);
 int itb_p2p_barrier_status(itb_ctx* ctx, const void* local_flags, int64_t* epoch, int64_t* error);
+/* modelled device work of a plan as currently restricted (row slices included): cycles of the DMMA tile class summed over all
+ * CTAs of the persistent grid, and algorithmic bytes of the HBM-bound streaming class — what a multi-GPU row partition
+ * balances (a cut that leaves a short remainder tile costs almost a full tile per K-chunk; flops do not see that) */
+int itb_contract_plan_model_work(const itb_contract_plan* plan, double* tile_cycles, double* stream_bytes);
 /* flops of every C block of a plan (2*M*N*K summed over its pairs, complex multipliers included): the weights of a row partition */
 int itb_contract_plan_cblock_flops(const itb_contract_plan* plan, double* out /*[c_nblocks]*/);
 

@@ -1306,6 +1306,28 @@ int itb_contract_plan_cblock_flops(const itb_contract_plan* P, double* out) {
     return ITB_OK;
 }
 
+// Modelled device work of the plan as currently restricted (range / mask / row slices): cycles of the DMMA tile class summed over
+// all CTAs (the quantity the stream-K partition divides by the grid width) and the algorithmic bytes of the streaming class.
+// What a multi-GPU row partition balances instead of flops: a cut through a sector that leaves a short remainder tile costs
+// almost a full tile per K-chunk, and the cycle model knows it.
+int itb_contract_plan_model_work(const itb_contract_plan* P, double* tile_cycles, double* stream_bytes) {
+    if (!P) { set_error("plan_model_work: null"); return ITB_ERR_INVALID; }
+    if (ensure_tables(P) != ITB_OK) return ITB_ERR_INVALID;
+    double cyc = 0;
+    for (double c : P->item_cost) cyc += c;
+    if (tile_cycles) *tile_cycles = cyc;
+    if (stream_bytes) {
+        double bytes = 0;
+        auto add = [&](int32_t c) { const ItbCBlk& cb = P->cblks[c]; bytes += 8.0 * ((double)cb.M * cb.N + (double)std::max(cb.M, cb.N) * cb.ksum); };
+        for (auto& it : P->skinny) if (it.row0 == 0) add(it.cblk);
+        for (auto& it : P->skinny_q4) if (it.row0 == 0) add(it.cblk);
+        for (auto& it : P->skinny_q8) if (it.row0 == 0) add(it.cblk);
+        for (auto& g : P->rgroups) bytes += 8.0 * (double)g.L * ((double)g.nin + (double)g.nout);
+        *stream_bytes = bytes;
+    }
+    return ITB_OK;
+}
+
 int itb_contract_plan_set_index_slices(itb_contract_plan* P, int32_t c_index, const int64_t* lo, const int64_t* hi) {
     if (!P) { set_error("set_index_slices: null"); return ITB_ERR_INVALID; }
     const int32_t old_index = P->slice_index;

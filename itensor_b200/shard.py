@@ -33,7 +33,8 @@ def sector_assignment(weights: Sequence[float], world: int) -> np.ndarray:
     return owner
 
 
-def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, align: int = 8, shares: Optional[Sequence[float]] = None):
+def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, align: int = 8, shares: Optional[Sequence[float]] = None,
+                  return_cuts: bool = False):
     """Cut the concatenated rows of all sectors into `world` contiguous segments of equal weight (or of the given
     `shares` of the total weight, one per rank: the measured re-balancing of bench.py hands a slower rank less).
 
@@ -66,7 +67,79 @@ def row_partition(sizes: Sequence[int], weights: Sequence[float], world: int, al
         a, b = cuts[g], cuts[g + 1]
         lo[g] = np.clip(a - start[:-1], 0, sizes)
         hi[g] = np.clip(b - start[:-1], 0, sizes)
+    if return_cuts:
+        return lo, hi, cuts
     return lo, hi
+
+
+def ranges_from_cuts(sizes: Sequence[int], cuts: Sequence[int], world: int):
+    """lo, hi (world x nsect) of the contiguous global row segments [cuts[g], cuts[g+1])"""
+    sizes = np.asarray(sizes, np.int64)
+    start = np.concatenate([[0], np.cumsum(sizes)])
+    lo = np.zeros((world, len(sizes)), np.int64)
+    hi = np.zeros((world, len(sizes)), np.int64)
+    for g in range(world):
+        lo[g] = np.clip(cuts[g] - start[:-1], 0, sizes)
+        hi[g] = np.clip(cuts[g + 1] - start[:-1], 0, sizes)
+    return lo, hi
+
+
+def optimise_cuts(plans, pos, sizes, cuts, world, factors=None, sweeps: int = 2):
+    """Move the cut points of a row partition to where the planner's CYCLE MODEL (itb_contract_plan_model_work) says the
+    slowest rank is fastest. Equal flops is only the starting point: a cut inside a sector leaves each side with a
+    remainder tile row that costs almost a full 128-row tile per K-chunk whatever its height, so a cut on a multiple of the
+    tile height from the sector start is free while one 8 rows further costs a tile row on both sides. Candidates per cut:
+    where it is, the neighbouring multiples of 128 / 64 rows inside its sector, and small shifts; a move is accepted when
+    it lowers the larger of the two adjacent ranks' modelled times (factors[r]: measured / modelled time of rank r)."""
+    sizes = np.asarray(sizes, np.int64)
+    start = np.concatenate([[0], np.cumsum(sizes)])
+    total = int(start[-1])
+    f = np.ones(world) if factors is None else np.asarray(factors, float)
+    cuts = [int(c) for c in cuts]
+    cache = {}
+
+    def cost(r, a, b):
+        key = (r, a, b)
+        if key not in cache:
+            lo = np.clip(a - start[:-1], 0, sizes)
+            hi = np.clip(b - start[:-1], 0, sizes)
+            t = 0.0
+            for p, j in zip(plans, pos):
+                p.set_index_slices(j, lo, hi)
+                t += p.model_cycles()
+            cache[key] = t
+        return cache[key] * f[r]
+
+    for _ in range(sweeps):
+        moved = False
+        for g in range(1, world):
+            c = cuts[g]
+            s = int(np.searchsorted(start, c, side="right") - 1)
+            s = min(max(s, 0), len(sizes) - 1)
+            cands = {c}
+            for snap in (128, 64):
+                k = (c - int(start[s])) // snap
+                for kk in (k, k + 1):
+                    cands.add(int(start[s]) + kk * snap)
+            for d in (-32, -16, -8, 8, 16, 32):
+                cands.add(c + d)
+            cands.add(int(start[s]))
+            cands.add(int(start[s + 1]))
+            best, best_key = c, None
+            for x in sorted(cands):
+                if not (cuts[g - 1] < x < cuts[g + 1]) or not (0 < x < total):
+                    continue
+                a, b = cost(g - 1, cuts[g - 1], x), cost(g, x, cuts[g + 1])
+                key = (max(a, b), a + b)
+                if best_key is None or key < best_key:
+                    best, best_key = x, key
+            if best != c:
+                cuts[g] = best
+                moved = True
+        if not moved:
+            break
+    times = [cost(r, cuts[r], cuts[r + 1]) / f[r] for r in range(world)]
+    return cuts, times
 
 
 def pair_flops(plan) -> np.ndarray:
@@ -113,7 +186,8 @@ class ChainShard:
     """Row partition of l' over `world` ranks for a chain of plans; slices every plan to this rank's rows."""
 
     def __init__(self, plans: List, world: int, rank: int, shard_index_id: int = 1, shard_index_plev: int = 1, align: int = 8,
-                 shares: Optional[Sequence[float]] = None):
+                 shares: Optional[Sequence[float]] = None, cuts: Optional[Sequence[int]] = None, optimise: bool = False,
+                 factors: Optional[Sequence[float]] = None):
         self.world, self.rank, self.plans = world, rank, plans
         pos, flops = [], []
         sizes = None
@@ -130,9 +204,17 @@ class ChainShard:
         self.sector_work = w
         self.total_flops = float(sum(f.sum() for f in flops))
         self.shares = None if shares is None else [float(x) for x in shares]
-        self.lo, self.hi = row_partition(sizes, w, world, align, shares)
+        self.lo, self.hi, flop_cuts = row_partition(sizes, w, world, align, shares, return_cuts=True)
         self.mode = "rows"
+        self.model_ms = None
         try:
+            if cuts is None:
+                cuts = flop_cuts
+            if optimise:
+                cuts, cyc = optimise_cuts(plans, pos, sizes, cuts, world, factors)
+                self.model_ms = [c / 1.965e6 for c in cyc]
+            self.cuts = [int(c) for c in cuts]
+            self.lo, self.hi = ranges_from_cuts(sizes, self.cuts, world)
             for p, j in zip(plans, pos):
                 p.set_index_slices(j, self.lo[rank], self.hi[rank])
         except Exception:
@@ -389,5 +471,5 @@ class ChainShard:
         self._pack = self._unpack = None
 
 
-def shard_chain(plans, world, rank, shares=None) -> ChainShard:
-    return ChainShard(plans, world, rank, shares=shares)
+def shard_chain(plans, world, rank, shares=None, cuts=None, optimise=False, factors=None) -> ChainShard:
+    return ChainShard(plans, world, rank, shares=shares, cuts=cuts, optimise=optimise, factors=factors)

@@ -213,6 +213,14 @@ class ContractPlan:
         """flops of the C blocks / slices this plan executes (== flops when nothing is masked or sliced)"""
         return float(sum(self.info.class_flops))
 
+    def model_cycles(self, sms: int = 148, stream_bytes_per_cycle: float = 2100.0, launch_cycles: float = 30000.0) -> float:
+        """modelled device time of the plan as currently sliced, in SM cycles: tile cycles / grid width + streaming bytes at
+        the measured 4.2 TB/s (2100 B per 1.965 GHz cycle) + a fixed launch / ramp / reduce cost when there is any work"""
+        cyc, byt = C.c_double(), C.c_double()
+        check(lib().itb_contract_plan_model_work(self._h, C.byref(cyc), C.byref(byt)))
+        t = cyc.value / sms + byt.value / stream_bytes_per_cycle
+        return t + (launch_cycles if t > 0 else 0.0)
+
     def refine(self, ctx, a_ptr, b_ptr, c_ptr, rounds: int = 3) -> float:
         """itb_contract_plan_refine: re-partition the tile work from measured per-CTA cycles; returns longest CTA span
         before / after"""
