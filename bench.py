@@ -231,6 +231,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-refine", action="store_true", help="keep the modelled tile partition (no measured re-partitioning of the plans)")
     ap.add_argument("--refine-rounds", type=int, default=4)
+    ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: push the owned rows with a separate block-copy launch instead of from the last contraction's epilogue")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: re-replicate H*phi with pack / NCCL all-gather / scatter instead of direct peer-memory stores")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep equal flops per rank (no measured re-balancing of the row partition)")
     ap.add_argument("--rebalance-rounds", type=int, default=3)
@@ -294,6 +295,7 @@ def main():
 
     p2p_out = None  # N > 1: H*phi in peer-mapped buffers, rows exchanged by direct NVLink stores (set up below)
     step_no = [0]
+    fused = [False]  # the row exchange rides the epilogue of the last contraction (itb_contract_run_mirrored)
 
     def step(b=None):
         if b is None:  # alternate between the two H*phi buffers (see ChainShard.prepare_p2p)
@@ -301,10 +303,15 @@ def main():
             step_no[0] += 1
         cur = dts[0]
         for k, p in enumerate(plans):  # sharded: every plan is sliced to this rank's rows of l'
-            dst = p2p_out[b] if (p2p_out is not None and k == len(plans) - 1) else outs[k]
+            last = k == len(plans) - 1
+            if last and fused[0]:
+                # the *R step stores every tile into the peers' buffers from its epilogue; then the arrival barrier
+                shard.run_last_mirrored(ctx.handle, p, cur.ptr, dts[k + 1].ptr, b)
+                break
+            dst = p2p_out[b] if (p2p_out is not None and last) else outs[k]
             check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, dst.ptr))
             cur = dst
-        if shard is not None:
+        if shard is not None and not fused[0]:
             if p2p_out is not None:
                 shard.push(ctx.handle, b)   # own rows -> every peer's buffer b over NVLink, then the arrival barrier
             else:
@@ -395,6 +402,19 @@ def main():
             if bufs is not None:
                 p2p_out = [itb.QTensor(ctx, plans[-1].C, t) for t in bufs]
                 exchange = "direct NVLink stores of the owned rows into every peer's H*phi buffer (CUDA IPC peer memory, block-copy kernel) + flag barrier over peer memory (itb_p2p_barrier); two buffers used alternately"
+                if not args.no_fused_exchange:
+                    try:   # (every rank plans the same classes for its slice or none does: the decision is all-reduced)
+                        fused[0] = True
+                        step(0)
+                        ok = 1
+                    except Exception:  # noqa: BLE001
+                        ok = 0
+                    fused[0] = False
+                    t = torch.tensor([ok], dtype=torch.int32, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    if int(t.item()) == 1:
+                        fused[0] = True
+                        exchange = "the *R step stores every C tile into the peers' H*phi buffers from its own epilogue (itb_contract_run_mirrored: CUDA IPC peer memory, NVLink stores) + flag barrier over peer memory (itb_p2p_barrier); two buffers used alternately"
                 # every rank's assembled H*phi against its own UNSHARDED recomputation of the chain
                 for b in (0, 1):
                     p2p_out[b].data.fill_(float("nan"))
@@ -495,9 +515,19 @@ def main():
             evs[4].record()
             cur = dts[0]
             for k, p in enumerate(plans):
+                if fused[0] and k == len(plans) - 1:
+                    shard.run_last_mirrored(ctx.handle, p, cur.ptr, dts[k + 1].ptr, 0, barrier=False)
+                    break
                 check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts[k + 1].ptr, outs[k].ptr))
                 cur = outs[k]
-            if p2p_out is not None:
+            if fused[0]:
+                evs[0].record()
+                evs[1].record()
+                shard.barrier(ctx.handle)
+                evs[2].record()
+                torch.cuda.synchronize()
+                acc += np.array([evs[4].elapsed_time(evs[0]), 0.0, evs[1].elapsed_time(evs[2]), 0.0])
+            elif p2p_out is not None:
                 evs[3].record()  # (unused slot)
                 shard.push(ctx.handle, 0, evs[:3])
                 torch.cuda.synchronize()
@@ -508,7 +538,8 @@ def main():
                 acc += np.array([evs[4].elapsed_time(evs[0]), evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])])
         acc /= 5
         if p2p_out is not None:
-            phases = {"contractions_ms": float(acc[0]), "push_ms": float(acc[1]), "arrival_barrier_ms": float(acc[2]),
+            phases = {"contractions_ms": float(acc[0]), "push_ms": (None if fused[0] else float(acc[1])), "arrival_barrier_ms": float(acc[2]),
+                      "exchange": ("inside the last contraction's epilogue" if fused[0] else "separate block-copy launch"),
                       "pushed_bytes_per_rank": int(shard.seg_elems[rank] * (16 if plans[-1].C.is_complex else 8) * (world - 1)),
                       "note": "rank 0, CUDA events, mean of 5 steps (the contractions here write the ordinary output buffer; the barrier includes waiting for the slowest rank)"}
         else:
@@ -574,11 +605,16 @@ def main():
             b = e2e_no[0] & 1
             e2e_no[0] += 1
             for k, p in enumerate(plans):
-                dst = p2p_out[b] if (p2p_out is not None and k == len(plans) - 1) else outs[k]
+                last = k == len(plans) - 1
+                if last and fused[0]:
+                    shard.run_last_mirrored(ctx.handle, p, cur.ptr, dts_e[k + 1].ptr, b)
+                    break
+                dst = p2p_out[b] if (p2p_out is not None and last) else outs[k]
                 check(lib().itb_contract_run(ctx.handle, p._h, cur.ptr, dts_e[k + 1].ptr, dst.ptr))
                 cur = dst
             if p2p_out is not None:
-                shard.push(ctx.handle, b)
+                if not fused[0]:
+                    shard.push(ctx.handle, b)
                 shard.pack_own(ctx.handle, p2p_out[b].data)
             else:
                 shard.allgather(ctx.handle, outs[-1].data)

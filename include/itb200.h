@@ -265,6 +265,12 @@ int32_t itb_comm_rank(const itb_comm* comm);
  * dSend == (double*)dRecv + rank*count); ordered on the context's stream */
 int itb_comm_allgather(itb_comm* comm, itb_ctx* ctx, const void* dSend, void* dRecv, int64_t count);
 int itb_comm_destroy(itb_comm* comm);
+/* The contraction with its result additionally stored into n <= 7 peer copies of C (other ranks' buffers mapped with
+ * itb_p2p_open; same layout as dC): the row exchange of a multi-GPU product rides the epilogue of the kernel that produces
+ * the rows, tile by tile over NVLink, instead of following it as a collective (the reference's OpenMP workers write into
+ * one shared C, itensor/itdata/qutil.h:285-348). ITB_ERR_UNSUPPORTED when the plan has work outside the static DMMA tile class
+ * (nothing has been launched then): push the rows with a block-copy plan after itb_contract_run instead. */
+int itb_contract_run_mirrored(itb_ctx* ctx, itb_contract_plan* plan, const void* dA, const void* dB, void* dC, int32_t n, void* const* peer_dC);
 /* Peer memory for the direct row exchange (no counterpart in the reference: its OpenMP workers share one address space,
  * itensor/itdata/qutil.h:285-348). itb_p2p_alloc: a device buffer other ranks may map + its 64-byte export handle (publish it
  * through any host channel); itb_p2p_open: map a peer's buffer into this process (enables peer access over NVLink from the

@@ -139,6 +139,7 @@ SYMBOLS = {
     "itb_eigh_batch_destroy": (C.c_int, [_P]),
     "itb_peak_fp64": (C.c_int, [_P, C.c_int, C.c_int, _DP]),
     "itb_contract_plan_model_work": (C.c_int, [_P, _DP, _DP]),
+    "itb_contract_run_mirrored": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_void_p)]),
     "itb_contract_plan_refine": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.POINTER(C.c_double)]),
     "itb_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "itb_contract_last_cta_cycles": (C.c_int64, [_P, _I64P, C.c_int64]),

@@ -20,7 +20,7 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const in
                         cudaStream_t st);
 cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
                                const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
-                               long long* cta_cycles, cudaStream_t st);
+                               long long* cta_cycles, const ItbMirrors* mir, cudaStream_t st);
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
                           const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, cudaStream_t st);
 cudaError_t launch_dot(const ItbDot* items, int n, const ItbDotOut* outs, int nouts, const ItbCBlk* cblks, const ItbPair* pairs,
@@ -432,7 +432,29 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     return ITB_OK;
 }
 
-int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC) {
+static int contract_run_impl(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC, const ItbMirrors* mir);
+int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC) { return contract_run_impl(c, P, dA, dB, dC, nullptr); }
+
+// Multi-GPU: the same contraction, every element of C additionally stored into n peer copies of C (buffers of other ranks mapped
+// with itb_p2p_open): the exchange of the rows a rank owns rides the epilogue of the kernel that produces them, tile by
+// tile over NVLink, instead of following it as a collective. Supported when all executed C blocks are in the DMMA tile class
+// on the static kernel (the *R step of LocalOp::product); otherwise ITB_ERR_UNSUPPORTED and the caller pushes the rows
+// with a block-copy plan after itb_contract_run.
+int itb_contract_run_mirrored(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC, int32_t n, void* const* peer_dC) {
+    if (!c || !P || n < 0 || n > ITB_MAX_MIRRORS || (n > 0 && !peer_dC)) { set_error("contract_run_mirrored: bad arguments"); return ITB_ERR_INVALID; }
+    if (n == 0) return contract_run_impl(c, P, dA, dB, dC, nullptr);
+    ItbMirrors mir;
+    mir.n = n; mir.pad_ = 0;
+    for (int q = 0; q < ITB_MAX_MIRRORS; ++q) mir.delta[q] = 0;
+    for (int q = 0; q < n; ++q) {
+        const long long d = (const char*)peer_dC[q] - (const char*)dC;
+        if (d % 8 != 0) { set_error("contract_run_mirrored: peer buffer not 8-byte aligned relative to C"); return ITB_ERR_INVALID; }
+        mir.delta[q] = d / 8;
+    }
+    return contract_run_impl(c, P, dA, dB, dC, &mir);
+}
+
+static int contract_run_impl(itb_ctx* c, itb_contract_plan* P, const void* dA, const void* dB, void* dC, const ItbMirrors* mir) {
     if (!c || !P) { set_error("contract_run: null"); return ITB_ERR_INVALID; }
     CUDA_TRY(cudaSetDevice(c->device));
     if (P->C.nelems == 0 || P->triples.empty()) return ITB_OK; // no output blocks: nothing to do
@@ -454,6 +476,16 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
     const bool has_tiles = !P->tiles.empty();
     const bool has_stream = !P->skinny.empty() || !P->skinny_q4.empty() || !P->skinny_q8.empty() || !P->rg_items.empty();
     const bool has_dots = !P->dots.empty();
+    if (mir) {
+        // mirrored stores exist in the static tile kernel's epilogue and in the split-K reduction only
+        static const bool ring_forced = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "ring"; }();
+        const int ns = (int)P->cta_begin.size() - 2;
+        const bool static_sched = ns > 0 && has_tiles && P->cta_begin[ns] == (int32_t)P->tiles.size();
+        if (!has_tiles || has_stream || has_dots || !static_sched || ring_forced) {
+            set_error("contract_run_mirrored: this plan has work outside the static DMMA tile class");
+            return ITB_ERR_UNSUPPORTED;
+        }
+    }
     const bool fork = has_tiles && (has_stream || has_dots) && !c->profile;
     cudaStream_t side = fork ? c->aux : c->stream;
     if (fork) {
@@ -510,7 +542,7 @@ int itb_contract_run(itb_ctx* c, itb_contract_plan* P, const void* dA, const voi
         static const bool force_ring = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "ring"; }();
         if (!force_ring && has_static && P->cta_begin[n_static] == (int32_t)P->tiles.size()) {
             SIDE_TRY(launch_gemm_static(d->qitems, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
-                                        c->profile ? c->d_cta_cycles : nullptr, c->stream));
+                                        c->profile ? c->d_cta_cycles : nullptr, mir, c->stream));
             c->h_item_cycles.clear();
         } else
         SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, d->cta_begin, n_static, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,

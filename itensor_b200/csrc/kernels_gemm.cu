@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_kernel(const ItbQItem* __res
 // C tile = sum of its split-K partials, in split order (deterministic). SR_PARTS CTAs per tile.
 constexpr int SR_PARTS = 8;
 __global__ void __launch_bounds__(256) bsc_splitk_reduce_kernel(const ItbSplitOut* __restrict__ outs, const ItbCBlk* __restrict__ cblks,
-                                                                 const double* __restrict__ ws, double* __restrict__ C) {
+                                                                 const double* __restrict__ ws, double* __restrict__ C, const ItbMirrors mir) {
     const ItbSplitOut o = outs[blockIdx.x / SR_PARTS];
     const int part = blockIdx.x % SR_PARTS;
     const ItbCBlk* cb = cblks + o.cblk;
@@ -621,7 +621,9 @@ __global__ void __launch_bounds__(256) bsc_splitk_reduce_kernel(const ItbSplitOu
         if (m >= M || n >= N) continue;
         double s = 0.0;
         for (int q = 0; q < o.nsplit; ++q) s += ws[(int64_t)(o.ws_slot0 + q) * ITB_WS_TILE + ml + T * nl];
-        Cp[(int64_t)m * cb->c_ms + (n & cb->c_nmask) + (int64_t)(n >> cb->c_nshift) * cb->c_ns] = s;
+        double* dst = Cp + ((int64_t)m * cb->c_ms + (n & cb->c_nmask) + (int64_t)(n >> cb->c_nshift) * cb->c_ns);
+        *dst = s;
+        for (int q = 0; q < mir.n; ++q) dst[mir.delta[q]] = s; // peers' copies of C (multi-GPU)
     }
 }
 
@@ -1070,14 +1072,20 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const in
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (nsouts > 0) {
-        bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C);
+        ItbMirrors none;
+        none.n = 0;
+        bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C, none);
         e = cudaGetLastError();
     }
     return e;
 }
 
-cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks, const double* ws, double* C, cudaStream_t st) {
-    bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C);
+cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks, const double* ws, double* C, const ItbMirrors* mir,
+                                 cudaStream_t st) {
+    ItbMirrors m;
+    m.n = 0;
+    if (mir) m = *mir;
+    bsc_splitk_reduce_kernel<<<nsouts * SR_PARTS, 256, 0, st>>>(souts, cblks, ws, C, m);
     return cudaGetLastError();
 }
 

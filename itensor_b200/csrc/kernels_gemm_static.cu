@@ -134,10 +134,10 @@ __device__ __forceinline__ void consume_pair(double (&acc)[BM / 32][BN / 32][2],
     }
 }
 
-template <int BM, int BN>
+template <int BM, int BN, bool MIRROR>
 __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk* __restrict__ cb, const ItbPair* __restrict__ pairs,
                                              double* __restrict__ C, double* __restrict__ ws, const double* As, const double* Bs,
-                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute) {
+                                             uint64_t* full, uint64_t* empty, PipeState& ps, int dbg_nocompute, const ItbMirrors& mir) {
     constexpr int BK = G_BK;
     constexpr int WM = BM / 4, WN = BN / 4, FM = WM / 8, FN = WN / 8;
     static_assert(FM >= 1 && FN >= 1, "tile too small for a 4x4 warp grid");
@@ -202,7 +202,13 @@ __device__ __forceinline__ void consume_tile(const ItbTile& tile, const ItbCBlk*
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int n = n0 + wn0 + j * 8 + 2 * t4 + h;
-                    if (m < M && n < N) Cp[(int64_t)m * cms + (n & nmask) + (int64_t)(n >> nshift) * cns] = acc[i][j][h];
+                    if (m < M && n < N) {
+                        double* dst = Cp + ((int64_t)m * cms + (n & nmask) + (int64_t)(n >> nshift) * cns);
+                        *dst = acc[i][j][h];
+                        if (MIRROR) { // the same element into every peer's copy of C (stores over NVLink, posted)
+                            for (int q = 0; q < mir.n; ++q) dst[mir.delta[q]] = acc[i][j][h];
+                        }
+                    }
                 }
             }
         }
@@ -366,11 +372,12 @@ __device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk*
     }
 }
 
+template <bool MIRROR>
 __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbQItem* __restrict__ tiles, const int32_t* __restrict__ cta_begin,
                                                             const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
                                                             double* __restrict__ C, double* __restrict__ ws,
-                                                            long long* __restrict__ cta_cycles, int dbg_nocompute) {
+                                                            long long* __restrict__ cta_cycles, int dbg_nocompute, const ItbMirrors mir) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const long long t_begin = cta_cycles ? clock64() : 0;
     double* As = reinterpret_cast<double*>(smem_raw);
@@ -406,9 +413,9 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbQItem
             else if (tile.cfg == 1) produce_tile<64, 64>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
             else produce_tile<32, 32>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
         } else {
-            if (tile.cfg == 0) consume_tile<128, 128>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
-            else if (tile.cfg == 1) consume_tile<64, 64>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
-            else consume_tile<32, 32>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute);
+            if (tile.cfg == 0) consume_tile<128, 128, MIRROR>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, mir);
+            else if (tile.cfg == 1) consume_tile<64, 64, MIRROR>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, mir);
+            else consume_tile<32, 32, MIRROR>(tile, cb, pairs, C, ws, As, Bs, full, empty, ps, dbg_nocompute, mir);
         }
     }
     if (cta_cycles && threadIdx.x == 0) cta_cycles[blockIdx.x] = clock64() - t_begin; // schedule calibration (profile mode)
@@ -417,21 +424,27 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbQItem
 
 } // namespace r1
 
-cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks, const double* ws, double* C, cudaStream_t st); // kernels_gemm.cu
+cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const ItbCBlk* cblks, const double* ws, double* C, const ItbMirrors* mir,
+                                 cudaStream_t st); // kernels_gemm.cu
 
+// mir != nullptr (multi-GPU): every element of C is also stored into the peers' copies by the epilogue / the split-K reduction
 cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
                                const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
-                               long long* cta_cycles, cudaStream_t st) {
+                               long long* cta_cycles, const ItbMirrors* mir, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(r1::bsc_gemm_static_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r1::G_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(r1::bsc_gemm_static_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r1::G_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(r1::bsc_gemm_static_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r1::G_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    r1::bsc_gemm_static_kernel<<<grid, r1::G_NT, r1::G_SMEM, st>>>(items, cta_begin, cblks, pairs, A, B, C, ws, cta_cycles, 0);
+    ItbMirrors none;
+    none.n = 0;
+    if (mir && mir->n > 0) r1::bsc_gemm_static_kernel<true><<<grid, r1::G_NT, r1::G_SMEM, st>>>(items, cta_begin, cblks, pairs, A, B, C, ws, cta_cycles, 0, *mir);
+    else r1::bsc_gemm_static_kernel<false><<<grid, r1::G_NT, r1::G_SMEM, st>>>(items, cta_begin, cblks, pairs, A, B, C, ws, cta_cycles, 0, none);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || nsouts == 0) return e;
-    return launch_splitk_reduce(souts, nsouts, cblks, ws, C, st);
+    return launch_splitk_reduce(souts, nsouts, cblks, ws, C, mir, st);
 }
 
 } // namespace itb

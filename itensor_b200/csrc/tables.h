@@ -68,6 +68,12 @@ struct ItbSplitOut { // split-K tile: C tile = sum of workspace slots [ws_slot0,
 };
 #define ITB_BK 16              // K-chunk of the tile kernel
 #define ITB_WS_TILE (128 * 128) // doubles per workspace slot
+// Peer copies of the result (multi-GPU, see itb_contract_run_mirrored): every C element the tile class writes is also stored at
+// the same offset of up to ITB_MAX_MIRRORS other buffers (peer GPUs' copies of C mapped over NVLink); delta = element offset of
+// the mirror's base relative to C.
+#define ITB_MAX_MIRRORS 7
+struct ItbMirrors { int32_t n; int32_t pad_; long long delta[ITB_MAX_MIRRORS]; };
+
 struct ItbSkinny { // work item of the streaming kernel: rows [row0,row0+rows) of the long side
     int32_t cblk, row0, rows, long_is_n; // long_is_n: 1 -> threads run over n, short side is m
 };

@@ -432,6 +432,28 @@ class ChainShard:
         if events:
             events[2].record()
 
+    def run_last_mirrored(self, ctx_handle, plan, a_ptr, b_ptr, b: int, barrier: bool = True) -> None:
+        """the chain's last contraction writing local buffer b AND, from the kernel's epilogue, every peer's buffer b
+        (itb_contract_run_mirrored), followed by the arrival barrier: no separate push. Raises when the plan has work
+        outside the static tile class (use push() then)."""
+        from ._lib import check, lib
+
+        peers = self._p2p_peers[b]
+        arr = (C.c_void_p * max(len(peers), 1))(*[peers[r] for r in sorted(peers)])
+        check(lib().itb_contract_run_mirrored(ctx_handle, plan._h, a_ptr, b_ptr, C.c_void_p(self._p2p_local[b]), len(peers), arr))
+        if barrier:
+            self.barrier(ctx_handle)
+
+    def barrier(self, ctx_handle) -> None:
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+
+        if self.flag_barrier:
+            check(lib().itb_p2p_barrier(ctx_handle, C.c_void_p(self._p2p_flags), self._p2p_flag_peers, self.world, self.rank))
+        else:
+            dist.all_reduce(self._p2p_token)
+
     def pack_own(self, ctx_handle, flat) -> None:
         """this rank's rows of `flat` -> its packed segment (self.send): what an end-to-end caller reads back"""
         from ._lib import check, lib

@@ -398,6 +398,13 @@ int itb_comm_allgather(itb_comm* c, itb_ctx*, const void* send, void* recv, int6
     return ITB_OK;
 }
 int itb_comm_destroy(itb_comm* c) { delete c; return ITB_OK; }
+int itb_contract_run_mirrored(itb_ctx* c, itb_contract_plan* P, const void* A, const void* B, void* C, int32_t n, void* const* peers) {
+    // host "peers" are plain buffers of this process: run, then copy the whole result (test infrastructure only)
+    int rc = itb_contract_run(c, P, A, B, C);
+    const size_t bytes = (size_t)P->C.nelems * (P->C.dtype == ITB_C64 ? 16 : 8);
+    for (int32_t q = 0; rc == ITB_OK && q < n; ++q) std::memcpy(peers[q], C, bytes);
+    return rc;
+}
 // no peer memory between host processes: callers fall back to the all-gather
 int itb_p2p_alloc(itb_ctx*, int64_t, void**, uint8_t*) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }
 int itb_p2p_open(itb_ctx*, const uint8_t*, void**) { itb::set_error("mock: no peer memory"); return ITB_ERR_UNSUPPORTED; }

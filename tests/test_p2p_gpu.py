@@ -57,6 +57,19 @@ def _worker(rank, world, port, q):
         sh.push(ctx.handle, b)
         torch.cuda.synchronize()
         errs.append(float(((bufs[b] - want).abs().max() / want.abs().max()).item()))
+    # the exchange fused into the last contraction's epilogue (itb_contract_run_mirrored)
+    import ctypes as C
+    for b in (1, 0):
+        bufs[b].fill_(float("nan"))
+        dist.barrier()
+        cur_ptr = dts[0].ptr
+        for k, p in enumerate(plans[:3]):
+            check(lib().itb_contract_run(ctx.handle, p._h, cur_ptr, dts[k + 1].ptr, outs[k].ptr))
+            cur_ptr = outs[k].ptr
+        sh.run_last_mirrored(ctx.handle, plans[3], cur_ptr, dts[4].ptr, b)
+        torch.cuda.synchronize()
+        errs.append(float(((bufs[b] - want).abs().max() / want.abs().max()).item()))
+    assert sh.barrier_status()[1] == 0
     # the all-gather path on the same sliced plans
     cur_ptr = dts[0].ptr
     for k, p in enumerate(plans):
