@@ -231,7 +231,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-refine", action="store_true", help="keep the modelled tile partition (no measured re-partitioning of the plans)")
     ap.add_argument("--refine-rounds", type=int, default=4)
-    ap.add_argument("--no-fused-exchange", action="store_true", help="N > 1: push the owned rows with a separate block-copy launch instead of from the last contraction's epilogue")
+    ap.add_argument("--fused-exchange", action="store_true", help="N > 1: store the owned rows into the peers' buffers from the last contraction's epilogue (itb_contract_run_mirrored) instead of a separate block-copy launch; measured equal or slower (the remote stores stall the consumer warps: 0.760 vs 0.751 ms per step on 2 GPUs), so off by default")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: re-replicate H*phi with pack / NCCL all-gather / scatter instead of direct peer-memory stores")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep equal flops per rank (no measured re-balancing of the row partition)")
     ap.add_argument("--rebalance-rounds", type=int, default=3)
@@ -402,7 +402,7 @@ def main():
             if bufs is not None:
                 p2p_out = [itb.QTensor(ctx, plans[-1].C, t) for t in bufs]
                 exchange = "direct NVLink stores of the owned rows into every peer's H*phi buffer (CUDA IPC peer memory, block-copy kernel) + flag barrier over peer memory (itb_p2p_barrier); two buffers used alternately"
-                if not args.no_fused_exchange:
+                if args.fused_exchange:
                     try:   # (every rank plans the same classes for its slice or none does: the decision is all-reduced)
                         fused[0] = True
                         step(0)
