@@ -18,6 +18,9 @@
 #include <algorithm>
 #include <chrono>
 #include <thread>
+#include <atomic>
+#include <mutex>
+#include <exception>
 #include <cstdio>
 #include <functional>
 #include <vector>
@@ -465,7 +468,7 @@ eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args c
     for(auto b : range(nb)) first[b+1] = first[b] + nn[b];
     auto eig = std::vector<Real>(size_t(first[nb])); // per block, largest first
     auto Uh = std::vector<Mat<T>>(nb);
-    for(auto i : range(host_blocks.size()))
+    auto hostBlock = [&](size_t i)
         {
         auto b = host_blocks[i];
         auto S = makeMatRef(hbuf[i].data(),hbuf[i].size(),nn[b],nn[b]);
@@ -474,7 +477,31 @@ eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args c
         // conjugations are applied when the columns are placed (below), identically for host and device blocks
         diagHermitian(S,Uh[b],dv);
         for(auto j : range(dv.size())) eig[first[b]+j] = dv(j);
+        };
+    // the small blocks are independent LAPACK calls on private copies (a Hubbard-scale density matrix has ~25 of them per
+    // call, 0.1 ms each): a few host threads take them from a shared counter, largest first. Results do not depend on
+    // which thread ran a block.
+    static const int hostThreads = [] { auto* e = std::getenv("ITB_EIGH_HOST_THREADS"); int t = e ? std::atoi(e) : int(std::thread::hardware_concurrency()/2); return std::max(1,std::min(t,8)); }();
+    if(hostThreads > 1 && host_blocks.size() >= 8)
+        {
+        std::vector<size_t> order(host_blocks.size());
+        for(auto i : range(order.size())) order[i] = i;
+        std::sort(order.begin(),order.end(),[&](size_t x, size_t y) { return nn[host_blocks[x]] > nn[host_blocks[y]]; });
+        std::atomic<size_t> next{0};
+        std::exception_ptr err;
+        std::mutex errMutex;
+        auto work = [&]
+            {
+            try { for(size_t q = next++; q < order.size(); q = next++) hostBlock(order[q]); }
+            catch(...) { std::lock_guard<std::mutex> g(errMutex); if(!err) err = std::current_exception(); }
+            };
+        std::vector<std::thread> pool;
+        for(int t = 1; t < hostThreads; ++t) pool.emplace_back(work);
+        work();
+        for(auto& th : pool) th.join();
+        if(err) std::rethrow_exception(err);
         }
+    else for(auto i : range(host_blocks.size())) hostBlock(i);
     if(devThread.joinable()) devThread.join();
     if(devRc != ITB_OK) throw ITError("itensor_b200 (eigh batch): "+devErr);
     mark(1);
