@@ -856,7 +856,10 @@ contractQ(Contract& Con,
     itb_contract_plan* sliced = nullptr;
     if(gpu::world() > 1 && info.c_nblocks > 0 && rC > 0)
         {
-        static const double min_flops = [] { auto* e = std::getenv("ITB_SHARD_MIN_FLOPS"); return e ? std::atof(e) : 2e8; }();
+        // sharding a contraction costs a second (sliced) plan and, sooner or later, an exchange that waits for the slowest rank:
+        // measured on 2 GPUs, the Hubbard 16x4 ramp to maxdim 800 (contractions of 1e8-1e10 flops) ran 2x SLOWER with a
+        // threshold of 2e8 (23.6 s vs 11.7 s on one GPU). Only contractions worth >= ~0.5 ms of device time are sharded.
+        static const double min_flops = [] { auto* e = std::getenv("ITB_SHARD_MIN_FLOPS"); return e ? std::atof(e) : 1e10; }();
         auto pa = Abuf.pending(), pb = Bbuf.pending();
         if(pa && pb) { Bbuf.data(); pb.reset(); }       // two sharded operands: complete one of them
         auto& pend = pa ? pa : pb;

@@ -18,9 +18,6 @@
 #include <algorithm>
 #include <chrono>
 #include <thread>
-#include <atomic>
-#include <mutex>
-#include <exception>
 #include <cstdio>
 #include <functional>
 #include <vector>
@@ -478,30 +475,10 @@ eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args c
         diagHermitian(S,Uh[b],dv);
         for(auto j : range(dv.size())) eig[first[b]+j] = dv(j);
         };
-    // the small blocks are independent LAPACK calls on private copies (a Hubbard-scale density matrix has ~25 of them per
-    // call, 0.1 ms each): a few host threads take them from a shared counter, largest first. Results do not depend on
-    // which thread ran a block.
-    static const int hostThreads = [] { auto* e = std::getenv("ITB_EIGH_HOST_THREADS"); int t = e ? std::atoi(e) : int(std::thread::hardware_concurrency()/2); return std::max(1,std::min(t,8)); }();
-    if(hostThreads > 1 && host_blocks.size() >= 8)
-        {
-        std::vector<size_t> order(host_blocks.size());
-        for(auto i : range(order.size())) order[i] = i;
-        std::sort(order.begin(),order.end(),[&](size_t x, size_t y) { return nn[host_blocks[x]] > nn[host_blocks[y]]; });
-        std::atomic<size_t> next{0};
-        std::exception_ptr err;
-        std::mutex errMutex;
-        auto work = [&]
-            {
-            try { for(size_t q = next++; q < order.size(); q = next++) hostBlock(order[q]); }
-            catch(...) { std::lock_guard<std::mutex> g(errMutex); if(!err) err = std::current_exception(); }
-            };
-        std::vector<std::thread> pool;
-        for(int t = 1; t < hostThreads; ++t) pool.emplace_back(work);
-        work();
-        for(auto& th : pool) th.join();
-        if(err) std::rethrow_exception(err);
-        }
-    else for(auto i : range(host_blocks.size())) hostBlock(i);
+    // (one after the other: handing these small LAPACK calls to several host threads was tried — 2.1 -> 0.3 s in the Hubbard
+    // ramp — and dropped: the OpenBLAS this build links is not safe under concurrent callers, dsyev returned info != 0 in one
+    // of the GPU-box runs)
+    for(auto i : range(host_blocks.size())) hostBlock(i);
     if(devThread.joinable()) devThread.join();
     if(devRc != ITB_OK) throw ITError("itensor_b200 (eigh batch): "+devErr);
     mark(1);
