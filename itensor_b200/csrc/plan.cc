@@ -656,7 +656,10 @@ int build_contract_tables(itb_contract_plan& P) {
             if (ride) { to_tiles(c); continue; }
             const ItbCBlk& cb = P.cblks[c];
             P.class_flops[3] += 2.0 * (double)cb.M * (double)cb.N * (double)cb.ksum;
-            const bool eligible = !cA && !cB && cb.M >= cb.N && kUseRowGroups;
+            // real B (the MPO tensor of a real Hamiltonian) with real OR complex A: interleaved (re,im) makes a complex A block a
+            // real block with a doubled leading extent, row for row what the kernel streams. Complex B needs complex weights
+            // and (real A) a strided C row: those stay on the C-stationary kernels.
+            const bool eligible = !cB && cb.M >= cb.N && kUseRowGroups;
             if (eligible && want_rg) rg_cands.push_back(c); // row-group kernel (below); else C-stationary kernels
             else { push_skinny(c); P.rg_deferred |= eligible; }
         }
@@ -711,6 +714,7 @@ int build_contract_tables(itb_contract_plan& P) {
             struct LDim { int64_t ext; std::vector<int64_t> str; };
             std::vector<LDim> ld;
             const int64_t sl_ext = cblk_sl[cs[0]]; // all C blocks of a group share the long-side sectors, hence the slice
+            if (cA) ld.push_back({2, std::vector<int64_t>(A_blocks.size(), 1)}); // (re,im): fuses with the first long dim below
             for (size_t u = 0; u < uncA.size(); ++u) {
                 const bool sliced = sl_ext > 0 && P.slice_index == (int)u; // (C's leading indices are A's uncontracted ones)
                 const int64_t e = sliced ? sl_ext : A.ext(uncA[u], key[u]);
@@ -718,7 +722,7 @@ int build_contract_tables(itb_contract_plan& P) {
                 LDim d{e, {}};
                 d.str.reserve(A_blocks.size());
                 for (int64_t ia : A_blocks) {
-                    int64_t st = 1;
+                    int64_t st = csA; // strides in REAL elements
                     for (int i = 0; i < uncA[u]; ++i) st *= A.ext(i, A.block(ia)[i]);
                     d.str.push_back(st);
                 }

@@ -88,6 +88,17 @@ for sizes, dt in (([3, 9, 14, 8, 2], ITB_F64), ([3, 9, 14, 8, 2], ITB_C64), ([20
     braket_inds = [Index(ix.id, ix.sizes, ix.qns, -ix.dir, ix.mods, ix.plev) for ix in cur.inds]
     bra = BlockStruct(braket_inds, cur.blocks, cur.dtype)
     run(bra, synth.random_values(bra, 99), cur, cv, f"heff {sizes} dtype {dt} dot")
+# complex state, real operators (a real Hamiltonian applied to a complex phi): the MPO steps stream through the ROW-GROUP kernel
+# with the complex operand read as a real one of doubled leading extent
+for sizes in ([3, 9, 14, 8, 2], [20, 70, 45]):
+    sc, sr = synth.heff_chain(sizes, dtype=ITB_C64), synth.heff_chain(sizes, dtype=ITB_F64)
+    structs = (sc[0],) + tuple(sr[1:])
+    vals = [synth.random_values(s, 70 + i) for i, s in enumerate(structs)]
+    cur, cv = structs[0], vals[0]
+    before = stats["rowgroups"]
+    for k in range(1, 5):
+        cur, cv = run(cur, cv, structs[k], vals[k], f"heff complex phi x real operators {sizes} step {k}")
+    assert stats["rowgroups"] > before, "expected row groups for complex A x real B"
 # long K on few tiles: the stream-K partition must cut tiles into pieces (workspace slots + ordered reduction)
 for M, K, N, dt in ((64, 4096, 64, ITB_F64), (150, 3000, 40, ITB_F64), (40, 2500, 33, ITB_C64)):
     im, ik, inn = Index(1, (M,)), Index(2, (K,)), Index(3, (N,))

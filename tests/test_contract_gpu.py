@@ -8,6 +8,7 @@ import pytest
 
 import itensor_b200 as itb
 from itensor_b200 import synth
+from itensor_b200._lib import lib
 from itensor_b200.tensor import BlockStruct, Index
 from oracle import orc
 from util import assert_close, assert_struct_equal, gpu_contract_vs_oracle
@@ -121,6 +122,31 @@ def test_heff_product_chain(ctx, dtype, order):
         ref_s = plan.C
     assert [i.label for i in t.inds] == [i.prime().label for i in
                                          (structs[0].inds[k] for k in _order_lsr(structs[0]))]
+
+
+@pytest.mark.parametrize("sizes", [[3, 11, 17, 9, 2], [40, 130, 90]])
+def test_heff_chain_complex_state_real_operators(ctx, sizes):
+    """complex phi, real L / W1 / W2 / R (a real Hamiltonian applied to a complex state): real*complex and complex*real
+    pairings, and the MPO steps on the row-group streaming kernel (complex A read as a real operand of doubled leading
+    extent). Every plan is executed three times: the planner is tiered (C-stationary kernels first, row groups from the
+    third execution of a small streaming class), all three results must match the oracle."""
+    sc, sr = synth.heff_chain(sizes, dtype=Z), synth.heff_chain(sizes, dtype=F)
+    structs = (sc[0],) + tuple(sr[1:])
+    hosts = [synth.random_values(s, 30 + i) for i, s in enumerate(structs)]
+    t = itb.QTensor.from_host(ctx, structs[0], hosts[0])
+    ref_s, ref_v = structs[0], hosts[0]
+    saw_rowgroups = False
+    for s, h in zip(structs[1:], hosts[1:]):
+        plan = itb.ContractPlan(t.struct, s)
+        cs, tr, ref_v = orc.contract(ref_s, ref_v, s, h)
+        assert_struct_equal(plan.C, cs)
+        tb = itb.QTensor.from_host(ctx, s, h)
+        for _ in range(3):
+            out = itb.contract(t, tb, plan)
+            assert_close(out.to_host(), ref_v, what="heff step (complex state, real operators)")
+        saw_rowgroups |= lib().itb_contract_plan_rowgroups(plan._h, None, 0) > 0
+        t, ref_s = out, plan.C
+    assert saw_rowgroups
 
 
 def _order_lsr(phi):
