@@ -591,6 +591,13 @@ struct itb_eigh_batch {
     itb_svd_lanes* lanes = nullptr;
     cudaStream_t main = nullptr;
     bool joined = false;
+    // one host thread per busy lane (syevd / heevd synchronise their caller inside the call: issued from one thread the
+    // lanes run one after the other — 1.7 ms per block in the Hubbard ramp to maxdim 2000, 10 s of a 36 s run)
+    std::vector<int64_t> a_off;
+    std::vector<int64_t> mine[SVD_LANES];
+    std::vector<std::thread> threads;
+    int lane_rc[SVD_LANES] = {0, 0, 0, 0};
+    std::string lane_err[SVD_LANES];
 };
 
 template <typename T> struct NegOp;
@@ -603,6 +610,8 @@ __global__ void copy_scale_kernel(const T* __restrict__ in, T* __restrict__ out,
 
 static int eigh_batch_join(itb_eigh_batch* B) {
     if (B->joined) return ITB_OK;
+    for (auto& t : B->threads) t.join();
+    B->threads.clear();
     B->joined = true;
     int rc = ITB_OK;
     for (auto& ln : B->lanes->lane) {
@@ -612,8 +621,38 @@ static int eigh_batch_join(itb_eigh_batch* B) {
             rc = ITB_ERR_CUDA;
         }
     }
+    for (int q = 0; q < SVD_LANES; ++q)
+        if (B->lane_rc[q]) { itb::set_error(B->lane_err[q]); return B->lane_rc[q]; }
     if (rc) itb::set_error("eigh batch: could not order the solver lanes before the context stream");
     return rc;
+}
+
+// one block on one lane (called from that lane's host thread)
+static int eigh_one(SvdLane& ln, itb_eigh_batch* B, int64_t b, const void* dA, int negate) {
+    const int32_t dtype = B->dtype;
+    const size_t es = dtype == ITB_C64 ? 16 : 8;
+    const int nb = B->n[b];
+    void* dv = (char*)B->d_v + B->v_off[b];
+    double* dw = B->d_w + B->w_off[b];
+    const size_t ne = (size_t)nb * nb;
+    const int grid = (int)std::min<size_t>(148 * 4, (ne + 255) / 256);
+    if (dtype == ITB_F64) copy_scale_kernel<double><<<grid, 256, 0, ln.st>>>((const double*)dA + B->a_off[b], (double*)dv, ne, negate);
+    else copy_scale_kernel<double2><<<grid, 256, 0, ln.st>>>((const double2*)dA + B->a_off[b], (double2*)dv, ne, negate);
+    int lwork = 0;
+    cusolverStatus_t st = dtype == ITB_F64
+        ? cusolverDnDsyevd_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (double*)dv, nb, dw, &lwork)
+        : cusolverDnZheevd_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (cuDoubleComplex*)dv, nb, dw, &lwork);
+    if (st != CUSOLVER_STATUS_SUCCESS) { itb::set_error("eigh batch: syevd_bufferSize status " + std::to_string((int)st)); return ITB_ERR_CUDA; }
+    if (ln.work_bytes < (size_t)lwork * es + 256) {
+        // growing a lane's workspace: everything queued on that lane so far must have finished with the old one
+        if (cudaStreamSynchronize(ln.st) != cudaSuccess) { itb::set_error("eigh batch: lane synchronise failed"); return ITB_ERR_CUDA; }
+        if (grow(&ln.d_work, &ln.work_bytes, (size_t)lwork * es + 256) != ITB_OK) { itb::set_error("eigh batch: out of device memory (workspace)"); return ITB_ERR_NOMEM; }
+    }
+    st = dtype == ITB_F64
+        ? cusolverDnDsyevd(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (double*)dv, nb, dw, (double*)ln.d_work, lwork, B->d_info + b)
+        : cusolverDnZheevd(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (cuDoubleComplex*)dv, nb, dw, (cuDoubleComplex*)ln.d_work, lwork, B->d_info + b);
+    if (st != CUSOLVER_STATUS_SUCCESS) { itb::set_error("eigh batch: syevd status " + std::to_string((int)st)); return ITB_ERR_CUDA; }
+    return ITB_OK;
 }
 
 extern "C" {
@@ -650,38 +689,29 @@ int itb_solver_eigh_batch_run(itb_solver* s, int32_t dtype, int64_t nblocks, con
     for (auto& ln : s->lanes->lane)
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ln.st, s->lanes->ready, 0);
     if (e != cudaSuccess) return fail(std::string("eigh batch: ") + cudaGetErrorString(e), ITB_ERR_CUDA);
-    // largest blocks first, each onto the least loaded lane (cost ~ n^3)
+    // largest blocks first, each onto the least loaded lane (cost ~ n^3); one host thread drives each busy lane and the call
+    // returns at once (itb_eigh_batch_values joins)
     std::vector<int64_t> order(nblocks);
     for (int64_t b = 0; b < nblocks; ++b) order[b] = b;
     std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return n[x] > n[y]; });
     double load[SVD_LANES] = {0, 0, 0, 0};
+    B->a_off.assign(a_off, a_off + nblocks);
     for (int64_t b : order) {
         int q = 0;
         for (int t = 1; t < SVD_LANES; ++t) if (load[t] < load[q]) q = t;
         load[q] += (double)n[b] * n[b] * n[b] + 2e6;
-        SvdLane& ln = s->lanes->lane[q];
-        const int nb = n[b];
-        void* dv = (char*)B->d_v + B->v_off[b];
-        double* dw = B->d_w + B->w_off[b];
-        const size_t ne = (size_t)nb * nb;
-        const int grid = (int)std::min<size_t>(148 * 4, (ne + 255) / 256);
-        if (dtype == ITB_F64) copy_scale_kernel<double><<<grid, 256, 0, ln.st>>>((const double*)dA + a_off[b], (double*)dv, ne, negate);
-        else copy_scale_kernel<double2><<<grid, 256, 0, ln.st>>>((const double2*)dA + a_off[b], (double2*)dv, ne, negate);
-        int lwork = 0;
-        cusolverStatus_t st = dtype == ITB_F64
-            ? cusolverDnDsyevd_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (double*)dv, nb, dw, &lwork)
-            : cusolverDnZheevd_bufferSize(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (cuDoubleComplex*)dv, nb, dw, &lwork);
-        if (st != CUSOLVER_STATUS_SUCCESS) return fail("eigh batch: syevd_bufferSize status " + std::to_string((int)st), ITB_ERR_CUDA);
-        if (ln.work_bytes < (size_t)lwork * es + 256) {
-            // growing a lane's workspace: everything queued on that lane so far must have finished with the old one
-            if (cudaStreamSynchronize(ln.st) != cudaSuccess) return fail("eigh batch: lane synchronise failed", ITB_ERR_CUDA);
-            if (grow(&ln.d_work, &ln.work_bytes, (size_t)lwork * es + 256) != ITB_OK) return fail("eigh batch: out of device memory (workspace)", ITB_ERR_NOMEM);
-        }
-        st = dtype == ITB_F64
-            ? cusolverDnDsyevd(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (double*)dv, nb, dw, (double*)ln.d_work, lwork, B->d_info + b)
-            : cusolverDnZheevd(ln.h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, nb, (cuDoubleComplex*)dv, nb, dw, (cuDoubleComplex*)ln.d_work, lwork, B->d_info + b);
-        if (st != CUSOLVER_STATUS_SUCCESS) return fail("eigh batch: syevd status " + std::to_string((int)st), ITB_ERR_CUDA);
+        B->mine[q].push_back(b);
     }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto work = [B, dev, dA, negate](int q) {
+        cudaSetDevice(dev);
+        for (int64_t b : B->mine[q]) {
+            const int r = eigh_one(B->lanes->lane[q], B, b, dA, negate);
+            if (r) { B->lane_rc[q] = r; B->lane_err[q] = itb_last_error(); return; }
+        }
+    };
+    for (int q = 0; q < SVD_LANES; ++q) if (!B->mine[q].empty()) B->threads.emplace_back(work, q);
     *out = B;
     return ITB_OK;
 }

@@ -441,25 +441,14 @@ eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args c
         checkSvd(itb_memcpy_d2h(gpu::context(),hbuf[i].data(),static_cast<const char*>(d.buf.data())+size_t(off[b])*sizeof(T),hbuf[i].size()*sizeof(T)),"eigh block download");
         }
     EighGuard batch;
-    // cuSOLVER's syevd/heevd synchronise the calling thread inside every call (measured in the Hubbard ramp: 3.6 ms per
-    // diag_hermitian inside the "launch"), so the device blocks are driven from a helper thread while this thread
-    // diagonalises the small blocks with host LAPACK; nothing else touches the context until the join below
-    std::thread devThread;
-    int devRc = ITB_OK;
-    std::string devErr;
-    std::vector<int64_t> devOff; std::vector<int32_t> devN;
+    // (cuSOLVER's syevd/heevd synchronise their caller inside every call: itb_eigh_batch_run drives each solver lane from its
+    // own host thread and returns at once, so this thread diagonalises the small blocks with host LAPACK meanwhile)
     if(!dev_blocks.empty())
         {
-        for(auto b : dev_blocks) { devOff.push_back(off[b]); devN.push_back(nn[b]); }
-        auto* ctx = gpu::context();
-        const void* base = d.buf.data();
-        devThread = std::thread([&,ctx,base]
-            {
-            devRc = itb_eigh_batch_run(ctx,dtypeFor<T>(),int64_t(devOff.size()),devOff.data(),devN.data(),base,1,&batch.b);
-            if(devRc != ITB_OK) devErr = itb_last_error();
-            });
+        std::vector<int64_t> o; std::vector<int32_t> n2;
+        for(auto b : dev_blocks) { o.push_back(off[b]); n2.push_back(nn[b]); }
+        checkSvd(itb_eigh_batch_run(gpu::context(),dtypeFor<T>(),int64_t(dev_blocks.size()),o.data(),n2.data(),d.buf.data(),1,&batch.b),"eigh batch");
         }
-    struct Joiner { std::thread& t; ~Joiner() { if(t.joinable()) t.join(); } } joiner{devThread};
     mark(0);
     std::vector<long> first(nb+1,0);
     for(auto b : range(nb)) first[b+1] = first[b] + nn[b];
@@ -479,8 +468,6 @@ eighBlocksGPU(ITensor H, QDenseGPU<T> const& d, ITensor & U, ITensor & D, Args c
     // ramp — and dropped: the OpenBLAS this build links is not safe under concurrent callers, dsyev returned info != 0 in one
     // of the GPU-box runs)
     for(auto i : range(host_blocks.size())) hostBlock(i);
-    if(devThread.joinable()) devThread.join();
-    if(devRc != ITB_OK) throw ITError("itensor_b200 (eigh batch): "+devErr);
     mark(1);
     if(batch.b)
         {
