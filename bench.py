@@ -232,7 +232,6 @@ def main():
     ap.add_argument("--no-refine", action="store_true", help="keep the modelled tile partition (no measured re-partitioning of the plans)")
     ap.add_argument("--refine-rounds", type=int, default=4)
     ap.add_argument("--fused-exchange", action="store_true", help="N > 1: store the owned rows into the peers' buffers from the last contraction's epilogue (itb_contract_run_mirrored) instead of a separate block-copy launch; measured equal or slower (the remote stores stall the consumer warps: 0.760 vs 0.751 ms per step on 2 GPUs), so off by default")
-    ap.add_argument("--no-wide-push", action="store_true", help="N > 1: push every box with 8-byte elements (default: 16-byte elements where offsets, run lengths and strides are even)")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: re-replicate H*phi with pack / NCCL all-gather / scatter instead of direct peer-memory stores")
     ap.add_argument("--no-rebalance", action="store_true", help="N > 1: keep equal flops per rank (no measured re-balancing of the row partition)")
     ap.add_argument("--rebalance-rounds", type=int, default=3)
@@ -277,10 +276,7 @@ def main():
     # stays an uncontracted index of every later intermediate) -> contiguous C-block ranges per rank
     shard = None
     if world > 1:
-        from itensor_b200.shard import ChainShard, shard_chain
-
-        if args.no_wide_push:
-            ChainShard.wide_push = False
+        from itensor_b200.shard import shard_chain
 
         shard = shard_chain(plans, world, rank).prepare(ctx.empty)
     max_share = 1.0
@@ -545,7 +541,6 @@ def main():
             phases = {"contractions_ms": float(acc[0]), "push_ms": (None if fused[0] else float(acc[1])), "arrival_barrier_ms": float(acc[2]),
                       "exchange": ("inside the last contraction's epilogue" if fused[0] else "separate block-copy launch"),
                       "pushed_bytes_per_rank": int(shard.seg_elems[rank] * (16 if plans[-1].C.is_complex else 8) * (world - 1)),
-                      "push_boxes_8_byte_and_16_byte": list(getattr(shard, "push_items", (0, 0))),
                       "note": "rank 0, CUDA events, mean of 5 steps (the contractions here write the ordinary output buffer; the barrier includes waiting for the slowest rank)"}
         else:
             phases = {"contractions_ms": float(acc[0]), "pack_ms": float(acc[1]), "allgather_ms": float(acc[2]), "scatter_ms": float(acc[3]),

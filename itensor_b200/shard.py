@@ -266,12 +266,12 @@ class ChainShard:
                 items.append(it)
         return items
 
-    def _plan(self, items, dtype=None):
+    def _plan(self, items):
         from ._lib import check, lib
 
         arr = (CopyItem * max(len(items), 1))(*items)
         h = C.c_void_p()
-        dt = self.out_struct.dtype if dtype is None else dtype
+        dt = self.out_struct.dtype
         check(lib().itb_blockcopy_plan_create(len(items), C.cast(arr, C.c_void_p), dt, dt, C.byref(h)))
         return h
 
@@ -308,8 +308,6 @@ class ChainShard:
             events[3].record()
 
     # ---- direct exchange over peer memory (NVLink stores, no NCCL on the data path) -----------------------------------
-    wide_push = True   # 16-byte elements for the boxes that allow it (class attribute: set False to measure the difference)
-
     def prepare_p2p(self, ctx, nbuf: int = 2):
         """H*phi lives in `nbuf` peer-mapped buffers per rank (itb_p2p_alloc / itb_p2p_open); returns the list of local
         output tensors (flat float64, one per buffer) or None when peer memory is unavailable (caller keeps the all-gather).
@@ -379,32 +377,22 @@ class ChainShard:
             self.close_p2p()
             return None
         cs = 2 if self.out_struct.is_complex else 1
-        self._p2p_push16 = []
         for b in range(nbuf):
-            items, items16 = [], []
+            items = []
             for r, pptr in self._p2p_peers[b].items():
                 delta = pptr - self._p2p_local[b]
                 assert delta % (8 * cs) == 0
-                de = delta // (8 * cs)
                 for off, box, strides in self._boxes[self.rank]:
                     it = CopyItem()
                     it.n = len(box)
-                    # a real box whose runs start on even offsets, have even length and even strides is the same bytes as a
-                    # box of 16-byte elements: the copy kernel then moves it with 128-bit loads / stores, which is what the
-                    # NVLink store path wants (8-byte stores reach ~400 of 900 GB/s)
-                    wide = (cs == 1 and self.wide_push and strides[0] == 1 and box[0] % 2 == 0 and off % 2 == 0 and de % 2 == 0
-                            and all(st % 2 == 0 for st in strides[1:]))
-                    h = 2 if wide else 1
                     for d in range(len(box)):
-                        it.ext[d] = box[d] // h if d == 0 else box[d]
-                        it.sstr[d] = strides[d] if d == 0 else strides[d] // h
-                        it.dstr[d] = it.sstr[d]
-                    it.s_off = off // h
-                    it.d_off = (off + de) // h   # (offsets are in elements of the plan's dtype)
-                    (items16 if wide else items).append(it)
+                        it.ext[d] = box[d]
+                        it.sstr[d] = strides[d]
+                        it.dstr[d] = strides[d]
+                    it.s_off = off
+                    it.d_off = off + delta // (8 * cs)   # (offsets are in elements of the tensor's dtype)
+                    items.append(it)
             self._p2p_push.append(self._plan(items))
-            self._p2p_push16.append(self._plan(items16, dtype=1) if items16 else None)
-            self.push_items = (len(items), len(items16))
 
             class _Raw:  # zero-copy torch view of the peer-mappable buffer
                 pass
@@ -435,8 +423,6 @@ class ChainShard:
         if events:
             events[0].record()
         check(lib().itb_permute_run(ctx_handle, self._p2p_push[b], base, base, 1.0, 0.0, 0))
-        if self._p2p_push16[b] is not None:
-            check(lib().itb_permute_run(ctx_handle, self._p2p_push16[b], base, base, 1.0, 0.0, 0))
         if events:
             events[1].record()
         if self.flag_barrier:
@@ -479,9 +465,8 @@ class ChainShard:
         from ._lib import lib
 
         ctx = getattr(self, "_p2p_ctx", None)
-        for h in list(getattr(self, "_p2p_push", [])) + [x for x in getattr(self, "_p2p_push16", []) if x is not None]:
+        for h in getattr(self, "_p2p_push", []):
             lib().itb_permute_plan_destroy(h)
-        self._p2p_push16 = []
         for peers in getattr(self, "_p2p_peers", []):
             for pp in peers.values():
                 lib().itb_p2p_close(ctx.handle if ctx else None, C.c_void_p(pp))
