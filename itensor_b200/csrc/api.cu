@@ -18,7 +18,7 @@ cudaError_t launch_gemm(const ItbQItem* items, int n_items, int* queue, const in
                         const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                         long long* cta_cycles,
                         cudaStream_t st);
-cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm_static(const ItbTile* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
                                const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                                long long* cta_cycles, const ItbMirrors* mir, cudaStream_t st);
 cudaError_t launch_skinny(const ItbSkinny* items, int n, const ItbSkinny* q4, int nq4, const ItbSkinny* q8, int nq8,
@@ -47,6 +47,7 @@ struct DeviceTables {
     const ItbPair* pairs = nullptr;
     const ItbCBlk* cblks = nullptr;
     const ItbQItem* qitems = nullptr;
+    const ItbTile* tiles = nullptr;
     const int32_t* cta_begin = nullptr;
     const ItbSplitOut* splits = nullptr;
     const ItbRowGroup* rgroups = nullptr;
@@ -389,6 +390,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     const size_t o_pairs = pk.add(P->pairs.data(), P->pairs.size() * sizeof(ItbPair));
     const size_t o_cblk = pk.add(P->cblks.data(), P->cblks.size() * sizeof(ItbCBlk));
     const size_t o_tiles = pk.add(P->qitems.data(), P->qitems.size() * sizeof(ItbQItem));
+    const size_t o_tiles32 = pk.add(P->tiles.data(), P->tiles.size() * sizeof(ItbTile));
     const size_t o_splits = pk.add(P->splits.data(), P->splits.size() * sizeof(ItbSplitOut));
     const size_t o_cta = pk.add(P->cta_begin.data(), P->cta_begin.size() * sizeof(int32_t));
     const size_t o_rg = pk.add(P->rgroups.data(), P->rgroups.size() * sizeof(ItbRowGroup));
@@ -410,6 +412,7 @@ static int ensure_contract_tables(itb_ctx* c, itb_contract_plan* P) {
     dev->pairs = (const ItbPair*)(b + o_pairs);
     dev->cblks = (const ItbCBlk*)(b + o_cblk);
     dev->qitems = (const ItbQItem*)(b + o_tiles);
+    dev->tiles = (const ItbTile*)(b + o_tiles32);
     dev->cta_begin = (const int32_t*)(b + o_cta);
     dev->splits = (const ItbSplitOut*)(b + o_splits);
     dev->rgroups = (const ItbRowGroup*)(b + o_rg);
@@ -541,9 +544,13 @@ static int contract_run_impl(itb_ctx* c, itb_contract_plan* P, const void* dA, c
         // forces the other one), anything with a dynamic part on the ring kernel (kernels_gemm.cu)
         static const bool force_ring = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "ring"; }();
         if (!force_ring && has_static && P->cta_begin[n_static] == (int32_t)P->tiles.size()) {
-            SIDE_TRY(launch_gemm_static(d->qitems, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
+            SIDE_TRY(launch_gemm_static(d->tiles, d->cta_begin, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs, A, B, C, c->ws,
                                         c->profile ? c->d_cta_cycles : nullptr, mir, c->stream));
             c->h_item_cycles.clear();
+        } else if (P->qitems.size() != P->tiles.size()) {
+            join_side();
+            set_error("contract_run: the dynamic-queue kernel was selected but the plan carries no queue records");
+            return ITB_ERR_INVALID;
         } else
         SIDE_TRY(launch_gemm(d->qitems, (int)P->tiles.size(), d->counters, d->cta_begin, n_static, grid, d->splits, (int)P->splits.size(), d->cblks, d->pairs,
                              A, B, C, c->ws, c->profile ? c->d_cta_cycles : nullptr, c->stream));

@@ -373,7 +373,7 @@ __device__ __forceinline__ void produce_tile(const ItbTile& tile, const ItbCBlk*
 }
 
 template <bool MIRROR>
-__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbQItem* __restrict__ tiles, const int32_t* __restrict__ cta_begin,
+__global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbTile* __restrict__ tiles, const int32_t* __restrict__ cta_begin,
                                                             const ItbCBlk* __restrict__ cblks, const ItbPair* __restrict__ pairs,
                                                             const double* __restrict__ A, const double* __restrict__ B,
                                                             double* __restrict__ C, double* __restrict__ ws,
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(G_NT, 1) bsc_gemm_static_kernel(const ItbQItem
     // (stream-K partition, plan.cc); both roles walk it in the same order
     const int item_end = cta_begin[blockIdx.x + 1];
     for (int item = cta_begin[blockIdx.x]; item < item_end; ++item) {
-        const ItbTile tile = tiles[item].tile;
+        const ItbTile tile = tiles[item];
         const ItbCBlk* cb = cblks + tile.cblk;
         if (producer) {
             if (tile.cfg == 0) produce_tile<128, 128>(tile, cb, pairs, A, B, As, Bs, offM_s, offN_s, offKa_s, offKb_s, full, empty, ps);
@@ -428,7 +428,7 @@ cudaError_t launch_splitk_reduce(const ItbSplitOut* souts, int nsouts, const Itb
                                  cudaStream_t st); // kernels_gemm.cu
 
 // mir != nullptr (multi-GPU): every element of C is also stored into the peers' copies by the epilogue / the split-K reduction
-cudaError_t launch_gemm_static(const ItbQItem* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
+cudaError_t launch_gemm_static(const ItbTile* items, const int32_t* cta_begin, int grid, const ItbSplitOut* souts, int nsouts,
                                const ItbCBlk* cblks, const ItbPair* pairs, const double* A, const double* B, double* C, double* ws,
                                long long* cta_cycles, const ItbMirrors* mir, cudaStream_t st) {
     static bool configured = false;

@@ -965,9 +965,11 @@ int build_contract_tables(itb_contract_plan& P) {
         }
         P.cta_begin[G + 1] = (int32_t)P.tiles.size();
         PLAN_PHASE(4);
-        // flattened device records
-        P.qitems.resize(P.tiles.size());
-        for (size_t i = 0; i < P.tiles.size(); ++i) {
+        // flattened device records of the dynamic-queue kernel (160 bytes per item: only built when that kernel will run —
+        // the static kernel reads the 32-byte tile records themselves)
+        static const bool ring_forced = [] { const char* e = getenv("ITB_TILE_KERNEL"); return e && std::string(e) == "ring"; }();
+        P.qitems.resize((!kSchedStreamK || ring_forced) ? P.tiles.size() : 0);
+        for (size_t i = 0; i < P.qitems.size(); ++i) {
             ItbQItem& q = P.qitems[i];
             std::memset(&q, 0, sizeof(q));
             q.tile = P.tiles[i];
