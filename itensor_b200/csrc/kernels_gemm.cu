@@ -884,11 +884,12 @@ __global__ void __launch_bounds__(RG_NT, MINB) bsc_rowgroup_kernel(const ItbRgIt
         const int wb = gp->w_begin, wc = gp->w_count;
         for (int i = tid; i < wc; i += RG_NT) {
             const ItbRgW e = wents[wb + i];
-            W[e.j][e.o] = B[e.b_off];
+            W[e.j][e.o] = e.b_off < 0 ? -B[~e.b_off] : B[e.b_off];
         }
     }
     __syncthreads();
     const int e0 = gp->ext[0], e1 = gp->ext[1];
+    const int ostr = gp->ostr;
     for (int r0 = tid; r0 < it.rows; r0 += RG_NT * RG_RPT) {
         int i0[RG_RPT], i1[RG_RPT], i2[RG_RPT];
         bool valid[RG_RPT];
@@ -937,7 +938,7 @@ __global__ void __launch_bounds__(RG_NT, MINB) bsc_rowgroup_kernel(const ItbRgIt
 #pragma unroll
         for (int q = 0; q < RG_RPT; ++q) {
             if (!valid[q]) continue;
-            const int64_t l = it.row0 + r0 + q * RG_NT;
+            const int64_t l = (int64_t)(it.row0 + r0 + q * RG_NT) * ostr;
 #pragma unroll
             for (int o = 0; o < NOUT; ++o)
                 if (o < nout) C[out_s[o] + l] = y[q][o];

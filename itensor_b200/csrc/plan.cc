@@ -656,10 +656,11 @@ int build_contract_tables(itb_contract_plan& P) {
             if (ride) { to_tiles(c); continue; }
             const ItbCBlk& cb = P.cblks[c];
             P.class_flops[3] += 2.0 * (double)cb.M * (double)cb.N * (double)cb.ksum;
-            // real B (the MPO tensor of a real Hamiltonian) with real OR complex A: interleaved (re,im) makes a complex A block a
-            // real block with a doubled leading extent, row for row what the kernel streams. Complex B needs complex weights
-            // and (real A) a strided C row: those stay on the C-stationary kernels.
-            const bool eligible = !cB && cb.M >= cb.N && kUseRowGroups;
+            // All four real / complex pairings stream through the row-group kernel when A is the long operand. Real B with
+            // complex A: interleaved (re,im) makes a complex A block a real block with a doubled leading extent. Complex B:
+            // the output slots are the (re,im) components of C (row stride 2), and for complex A the input slots are the
+            // components of A with the weights +-B.re / B.im of the complex product.
+            const bool eligible = cb.M >= cb.N && kUseRowGroups;
             if (eligible && want_rg) rg_cands.push_back(c); // row-group kernel (below); else C-stationary kernels
             else { push_skinny(c); P.rg_deferred |= eligible; }
         }
@@ -714,7 +715,7 @@ int build_contract_tables(itb_contract_plan& P) {
             struct LDim { int64_t ext; std::vector<int64_t> str; };
             std::vector<LDim> ld;
             const int64_t sl_ext = cblk_sl[cs[0]]; // all C blocks of a group share the long-side sectors, hence the slice
-            if (cA) ld.push_back({2, std::vector<int64_t>(A_blocks.size(), 1)}); // (re,im): fuses with the first long dim below
+            if (cA && !cB) ld.push_back({2, std::vector<int64_t>(A_blocks.size(), 1)}); // (re,im): fuses with the first long dim below
             for (size_t u = 0; u < uncA.size(); ++u) {
                 const bool sliced = sl_ext > 0 && P.slice_index == (int)u; // (C's leading indices are A's uncontracted ones)
                 const int64_t e = sliced ? sl_ext : A.ext(uncA[u], key[u]);
@@ -736,8 +737,11 @@ int build_contract_tables(itb_contract_plan& P) {
             }
             int64_t L = 1;
             for (auto& d : ld) L *= d.ext;
-            bool eligible = (int)ld.size() <= ITB_RG_MAXL && L < (1ll << 31);
-            for (int32_t c : cs) eligible = eligible && P.cblks[c].N <= ITB_RG_MAXOUT && P.cblks[c].ksum <= ITB_RG_MAXIN && P.cblks[c].M == L;
+            const bool cc = cA && cB;                // complex * complex: rows are complex elements, slots are components
+            const int out_per_n = cc ? 2 : 1;        // output slots per column of the C block
+            bool eligible = (int)ld.size() <= ITB_RG_MAXL && L < (1ll << 30);
+            for (int32_t c : cs)
+                eligible = eligible && P.cblks[c].N * out_per_n <= ITB_RG_MAXOUT && P.cblks[c].ksum <= ITB_RG_MAXIN && P.cblks[c].M == L * (cc ? 2 : 1);
             if (!eligible) { for (int32_t c : cs) push_skinny(c); continue; }
             if (ld.empty()) ld.push_back({1, std::vector<int64_t>(A_blocks.size(), 0)});
             // sub-groups of whole C blocks: <= ITB_RG_MAXOUT output slots and <= ITB_RG_MAXIN input slots each
@@ -746,6 +750,7 @@ int build_contract_tables(itb_contract_plan& P) {
                 ItbRowGroup g;
                 std::memset(&g, 0, sizeof(g));
                 g.nL = (int32_t)ld.size();
+                g.ostr = cB ? 2 : 1;
                 for (int d = 0; d < ITB_RG_MAXL; ++d) g.ext[d] = d < g.nL ? (int32_t)ld[d].ext : 1;
                 g.L = L;
                 g.in_begin = (int32_t)P.rg_in.size(); g.out_begin = (int32_t)P.rg_out.size(); g.w_begin = (int32_t)P.rg_w.size();
@@ -761,7 +766,7 @@ int build_contract_tables(itb_contract_plan& P) {
                             const int64_t ae = P.pairs[p].a_off + host_off(k, P.pairs[p].k_ext, P.pairs[p].ak_str, P.pairs[p].k_n);
                             if (find_slot(ae) < 0 && std::find(fresh, fresh + nfresh, ae) == fresh + nfresh && nfresh <= ITB_RG_MAXIN) fresh[nfresh++] = ae;
                         }
-                    if (g.nout > 0 && (g.nout + cb.N > ITB_RG_MAXOUT || g.nin + nfresh > ITB_RG_MAXIN)) break;
+                    if (g.nout > 0 && (g.nout + cb.N * out_per_n > ITB_RG_MAXOUT || g.nin + nfresh > ITB_RG_MAXIN)) break;
                     for (int32_t p = cb.pair_begin; p < cb.pair_end; ++p) {
                         const ItbPair& pr = P.pairs[p];
                         const size_t qa = std::find(A_blocks.begin(), A_blocks.end(), pair_ia[p]) - A_blocks.begin();
@@ -778,12 +783,25 @@ int build_contract_tables(itb_contract_plan& P) {
                                 P.rg_in.push_back(in);
                             }
                             const int64_t bk = pr.b_off + host_off(k, pr.k_ext, pr.bk_str, pr.k_n);
-                            for (int32_t n = 0; n < cb.N; ++n)
-                                P.rg_w.push_back({slot, g.nout + n, bk + host_off(n, pr.n_ext, pr.bn_str, pr.n_n)});
+                            for (int32_t n = 0; n < cb.N; ++n) {
+                                const int64_t bn = host_off(n, pr.n_ext, pr.bn_str, pr.n_n);
+                                if (!cc) { P.rg_w.push_back({slot, g.nout + n, bk + bn}); continue; }
+                                // input slot = component pp = k & 1 of A (the folded k runs (re,im) fastest); output slots 2n, 2n+1 =
+                                // re, im of C: C.re = A.re B.re - A.im B.im, C.im = A.re B.im + A.im B.re
+                                const int pp = k & 1;
+                                const int64_t b0 = bk - pp + bn; // B(k,n).re
+                                for (int p = 0; p < 2; ++p) {
+                                    const int64_t bo = b0 + (p ^ pp);
+                                    P.rg_w.push_back({slot, g.nout + 2 * n + p, (pp == 1 && p == 0) ? ~bo : bo});
+                                }
+                            }
                         }
                     }
-                    for (int32_t n = 0; n < cb.N; ++n) P.rg_out.push_back(cb.c_off + (int64_t)n * cb.c_ns);
-                    g.nout += cb.N;
+                    for (int32_t n = 0; n < cb.N; ++n) {
+                        if (cc) { for (int p = 0; p < 2; ++p) P.rg_out.push_back(cb.c_off + p + (int64_t)n * cb.c_ns); }
+                        else P.rg_out.push_back(cb.c_off + (n & cb.c_nmask) + (int64_t)(n >> cb.c_nshift) * cb.c_ns);
+                    }
+                    g.nout += cb.N * out_per_n;
                     ++ci;
                 }
                 g.w_count = (int32_t)P.rg_w.size() - g.w_begin;

@@ -89,7 +89,9 @@ struct ItbSkinny { // work item of the streaming kernel: rows [row0,row0+rows) o
 #define ITB_RG_MAXOUT 16
 #define ITB_RG_MAXL 3
 struct ItbRowGroup {
-    int32_t nin, nout, nL, pad_;
+    int32_t nin, nout, nL;
+    int32_t ostr;                // stride (in reals) between consecutive long-side rows of an output slot: 1, or 2 when the
+                                 // slots are the (re, im) components of a complex C whose rows are complex elements
     int32_t ext[ITB_RG_MAXL];
     int32_t in_begin, out_begin; // into the slot tables
     int32_t w_begin, w_count;    // into the W entry table
@@ -97,7 +99,7 @@ struct ItbRowGroup {
     int64_t L;                   // rows
 };
 struct ItbRgIn { int64_t base; int64_t str[ITB_RG_MAXL]; }; // REAL-element offsets into A
-struct ItbRgW { int32_t j, o; int64_t b_off; };              // W[j][o] = B[b_off]
+struct ItbRgW { int32_t j, o; int64_t b_off; };              // W[j][o] = B[b_off]; b_off < 0: W[j][o] = -B[~b_off] (complex weights)
 struct ItbRgItem { int32_t group, row0, rows, pad_; };
 
 struct ItbDot { // work item of the split-K reduction kernel

@@ -136,7 +136,10 @@ static int emu_contract(itb_contract_plan* P, const double* A, const double* B, 
     for (auto& it : P->rg_items) {
         const ItbRowGroup& g = P->rgroups[it.group];
         std::vector<double> W((size_t)g.nin * g.nout, 0.0);
-        for (int32_t w = g.w_begin; w < g.w_begin + g.w_count; ++w) W[(size_t)P->rg_w[w].j * g.nout + P->rg_w[w].o] = B[P->rg_w[w].b_off];
+        for (int32_t w = g.w_begin; w < g.w_begin + g.w_count; ++w) {
+            const int64_t bo = P->rg_w[w].b_off;
+            W[(size_t)P->rg_w[w].j * g.nout + P->rg_w[w].o] = bo < 0 ? -B[~bo] : B[bo];
+        }
         for (int64_t l = it.row0; l < (int64_t)it.row0 + it.rows; ++l) {
             const int64_t a = l / g.ext[0], i0 = l - a * g.ext[0], b2 = a / g.ext[1], i1 = a - b2 * g.ext[1], i2 = b2;
             for (int o = 0; o < g.nout; ++o) {
@@ -145,7 +148,7 @@ static int emu_contract(itb_contract_plan* P, const double* A, const double* B, 
                     const ItbRgIn& in = P->rg_in[g.in_begin + j];
                     y += A[in.base + i0 * in.str[0] + i1 * in.str[1] + i2 * in.str[2]] * W[(size_t)j * g.nout + o];
                 }
-                C[P->rg_out[g.out_begin + o] + l] = y;
+                C[P->rg_out[g.out_begin + o] + l * g.ostr] = y;
             }
         }
     }

@@ -90,15 +90,18 @@ for sizes, dt in (([3, 9, 14, 8, 2], ITB_F64), ([3, 9, 14, 8, 2], ITB_C64), ([20
     run(bra, synth.random_values(bra, 99), cur, cv, f"heff {sizes} dtype {dt} dot")
 # complex state, real operators (a real Hamiltonian applied to a complex phi): the MPO steps stream through the ROW-GROUP kernel
 # with the complex operand read as a real one of doubled leading extent
+# ... and the other pairings: complex weights (complex operators: input / output slots are the (re,im) components, signed
+# weights) and real phi with complex operators (strided C rows)
 for sizes in ([3, 9, 14, 8, 2], [20, 70, 45]):
     sc, sr = synth.heff_chain(sizes, dtype=ITB_C64), synth.heff_chain(sizes, dtype=ITB_F64)
-    structs = (sc[0],) + tuple(sr[1:])
-    vals = [synth.random_values(s, 70 + i) for i, s in enumerate(structs)]
-    cur, cv = structs[0], vals[0]
-    before = stats["rowgroups"]
-    for k in range(1, 5):
-        cur, cv = run(cur, cv, structs[k], vals[k], f"heff complex phi x real operators {sizes} step {k}")
-    assert stats["rowgroups"] > before, "expected row groups for complex A x real B"
+    for what, structs in (("complex phi x real operators", (sc[0],) + tuple(sr[1:])), ("complex phi x complex operators", sc),
+                          ("real phi x complex operators", (sr[0],) + tuple(sc[1:]))):
+        vals = [synth.random_values(s, 70 + i) for i, s in enumerate(structs)]
+        cur, cv = structs[0], vals[0]
+        before = stats["rowgroups"]
+        for k in range(1, 5):
+            cur, cv = run(cur, cv, structs[k], vals[k], f"heff {what} {sizes} step {k}")
+        assert stats["rowgroups"] > before, f"expected row groups for {what}"
 # long K on few tiles: the stream-K partition must cut tiles into pieces (workspace slots + ordered reduction)
 for M, K, N, dt in ((64, 4096, 64, ITB_F64), (150, 3000, 40, ITB_F64), (40, 2500, 33, ITB_C64)):
     im, ik, inn = Index(1, (M,)), Index(2, (K,)), Index(3, (N,))

@@ -124,14 +124,18 @@ def test_heff_product_chain(ctx, dtype, order):
                                          (structs[0].inds[k] for k in _order_lsr(structs[0]))]
 
 
+@pytest.mark.parametrize("mix", ["complex_state_real_ops", "complex_state_complex_ops", "real_state_complex_ops"])
 @pytest.mark.parametrize("sizes", [[3, 11, 17, 9, 2], [40, 130, 90]])
-def test_heff_chain_complex_state_real_operators(ctx, sizes):
-    """complex phi, real L / W1 / W2 / R (a real Hamiltonian applied to a complex state): real*complex and complex*real
-    pairings, and the MPO steps on the row-group streaming kernel (complex A read as a real operand of doubled leading
-    extent). Every plan is executed three times: the planner is tiered (C-stationary kernels first, row groups from the
-    third execution of a small streaming class), all three results must match the oracle."""
+def test_heff_chain_mixed_dtypes_rowgroups(ctx, sizes, mix):
+    """The three pairings with a complex tensor in the chain: complex phi with real L / W1 / W2 / R (a real Hamiltonian
+    applied to a complex state: the complex operand is streamed as a real one of doubled leading extent), complex phi with
+    complex operators (input / output slots = (re,im) components, signed weights) and real phi with complex operators
+    (strided C rows). The MPO steps run on the row-group streaming kernel. Every plan is executed three times: the planner is
+    tiered (C-stationary kernels first, row groups from the third execution of a small streaming class), all three results
+    must match the oracle."""
     sc, sr = synth.heff_chain(sizes, dtype=Z), synth.heff_chain(sizes, dtype=F)
-    structs = (sc[0],) + tuple(sr[1:])
+    structs = {"complex_state_real_ops": (sc[0],) + tuple(sr[1:]), "complex_state_complex_ops": tuple(sc),
+               "real_state_complex_ops": (sr[0],) + tuple(sc[1:])}[mix]
     hosts = [synth.random_values(s, 30 + i) for i, s in enumerate(structs)]
     t = itb.QTensor.from_host(ctx, structs[0], hosts[0])
     ref_s, ref_v = structs[0], hosts[0]
