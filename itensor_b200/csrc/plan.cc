@@ -250,19 +250,19 @@ int build_contract_plan(itb_contract_plan& P) {
     P.triples.resize(nrec * 3);
     P.flops = 0;
     const double cmul = (A.dtype == ITB_C64 ? 2.0 : 1.0) * (B.dtype == ITB_C64 ? 2.0 : 1.0);
+    // 2*M*N*K of a pair = 2 * (elements of the A block) * (product of B's uncontracted extents): one product per block
+    std::vector<double> a_elems((size_t)A.nblocks, 1.0), b_unc((size_t)B.nblocks, 1.0);
+    for (int64_t a = 0; a < A.nblocks; ++a)
+        for (int i = 0; i < rA; ++i) a_elems[a] *= (double)A.ext(i, A.block(a)[i]);
+    for (int64_t b = 0; b < B.nblocks; ++b)
+        for (int j = 0; j < rB; ++j)
+            if (BtoA[j] < 0) b_unc[b] *= (double)B.ext(j, B.block(b)[j]);
     for (size_t p = 0; p < nrec; ++p) {
         const int64_t ra = packed ? precs[p].a : recs[p].a, rb = packed ? precs[p].b : recs[p].b;
         P.triples[3 * p + 0] = ra;
         P.triples[3 * p + 1] = rb;
         P.triples[3 * p + 2] = packed ? (int64_t)(std::lower_bound(ckeys.begin(), ckeys.end(), precs[p].ck) - ckeys.begin()) : cpos[recs[p].cb];
-        double m = 1, n = 1, k = 1;
-        for (int i = 0; i < rA; ++i) {
-            double e = (double)A.ext(i, A.block(ra)[i]);
-            if (AtoB[i] >= 0) k *= e; else m *= e;
-        }
-        for (int j = 0; j < rB; ++j)
-            if (BtoA[j] < 0) n *= (double)B.ext(j, B.block(rb)[j]);
-        P.flops += 2.0 * m * n * k * cmul;
+        P.flops += 2.0 * a_elems[ra] * b_unc[rb] * cmul;
     }
     PLAN_PHASE(6);
     P.tables_built = false;
