@@ -84,6 +84,11 @@ context()
         {
         int dev = 0;
         if(auto* e = std::getenv("ITB_DEVICE")) dev = std::atoi(e);
+        // One process per GPU: every rank must take the SAME numerical route for every block, or their states drift apart
+        // by rounding, then their control flow (Davidson iterations, kept dimensions), and the next collective never
+        // matches. The library warm-up makes "is the device solver ready yet" a matter of timing, so it is switched off
+        // here: the device solvers are used from the first call on every rank (first-use stalls instead).
+        if(std::getenv("ITB_WORLD") && std::atoi(std::getenv("ITB_WORLD")) > 1) setenv("ITB_WARM_LIBS","0",1);
         check(itb_ctx_create(dev,&g_ctx),"no CUDA device: DenseGPU/QDenseGPU have no CPU fallback");
         }
     return g_ctx;

@@ -94,11 +94,17 @@ def test_p2p_row_exchange_two_gpus():
 
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
-    procs = [ctxm.Process(target=_worker, args=(r, 2, 29577, q)) for r in range(2)]
+    procs = [ctxm.Process(target=_worker, args=(r, 2, 29577, q), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(2)]
-    for p in procs:
-        p.join(timeout=120)
+    try:
+        res = [q.get(timeout=240) for _ in range(2)]
+        for p in procs:
+            p.join(timeout=60)
+    finally:   # a rank that raised leaves its peer inside a collective: never wait for it
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+                p.join(timeout=10)
     for rank, errs in res:
         assert all(e == e and e <= 1e-12 for e in errs), (rank, errs)

@@ -280,10 +280,16 @@ def _run_ranks(binary, world, argv, env_extra, tmp_path):
                    ITB_COMM_FILE=comm_file, ITB_PROFILE="1", **env_extra)
         procs.append(subprocess.Popen([binary] + [str(a) for a in argv], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
-    for p in procs:
-        o, e = p.communicate(timeout=3000)
-        assert p.returncode == 0, e[-2000:]
-        outs.append((json.loads(o.strip().split("\n")[-1]), e))
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=900)   # (a rank that died leaves its peers inside a collective: fail, do not hang)
+            assert p.returncode == 0, e[-2000:]
+            outs.append((json.loads(o.strip().split("\n")[-1]), e))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+                p.wait()
     return outs
 
 
