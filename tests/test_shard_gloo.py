@@ -40,12 +40,16 @@ def _worker(rank, world, port, q):
     assert sh.mode == "rows" and 0 < sh.my_flops < sh.total_flops
     ctx = C.c_void_p()
     check(lib().itb_ctx_create(0, C.byref(ctx)))
-    cur = hosts[0]
-    for k, p in enumerate(plans):
-        # rows owned by other ranks stay NaN in every tensor of the chain: they must never be read by this rank
-        out = np.full(p.C.nelems, np.nan)
-        check(lib().itb_contract_run(ctx, p._h, cur.ctypes.data_as(C.c_void_p), hosts[k + 1].ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
-        cur = out
+    # three passes over the chain: the planner is tiered (a small streaming class starts on the C-stationary kernels and is
+    # re-planned with row groups at a plan's third execution), so the third pass walks the SLICED row-group tables
+    for _ in range(3):
+        cur = hosts[0]
+        for k, p in enumerate(plans):
+            # rows owned by other ranks stay NaN in every tensor of the chain: they must never be read by this rank
+            out = np.full(p.C.nelems, np.nan)
+            check(lib().itb_contract_run(ctx, p._h, cur.ctypes.data_as(C.c_void_p), hosts[k + 1].ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+            cur = out
+    assert sum(lib().itb_contract_plan_rowgroups(p._h, None, 0) for p in plans) > 0
     own = np.isfinite(cur).sum()
     t = torch.from_numpy(cur)
     sh.prepare(lambda n: torch.zeros(n, dtype=torch.float64))
