@@ -109,6 +109,17 @@ for M, K, N, dt in ((64, 4096, 64, ITB_F64), (150, 3000, 40, ITB_F64), (40, 2500
     before = stats["split_pieces"]
     run(A, synth.random_values(A, 7), B, synth.random_values(B, 8), f"dense long-K {M}x{K}x{N}")
     assert stats["split_pieces"] > before, "expected cut tiles"
+# itb_contract_run_mirrored (multi-GPU row exchange from the epilogue): on the mock the "peer copies" are plain host buffers
+A, B = BlockStruct.dense([Index(2, (300,)), Index(1, (70,))], ITB_F64), BlockStruct.dense([Index(3, (50,)), Index(2, (300,))], ITB_F64)
+av, bv = synth.random_values(A, 5), synth.random_values(B, 6)
+P = itb.ContractPlan(A, B)
+_, _, ref = orc.contract(A, av, B, bv)
+out = np.full(P.C.nreal, np.nan)
+peers = [np.full(P.C.nreal, np.nan) for _ in range(2)]
+arr = (C.c_void_p * 2)(*[p_.ctypes.data for p_ in peers])
+check(lib().itb_contract_run_mirrored(ctx, P._h, av.ctypes.data_as(C.c_void_p), bv.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 2, arr))
+want = np.ascontiguousarray(ref).view(np.float64).reshape(-1)
+assert np.abs(out - want).max() <= 1e-12 * np.abs(want).max() and all(np.array_equal(p_, out) for p_ in peers)
 # ---- permute / permuting accumulate: per-work-item records (4096-element chunks, PT x PT tiles, zero-fill items) ----
 from itensor_b200.tensor import PermutePlan, permuted_struct
 
